@@ -1,0 +1,141 @@
+/* spam_cuda.h — C ABI of libspam_cuda.so: the B200 (sm_100a) drop-in for the hot path of
+ * sledgehammervampire/sparse_matrix.
+ *
+ * What each entry point replaces (paths relative to the reference repo):
+ *   spam_spgemm_symbolic / spam_spgemm_numeric   body of CsrMatrix::mul_hash
+ *       spam_csr/src/mul_hash.rs:13-36  (rows_to_threads :38-64, mul_hash_symbolic :66-103,
+ *       mul_hash_numeric :105-201), reached from `impl Mul for &CsrMatrix`
+ *       spam_csr/src/lib.rs:292-297.  Two-phase because the reference allocates the result
+ *       Vecs with exact capacity after the symbolic scan (mul_hash.rs:117-119): the caller
+ *       (Rust) allocates, the library fills.
+ *   spam_dok_to_csr / spam_dok_to_csr_fetch      `impl From<DokMatrix<T>> for CsrMatrix<T,true>`
+ *       spam_csr/src/lib.rs:315-334 fed by DokMatrix::set_element spam_dok/src/lib.rs:167-176.
+ *   spam_spmv                                    NEW API (the reference has no SpMV);
+ *       semantics = a.mul_hash::<_,true>(&x) with x an n x 1 CsrMatrix.
+ *   spam_rows_to_parts                           rows_to_threads partition formula
+ *       spam_csr/src/mul_hash.rs:51-62 with tnum = number of GPUs.
+ *
+ * Conventions
+ *   - Host-side indices are uint64_t (Rust usize on 64-bit; CsrMatrix fields
+ *     spam_csr/src/lib.rs:25-32: vals, indices, offsets).  On the device col_idx is u32
+ *     (the reference truncates keys to u32, mul_hash.rs:92,157), row_ptr u64.
+ *   - Output rows are always emitted sorted by column (valid for both IS_SORTED
+ *     variants: invariant6, lib.rs:69-77).  Cancellation zeros are kept (mul_hash.rs:88-96).
+ *   - Integer dtypes wrap (two's complement), floats: products mul-then-add, no FMA.
+ *   - Every function returns a spam_status; nothing unwinds across the boundary.  The
+ *     reference panics where we return an error (mul_hash.rs:47-48, lib.rs:270).
+ *   - A handle owns one CUDA stream + workspace and is NOT thread-safe; use one handle
+ *     per thread.  There is no CPU fallback: without a CUDA device spam_cuda_create fails.
+ */
+#ifndef SPAM_CUDA_H
+#define SPAM_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct spam_handle spam_handle;
+typedef struct spam_dcsr spam_dcsr; /* device-resident CSR: u64 row_ptr[rows+1], u32 col_idx[nnz], T val[nnz] */
+
+typedef enum spam_dtype { SPAM_F32 = 0, SPAM_F64 = 1, SPAM_I32 = 2, SPAM_I64 = 3 } spam_dtype;
+
+typedef enum spam_status {
+  SPAM_OK = 0,
+  SPAM_EINVAL = 1,    /* null pointer / bad dtype / bad argument */
+  SPAM_EDIM = 2,      /* A.cols != B.rows (the reference would panic out-of-bounds, mul_hash.rs:46) */
+  SPAM_ECOLS = 3,     /* a dimension >= 2^32-1: u32::MAX is the empty-slot sentinel (mul_hash.rs:12, set.rs:110) */
+  SPAM_ENOMEM = 4,    /* device or host allocation failed */
+  SPAM_ECUDA = 5,     /* CUDA runtime error; see spam_last_error */
+  SPAM_ESTATE = 6,    /* numeric/fetch called without a matching symbolic/build */
+  SPAM_EOVERFLOW = 7, /* flop or nnz count overflowed (reference: checked_add().unwrap()) */
+  SPAM_EINDEX = 8,    /* IndexError: a triplet or column index out of range (spam_matrix/src/lib.rs:13) */
+  SPAM_EDTYPE = 9     /* operand dtypes differ */
+} spam_status;
+
+/* Per-call statistics of the last SpGEMM on this handle (device-side event timing). */
+typedef struct spam_stats {
+  uint64_t flops;        /* intermediate products P = sum over A entries of nnz(B row) (mul_hash.rs:44-48) */
+  uint64_t nnz_c;
+  uint64_t kernel_launches; /* number of kernels this library launched for the last call */
+  uint64_t bytes_h2d, bytes_d2h;
+  float ms_flop, ms_symbolic, ms_scan, ms_numeric, ms_total; /* CUDA-event times; 0 when timing disabled */
+  uint32_t sym_bin_rows[8]; /* rows per symbolic bin (by flop) */
+  uint32_t num_bin_rows[8]; /* rows per numeric bin (by nnz) */
+} spam_stats;
+
+/* ---- lifecycle --------------------------------------------------------------------- */
+int spam_cuda_create(spam_handle** h, int device);
+int spam_cuda_destroy(spam_handle* h);
+/* run on an existing CUDA stream (cudaStream_t as void*); NULL restores the handle's own stream */
+int spam_cuda_set_stream(spam_handle* h, void* cuda_stream);
+/* enable per-phase event timing into spam_stats (adds event records, no syncs beyond the API's own) */
+int spam_cuda_set_timing(spam_handle* h, int enabled);
+int spam_cuda_get_stats(spam_handle* h, spam_stats* out); /* syncs on the last product when timing is on */
+int spam_cuda_synchronize(spam_handle* h);
+const char* spam_strerror(int status);
+const char* spam_last_error(const spam_handle* h);
+/* number of symbols below that the library exports, and the ABI version (tests check this) */
+int spam_cuda_abi_version(void);
+
+/* pinned host memory for callers that want full-rate PCIe copies */
+int spam_host_alloc(void** p, uint64_t bytes);
+int spam_host_free(void* p);
+
+/* ---- host-buffer path (what the vendored spam_csr::mul_hash body calls) ---------------- */
+/* Phase 1: uploads A and B (B may alias A: same pointers => uploaded once), runs flop count +
+ * symbolic + scan.  Writes c_ptr[0..a_rows] (caller-owned, a_rows+1 entries) and *c_nnz. */
+int spam_spgemm_symbolic(spam_handle* h, int dtype, uint64_t a_rows, uint64_t a_cols, const uint64_t* a_ptr,
+                         const uint64_t* a_idx, const void* a_val, uint64_t b_rows, uint64_t b_cols,
+                         const uint64_t* b_ptr, const uint64_t* b_idx, const void* b_val, uint64_t* c_ptr,
+                         uint64_t* c_nnz);
+/* Phase 2: numeric pass + per-row column sort; fills caller-owned c_idx[c_nnz], c_val[c_nnz].
+ * `sorted` must be 1 (rows sorted by column; see header note). Releases the pending product. */
+int spam_spgemm_numeric(spam_handle* h, uint64_t* c_idx, void* c_val, int sorted);
+
+/* y = A x with dense x (a_cols) and y (a_rows); empty rows give 0. */
+int spam_spmv(spam_handle* h, int dtype, uint64_t a_rows, uint64_t a_cols, const uint64_t* a_ptr,
+              const uint64_t* a_idx, const void* a_val, const void* x, void* y);
+
+/* Triplet stream (DokMatrix::set_element order: last write wins, writing zero deletes) -> sorted CSR.
+ * Phase 1 writes c_ptr[rows+1] and *c_nnz; phase 2 fills c_idx/c_val. */
+int spam_dok_to_csr(spam_handle* h, int dtype, uint64_t rows, uint64_t cols, uint64_t n_triplets,
+                    const uint64_t* tri_rows, const uint64_t* tri_cols, const void* tri_vals, uint64_t* c_ptr,
+                    uint64_t* c_nnz);
+int spam_dok_to_csr_fetch(spam_handle* h, uint64_t* c_idx, void* c_val);
+
+/* ---- device-resident path (benchmarks, multi-GPU, chained products) ---------------------- */
+int spam_csr_upload(spam_handle* h, int dtype, uint64_t rows, uint64_t cols, uint64_t nnz, const uint64_t* ptr,
+                    const uint64_t* idx, const void* val, spam_dcsr** out);
+/* non-owning view over caller-managed device memory (e.g. torch tensors): u64 ptr, u32 idx, T val */
+int spam_dcsr_wrap(spam_handle* h, int dtype, uint64_t rows, uint64_t cols, uint64_t nnz, const void* d_ptr_u64,
+                   const void* d_idx_u32, const void* d_val, spam_dcsr** out);
+int spam_dcsr_info(const spam_dcsr* m, int* dtype, uint64_t* rows, uint64_t* cols, uint64_t* nnz, void** d_ptr,
+                   void** d_idx, void** d_val);
+int spam_dcsr_download(spam_handle* h, const spam_dcsr* m, uint64_t* ptr, uint64_t* idx, void* val);
+int spam_dcsr_free(spam_handle* h, spam_dcsr* m);
+/* rows [r0, r1) of m as a new owning matrix with row_ptr rebased to 0 (the per-rank A block) */
+int spam_dcsr_slice_rows(spam_handle* h, const spam_dcsr* m, uint64_t r0, uint64_t r1, spam_dcsr** out);
+
+/* C = A * B, all on the device; *c is a new owning matrix (stream-ordered allocation). */
+int spam_spgemm_dev(spam_handle* h, const spam_dcsr* a, const spam_dcsr* b, spam_dcsr** c);
+int spam_spmv_dev(spam_handle* h, const spam_dcsr* a, const void* d_x, void* d_y);
+/* device triplets (u64 rows, u64 cols, T vals) -> device CSR */
+int spam_dok_to_csr_dev(spam_handle* h, int dtype, uint64_t rows, uint64_t cols, uint64_t n_triplets,
+                        const void* d_tri_rows, const void* d_tri_cols, const void* d_tri_vals, spam_dcsr** out);
+
+/* Flop-balanced contiguous row blocks: row_starts[0]=0, row_starts[parts]=a.rows,
+ * row_starts[t] = partition_point(ps <= ceil(total/parts)*t) - 1   (mul_hash.rs:51-62).
+ * Also returns the total intermediate-product count. */
+int spam_rows_to_parts(spam_handle* h, const spam_dcsr* a, const spam_dcsr* b, uint32_t parts,
+                       uint64_t* row_starts /* parts+1, host */, uint64_t* total_flops);
+
+/* add `offset` to every entry of a device u64 array (offset-fixing a rank's row_ptr shard before the
+ * all-gather-v); n entries */
+int spam_offset_u64(spam_handle* h, void* d_ptr_u64, uint64_t n, uint64_t offset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPAM_CUDA_H */

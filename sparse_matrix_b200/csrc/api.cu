@@ -1,0 +1,524 @@
+// api.cu — the extern "C" boundary of libspam_cuda.so (see include/spam_cuda.h for what each
+// entry point replaces in the reference).  Plain pointers and sizes only; no exceptions cross it.
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "common.cuh"
+
+int spam_fail(spam_handle* h, int status, const char* what, cudaError_t ce) {
+  if (h) {
+    h->err = what ? what : "";
+    if (ce != cudaSuccess) {
+      h->err += ": ";
+      h->err += cudaGetErrorString(ce);
+    }
+  }
+  return status;
+}
+
+int dev_alloc(spam_handle* h, void** p, size_t bytes) {
+  *p = nullptr;
+  if (bytes == 0) bytes = 16;
+  cudaError_t e = cudaMallocAsync(p, bytes, h->stream);
+  if (e == cudaErrorMemoryAllocation) {
+    cudaGetLastError();
+    return spam_fail(h, SPAM_ENOMEM, "device allocation failed", e);
+  }
+  if (e != cudaSuccess) return spam_fail(h, SPAM_ECUDA, "cudaMallocAsync", e);
+  return SPAM_OK;
+}
+
+int dev_free(spam_handle* h, void* p) {
+  if (!p) return SPAM_OK;
+  cudaError_t e = cudaFreeAsync(p, h->stream);
+  if (e != cudaSuccess) return spam_fail(h, SPAM_ECUDA, "cudaFreeAsync", e);
+  return SPAM_OK;
+}
+
+struct SpgemmHostState {  // what lives between spam_spgemm_symbolic and spam_spgemm_numeric
+  spam_dcsr* a;
+  spam_dcsr* b;  // may alias a
+  SpgemmPending* pend;
+};
+struct DokPending {
+  spam_dcsr* c;
+};
+
+namespace {
+
+__global__ void k_partition_points(const u64* __restrict__ ps, u64 m, u32 parts, u64* __restrict__ out) {
+  // mul_hash.rs:52-62: avg = ceil(total / tnum); rows_offset[t] = partition_point(ps <= avg*t) - 1
+  const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t > parts) return;
+  if (t == 0) { out[0] = 0; return; }
+  if (t == parts) { out[parts] = m; return; }
+  const u64 total = ps[m];
+  const u64 avg = (total + parts - 1) / parts;
+  const u64 bound = avg * t;
+  u64 lo = 0, hi = m + 1;  // first index with ps[idx] > bound
+  while (lo < hi) {
+    const u64 mid = (lo + hi) >> 1;
+    if (ps[mid] <= bound) lo = mid + 1; else hi = mid;
+  }
+  out[t] = lo - 1;  // ps[0] = 0 <= bound so lo >= 1
+}
+
+__global__ void __launch_bounds__(256) k_rebase_ptr(const u64* __restrict__ in, u64* __restrict__ out, u64 n) {
+  const u64 base = in[0];
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = in[i] - base;
+}
+
+int set_device(spam_handle* h) {
+  CK(cudaSetDevice(h->device));
+  return SPAM_OK;
+}
+
+void free_dcsr(spam_handle* h, spam_dcsr* m) {
+  if (!m) return;
+  if (m->owning) {
+    dev_free(h, m->ptr);
+    dev_free(h, m->idx);
+    dev_free(h, m->val);
+  }
+  delete m;
+}
+
+void drop_spgemm_state(spam_handle* h) {
+  SpgemmHostState* s = static_cast<SpgemmHostState*>(h->pending);
+  if (!s) return;
+  if (s->pend) spgemm_pending_free(h, s->pend);
+  if (s->b && s->b != s->a) free_dcsr(h, s->b);
+  free_dcsr(h, s->a);
+  delete s;
+  h->pending = nullptr;
+}
+
+void drop_dok_state(spam_handle* h) {
+  if (!h->dok_pending) return;
+  free_dcsr(h, h->dok_pending->c);
+  delete h->dok_pending;
+  h->dok_pending = nullptr;
+}
+
+int valid_dtype(int dt) { return dt == SPAM_F32 || dt == SPAM_F64 || dt == SPAM_I32 || dt == SPAM_I64; }
+
+void finish_timing(spam_handle* h) {
+  if (!h->timing || !h->stats.kernel_launches) return;
+  if (cudaEventSynchronize(h->ev[4]) != cudaSuccess) return;
+  float t;
+  if (cudaEventElapsedTime(&t, h->ev[0], h->ev[1]) == cudaSuccess) h->stats.ms_flop = t;
+  if (cudaEventElapsedTime(&t, h->ev[1], h->ev[2]) == cudaSuccess) h->stats.ms_symbolic = t;
+  if (cudaEventElapsedTime(&t, h->ev[2], h->ev[3]) == cudaSuccess) h->stats.ms_scan = t;
+  if (cudaEventElapsedTime(&t, h->ev[3], h->ev[4]) == cudaSuccess) h->stats.ms_numeric = t;
+  if (cudaEventElapsedTime(&t, h->ev[0], h->ev[4]) == cudaSuccess) h->stats.ms_total = t;
+}
+
+}  // namespace
+
+extern "C" {
+
+int spam_cuda_abi_version(void) { return 1; }
+
+const char* spam_strerror(int s) {
+  switch (s) {
+    case SPAM_OK: return "ok";
+    case SPAM_EINVAL: return "invalid argument";
+    case SPAM_EDIM: return "dimension mismatch: A.cols != B.rows";
+    case SPAM_ECOLS: return "dimension >= 2^32-1 not representable (u32::MAX is the empty-slot sentinel)";
+    case SPAM_ENOMEM: return "out of memory";
+    case SPAM_ECUDA: return "CUDA error";
+    case SPAM_ESTATE: return "call out of sequence (no pending symbolic/build phase)";
+    case SPAM_EOVERFLOW: return "flop or nnz count overflow";
+    case SPAM_EINDEX: return "index out of range";
+    case SPAM_EDTYPE: return "operand dtypes differ";
+    default: return "unknown status";
+  }
+}
+
+const char* spam_last_error(const spam_handle* h) { return h ? h->err.c_str() : "null handle"; }
+
+int spam_cuda_create(spam_handle** out, int device) {
+  if (!out) return SPAM_EINVAL;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return SPAM_ECUDA; }  // no CPU fallback
+  if (device < 0 || device >= ndev) return SPAM_EINVAL;
+  spam_handle* h = new (std::nothrow) spam_handle();
+  if (!h) return SPAM_ENOMEM;
+  h->device = device; h->timing = false; h->pending = nullptr; h->dok_pending = nullptr;
+  h->d_cnt = nullptr; h->h_cnt = nullptr; h->own_stream = nullptr; h->stream = nullptr;
+  h->stats = spam_stats{};
+  for (auto& e : h->ev) e = nullptr;
+  cudaError_t e = cudaSetDevice(device);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
+  h->stream = h->own_stream;
+  if (e == cudaSuccess) e = cudaMalloc((void**)&h->d_cnt, sizeof(Counters));
+  if (e == cudaSuccess) e = cudaHostAlloc((void**)&h->h_cnt, sizeof(Counters), cudaHostAllocDefault);
+  for (int i = 0; i < 6 && e == cudaSuccess; ++i) e = cudaEventCreate(&h->ev[i]);
+  cudaDeviceProp prop;
+  if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, device);
+  if (e == cudaSuccess) {
+    h->num_sms = prop.multiProcessorCount;
+    h->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    // keep freed blocks in the stream-ordered pool: steady-state products do no cudaMalloc
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      unsigned long long thr = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+  }
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    spam_cuda_destroy(h);
+    return SPAM_ECUDA;
+  }
+  *out = h;
+  return SPAM_OK;
+}
+
+int spam_cuda_destroy(spam_handle* h) {
+  if (!h) return SPAM_EINVAL;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  drop_spgemm_state(h);
+  drop_dok_state(h);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+  if (h->d_cnt) cudaFree(h->d_cnt);
+  if (h->h_cnt) cudaFreeHost(h->h_cnt);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  delete h;
+  return SPAM_OK;
+}
+
+int spam_cuda_set_stream(spam_handle* h, void* s) {
+  if (!h) return SPAM_EINVAL;
+  h->stream = s ? (cudaStream_t)s : h->own_stream;
+  return SPAM_OK;
+}
+
+int spam_cuda_set_timing(spam_handle* h, int enabled) {
+  if (!h) return SPAM_EINVAL;
+  h->timing = enabled != 0;
+  return SPAM_OK;
+}
+
+int spam_cuda_get_stats(spam_handle* h, spam_stats* out) {
+  if (!h || !out) return SPAM_EINVAL;
+  finish_timing(h);
+  *out = h->stats;
+  return SPAM_OK;
+}
+
+int spam_cuda_synchronize(spam_handle* h) {
+  if (!h) return SPAM_EINVAL;
+  CKS(set_device(h));
+  CK(cudaStreamSynchronize(h->stream));
+  return SPAM_OK;
+}
+
+int spam_host_alloc(void** p, uint64_t bytes) {
+  if (!p) return SPAM_EINVAL;
+  cudaError_t e = cudaHostAlloc(p, bytes ? bytes : 1, cudaHostAllocDefault);
+  if (e != cudaSuccess) { cudaGetLastError(); *p = nullptr; return SPAM_ENOMEM; }
+  return SPAM_OK;
+}
+int spam_host_free(void* p) {
+  if (!p) return SPAM_OK;
+  return cudaFreeHost(p) == cudaSuccess ? SPAM_OK : SPAM_ECUDA;
+}
+
+/* ---------------- device-resident matrices ---------------- */
+
+int spam_csr_upload(spam_handle* h, int dtype, uint64_t rows, uint64_t cols, uint64_t nnz, const uint64_t* ptr,
+                    const uint64_t* idx, const void* val, spam_dcsr** out) {
+  if (!h || !out || !ptr || (nnz && (!idx || !val)) || !valid_dtype(dtype)) return spam_fail(h, SPAM_EINVAL, "bad argument");
+  *out = nullptr;
+  if (rows >= 0xFFFFFFFFull || cols >= 0xFFFFFFFFull) return spam_fail(h, SPAM_ECOLS, "dimension >= 2^32-1");
+  CKS(set_device(h));
+  spam_dcsr* m = new spam_dcsr();
+  m->dtype = dtype; m->rows = rows; m->cols = cols; m->nnz = nnz; m->owning = true;
+  m->ptr = nullptr; m->idx = nullptr; m->val = nullptr;
+  u64* tmp = nullptr;
+  int st = dev_alloc_t(h, &m->ptr, rows + 1);
+  if (st == SPAM_OK) st = dev_alloc_t(h, &m->idx, nnz);
+  if (st == SPAM_OK) st = dev_alloc(h, &m->val, nnz * dtype_size(dtype));
+  if (st == SPAM_OK) st = dev_alloc_t(h, &tmp, nnz);
+  cudaError_t e = cudaSuccess;
+  if (st == SPAM_OK) {
+    e = cudaMemcpyAsync(m->ptr, ptr, (rows + 1) * sizeof(u64), cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess && nnz) e = cudaMemcpyAsync(tmp, idx, nnz * sizeof(u64), cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess && nnz) e = cudaMemcpyAsync(m->val, val, nnz * dtype_size(dtype), cudaMemcpyHostToDevice, h->stream);
+    if (e != cudaSuccess) st = spam_fail(h, SPAM_ECUDA, "cudaMemcpyAsync H2D", e);
+  }
+  if (st == SPAM_OK) st = narrow_u64_to_u32(h, tmp, m->idx, nnz);
+  dev_free(h, tmp);
+  if (st != SPAM_OK) { free_dcsr(h, m); return st; }
+  h->stats.bytes_h2d += (rows + 1) * 8 + nnz * (8 + dtype_size(dtype));
+  *out = m;
+  return SPAM_OK;
+}
+
+int spam_dcsr_wrap(spam_handle* h, int dtype, uint64_t rows, uint64_t cols, uint64_t nnz, const void* d_ptr,
+                   const void* d_idx, const void* d_val, spam_dcsr** out) {
+  if (!h || !out || !d_ptr || !valid_dtype(dtype)) return spam_fail(h, SPAM_EINVAL, "bad argument");
+  if (rows >= 0xFFFFFFFFull || cols >= 0xFFFFFFFFull) return spam_fail(h, SPAM_ECOLS, "dimension >= 2^32-1");
+  spam_dcsr* m = new spam_dcsr();
+  m->dtype = dtype; m->rows = rows; m->cols = cols; m->nnz = nnz; m->owning = false;
+  m->ptr = (u64*)d_ptr; m->idx = (u32*)d_idx; m->val = (void*)d_val;
+  *out = m;
+  return SPAM_OK;
+}
+
+int spam_dcsr_info(const spam_dcsr* m, int* dtype, uint64_t* rows, uint64_t* cols, uint64_t* nnz, void** d_ptr,
+                   void** d_idx, void** d_val) {
+  if (!m) return SPAM_EINVAL;
+  if (dtype) *dtype = m->dtype;
+  if (rows) *rows = m->rows;
+  if (cols) *cols = m->cols;
+  if (nnz) *nnz = m->nnz;
+  if (d_ptr) *d_ptr = m->ptr;
+  if (d_idx) *d_idx = m->idx;
+  if (d_val) *d_val = m->val;
+  return SPAM_OK;
+}
+
+int spam_dcsr_download(spam_handle* h, const spam_dcsr* m, uint64_t* ptr, uint64_t* idx, void* val) {
+  if (!h || !m) return spam_fail(h, SPAM_EINVAL, "bad argument");
+  CKS(set_device(h));
+  if (ptr) CK(cudaMemcpyAsync(ptr, m->ptr, (m->rows + 1) * sizeof(u64), cudaMemcpyDeviceToHost, h->stream));
+  u64* wide = nullptr;
+  if (idx && m->nnz) {
+    CKS(dev_alloc_t(h, &wide, m->nnz));
+    CKS(widen_u32_to_u64(h, m->idx, wide, m->nnz));
+    CK(cudaMemcpyAsync(idx, wide, m->nnz * sizeof(u64), cudaMemcpyDeviceToHost, h->stream));
+    CKS(dev_free(h, wide));
+  }
+  if (val && m->nnz) CK(cudaMemcpyAsync(val, m->val, m->nnz * dtype_size(m->dtype), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  h->stats.bytes_d2h += (ptr ? (m->rows + 1) * 8 : 0) + (idx ? m->nnz * 8 : 0) + (val ? m->nnz * dtype_size(m->dtype) : 0);
+  return SPAM_OK;
+}
+
+int spam_dcsr_free(spam_handle* h, spam_dcsr* m) {
+  if (!h) return SPAM_EINVAL;
+  if (!m) return SPAM_OK;
+  CKS(set_device(h));
+  free_dcsr(h, m);
+  return SPAM_OK;
+}
+
+int spam_dcsr_slice_rows(spam_handle* h, const spam_dcsr* m, uint64_t r0, uint64_t r1, spam_dcsr** out) {
+  if (!h || !m || !out || r0 > r1 || r1 > m->rows) return spam_fail(h, SPAM_EINVAL, "bad row range");
+  *out = nullptr;
+  CKS(set_device(h));
+  u64 ends[2];
+  CK(cudaMemcpyAsync(&ends[0], m->ptr + r0, sizeof(u64), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(&ends[1], m->ptr + r1, sizeof(u64), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  const u64 nnz = ends[1] - ends[0], rows = r1 - r0;
+  spam_dcsr* s = new spam_dcsr();
+  s->dtype = m->dtype; s->rows = rows; s->cols = m->cols; s->nnz = nnz; s->owning = true;
+  s->ptr = nullptr; s->idx = nullptr; s->val = nullptr;
+  int st = dev_alloc_t(h, &s->ptr, rows + 1);
+  if (st == SPAM_OK) st = dev_alloc_t(h, &s->idx, nnz);
+  if (st == SPAM_OK) st = dev_alloc(h, &s->val, nnz * dtype_size(m->dtype));
+  if (st == SPAM_OK) {
+    k_rebase_ptr<<<(unsigned)((rows + 1 + 255) / 256 > 2048 ? 2048 : (rows + 1 + 255) / 256), 256, 0, h->stream>>>(
+        m->ptr + r0, s->ptr, rows + 1);
+    count_launch(h);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess && nnz) e = cudaMemcpyAsync(s->idx, m->idx + ends[0], nnz * sizeof(u32), cudaMemcpyDeviceToDevice, h->stream);
+    if (e == cudaSuccess && nnz)
+      e = cudaMemcpyAsync(s->val, (const char*)m->val + ends[0] * dtype_size(m->dtype), nnz * dtype_size(m->dtype),
+                          cudaMemcpyDeviceToDevice, h->stream);
+    if (e != cudaSuccess) st = spam_fail(h, SPAM_ECUDA, "slice copy", e);
+  }
+  if (st != SPAM_OK) { free_dcsr(h, s); return st; }
+  *out = s;
+  return SPAM_OK;
+}
+
+/* ---------------- SpGEMM ---------------- */
+
+int spam_spgemm_dev(spam_handle* h, const spam_dcsr* a, const spam_dcsr* b, spam_dcsr** c) {
+  if (!h || !a || !b || !c) return spam_fail(h, SPAM_EINVAL, "null argument");
+  *c = nullptr;
+  CKS(set_device(h));
+  SpgemmPending* p = nullptr;
+  CKS(spgemm_symbolic_dev(h, a, b, &p));
+  CKS(spgemm_numeric_dev(h, p, c));
+  return SPAM_OK;
+}
+
+int spam_spgemm_symbolic(spam_handle* h, int dtype, uint64_t a_rows, uint64_t a_cols, const uint64_t* a_ptr,
+                         const uint64_t* a_idx, const void* a_val, uint64_t b_rows, uint64_t b_cols,
+                         const uint64_t* b_ptr, const uint64_t* b_idx, const void* b_val, uint64_t* c_ptr,
+                         uint64_t* c_nnz) {
+  if (!h || !a_ptr || !b_ptr || !c_ptr || !c_nnz || !valid_dtype(dtype)) return spam_fail(h, SPAM_EINVAL, "bad argument");
+  if (a_cols != b_rows) return spam_fail(h, SPAM_EDIM, "A.cols != B.rows");
+  CKS(set_device(h));
+  drop_spgemm_state(h);
+  h->stats = spam_stats{};
+  // a_ptr[a_rows] is nnz(A): offsets[rows] == indices.len() (invariant4, lib.rs:59-61)
+  const u64 a_nnz = a_ptr[a_rows], b_nnz = b_ptr[b_rows];
+  SpgemmHostState* s = new SpgemmHostState{nullptr, nullptr, nullptr};
+  h->pending = s;
+  const spam_stats keep = h->stats;
+  int st = spam_csr_upload(h, dtype, a_rows, a_cols, a_nnz, a_ptr, a_idx, a_val, &s->a);
+  const bool alias = (b_ptr == a_ptr && b_idx == a_idx && b_val == a_val && b_rows == a_rows && b_cols == a_cols);
+  if (st == SPAM_OK) {
+    if (alias) s->b = s->a;
+    else st = spam_csr_upload(h, dtype, b_rows, b_cols, b_nnz, b_ptr, b_idx, b_val, &s->b);
+  }
+  const u64 h2d = h->stats.bytes_h2d;
+  (void)keep;
+  if (st == SPAM_OK) st = spgemm_symbolic_dev(h, s->a, s->b, &s->pend);  // resets stats
+  if (st != SPAM_OK) { drop_spgemm_state(h); return st; }
+  h->stats.bytes_h2d = h2d;
+  cudaError_t e = cudaMemcpyAsync(c_ptr, spgemm_pending_cptr(s->pend), (a_rows + 1) * sizeof(u64), cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  if (e != cudaSuccess) { drop_spgemm_state(h); return spam_fail(h, SPAM_ECUDA, "D2H row_ptr", e); }
+  h->stats.bytes_d2h += (a_rows + 1) * 8;
+  *c_nnz = spgemm_pending_nnz(s->pend);
+  return SPAM_OK;
+}
+
+int spam_spgemm_numeric(spam_handle* h, uint64_t* c_idx, void* c_val, int sorted) {
+  if (!h) return SPAM_EINVAL;
+  SpgemmHostState* s = static_cast<SpgemmHostState*>(h->pending);
+  if (!s || !s->pend) return spam_fail(h, SPAM_ESTATE, "spam_spgemm_numeric without spam_spgemm_symbolic");
+  if (sorted != 1) return spam_fail(h, SPAM_EINVAL, "only sorted output (B2=true) is produced on the device");
+  const u64 nnz = spgemm_pending_nnz(s->pend);
+  if (nnz && (!c_idx || !c_val)) return spam_fail(h, SPAM_EINVAL, "null output buffer");
+  CKS(set_device(h));
+  spam_dcsr* c = nullptr;
+  SpgemmPending* p = s->pend;
+  s->pend = nullptr;  // consumed by numeric whatever the outcome
+  int st = spgemm_numeric_dev(h, p, &c);
+  if (st == SPAM_OK) st = spam_dcsr_download(h, c, nullptr, c_idx, c_val);
+  if (st == SPAM_OK) finish_timing(h);
+  free_dcsr(h, c);
+  drop_spgemm_state(h);
+  return st;
+}
+
+/* ---------------- SpMV ---------------- */
+
+int spam_spmv_dev(spam_handle* h, const spam_dcsr* a, const void* d_x, void* d_y) {
+  if (!h || !a || !d_x || !d_y) return spam_fail(h, SPAM_EINVAL, "null argument");
+  CKS(set_device(h));
+  return spmv_dev(h, a, d_x, d_y);
+}
+
+int spam_spmv(spam_handle* h, int dtype, uint64_t a_rows, uint64_t a_cols, const uint64_t* a_ptr,
+              const uint64_t* a_idx, const void* a_val, const void* x, void* y) {
+  if (!h || !a_ptr || !x || !y || !valid_dtype(dtype)) return spam_fail(h, SPAM_EINVAL, "bad argument");
+  CKS(set_device(h));
+  spam_dcsr* a = nullptr;
+  CKS(spam_csr_upload(h, dtype, a_rows, a_cols, a_ptr[a_rows], a_ptr, a_idx, a_val, &a));
+  void *dx = nullptr, *dy = nullptr;
+  const size_t es = dtype_size(dtype);
+  int st = dev_alloc(h, &dx, a_cols * es);
+  if (st == SPAM_OK) st = dev_alloc(h, &dy, a_rows * es);
+  cudaError_t e = cudaSuccess;
+  if (st == SPAM_OK) e = cudaMemcpyAsync(dx, x, a_cols * es, cudaMemcpyHostToDevice, h->stream);
+  if (st == SPAM_OK && e == cudaSuccess) st = spmv_dev(h, a, dx, dy);
+  if (st == SPAM_OK && e == cudaSuccess) e = cudaMemcpyAsync(y, dy, a_rows * es, cudaMemcpyDeviceToHost, h->stream);
+  if (st == SPAM_OK && e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  if (st == SPAM_OK && e != cudaSuccess) st = spam_fail(h, SPAM_ECUDA, "spmv copies", e);
+  dev_free(h, dx); dev_free(h, dy);
+  free_dcsr(h, a);
+  return st;
+}
+
+/* ---------------- DOK -> CSR ---------------- */
+
+int spam_dok_to_csr_dev(spam_handle* h, int dtype, uint64_t rows, uint64_t cols, uint64_t n, const void* d_r,
+                        const void* d_c, const void* d_v, spam_dcsr** out) {
+  if (!h || !out || !valid_dtype(dtype) || (n && (!d_r || !d_c || !d_v))) return spam_fail(h, SPAM_EINVAL, "bad argument");
+  *out = nullptr;
+  if (rows >= 0xFFFFFFFFull || cols >= 0xFFFFFFFFull) return spam_fail(h, SPAM_ECOLS, "dimension >= 2^32-1");
+  CKS(set_device(h));
+  return dok_to_csr_dev(h, dtype, rows, cols, n, (const u64*)d_r, (const u64*)d_c, d_v, out);
+}
+
+int spam_dok_to_csr(spam_handle* h, int dtype, uint64_t rows, uint64_t cols, uint64_t n, const uint64_t* tr,
+                    const uint64_t* tc, const void* tv, uint64_t* c_ptr, uint64_t* c_nnz) {
+  if (!h || !c_ptr || !c_nnz || !valid_dtype(dtype) || (n && (!tr || !tc || !tv))) return spam_fail(h, SPAM_EINVAL, "bad argument");
+  CKS(set_device(h));
+  drop_dok_state(h);
+  u64 *dr = nullptr, *dc = nullptr;
+  void* dv = nullptr;
+  const size_t es = dtype_size(dtype);
+  int st = dev_alloc_t(h, &dr, n);
+  if (st == SPAM_OK) st = dev_alloc_t(h, &dc, n);
+  if (st == SPAM_OK) st = dev_alloc(h, &dv, n * es);
+  cudaError_t e = cudaSuccess;
+  if (st == SPAM_OK && n) {
+    e = cudaMemcpyAsync(dr, tr, n * 8, cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dc, tc, n * 8, cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dv, tv, n * es, cudaMemcpyHostToDevice, h->stream);
+    if (e != cudaSuccess) st = spam_fail(h, SPAM_ECUDA, "triplet H2D", e);
+  }
+  spam_dcsr* c = nullptr;
+  if (st == SPAM_OK) st = spam_dok_to_csr_dev(h, dtype, rows, cols, n, dr, dc, dv, &c);
+  dev_free(h, dr); dev_free(h, dc); dev_free(h, dv);
+  if (st != SPAM_OK) return st;
+  e = cudaMemcpyAsync(c_ptr, c->ptr, (rows + 1) * 8, cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  if (e != cudaSuccess) { free_dcsr(h, c); return spam_fail(h, SPAM_ECUDA, "D2H row_ptr", e); }
+  *c_nnz = c->nnz;
+  h->dok_pending = new DokPending{c};
+  return SPAM_OK;
+}
+
+int spam_dok_to_csr_fetch(spam_handle* h, uint64_t* c_idx, void* c_val) {
+  if (!h) return SPAM_EINVAL;
+  if (!h->dok_pending) return spam_fail(h, SPAM_ESTATE, "spam_dok_to_csr_fetch without spam_dok_to_csr");
+  CKS(set_device(h));
+  spam_dcsr* c = h->dok_pending->c;
+  int st = SPAM_OK;
+  if (c->nnz && (!c_idx || !c_val)) st = spam_fail(h, SPAM_EINVAL, "null output buffer");
+  if (st == SPAM_OK) st = spam_dcsr_download(h, c, nullptr, c_idx, c_val);
+  drop_dok_state(h);
+  return st;
+}
+
+/* ---------------- multi-GPU helpers ---------------- */
+
+int spam_rows_to_parts(spam_handle* h, const spam_dcsr* a, const spam_dcsr* b, uint32_t parts, uint64_t* row_starts,
+                       uint64_t* total_flops) {
+  if (!h || !a || !b || !row_starts || parts == 0) return spam_fail(h, SPAM_EINVAL, "bad argument");
+  if (a->cols != b->rows) return spam_fail(h, SPAM_EDIM, "A.cols != B.rows");
+  CKS(set_device(h));
+  const u64 m = a->rows;
+  u32* flop = nullptr;
+  u64 *ps = nullptr, *d_out = nullptr;
+  CKS(dev_alloc_t(h, &flop, m));
+  CKS(dev_alloc_t(h, &ps, m + 1));
+  CKS(dev_alloc_t(h, &d_out, (u64)parts + 1));
+  CK(cudaMemsetAsync(h->d_cnt, 0, sizeof(Counters), h->stream));
+  CKS(flop_count_dev(h, a, b, flop, false));
+  CKS(scan_u32_to_u64(h, flop, ps, m, nullptr));
+  k_partition_points<<<(parts + 1 + 127) / 128, 128, 0, h->stream>>>(ps, m, parts, d_out);
+  count_launch(h);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(row_starts, d_out, ((u64)parts + 1) * 8, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(h->h_cnt, h->d_cnt, sizeof(Counters), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  dev_free(h, flop); dev_free(h, ps); dev_free(h, d_out);
+  if (h->h_cnt->error & 1u) return spam_fail(h, SPAM_EINDEX, "a column index of A is >= rows(B)");
+  if (total_flops) *total_flops = h->h_cnt->total_flops;
+  return SPAM_OK;
+}
+
+int spam_offset_u64(spam_handle* h, void* d_ptr_u64, uint64_t n, uint64_t offset) {
+  if (!h || (!d_ptr_u64 && n)) return spam_fail(h, SPAM_EINVAL, "bad argument");
+  CKS(set_device(h));
+  return add_offset_u64(h, (u64*)d_ptr_u64, n, offset);
+}
+
+}  // extern "C"

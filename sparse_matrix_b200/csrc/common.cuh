@@ -1,0 +1,194 @@
+// common.cuh — shared types for libspam_cuda (sm_100a).  Device layout of a CSR matrix:
+//   row_ptr : u64[rows+1]   (nnz(C) and flop prefix sums exceed 2^32 on the big configs)
+//   col_idx : u32[nnz]      (the reference truncates keys to u32: spam_csr/src/mul_hash.rs:92,157;
+//                            u32::MAX is the empty-slot sentinel: linprobe/src/set.rs:45,110)
+//   val     : T[nnz]
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/spam_cuda.h"
+
+typedef uint32_t u32;
+typedef uint64_t u64;
+typedef unsigned long long ull;
+
+constexpr u32 EMPTY_KEY = 0xFFFFFFFFu;  // linprobe/src/set.rs:45
+constexpr u32 HASH_SCAL = 107u;         // linprobe/src/lib.rs:13
+constexpr u32 MIN_TABLE = 16u;          // linprobe/src/lib.rs:14
+
+constexpr int NBINS = 8;
+
+// ---- row bins ---------------------------------------------------------------------------
+// Symbolic bins by flop f (intermediate products of the row).  The table must hold up to
+// min(f, cols(B)) distinct keys at load <= 1/2 (linprobe sizing rule, set.rs:38-43).
+//   0 tiny   f <= 32      thread-per-row, 64-slot private smem table
+//   1 G1     f <= 256     32-thread block,   512-key smem table
+//   2 G2     f <= 1024    64-thread block,   2048-key
+//   3 G3     f <= 4096    256-thread block,  8192-key
+//   4 G4     f <= 16384   1024-thread block, 32768-key
+//   5 heavy  f  > 16384   global-memory table, persistent 1024-thread blocks
+constexpr u32 SYM_TINY_MAX = 32, SYM_G1_MAX = 256, SYM_G2_MAX = 1024, SYM_G3_MAX = 4096, SYM_G4_MAX = 16384;
+// Numeric bins by row nnz z (table = max(16, 2*npow2(z)) slots of key+value, map.rs:49-58).
+//   0 tiny   z <= 16 and f <= 128   thread-per-row (sequential, reference accumulation order)
+//   1 G1     z <= 128    32-thread block,   256 slots
+//   2 G2     z <= 512    128-thread block,  1024 slots
+//   3 G3     z <= 2048   512-thread block,  4096 slots
+//   4 G4     z <= 8192   1024-thread block, 16384 slots (192 KB smem for 8-byte values)
+//   5 heavy  z  > 8192   global-memory table
+constexpr u32 NUM_TINY_MAX = 16, NUM_TINY_FLOP_MAX = 128, NUM_G1_MAX = 128, NUM_G2_MAX = 512, NUM_G3_MAX = 2048,
+              NUM_G4_MAX = 8192;
+
+__host__ __device__ __forceinline__ int sym_bin_of(u32 f) {
+  return f <= SYM_TINY_MAX ? 0 : f <= SYM_G1_MAX ? 1 : f <= SYM_G2_MAX ? 2 : f <= SYM_G3_MAX ? 3 : f <= SYM_G4_MAX ? 4 : 5;
+}
+__host__ __device__ __forceinline__ int num_bin_of(u32 z, u32 f) {
+  if (z <= NUM_TINY_MAX) return (f <= NUM_TINY_FLOP_MAX) ? 0 : 1;
+  return z <= NUM_G1_MAX ? 1 : z <= NUM_G2_MAX ? 2 : z <= NUM_G3_MAX ? 3 : z <= NUM_G4_MAX ? 4 : 5;
+}
+
+// ---- device counters block (one per handle, zeroed per product) ---------------------------
+struct Counters {
+  ull total_flops;
+  ull total_nnz;
+  u32 sym_bins[NBINS];
+  u32 num_bins[NBINS];
+  u32 sym_cursor[NBINS];
+  u32 num_cursor[NBINS];
+  u32 max_flop;
+  u32 max_nnz;
+  u32 error;      // bit0: column index of A >= rows(B); bit1: triplet index out of range
+  u32 work_a;     // dynamic work counters for the persistent heavy-row kernels
+  u32 work_b;
+  u32 scan_tile;  // dynamic tile id for the look-back scan
+  u32 pad[2];
+};
+
+struct BinBase { u32 v[NBINS]; };
+
+// ---- element arithmetic --------------------------------------------------------------------
+// mul_hash.rs:154-161: product `t * t1`, then `*t += t1`: two roundings, never fused.
+template <class T> struct Num;
+template <> struct Num<float> {
+  static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+  static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+  static __device__ __forceinline__ void atomic_add(float* p, float v) { atomicAdd(p, v); }
+  static __device__ __forceinline__ float zero() { return 0.f; }
+};
+template <> struct Num<double> {
+  static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+  static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+  static __device__ __forceinline__ void atomic_add(double* p, double v) { atomicAdd(p, v); }
+  static __device__ __forceinline__ double zero() { return 0.0; }
+};
+// integers wrap (release-mode Rust / Wrapping<iN>): do the arithmetic unsigned
+template <> struct Num<int32_t> {
+  static __device__ __forceinline__ int32_t mul(int32_t a, int32_t b) { return (int32_t)((u32)a * (u32)b); }
+  static __device__ __forceinline__ int32_t add(int32_t a, int32_t b) { return (int32_t)((u32)a + (u32)b); }
+  static __device__ __forceinline__ void atomic_add(int32_t* p, int32_t v) { atomicAdd((u32*)p, (u32)v); }
+  static __device__ __forceinline__ int32_t zero() { return 0; }
+};
+template <> struct Num<int64_t> {
+  static __device__ __forceinline__ int64_t mul(int64_t a, int64_t b) { return (int64_t)((u64)a * (u64)b); }
+  static __device__ __forceinline__ int64_t add(int64_t a, int64_t b) { return (int64_t)((u64)a + (u64)b); }
+  static __device__ __forceinline__ void atomic_add(int64_t* p, int64_t v) { atomicAdd((ull*)p, (ull)v); }
+  static __device__ __forceinline__ int64_t zero() { return 0; }
+};
+
+// next power of two, npow2(0) = npow2(1) = 1  (usize::next_power_of_two)
+__host__ __device__ __forceinline__ u32 npow2_u32(u32 x) {
+  if (x <= 1) return 1;
+#ifdef __CUDA_ARCH__
+  return 1u << (32 - __clz(x - 1));
+#else
+  u32 p = 1;
+  while (p < x) p <<= 1;
+  return p;
+#endif
+}
+__host__ __device__ __forceinline__ u64 npow2_u64(u64 x) {
+  u64 p = 1;
+  while (p < x) p <<= 1;
+  return p;
+}
+// linprobe table size for `capacity` items: max(16, 2*npow2(capacity))  (map.rs:33-38)
+__host__ __device__ __forceinline__ u32 table_size_u32(u32 capacity) {
+  u32 t = 2u * npow2_u32(capacity);
+  return t < MIN_TABLE ? MIN_TABLE : t;
+}
+// linprobe/src/lib.rs:29-31 + set.rs:131 / map.rs:68: (key * 107) & (len - 1)
+__device__ __forceinline__ u32 slot_of(u32 key, u32 mask) { return (key * HASH_SCAL) & mask; }
+
+// ---- matrices and the handle -----------------------------------------------------------------
+struct spam_dcsr {
+  int dtype;
+  u64 rows, cols, nnz;
+  u64* ptr;   // device
+  u32* idx;   // device
+  void* val;  // device
+  bool owning;
+};
+
+struct SpgemmPending;  // state between the two host phases
+struct DokPending;
+
+struct spam_handle {
+  int device;
+  cudaStream_t own_stream, stream;
+  bool timing;
+  std::string err;
+  spam_stats stats;
+  Counters* d_cnt;   // device
+  Counters* h_cnt;   // pinned host mirror
+  int num_sms;
+  int max_smem_optin;
+  void* pending;             // SpgemmHostState* (api.cu) between the two host phases
+  DokPending* dok_pending;
+  cudaEvent_t ev[6];
+};
+
+static inline size_t dtype_size(int dt) { return (dt == SPAM_F32 || dt == SPAM_I32) ? 4 : 8; }
+
+// error plumbing: record message, return status
+int spam_fail(spam_handle* h, int status, const char* what, cudaError_t ce = cudaSuccess);
+#define CK(call)                                                             \
+  do {                                                                       \
+    cudaError_t _e = (call);                                                 \
+    if (_e != cudaSuccess) return spam_fail(h, SPAM_ECUDA, #call, _e);       \
+  } while (0)
+#define CKS(call)                                \
+  do {                                           \
+    int _s = (call);                             \
+    if (_s != SPAM_OK) return _s;                \
+  } while (0)
+
+// stream-ordered allocation on the handle's stream (pool keeps freed blocks: no cudaMalloc
+// in steady state, the analogue of the reference reusing its allocator's free lists)
+int dev_alloc(spam_handle* h, void** p, size_t bytes);
+int dev_free(spam_handle* h, void* p);
+template <class T>
+static inline int dev_alloc_t(spam_handle* h, T** p, size_t n) { return dev_alloc(h, (void**)p, n * sizeof(T)); }
+
+static inline void count_launch(spam_handle* h, u64 n = 1) { h->stats.kernel_launches += n; }
+
+// ---- entry points implemented across the .cu files ---------------------------------------------
+// scan.cu : exclusive scan of u32 counts into u64 offsets (out has n+1 entries), decoupled look-back
+int scan_u32_to_u64(spam_handle* h, const u32* in, u64* out, u64 n, ull* d_total);
+// spgemm.cu
+int spgemm_symbolic_dev(spam_handle* h, const spam_dcsr* a, const spam_dcsr* b, SpgemmPending** out);
+int spgemm_numeric_dev(spam_handle* h, SpgemmPending* p, spam_dcsr** c);
+void spgemm_pending_free(spam_handle* h, SpgemmPending* p);
+u64 spgemm_pending_nnz(const SpgemmPending* p);
+const u64* spgemm_pending_cptr(const SpgemmPending* p);
+int flop_count_dev(spam_handle* h, const spam_dcsr* a, const spam_dcsr* b, u32* d_flop, bool do_bins);
+// spmv.cu
+int spmv_dev(spam_handle* h, const spam_dcsr* a, const void* d_x, void* d_y);
+// dok.cu
+int dok_to_csr_dev(spam_handle* h, int dtype, u64 rows, u64 cols, u64 n, const u64* d_r, const u64* d_c,
+                   const void* d_v, spam_dcsr** out);
+// convert.cu : index width conversion at the host boundary
+int narrow_u64_to_u32(spam_handle* h, const u64* in, u32* out, u64 n);
+int widen_u32_to_u64(spam_handle* h, const u32* in, u64* out, u64 n);
+int add_offset_u64(spam_handle* h, u64* p, u64 n, u64 off, const u64* src = nullptr);

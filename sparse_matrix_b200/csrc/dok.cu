@@ -1,0 +1,236 @@
+// dok.cu — DOK -> sorted CSR on the device, as a stable sort plus a segmented "last write wins".
+//
+// Replaces `impl From<DokMatrix<T>> for CsrMatrix<T, true>` (spam_csr/src/lib.rs:315-334) fed by
+// a stream of DokMatrix::set_element calls (spam_dok/src/lib.rs:167-176): inserting a non-zero
+// replaces the entry, inserting zero removes it, so the final map holds, per (row, col) key, the
+// LAST write of the stream unless that write is zero.  BTreeMap iteration order is (row, col)
+// lexicographic (spam_dok/src/lib.rs:234-242); empty rows get repeated offsets (lib.rs:321,325).
+//
+//   1. key = row << cbits | col (only the bits the shape needs), payload = stream position
+//   2. hand-written LSD radix sort, 8 bits per pass, stable => equal keys stay in stream order
+//   3. keep entry i iff it ends its key run and its value is non-zero; count kept entries per row
+//   4. look-back scans (scan.cu) give output positions and row_ptr; scatter col_idx / val
+//
+// All integer work, HBM-bound: each pass streams keys+payload (12 B) in and out once.
+#include "common.cuh"
+
+namespace {
+
+constexpr int RS_T = 256;
+constexpr int RS_ITEMS = 16;
+constexpr int RS_TILE = RS_T * RS_ITEMS;
+constexpr int RADIX = 256;
+
+__global__ void __launch_bounds__(256) k_make_keys(u64 n, u64 rows, u64 cols, int cbits, const u64* __restrict__ r,
+                                                   const u64* __restrict__ c, u64* __restrict__ keys,
+                                                   u32* __restrict__ pay, Counters* cnt) {
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  bool bad = false;
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const u64 ri = r[i], ci = c[i];
+    u64 key = 0;
+    if (ri < rows && ci < cols) key = (ri << cbits) | ci; else bad = true;  // IndexError (spam_dok lib.rs:168-170)
+    keys[i] = key;
+    pay[i] = (u32)i;
+  }
+  if (bad) atomicOr(&cnt->error, 2u);
+}
+
+__global__ void __launch_bounds__(RS_T) k_radix_hist(const u64* __restrict__ keys, u64 n, int shift,
+                                                     u32* __restrict__ hist, u32 nblocks) {
+  __shared__ u32 s_hist[RADIX];
+  const int tid = threadIdx.x;
+  s_hist[tid] = 0;
+  __syncthreads();
+  const u64 base = (u64)blockIdx.x * RS_TILE;
+#pragma unroll 4
+  for (int r = 0; r < RS_ITEMS; ++r) {
+    const u64 i = base + (u64)r * RS_T + tid;
+    if (i < n) atomicAdd(&s_hist[(keys[i] >> shift) & (RADIX - 1)], 1u);
+  }
+  __syncthreads();
+  hist[(u64)tid * nblocks + blockIdx.x] = s_hist[tid];
+}
+
+// Stable scatter: element order inside a tile is (round r, warp, lane); ranks follow it.
+__global__ void __launch_bounds__(RS_T) k_radix_scatter(const u64* __restrict__ keys_in, const u32* __restrict__ pay_in,
+                                                        u64* __restrict__ keys_out, u32* __restrict__ pay_out, u64 n,
+                                                        int shift, const u64* __restrict__ offs, u32 nblocks) {
+  __shared__ u32 s_cnt[RS_T / 32][RADIX];
+  __shared__ u32 s_run[RADIX];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  s_run[tid] = 0;
+#pragma unroll
+  for (int w = 0; w < RS_T / 32; ++w) s_cnt[w][tid] = 0;
+  __syncthreads();
+  const u64 base = (u64)blockIdx.x * RS_TILE;
+  const u64 my_off = offs[(u64)tid * nblocks + blockIdx.x];  // global base of digit `tid` for this block
+  __shared__ u64 s_off[RADIX];
+  s_off[tid] = my_off;
+  __syncthreads();
+  for (int r = 0; r < RS_ITEMS; ++r) {
+    const u64 i = base + (u64)r * RS_T + tid;
+    const bool valid = i < n;
+    u64 key = 0;
+    u32 pay = 0;
+    if (valid) { key = keys_in[i]; pay = pay_in[i]; }
+    const u32 d = valid ? (u32)((key >> shift) & (RADIX - 1)) : (u32)RADIX;
+    const unsigned peers = __match_any_sync(0xffffffffu, d);
+    const u32 rank_w = __popc(peers & ((1u << lane) - 1u));
+    if (valid && rank_w == 0) s_cnt[wid][d] = __popc(peers);
+    __syncthreads();
+    if (valid) {
+      u32 pre = s_run[d];
+      for (int w = 0; w < wid; ++w) pre += s_cnt[w][d];
+      const u64 pos = s_off[d] + pre + rank_w;
+      keys_out[pos] = key;
+      pay_out[pos] = pay;
+    }
+    __syncthreads();
+    u32 s = 0;
+#pragma unroll
+    for (int w = 0; w < RS_T / 32; ++w) { s += s_cnt[w][tid]; s_cnt[w][tid] = 0; }
+    s_run[tid] += s;
+    __syncthreads();
+  }
+}
+
+template <class V>
+__global__ void __launch_bounds__(256) k_mark_last(u64 n, int cbits, const u64* __restrict__ keys,
+                                                   const u32* __restrict__ pay, const V* __restrict__ vals,
+                                                   u32* __restrict__ flags, u32* __restrict__ row_cnt) {
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const u64 k = keys[i];
+    const bool last = (i + 1 == n) || (keys[i + 1] != k);
+    // num_traits::Zero::is_zero: t == 0 (so -0.0 is zero, NaN is not)
+    const bool keep = last && !(vals[pay[i]] == (V)0);
+    flags[i] = keep ? 1u : 0u;
+    if (keep) atomicAdd(&row_cnt[k >> cbits], 1u);
+  }
+}
+
+template <class V>
+__global__ void __launch_bounds__(256) k_emit(u64 n, int cbits, const u64* __restrict__ keys, const u32* __restrict__ pay,
+                                              const V* __restrict__ vals, const u32* __restrict__ flags,
+                                              const u64* __restrict__ pos, u32* __restrict__ c_idx, V* __restrict__ c_val) {
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  const u64 cmask = (1ull << cbits) - 1;
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    if (flags[i]) {
+      const u64 p = pos[i];
+      c_idx[p] = (u32)(keys[i] & cmask);
+      c_val[p] = vals[pay[i]];
+    }
+  }
+}
+
+int bits_for(u64 x) {  // bits needed to represent values in [0, x)
+  int b = 0;
+  while (b < 63 && (1ull << b) < x) ++b;
+  return b;
+}
+
+unsigned grid_for(const spam_handle* h, u64 n) {
+  u64 g = (n + 255) / 256;
+  const u64 cap = (u64)h->num_sms * 16;
+  if (g > cap) g = cap;
+  if (g == 0) g = 1;
+  return (unsigned)g;
+}
+
+// stable LSD radix sort of (key, payload) on `keybits` low bits; result may end in either buffer
+int radix_sort_pairs(spam_handle* h, u64 n, int keybits, u64*& k0, u32*& p0, u64*& k1, u32*& p1) {
+  if (n == 0) return SPAM_OK;
+  const u32 nblocks = (u32)((n + RS_TILE - 1) / RS_TILE);
+  u32* hist = nullptr;
+  u64* offs = nullptr;
+  CKS(dev_alloc_t(h, &hist, (u64)RADIX * nblocks));
+  CKS(dev_alloc_t(h, &offs, (u64)RADIX * nblocks + 1));
+  for (int shift = 0; shift < keybits; shift += 8) {
+    k_radix_hist<<<nblocks, RS_T, 0, h->stream>>>(k0, n, shift, hist, nblocks);
+    count_launch(h);
+    CK(cudaGetLastError());
+    CKS(scan_u32_to_u64(h, hist, offs, (u64)RADIX * nblocks, nullptr));
+    k_radix_scatter<<<nblocks, RS_T, 0, h->stream>>>(k0, p0, k1, p1, n, shift, offs, nblocks);
+    count_launch(h);
+    CK(cudaGetLastError());
+    u64* tk = k0; k0 = k1; k1 = tk;
+    u32* tp = p0; p0 = p1; p1 = tp;
+  }
+  CKS(dev_free(h, hist));
+  CKS(dev_free(h, offs));
+  return SPAM_OK;
+}
+
+template <class V>
+int dok_typed(spam_handle* h, u64 rows, u64 cols, u64 n, const u64* d_r, const u64* d_c, const V* d_v, spam_dcsr* out) {
+  const int cbits = bits_for(cols), rbits = bits_for(rows);
+  u64 *k0 = nullptr, *k1 = nullptr, *pos = nullptr;
+  u32 *p0 = nullptr, *p1 = nullptr, *flags = nullptr, *row_cnt = nullptr;
+  CKS(dev_alloc_t(h, &k0, n));
+  CKS(dev_alloc_t(h, &k1, n));
+  CKS(dev_alloc_t(h, &p0, n));
+  CKS(dev_alloc_t(h, &p1, n));
+  CKS(dev_alloc_t(h, &flags, n));
+  CKS(dev_alloc_t(h, &pos, n + 1));
+  CKS(dev_alloc_t(h, &row_cnt, rows));
+  CKS(dev_alloc_t(h, &out->ptr, rows + 1));
+  CK(cudaMemsetAsync(h->d_cnt, 0, sizeof(Counters), h->stream));
+  CK(cudaMemsetAsync(row_cnt, 0, rows * sizeof(u32), h->stream));
+  if (n) {
+    k_make_keys<<<grid_for(h, n), 256, 0, h->stream>>>(n, rows, cols, cbits, d_r, d_c, k0, p0, h->d_cnt);
+    count_launch(h);
+    CK(cudaGetLastError());
+    CKS(radix_sort_pairs(h, n, cbits + rbits, k0, p0, k1, p1));
+    k_mark_last<V><<<grid_for(h, n), 256, 0, h->stream>>>(n, cbits, k0, p0, d_v, flags, row_cnt);
+    count_launch(h);
+    CK(cudaGetLastError());
+  }
+  CKS(scan_u32_to_u64(h, flags, pos, n, &h->d_cnt->total_nnz));
+  CKS(scan_u32_to_u64(h, row_cnt, out->ptr, rows, nullptr));
+  CK(cudaMemcpyAsync(h->h_cnt, h->d_cnt, sizeof(Counters), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  int st = SPAM_OK;
+  if (h->h_cnt->error & 2u) st = spam_fail(h, SPAM_EINDEX, "triplet index out of range");
+  if (st == SPAM_OK) {
+    out->nnz = h->h_cnt->total_nnz;
+    st = dev_alloc_t(h, &out->idx, out->nnz);
+    if (st == SPAM_OK) st = dev_alloc(h, &out->val, out->nnz * sizeof(V));
+    if (st == SPAM_OK && n) {
+      k_emit<V><<<grid_for(h, n), 256, 0, h->stream>>>(n, cbits, k0, p0, d_v, flags, pos, out->idx, (V*)out->val);
+      count_launch(h);
+      cudaError_t e = cudaGetLastError();
+      if (e != cudaSuccess) st = spam_fail(h, SPAM_ECUDA, "k_emit", e);
+    }
+  }
+  dev_free(h, k0); dev_free(h, k1); dev_free(h, p0); dev_free(h, p1);
+  dev_free(h, flags); dev_free(h, pos); dev_free(h, row_cnt);
+  return st;
+}
+
+}  // namespace
+
+int dok_to_csr_dev(spam_handle* h, int dtype, u64 rows, u64 cols, u64 n, const u64* d_r, const u64* d_c,
+                   const void* d_v, spam_dcsr** out) {
+  if (n >= 0xFFFFFFFFull) return spam_fail(h, SPAM_EOVERFLOW, "more than 2^32-1 triplets");
+  h->stats = spam_stats{};
+  spam_dcsr* m = new spam_dcsr();
+  m->dtype = dtype; m->rows = rows; m->cols = cols; m->nnz = 0; m->owning = true;
+  m->ptr = nullptr; m->idx = nullptr; m->val = nullptr;
+  int st;
+  switch (dtype) {
+    case SPAM_F32: st = dok_typed<float>(h, rows, cols, n, d_r, d_c, (const float*)d_v, m); break;
+    case SPAM_F64: st = dok_typed<double>(h, rows, cols, n, d_r, d_c, (const double*)d_v, m); break;
+    case SPAM_I32: st = dok_typed<int32_t>(h, rows, cols, n, d_r, d_c, (const int32_t*)d_v, m); break;
+    case SPAM_I64: st = dok_typed<int64_t>(h, rows, cols, n, d_r, d_c, (const int64_t*)d_v, m); break;
+    default: st = spam_fail(h, SPAM_EINVAL, "bad dtype");
+  }
+  if (st != SPAM_OK) {
+    dev_free(h, m->ptr); dev_free(h, m->idx); dev_free(h, m->val);
+    delete m;
+    return st;
+  }
+  *out = m;
+  return SPAM_OK;
+}

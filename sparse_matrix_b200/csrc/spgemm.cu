@@ -1,0 +1,878 @@
+// spgemm.cu — Gustavson CSR x CSR SpGEMM for sm_100a, the replacement for the body of
+// CsrMatrix::mul_hash (spam_csr/src/mul_hash.rs:13-36):
+//
+//   rows_to_threads   (mul_hash.rs:38-64)   -> k_flop_count   : per-row intermediate-product count
+//                                               + row binning (the GPU analogue of the thread blocks)
+//   mul_hash_symbolic (mul_hash.rs:66-103)  -> k_sym_*        : distinct columns per row (linear-probe set)
+//   checked_inclusive_scan (lib.rs:267-274) -> scan.cu        : row_ptr of C
+//   mul_hash_numeric  (mul_hash.rs:105-201) -> k_num_*        : linear-probe map accumulate, then the
+//                                               B2=true branch (:164-175): per-row sort by column
+//
+// Hash design = linprobe (linprobe/src/{lib,set,map}.rs): open addressing, linear probing,
+// hash = key*107 mod 2^32, table = max(16, 2*npow2(n)) slots, u32::MAX = empty.
+//
+// Bins (common.cuh): thread-per-row private smem tables for tiny rows (sequential insertion in the
+// reference's own order => float sums bit-identical to the reference for those rows), one thread
+// block per row with a shared-memory table for medium rows, and persistent blocks with
+// global-memory tables for heavy power-law rows.  Everything is integer/byte gather-scatter work
+// bounded by HBM/L2 and shared-memory throughput; no tensor cores.
+#include "common.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------
+// block helpers
+// ------------------------------------------------------------------------------------------
+template <int T>
+__device__ __forceinline__ u32 block_reduce_sum_u32(u32 v, u32* s_warp /* >= T/32 */) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+  if (T == 32) return v;
+  if (lane == 0) s_warp[wid] = v;
+  __syncthreads();
+  u32 r = 0;
+#pragma unroll
+  for (int w = 0; w < T / 32; ++w) r += s_warp[w];
+  __syncthreads();
+  return r;
+}
+
+// exclusive scan of one u32 per thread across the block; returns exclusive prefix, *total = sum
+template <int T>
+__device__ __forceinline__ u32 block_excl_scan_u32(u32 v, u32* s_warp /* >= T/32 */, u32* total) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  u32 x = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    u32 y = __shfl_up_sync(0xffffffffu, x, d);
+    if (lane >= d) x += y;
+  }
+  if (T == 32) {
+    *total = __shfl_sync(0xffffffffu, x, 31);
+    return x - v;
+  }
+  if (lane == 31) s_warp[wid] = x;
+  __syncthreads();
+  u32 woff = 0, tot = 0;
+#pragma unroll
+  for (int w = 0; w < T / 32; ++w) {
+    u32 s = s_warp[w];
+    if (w < wid) woff += s;
+    tot += s;
+  }
+  __syncthreads();
+  *total = tot;
+  return woff + x - v;
+}
+
+// ------------------------------------------------------------------------------------------
+// flop count: flop_i = sum_{k in A.row i} nnz(B.row k)          (mul_hash.rs:39-50)
+// thread per row; rows longer than 32 entries are swept cooperatively by the warp.
+// ------------------------------------------------------------------------------------------
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_flop_count(u64 m, u64 b_rows, const u64* __restrict__ a_ptr,
+                                                      const u32* __restrict__ a_col, const u64* __restrict__ b_ptr,
+                                                      u32* __restrict__ flop_out, Counters* cnt, int do_bins) {
+  __shared__ u32 s_hist[NBINS];
+  __shared__ ull s_total;
+  __shared__ u32 s_max;
+  const int tid = threadIdx.x, lane = tid & 31;
+  if (tid < NBINS) s_hist[tid] = 0;
+  if (tid == 0) { s_total = 0; s_max = 0; }
+  __syncthreads();
+  const u64 row = (u64)blockIdx.x * BLOCK + tid;
+  const bool valid = row < m;
+  u64 lo = 0, hi = 0;
+  if (valid) { lo = a_ptr[row]; hi = a_ptr[row + 1]; }
+  const u64 len = hi - lo;
+  u64 f = 0;
+  bool bad = false;
+  if (valid && len <= 32) {
+    for (u64 e = lo; e < hi; ++e) {
+      const u32 k = a_col[e];
+      if (k < b_rows) f += b_ptr[k + 1] - b_ptr[k]; else bad = true;
+    }
+  }
+  unsigned longmask = __ballot_sync(0xffffffffu, valid && len > 32);
+  while (longmask) {
+    const int src = __ffs(longmask) - 1;
+    longmask &= longmask - 1;
+    const u64 l = __shfl_sync(0xffffffffu, lo, src), hh = __shfl_sync(0xffffffffu, hi, src);
+    u64 part = 0;
+    for (u64 e = l + lane; e < hh; e += 32) {
+      const u32 k = a_col[e];
+      if (k < b_rows) part += b_ptr[k + 1] - b_ptr[k]; else bad = true;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+    if (lane == src) f = part;
+  }
+  if (bad) atomicOr(&cnt->error, 1u);
+  if (valid) {
+    const u32 fs = f > 0xFFFFFFFFull ? 0xFFFFFFFFu : (u32)f;  // saturate: still lands in the heavy bin
+    flop_out[row] = fs;
+    if (do_bins) {
+      atomicAdd(&s_hist[sym_bin_of(fs)], 1u);
+      atomicMax(&s_max, fs);
+    }
+  }
+  // block total of f
+  u64 t = f;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) t += __shfl_xor_sync(0xffffffffu, t, d);
+  if (lane == 0 && t) atomicAdd(&s_total, (ull)t);
+  __syncthreads();
+  if (tid < NBINS && s_hist[tid]) atomicAdd(&cnt->sym_bins[tid], s_hist[tid]);
+  if (tid == 0) {
+    if (s_total) atomicAdd(&cnt->total_flops, s_total);
+    if (s_max) atomicMax(&cnt->max_flop, s_max);
+  }
+}
+
+// histogram of the numeric bins, from (row nnz, flop)
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_num_bin_count(u64 m, const u32* __restrict__ row_nnz,
+                                                         const u32* __restrict__ flop, Counters* cnt) {
+  __shared__ u32 s_hist[NBINS];
+  __shared__ u32 s_max;
+  const int tid = threadIdx.x;
+  if (tid < NBINS) s_hist[tid] = 0;
+  if (tid == 0) s_max = 0;
+  __syncthreads();
+  const u64 row = (u64)blockIdx.x * BLOCK + tid;
+  if (row < m) {
+    const u32 z = row_nnz[row];
+    atomicAdd(&s_hist[num_bin_of(z, flop[row])], 1u);
+    if (z > NUM_G4_MAX) atomicMax(&s_max, z);
+  }
+  __syncthreads();
+  if (tid < NBINS && s_hist[tid]) atomicAdd(&cnt->num_bins[tid], s_hist[tid]);
+  if (tid == 0 && s_max) atomicMax(&cnt->max_nnz, s_max);
+}
+
+// scatter row ids into per-bin segments of perm[] (counting sort by bin; a block's rows stay
+// together inside each bin so neighbouring rows still share cache lines of A and B)
+template <int BLOCK, bool NUMERIC>
+__global__ void __launch_bounds__(BLOCK) k_bin_scatter(u64 m, const u32* __restrict__ row_nnz,
+                                                       const u32* __restrict__ flop, BinBase base, u32* cursors,
+                                                       u32* __restrict__ perm) {
+  __shared__ u32 s_cnt[NBINS];
+  __shared__ u32 s_base[NBINS];
+  const int tid = threadIdx.x;
+  if (tid < NBINS) s_cnt[tid] = 0;
+  __syncthreads();
+  const u64 row = (u64)blockIdx.x * BLOCK + tid;
+  int b = -1;
+  u32 r = 0;
+  if (row < m) {
+    b = NUMERIC ? num_bin_of(row_nnz[row], flop[row]) : sym_bin_of(flop[row]);
+    r = atomicAdd(&s_cnt[b], 1u);
+  }
+  __syncthreads();
+  if (tid < NBINS && s_cnt[tid]) s_base[tid] = base.v[tid] + atomicAdd(&cursors[tid], s_cnt[tid]);
+  __syncthreads();
+  if (b >= 0) perm[s_base[b] + r] = (u32)row;
+}
+
+// ------------------------------------------------------------------------------------------
+// SYMBOLIC, tiny rows (flop <= 32): one thread per row, private 64-slot key table in shared
+// memory laid out [slot][thread] so a warp's accesses never bank-conflict whatever the slots.
+// Sequential insertion exactly like linprobe::HashSet::insert (set.rs:109-160), no atomics.
+// ------------------------------------------------------------------------------------------
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_sym_tiny(u32 n, const u32* __restrict__ perm,
+                                                    const u64* __restrict__ a_ptr, const u32* __restrict__ a_col,
+                                                    const u64* __restrict__ b_ptr, const u32* __restrict__ b_col,
+                                                    const u32* __restrict__ flop, u32* __restrict__ row_nnz) {
+  extern __shared__ u32 sm_tab[];  // [2*SYM_TINY_MAX][BLOCK]
+  const int tid = threadIdx.x;
+  const u32 i = blockIdx.x * BLOCK + tid;
+  if (i >= n) return;
+  const u32 row = perm ? perm[i] : i;
+  const u32 f = flop[row];
+  if (f == 0) { row_nnz[row] = 0; return; }        // mul_hash.rs:84-86
+  const u32 cap = table_size_u32(f), mask = cap - 1;  // <= 64
+  u32* tab = sm_tab + tid;
+  for (u32 s = 0; s < cap; ++s) tab[s * BLOCK] = EMPTY_KEY;
+  u32 cnt = 0;
+  const u64 lo = a_ptr[row], hi = a_ptr[row + 1];
+  for (u64 e = lo; e < hi; ++e) {
+    const u32 k = a_col[e];
+    const u64 bl = b_ptr[k], bh = b_ptr[k + 1];
+    for (u64 j = bl; j < bh; ++j) {
+      const u32 key = b_col[j];
+      u32 s = slot_of(key, mask);
+      for (;;) {
+        const u32 cur = tab[s * BLOCK];
+        if (cur == key) break;
+        if (cur == EMPTY_KEY) { tab[s * BLOCK] = key; ++cnt; break; }
+        s = (s + 1) & mask;
+      }
+    }
+  }
+  row_nnz[row] = cnt;  // mul_hash.rs:95
+}
+
+// ------------------------------------------------------------------------------------------
+// SYMBOLIC, one thread block per row, key table in shared memory (atomicCAS insertion).
+// Sub-groups of W = 2^wshift lanes each take one A entry and stride over that B row, so short
+// B rows still fill the warp.
+// ------------------------------------------------------------------------------------------
+template <int T, int CAP>
+__global__ void __launch_bounds__(T) k_sym_group(const u32* __restrict__ perm, const u64* __restrict__ a_ptr,
+                                                 const u32* __restrict__ a_col, const u64* __restrict__ b_ptr,
+                                                 const u32* __restrict__ b_col, const u32* __restrict__ flop,
+                                                 u32* __restrict__ row_nnz, int wshift) {
+  extern __shared__ u32 keys[];  // [CAP]
+  __shared__ u32 s_warp[32];
+  const int tid = threadIdx.x;
+  const u32 row = perm ? perm[blockIdx.x] : blockIdx.x;
+  const u32 f = flop[row];
+  if (f == 0) { if (tid == 0) row_nnz[row] = 0; return; }
+  u32 cap = table_size_u32(f);
+  if (cap > (u32)CAP) cap = CAP;
+  const u32 mask = cap - 1;
+  for (u32 s = tid; s < cap; s += T) keys[s] = EMPTY_KEY;
+  __syncthreads();
+  volatile u32* vkeys = keys;
+  const int W = 1 << wshift, sub = tid >> wshift, lane = tid & (W - 1), nsub = T >> wshift;
+  u32 cnt = 0;
+  const u64 lo = a_ptr[row], hi = a_ptr[row + 1];
+  for (u64 e = lo + sub; e < hi; e += nsub) {
+    const u32 k = a_col[e];
+    const u64 bl = b_ptr[k], bh = b_ptr[k + 1];
+    for (u64 j = bl + lane; j < bh; j += W) {
+      const u32 key = b_col[j];
+      u32 s = slot_of(key, mask);
+      for (;;) {
+        const u32 cur = vkeys[s];
+        if (cur == key) break;
+        if (cur == EMPTY_KEY) {
+          const u32 old = atomicCAS(&keys[s], EMPTY_KEY, key);
+          if (old == EMPTY_KEY) { ++cnt; break; }
+          if (old == key) break;
+        }
+        s = (s + 1) & mask;
+      }
+    }
+  }
+  const u32 total = block_reduce_sum_u32<T>(cnt, s_warp);
+  if (tid == 0) row_nnz[row] = total;
+}
+
+// ------------------------------------------------------------------------------------------
+// SYMBOLIC, heavy rows: persistent blocks, one global-memory key table per block, rows handed
+// out through an atomic work counter.
+// ------------------------------------------------------------------------------------------
+template <int T>
+__global__ void __launch_bounds__(T) k_sym_heavy(u32 n, const u32* __restrict__ perm, const u64* __restrict__ a_ptr,
+                                                 const u32* __restrict__ a_col, const u64* __restrict__ b_ptr,
+                                                 const u32* __restrict__ b_col, const u32* __restrict__ flop,
+                                                 u32* __restrict__ row_nnz, u32* tables, u64 table_stride,
+                                                 u32 b_cols, u32* work, int wshift) {
+  __shared__ u32 s_item;
+  __shared__ u32 s_warp[32];
+  const int tid = threadIdx.x;
+  u32* keys = tables + (u64)blockIdx.x * table_stride;
+  const int W = 1 << wshift, sub = tid >> wshift, lane = tid & (W - 1), nsub = T >> wshift;
+  for (;;) {
+    if (tid == 0) s_item = atomicAdd(work, 1u);
+    __syncthreads();
+    const u32 item = s_item;
+    __syncthreads();
+    if (item >= n) break;
+    const u32 row = perm ? perm[item] : item;
+    u32 f = flop[row];
+    if (f > b_cols) f = b_cols;  // at most cols(B) distinct keys
+    const u64 cap = 2ull * npow2_u64(f), mask = cap - 1;
+    for (u64 s = tid; s < cap; s += T) __stcg(&keys[s], EMPTY_KEY);
+    __syncthreads();
+    u32 cnt = 0;
+    const u64 lo = a_ptr[row], hi = a_ptr[row + 1];
+    for (u64 e = lo + sub; e < hi; e += nsub) {
+      const u32 k = a_col[e];
+      const u64 bl = b_ptr[k], bh = b_ptr[k + 1];
+      for (u64 j = bl + lane; j < bh; j += W) {
+        const u32 key = b_col[j];
+        u64 s = (u64)(key * HASH_SCAL) & mask;
+        for (;;) {
+          const u32 cur = __ldcg(&keys[s]);
+          if (cur == key) break;
+          if (cur == EMPTY_KEY) {
+            const u32 old = atomicCAS(&keys[s], EMPTY_KEY, key);
+            if (old == EMPTY_KEY) { ++cnt; break; }
+            if (old == key) break;
+          }
+          s = (s + 1) & mask;
+        }
+      }
+    }
+    const u32 total = block_reduce_sum_u32<T>(cnt, s_warp);
+    if (tid == 0) row_nnz[row] = total;
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// NUMERIC, tiny rows (nnz <= 16, flop <= 128): one thread per row, private key/value table
+// [slot][thread] in shared memory, table size max(16, 2*npow2(nnz)) exactly as
+// HashMap::shrink_to (map.rs:49-58).  Products are visited in the reference's order
+// (mul_hash.rs:145-162) and accumulated sequentially with separate mul and add, the first product
+// stored — the sums are bit-identical to the reference's.  Rows are then ranked by column and
+// staged through shared memory so the block writes C with coalesced stores.
+// ------------------------------------------------------------------------------------------
+template <class V, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_num_tiny(u32 n, const u32* __restrict__ perm,
+                                                    const u64* __restrict__ a_ptr, const u32* __restrict__ a_col,
+                                                    const V* __restrict__ a_val, const u64* __restrict__ b_ptr,
+                                                    const u32* __restrict__ b_col, const V* __restrict__ b_val,
+                                                    const u64* __restrict__ c_ptr, u32* __restrict__ c_col,
+                                                    V* __restrict__ c_val) {
+  constexpr int SLOTS = 2 * NUM_TINY_MAX;  // 32
+  extern __shared__ __align__(16) unsigned char sm_raw[];
+  V* tvals = reinterpret_cast<V*>(sm_raw);                       // [SLOTS][BLOCK]
+  V* svals = tvals + SLOTS * BLOCK;                              // [NUM_TINY_MAX*BLOCK] staging
+  u64* s_cptr = reinterpret_cast<u64*>(svals + NUM_TINY_MAX * BLOCK);  // [BLOCK]
+  u32* tkeys = reinterpret_cast<u32*>(s_cptr + BLOCK);           // [SLOTS][BLOCK]
+  u32* skeys = tkeys + SLOTS * BLOCK;                            // [NUM_TINY_MAX*BLOCK]
+  u32* s_off = skeys + NUM_TINY_MAX * BLOCK;                     // [BLOCK+1]
+  u32* s_warp = s_off + BLOCK + 1;                               // [32]
+
+  const int tid = threadIdx.x;
+  const u32 i = blockIdx.x * BLOCK + tid;
+  const bool valid = i < n;
+  const u32 row = valid ? (perm ? perm[i] : i) : 0;
+  u64 c0 = 0;
+  u32 z = 0;
+  if (valid) { c0 = c_ptr[row]; z = (u32)(c_ptr[row + 1] - c0); }
+  u32 total;
+  const u32 off = block_excl_scan_u32<BLOCK>(z, s_warp, &total);
+  s_off[tid] = off;
+  s_cptr[tid] = c0;
+  if (tid == 0) s_off[BLOCK] = total;
+
+  if (z > 0) {
+    const u32 cap = table_size_u32(z), mask = cap - 1;
+    u32* keys = tkeys + tid;
+    V* vals = tvals + tid;
+    for (u32 s = 0; s < cap; ++s) keys[s * BLOCK] = EMPTY_KEY;
+    const u64 lo = a_ptr[row], hi = a_ptr[row + 1];
+    for (u64 e = lo; e < hi; ++e) {
+      const u32 k = a_col[e];
+      const V av = a_val[e];
+      const u64 bl = b_ptr[k], bh = b_ptr[k + 1];
+      for (u64 j = bl; j < bh; ++j) {
+        const u32 key = b_col[j];
+        const V prod = Num<V>::mul(av, b_val[j]);
+        u32 s = slot_of(key, mask);
+        for (;;) {
+          const u32 cur = keys[s * BLOCK];
+          if (cur == key) { vals[s * BLOCK] = Num<V>::add(vals[s * BLOCK], prod); break; }
+          if (cur == EMPTY_KEY) { keys[s * BLOCK] = key; vals[s * BLOCK] = prod; break; }
+          s = (s + 1) & mask;
+        }
+      }
+    }
+    // drain in slot order (map.rs:59-63), compacting in place (write index never passes read index)
+    u32 cntz = 0;
+    for (u32 s = 0; s < cap; ++s) {
+      const u32 kk = keys[s * BLOCK];
+      if (kk != EMPTY_KEY) {
+        const V vv = vals[s * BLOCK];
+        keys[cntz * BLOCK] = kk;
+        vals[cntz * BLOCK] = vv;
+        ++cntz;
+      }
+    }
+    // rank by column (keys are distinct) == sort_unstable_by_key (mul_hash.rs:166)
+    for (u32 x = 0; x < cntz; ++x) {
+      const u32 kx = keys[x * BLOCK];
+      u32 r = 0;
+      for (u32 y = 0; y < cntz; ++y) r += (keys[y * BLOCK] < kx) ? 1u : 0u;
+      skeys[off + r] = kx;
+      svals[off + r] = vals[x * BLOCK];
+    }
+  }
+  __syncthreads();
+  // coalesced copy-out: staged element q belongs to the last local row r with s_off[r] <= q
+  for (u32 q = tid; q < total; q += BLOCK) {
+    int lo_r = 0, hi_r = BLOCK;  // invariant: s_off[lo_r] <= q < s_off[hi_r]
+    while (hi_r - lo_r > 1) {
+      const int mid = (lo_r + hi_r) >> 1;
+      if (s_off[mid] <= q) lo_r = mid; else hi_r = mid;
+    }
+    const u64 dst = s_cptr[lo_r] + (q - s_off[lo_r]);
+    c_col[dst] = skeys[q];
+    c_val[dst] = svals[q];
+  }
+}
+
+template <class V, int BLOCK>
+constexpr size_t num_tiny_smem() {
+  return (size_t)(2 * NUM_TINY_MAX) * BLOCK * (sizeof(V) + 4) + (size_t)NUM_TINY_MAX * BLOCK * (sizeof(V) + 4) +
+         (size_t)BLOCK * 8 + (size_t)(BLOCK + 1 + 32) * 4;
+}
+
+// ------------------------------------------------------------------------------------------
+// bitonic sort of n2 (power of two) key/value pairs held in shared or global memory, by key
+// ascending; EMPTY_KEY pads sort to the end.  One thread block.
+// ------------------------------------------------------------------------------------------
+template <int T, class V, class KP, class VP>
+__device__ __forceinline__ void block_bitonic_sort(KP keys, VP vals, u32 n2) {
+  const int tid = threadIdx.x;
+  for (u32 k = 2; k <= n2; k <<= 1) {
+    for (u32 j = k >> 1; j > 0; j >>= 1) {
+      for (u32 p = tid; p < (n2 >> 1); p += T) {
+        const u32 i = 2 * p - (p & (j - 1));
+        const u32 l = i + j;
+        const bool up = (i & k) == 0;
+        const u32 ki = keys[i], kl = keys[l];
+        if ((ki > kl) == up && ki != kl) {
+          keys[i] = kl; keys[l] = ki;
+          const V vi = vals[i], vl = vals[l];
+          vals[i] = vl; vals[l] = vi;
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// NUMERIC, one thread block per row, key+value table in shared memory.
+// accumulate (atomicCAS on the key, atomicAdd on the value) -> compact in place through registers
+// -> bitonic sort by column -> coalesced store.
+// ------------------------------------------------------------------------------------------
+template <class V, int T, int CAP>
+__global__ void __launch_bounds__(T) k_num_group(const u32* __restrict__ perm, const u64* __restrict__ a_ptr,
+                                                 const u32* __restrict__ a_col, const V* __restrict__ a_val,
+                                                 const u64* __restrict__ b_ptr, const u32* __restrict__ b_col,
+                                                 const V* __restrict__ b_val, const u64* __restrict__ c_ptr,
+                                                 u32* __restrict__ c_col, V* __restrict__ c_val, int wshift) {
+  constexpr int ITEMS = CAP / T;
+  extern __shared__ __align__(16) unsigned char sm_raw[];
+  V* vals = reinterpret_cast<V*>(sm_raw);          // [CAP]
+  u32* keys = reinterpret_cast<u32*>(vals + CAP);  // [CAP]
+  u32* s_warp = keys + CAP;                        // [32]
+  const int tid = threadIdx.x;
+  const u32 row = perm ? perm[blockIdx.x] : blockIdx.x;
+  const u64 c0 = c_ptr[row];
+  const u32 z = (u32)(c_ptr[row + 1] - c0);
+  if (z == 0) return;                              // mul_hash.rs:141-143
+  u32 cap = table_size_u32(z);                     // map.rs:49-58
+  if (cap > (u32)CAP) cap = CAP;
+  const u32 mask = cap - 1;
+  for (u32 s = tid; s < cap; s += T) { keys[s] = EMPTY_KEY; vals[s] = Num<V>::zero(); }
+  __syncthreads();
+  volatile u32* vkeys = keys;
+  const int W = 1 << wshift, sub = tid >> wshift, lane = tid & (W - 1), nsub = T >> wshift;
+  const u64 lo = a_ptr[row], hi = a_ptr[row + 1];
+  for (u64 e = lo + sub; e < hi; e += nsub) {
+    const u32 k = a_col[e];
+    const V av = a_val[e];
+    const u64 bl = b_ptr[k], bh = b_ptr[k + 1];
+    for (u64 j = bl + lane; j < bh; j += W) {
+      const u32 key = b_col[j];
+      const V prod = Num<V>::mul(av, b_val[j]);
+      u32 s = slot_of(key, mask);
+      for (;;) {
+        const u32 cur = vkeys[s];
+        if (cur != key) {
+          if (cur != EMPTY_KEY) { s = (s + 1) & mask; continue; }
+          const u32 old = atomicCAS(&keys[s], EMPTY_KEY, key);
+          if (old != EMPTY_KEY && old != key) { s = (s + 1) & mask; continue; }
+        }
+        Num<V>::atomic_add(&vals[s], prod);
+        break;
+      }
+    }
+  }
+  __syncthreads();
+  // compaction through registers: slots tid, tid+T, ... -> front of the table
+  u32 rk[ITEMS];
+  V rv[ITEMS];
+  u32 mine = 0;
+#pragma unroll
+  for (int it = 0; it < ITEMS; ++it) {
+    const u32 s = it * T + tid;
+    rk[it] = EMPTY_KEY;
+    rv[it] = Num<V>::zero();
+    if (s < cap) { rk[it] = keys[s]; rv[it] = vals[s]; }
+    mine += (rk[it] != EMPTY_KEY) ? 1u : 0u;
+  }
+  u32 total;
+  u32 pos = block_excl_scan_u32<T>(mine, s_warp, &total);  // contains the barrier that ends the reads
+  if (T == 32) __syncwarp();
+#pragma unroll
+  for (int it = 0; it < ITEMS; ++it) {
+    if (rk[it] != EMPTY_KEY) { keys[pos] = rk[it]; vals[pos] = rv[it]; ++pos; }
+  }
+  const u32 n2 = npow2_u32(z);
+  for (u32 s = z + tid; s < n2; s += T) keys[s] = EMPTY_KEY;  // total == z by construction (mul_hash.rs:190)
+  __syncthreads();
+  block_bitonic_sort<T, V>(keys, vals, n2);
+  for (u32 s = tid; s < z; s += T) { c_col[c0 + s] = keys[s]; c_val[c0 + s] = vals[s]; }
+}
+
+// ------------------------------------------------------------------------------------------
+// NUMERIC, heavy rows: persistent blocks, global-memory key+value tables (ld.cg/st.cg: the
+// tables are updated by L2 atomics, so never read them through L1).
+// ------------------------------------------------------------------------------------------
+template <class V, int T>
+__global__ void __launch_bounds__(T) k_num_heavy(u32 n, const u32* __restrict__ perm, const u64* __restrict__ a_ptr,
+                                                 const u32* __restrict__ a_col, const V* __restrict__ a_val,
+                                                 const u64* __restrict__ b_ptr, const u32* __restrict__ b_col,
+                                                 const V* __restrict__ b_val, const u64* __restrict__ c_ptr,
+                                                 u32* __restrict__ c_col, V* __restrict__ c_val, u32* key_tables,
+                                                 V* val_tables, u64 table_stride, u32* work, int wshift) {
+  constexpr int ITEMS = 4;
+  __shared__ u32 s_item;
+  __shared__ u32 s_warp[32];
+  const int tid = threadIdx.x;
+  u32* keys = key_tables + (u64)blockIdx.x * table_stride;
+  V* vals = val_tables + (u64)blockIdx.x * table_stride;
+  const int W = 1 << wshift, sub = tid >> wshift, lane = tid & (W - 1), nsub = T >> wshift;
+  for (;;) {
+    if (tid == 0) s_item = atomicAdd(work, 1u);
+    __syncthreads();
+    const u32 item = s_item;
+    __syncthreads();
+    if (item >= n) break;
+    const u32 row = perm ? perm[item] : item;
+    const u64 c0 = c_ptr[row];
+    const u32 z = (u32)(c_ptr[row + 1] - c0);
+    if (z == 0) continue;
+    const u64 cap = 2ull * npow2_u64(z), mask = cap - 1;
+    for (u64 s = tid; s < cap; s += T) { __stcg(&keys[s], EMPTY_KEY); __stcg(&vals[s], Num<V>::zero()); }
+    __syncthreads();
+    const u64 lo = a_ptr[row], hi = a_ptr[row + 1];
+    for (u64 e = lo + sub; e < hi; e += nsub) {
+      const u32 k = a_col[e];
+      const V av = a_val[e];
+      const u64 bl = b_ptr[k], bh = b_ptr[k + 1];
+      for (u64 j = bl + lane; j < bh; j += W) {
+        const u32 key = b_col[j];
+        const V prod = Num<V>::mul(av, b_val[j]);
+        u64 s = (u64)(key * HASH_SCAL) & mask;
+        for (;;) {
+          const u32 cur = __ldcg(&keys[s]);
+          if (cur != key) {
+            if (cur != EMPTY_KEY) { s = (s + 1) & mask; continue; }
+            const u32 old = atomicCAS(&keys[s], EMPTY_KEY, key);
+            if (old != EMPTY_KEY && old != key) { s = (s + 1) & mask; continue; }
+          }
+          Num<V>::atomic_add(&vals[s], prod);
+          break;
+        }
+      }
+    }
+    __syncthreads();
+    // in-place chunked compaction: chunk c is read into registers, barrier, then written at the
+    // running output offset, which never passes the start of the next unread chunk.
+    u32 run = 0;
+    for (u64 cbase = 0; cbase < cap; cbase += (u64)T * ITEMS) {
+      u32 rk[ITEMS];
+      V rv[ITEMS];
+      u32 mine = 0;
+#pragma unroll
+      for (int it = 0; it < ITEMS; ++it) {
+        const u64 s = cbase + (u64)it * T + tid;
+        rk[it] = EMPTY_KEY;
+        rv[it] = Num<V>::zero();
+        if (s < cap) { rk[it] = __ldcg(&keys[s]); rv[it] = __ldcg(&vals[s]); }
+        mine += (rk[it] != EMPTY_KEY) ? 1u : 0u;
+      }
+      u32 total;
+      u32 pos = run + block_excl_scan_u32<T>(mine, s_warp, &total);  // barriers inside end the reads
+#pragma unroll
+      for (int it = 0; it < ITEMS; ++it) {
+        if (rk[it] != EMPTY_KEY) { __stcg(&keys[pos], rk[it]); __stcg(&vals[pos], rv[it]); ++pos; }
+      }
+      run += total;
+      __syncthreads();
+    }
+    const u32 n2 = npow2_u32(z);
+    for (u32 s = z + tid; s < n2; s += T) __stcg(&keys[s], EMPTY_KEY);
+    __syncthreads();
+    // bitonic sort in global memory (volatile accesses: L2-coherent within the block)
+    block_bitonic_sort<T, V>((volatile u32*)keys, (volatile V*)vals, n2);
+    for (u32 s = tid; s < z; s += T) { c_col[c0 + s] = __ldcg(&keys[s]); c_val[c0 + s] = __ldcg(&vals[s]); }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host orchestration
+// ------------------------------------------------------------------------------------------
+int wshift_for(const spam_dcsr* b, int tmax_shift) {
+  const double avg = b->rows ? (double)b->nnz / (double)b->rows : 1.0;
+  int ws = 2;  // at least 4 lanes per A entry
+  while ((1 << ws) < avg && ws < 5) ++ws;
+  if (ws > tmax_shift) ws = tmax_shift;
+  return ws;
+}
+
+template <class K>
+int set_smem(spam_handle* h, K kernel, size_t bytes) {
+  if (bytes > 48 * 1024) CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return SPAM_OK;
+}
+
+struct Bins {
+  u32 count[NBINS];
+  u32 base[NBINS];
+  u32* perm;  // device, null when one bin holds every row (identity)
+};
+
+int build_perm(spam_handle* h, u64 m, const u32* counts, bool numeric, const u32* d_row_nnz, const u32* d_flop,
+               Bins* out) {
+  u32 acc = 0;
+  bool identity = false;
+  for (int b = 0; b < NBINS; ++b) {
+    out->count[b] = counts[b];
+    out->base[b] = acc;
+    acc += counts[b];
+    if (counts[b] == m) identity = true;
+  }
+  out->perm = nullptr;
+  if (identity || m == 0) return SPAM_OK;
+  CKS(dev_alloc_t(h, &out->perm, m));
+  BinBase bb;
+  for (int b = 0; b < NBINS; ++b) bb.v[b] = out->base[b];
+  u32* cursors = numeric ? h->d_cnt->num_cursor : h->d_cnt->sym_cursor;
+  const unsigned grid = (unsigned)((m + 255) / 256);
+  if (numeric)
+    k_bin_scatter<256, true><<<grid, 256, 0, h->stream>>>(m, d_row_nnz, d_flop, bb, cursors, out->perm);
+  else
+    k_bin_scatter<256, false><<<grid, 256, 0, h->stream>>>(m, d_row_nnz, d_flop, bb, cursors, out->perm);
+  count_launch(h);
+  CK(cudaGetLastError());
+  return SPAM_OK;
+}
+
+}  // namespace
+
+struct SpgemmPending {
+  const spam_dcsr* a;
+  const spam_dcsr* b;
+  u32* d_flop;
+  u32* d_row_nnz;
+  u64* d_cptr;
+  u64 nnz;
+  u32 num_counts[NBINS];
+  u32 max_nnz;
+};
+
+u64 spgemm_pending_nnz(const SpgemmPending* p) { return p->nnz; }
+const u64* spgemm_pending_cptr(const SpgemmPending* p) { return p->d_cptr; }
+
+void spgemm_pending_free(spam_handle* h, SpgemmPending* p) {
+  if (!p) return;
+  dev_free(h, p->d_flop);
+  dev_free(h, p->d_row_nnz);
+  dev_free(h, p->d_cptr);
+  delete p;
+}
+
+int flop_count_dev(spam_handle* h, const spam_dcsr* a, const spam_dcsr* b, u32* d_flop, bool do_bins) {
+  const u64 m = a->rows;
+  if (m == 0) return SPAM_OK;
+  k_flop_count<256><<<(unsigned)((m + 255) / 256), 256, 0, h->stream>>>(m, b->rows, a->ptr, a->idx, b->ptr, d_flop,
+                                                                         h->d_cnt, do_bins ? 1 : 0);
+  count_launch(h);
+  CK(cudaGetLastError());
+  return SPAM_OK;
+}
+
+// Phase 1: flop count + binning, symbolic per bin, scan -> row_ptr(C), nnz(C), numeric bin histogram.
+int spgemm_symbolic_dev(spam_handle* h, const spam_dcsr* a, const spam_dcsr* b, SpgemmPending** out) {
+  *out = nullptr;
+  if (a->dtype != b->dtype) return spam_fail(h, SPAM_EDTYPE, "operand dtypes differ");
+  if (a->cols != b->rows) return spam_fail(h, SPAM_EDIM, "A.cols != B.rows");
+  const u64 m = a->rows;
+  if (m >= 0xFFFFFFFFull || b->cols >= 0xFFFFFFFFull || a->cols >= 0xFFFFFFFFull)
+    return spam_fail(h, SPAM_ECOLS, "dimension >= 2^32-1 (u32::MAX is the empty-slot sentinel)");
+
+  h->stats = spam_stats{};
+  SpgemmPending* p = new SpgemmPending();
+  p->a = a; p->b = b; p->d_flop = nullptr; p->d_row_nnz = nullptr; p->d_cptr = nullptr; p->nnz = 0; p->max_nnz = 0;
+  *out = p;
+#define FAIL_FREE(expr) do { int _s = (expr); if (_s != SPAM_OK) { spgemm_pending_free(h, p); *out = nullptr; return _s; } } while (0)
+#define CK_FREE(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { spgemm_pending_free(h, p); *out = nullptr; return spam_fail(h, SPAM_ECUDA, #call, _e); } } while (0)
+
+  FAIL_FREE(dev_alloc_t(h, &p->d_flop, m));
+  FAIL_FREE(dev_alloc_t(h, &p->d_row_nnz, m));
+  FAIL_FREE(dev_alloc_t(h, &p->d_cptr, m + 1));
+  CK_FREE(cudaMemsetAsync(h->d_cnt, 0, sizeof(Counters), h->stream));
+  if (h->timing) CK_FREE(cudaEventRecord(h->ev[0], h->stream));
+  FAIL_FREE(flop_count_dev(h, a, b, p->d_flop, true));
+  CK_FREE(cudaMemcpyAsync(h->h_cnt, h->d_cnt, sizeof(Counters), cudaMemcpyDeviceToHost, h->stream));
+  if (h->timing) CK_FREE(cudaEventRecord(h->ev[1], h->stream));
+  CK_FREE(cudaStreamSynchronize(h->stream));
+  const Counters c1 = *h->h_cnt;
+  if (c1.error & 1u) {
+    spgemm_pending_free(h, p); *out = nullptr;
+    return spam_fail(h, SPAM_EINDEX, "a column index of A is >= rows(B)");
+  }
+  h->stats.flops = c1.total_flops;
+  for (int i = 0; i < NBINS; ++i) h->stats.sym_bin_rows[i] = c1.sym_bins[i];
+
+  // ---- symbolic per bin ----
+  Bins sb;
+  FAIL_FREE(build_perm(h, m, c1.sym_bins, false, nullptr, p->d_flop, &sb));
+  u32* heavy_tab = nullptr;
+  {
+    const u64* ap = a->ptr; const u32* ac = a->idx; const u64* bp = b->ptr; const u32* bc = b->idx;
+    const u32* fl = p->d_flop; u32* rz = p->d_row_nnz;
+    auto seg = [&](int bin) -> const u32* { return sb.perm ? sb.perm + sb.base[bin] : nullptr; };
+    if (sb.count[0]) {
+      constexpr int BL = 128;
+      const size_t smem = (size_t)2 * SYM_TINY_MAX * BL * sizeof(u32);
+      k_sym_tiny<BL><<<(sb.count[0] + BL - 1) / BL, BL, smem, h->stream>>>(sb.count[0], seg(0), ap, ac, bp, bc, fl, rz);
+      count_launch(h);
+    }
+#define LAUNCH_SYM(BIN, T, CAP)                                                                          \
+    if (sb.count[BIN]) {                                                                                 \
+      constexpr size_t smem = (size_t)(CAP) * sizeof(u32);                                               \
+      FAIL_FREE(set_smem(h, k_sym_group<T, CAP>, smem));                                                 \
+      k_sym_group<T, CAP><<<sb.count[BIN], T, smem, h->stream>>>(seg(BIN), ap, ac, bp, bc, fl, rz, ws);  \
+      count_launch(h);                                                                                   \
+    }
+    const int ws = wshift_for(b, 5);
+    LAUNCH_SYM(1, 32, 2 * SYM_G1_MAX)
+    LAUNCH_SYM(2, 64, 2 * SYM_G2_MAX)
+    LAUNCH_SYM(3, 256, 2 * SYM_G3_MAX)
+    LAUNCH_SYM(4, 1024, 2 * SYM_G4_MAX)
+#undef LAUNCH_SYM
+    CK_FREE(cudaGetLastError());
+    if (sb.count[5]) {
+      const u32 nheavy = sb.count[5];
+      u32 fmax = c1.max_flop;
+      if (fmax > (u32)b->cols) fmax = (u32)b->cols;
+      const u64 stride = 2ull * npow2_u64(fmax);
+      u64 nblk = (u64)h->num_sms * 2;
+      if (nblk > nheavy) nblk = nheavy;
+      const u64 budget = 8ull << 30;
+      while (nblk > 1 && nblk * stride * sizeof(u32) > budget) nblk /= 2;
+      FAIL_FREE(dev_alloc_t(h, &heavy_tab, nblk * stride));
+      k_sym_heavy<1024><<<(unsigned)nblk, 1024, 0, h->stream>>>(nheavy, seg(5), ap, ac, bp, bc, fl, rz, heavy_tab, stride,
+                                                                (u32)b->cols, &h->d_cnt->work_a, ws);
+      count_launch(h);
+      CK_FREE(cudaGetLastError());
+    }
+  }
+  if (h->timing) CK_FREE(cudaEventRecord(h->ev[2], h->stream));
+  // ---- numeric bin histogram + row_ptr scan ----
+  if (m) {
+    k_num_bin_count<256><<<(unsigned)((m + 255) / 256), 256, 0, h->stream>>>(m, p->d_row_nnz, p->d_flop, h->d_cnt);
+    count_launch(h);
+    CK_FREE(cudaGetLastError());
+  }
+  FAIL_FREE(scan_u32_to_u64(h, p->d_row_nnz, p->d_cptr, m, &h->d_cnt->total_nnz));
+  CK_FREE(cudaMemcpyAsync(h->h_cnt, h->d_cnt, sizeof(Counters), cudaMemcpyDeviceToHost, h->stream));
+  if (h->timing) CK_FREE(cudaEventRecord(h->ev[3], h->stream));
+  if (heavy_tab) FAIL_FREE(dev_free(h, heavy_tab));
+  if (sb.perm) FAIL_FREE(dev_free(h, sb.perm));
+  CK_FREE(cudaStreamSynchronize(h->stream));
+  const Counters c2 = *h->h_cnt;
+  p->nnz = c2.total_nnz;
+  p->max_nnz = c2.max_nnz;
+  for (int i = 0; i < NBINS; ++i) { p->num_counts[i] = c2.num_bins[i]; h->stats.num_bin_rows[i] = c2.num_bins[i]; }
+  h->stats.nnz_c = p->nnz;
+  return SPAM_OK;
+#undef FAIL_FREE
+#undef CK_FREE
+}
+
+namespace {
+
+template <class V>
+int numeric_typed(spam_handle* h, SpgemmPending* p, spam_dcsr* c) {
+  const spam_dcsr* a = p->a;
+  const spam_dcsr* b = p->b;
+  const u64 m = a->rows;
+  Bins nb;
+  CKS(build_perm(h, m, p->num_counts, true, p->d_row_nnz, p->d_flop, &nb));
+  const u64* ap = a->ptr; const u32* ac = a->idx; const V* av = (const V*)a->val;
+  const u64* bp = b->ptr; const u32* bc = b->idx; const V* bv = (const V*)b->val;
+  const u64* cp = c->ptr; u32* cc = c->idx; V* cv = (V*)c->val;
+  auto seg = [&](int bin) -> const u32* { return nb.perm ? nb.perm + nb.base[bin] : nullptr; };
+  const int ws = wshift_for(b, 5);
+  if (nb.count[0]) {
+    constexpr int BL = 128;
+    constexpr size_t smem = num_tiny_smem<V, BL>();
+    CKS(set_smem(h, k_num_tiny<V, BL>, smem));
+    k_num_tiny<V, BL><<<(nb.count[0] + BL - 1) / BL, BL, smem, h->stream>>>(nb.count[0], seg(0), ap, ac, av, bp, bc, bv, cp, cc, cv);
+    count_launch(h);
+  }
+#define LAUNCH_GROUP(BIN, T, CAP)                                                                        \
+  if (nb.count[BIN]) {                                                                                   \
+    constexpr size_t smem = (size_t)(CAP) * (sizeof(V) + 4) + 32 * 4;                                   \
+    CKS(set_smem(h, k_num_group<V, T, CAP>, smem));                                                      \
+    k_num_group<V, T, CAP><<<nb.count[BIN], T, smem, h->stream>>>(seg(BIN), ap, ac, av, bp, bc, bv, cp, cc, cv, ws); \
+    count_launch(h);                                                                                     \
+  }
+  LAUNCH_GROUP(1, 32, 2 * NUM_G1_MAX)
+  LAUNCH_GROUP(2, 128, 2 * NUM_G2_MAX)
+  LAUNCH_GROUP(3, 512, 2 * NUM_G3_MAX)
+  LAUNCH_GROUP(4, 1024, 2 * NUM_G4_MAX)
+#undef LAUNCH_GROUP
+  CK(cudaGetLastError());
+  u32* hk = nullptr;
+  V* hv = nullptr;
+  if (nb.count[5]) {
+    u32 zmax = p->max_nnz;
+    const u64 stride = 2ull * npow2_u64(zmax);
+    u64 nblk = (u64)h->num_sms * 2;
+    if (nblk > nb.count[5]) nblk = nb.count[5];
+    const u64 budget = 16ull << 30;
+    while (nblk > 1 && nblk * stride * (sizeof(u32) + sizeof(V)) > budget) nblk /= 2;
+    CKS(dev_alloc_t(h, &hk, nblk * stride));
+    CKS(dev_alloc_t(h, &hv, nblk * stride));
+    k_num_heavy<V, 1024><<<(unsigned)nblk, 1024, 0, h->stream>>>(nb.count[5], seg(5), ap, ac, av, bp, bc, bv, cp, cc, cv, hk,
+                                                                hv, stride, &h->d_cnt->work_b, ws);
+    count_launch(h);
+    CK(cudaGetLastError());
+  }
+  if (hk) CKS(dev_free(h, hk));
+  if (hv) CKS(dev_free(h, hv));
+  if (nb.perm) CKS(dev_free(h, nb.perm));
+  return SPAM_OK;
+}
+
+}  // namespace
+
+// Phase 2: allocate C (exact nnz, like Vec::with_capacity(nnz), mul_hash.rs:119), numeric per bin.
+// Consumes the pending state.  On success *cout owns col_idx/val and takes over row_ptr.
+int spgemm_numeric_dev(spam_handle* h, SpgemmPending* p, spam_dcsr** cout) {
+  *cout = nullptr;
+  spam_dcsr* c = new spam_dcsr();
+  c->dtype = p->a->dtype; c->rows = p->a->rows; c->cols = p->b->cols; c->nnz = p->nnz;
+  c->ptr = p->d_cptr; c->idx = nullptr; c->val = nullptr; c->owning = true;
+  int st = dev_alloc_t(h, &c->idx, p->nnz ? p->nnz : 1);
+  if (st == SPAM_OK) st = dev_alloc(h, &c->val, (p->nnz ? p->nnz : 1) * dtype_size(c->dtype));
+  if (st == SPAM_OK && p->nnz) {
+    switch (c->dtype) {
+      case SPAM_F32: st = numeric_typed<float>(h, p, c); break;
+      case SPAM_F64: st = numeric_typed<double>(h, p, c); break;
+      case SPAM_I32: st = numeric_typed<int32_t>(h, p, c); break;
+      case SPAM_I64: st = numeric_typed<int64_t>(h, p, c); break;
+      default: st = spam_fail(h, SPAM_EINVAL, "bad dtype");
+    }
+  }
+  if (st == SPAM_OK && h->timing) {
+    cudaError_t e = cudaEventRecord(h->ev[4], h->stream);
+    if (e != cudaSuccess) st = spam_fail(h, SPAM_ECUDA, "cudaEventRecord", e);
+  }
+  if (st != SPAM_OK) {
+    dev_free(h, c->idx); dev_free(h, c->val);
+    delete c;
+    spgemm_pending_free(h, p);
+    return st;
+  }
+  p->d_cptr = nullptr;  // ownership moved to C
+  spgemm_pending_free(h, p);
+  *cout = c;
+  return SPAM_OK;
+}
