@@ -1,0 +1,332 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI (ctypes -> libspam_cuda.so),
+against the CPU oracle on the same seeded inputs.
+
+Bar (BASELINE.json north_star): row_ptr and col_idx bit-exact against mul_hash::<_, true>; integer
+values bit-exact; f64 / f32 values within 1e-12 / 1e-5 of each entry's sum of |products|.
+"""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+import sparse_matrix_b200 as S
+from sparse_matrix_b200 import generators as G
+from util import TOL, as_csr_matrix, check_against_oracle, random_csr
+
+pytestmark = pytest.mark.gpu
+
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "linprobe_kat.json")))
+ALL_DTYPES = [np.float64, np.float32, np.int32, np.int64]
+
+
+def gpu_mul(a, b, handle, sorted_output=True):
+    A = as_csr_matrix(a, is_sorted=False)
+    B = A if b is a else as_csr_matrix(b, is_sorted=False)
+    return A.mul_hash(B, sorted_output=sorted_output, handle=handle)
+
+
+# ---------------------------------------------------------------------------------------------
+# known answers and the reference's own property test
+# ---------------------------------------------------------------------------------------------
+def test_golden_kats_on_gpu(handle):
+    g = GOLD["map_slot_order"]
+    a = (1, 4, g["a"]["offsets"], g["a"]["indices"], np.array(g["a"]["vals"]))
+    b = (4, 4, g["b"]["offsets"], g["b"]["indices"], np.array(g["b"]["vals"]))
+    c = gpu_mul(a, b, handle)
+    assert c.offsets.tolist() == g["sorted"]["offsets"] and c.indices.tolist() == g["sorted"]["indices"]
+    assert c.vals.tolist() == g["sorted"]["vals"]
+    g = GOLD["unfused_cancellation"]
+    av = np.array([float.fromhex(x) for x in g["a"]["vals_hex"]])
+    bv = np.array([float.fromhex(x) for x in g["b"]["vals_hex"]])
+    c = gpu_mul((1, 2, g["a"]["offsets"], g["a"]["indices"], av), (2, 8, g["b"]["offsets"], g["b"]["indices"], bv),
+                handle)
+    assert c.offsets.tolist() == [0, 1] and c.indices.tolist() == [5]
+    assert c.vals.tolist() == [0.0]          # no FMA on the device either, and the zero is kept
+
+
+@pytest.mark.parametrize("dtype", [np.int32, np.int64])
+def test_reference_property_dense_dok_equivalence(oracle, handle, dtype):
+    """spam_csr/src/tests.rs:356-371 with a device scalar in place of Wrapping<i8>: dims <= 4,
+    shuffled rows, wrapping arithmetic; compare through the dense DOK product (zero-insensitive)."""
+    rng = np.random.default_rng(1234)
+    info = np.iinfo(dtype)
+    for _ in range(150):
+        l, m, n = (int(x) for x in rng.integers(1, 5, size=3))
+        da = np.zeros((l, m), dtype)
+        db = np.zeros((m, n), dtype)
+        for d in (da, db):
+            for _k in range(int(rng.integers(0, 2 * d.size + 1))):
+                d[rng.integers(0, d.shape[0]), rng.integers(0, d.shape[1])] = rng.integers(info.min, info.max,
+                                                                                            dtype=dtype)
+        a = _dense_to_unsorted(da, rng)
+        b = _dense_to_unsorted(db, rng)
+        c = gpu_mul(a, b, handle, sorted_output=False)
+        assert c.invariants()
+        got = np.zeros((l, n), dtype)
+        for (r, col), t in c.iter():
+            got[r, col] = t
+        assert np.array_equal(got, oracle.dok_dense_mul(da, db))
+
+
+def _dense_to_unsorted(dense, rng):
+    rows, cols = dense.shape
+    off, idx, val = [0], [], []
+    for r in range(rows):
+        c = rng.permutation(np.nonzero(dense[r])[0])
+        idx.extend(c.tolist())
+        val.extend(dense[r, c].tolist())
+        off.append(len(idx))
+    return rows, cols, np.array(off, np.uint64), np.array(idx, np.uint64), np.array(val, dense.dtype)
+
+
+# ---------------------------------------------------------------------------------------------
+# seeded random products against the oracle, every dtype
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", ALL_DTYPES)
+@pytest.mark.parametrize("shape", [(1, 1, 1), (7, 5, 9), (300, 200, 400), (2000, 2000, 2000), (50, 3000, 60)])
+def test_random_products(oracle, handle, dtype, shape):
+    l, m, n = shape
+    rng = np.random.default_rng(hash((l, m, n)) % 2**32)
+    a = random_csr(rng, l, m, rng.integers(0, min(m, 24) + 1, size=l), dtype=dtype, sorted_rows=False)
+    b = random_csr(rng, m, n, rng.integers(0, min(n, 24) + 1, size=m), dtype=dtype, sorted_rows=False)
+    c = gpu_mul(a, b, handle)
+    check_against_oracle(oracle, a, b, c)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.int64])
+def test_every_bin_is_exercised(oracle, handle, dtype):
+    """Rows whose flop / nnz land in each symbolic and numeric bin, heavy (global-table) bins included."""
+    rng = np.random.default_rng(99)
+    inner, n = 3000, 60000
+    # A row i has `deg[i]` entries; B rows have 40 entries => flop = 40*deg, nnz close to it
+    deg = np.array([0, 1, 2, 5, 8, 20, 40, 90, 150, 300, 420, 700, 1000, 1500, 2500] + [3] * 40 + [60] * 20)
+    a = random_csr(rng, len(deg), inner, deg, dtype=dtype, sorted_rows=False)
+    b = random_csr(rng, inner, n, 40, dtype=dtype, sorted_rows=False)
+    handle.set_timing(True)
+    c = gpu_mul(a, b, handle)
+    st = handle.stats()
+    handle.set_timing(False)
+    assert all(x > 0 for x in st["sym_bin_rows"][:6]), st["sym_bin_rows"]
+    assert all(x > 0 for x in st["num_bin_rows"][:6]), st["num_bin_rows"]
+    off, idx, val = check_against_oracle(oracle, a, b, c)
+    assert st["nnz_c"] == len(idx) and st["flops"] == 40 * int(deg.sum()) and st["kernel_launches"] >= 10
+    # many duplicates: few distinct columns but a large flop count (numeric bin chosen by nnz, not flop)
+    b2 = random_csr(rng, inner, 24, 20, dtype=dtype, sorted_rows=False)
+    c2 = gpu_mul(a, b2, handle)
+    check_against_oracle(oracle, a, b2, c2)
+
+
+def test_tiny_rows_are_bit_identical_for_floats(oracle, handle):
+    """The thread-per-row path visits products in the reference's order with unfused mul/add, so the
+    f64 sums must equal the oracle's bit for bit, not just within tolerance."""
+    for dtype in (np.float64, np.float32):
+        p = G.poisson2d(96, dtype=dtype)
+        rng = np.random.default_rng(5)
+        p = p[:4] + (rng.uniform(-1, 1, size=p[4].shape).astype(dtype),)
+        c = gpu_mul(p, p, handle)
+        check_against_oracle(oracle, p, p, c, exact_values=True)
+
+
+def test_edge_cases(oracle, handle):
+    # all-empty operands
+    a = S.CsrMatrix.new((5, 7))
+    b = S.CsrMatrix.new((7, 3))
+    c = a.mul_hash(b, sorted_output=True, handle=handle)
+    assert c.nnz() == 0 and c.offsets.tolist() == [0] * 6 and c.invariants() and (c.rows(), c.cols()) == (5, 3)
+    # empty rows in A and empty rows in B that A points at (flop 0 rows, mul_hash.rs:84-86)
+    rng = np.random.default_rng(2)
+    a = random_csr(rng, 40, 30, rng.integers(0, 3, size=40) * rng.integers(0, 6, size=40))
+    bdeg = rng.integers(0, 8, size=30)
+    bdeg[::2] = 0
+    b = random_csr(rng, 30, 50, bdeg)
+    check_against_oracle(oracle, a, b, gpu_mul(a, b, handle))
+    # explicit zeros in the inputs propagate; cancellation zeros are kept
+    a = random_csr(rng, 64, 64, 9, dtype=np.int64, zero_frac=0.3)
+    b = random_csr(rng, 64, 64, 9, dtype=np.int64, zero_frac=0.3, int_range=1)
+    c = gpu_mul(a, b, handle)
+    check_against_oracle(oracle, a, b, c)
+    assert (c.vals == 0).any()
+    # identity
+    i = S.CsrMatrix.identity(1000)
+    x = random_csr(rng, 1000, 1000, 7)
+    c = gpu_mul((1000, 1000, i.offsets, i.indices, i.vals), x, handle)
+    assert np.array_equal(c.offsets, x[2]) and np.array_equal(c.indices, x[3]) and np.array_equal(c.vals, x[4])
+    # wrapping integers
+    big = np.int64(2**62)
+    a = (1, 2, [0, 2], [0, 1], np.array([big, big], dtype=np.int64))
+    b = (2, 1, [0, 1, 2], [0, 0], np.array([2, 2], dtype=np.int64))
+    c = gpu_mul(a, b, handle)
+    assert c.vals.tolist() == [0] and c.indices.tolist() == [0]
+    # a * b operator (impl Mul for &CsrMatrix): Output = CsrMatrix<T, false>
+    A, B = as_csr_matrix(x), as_csr_matrix(x)
+    prod = A * B
+    assert prod.is_sorted is False and prod.invariants()
+    check_against_oracle(oracle, x, x, prod)
+    # A * A with the same object: uploaded once
+    check_against_oracle(oracle, x, x, A.mul_hash(A, True, handle=handle))
+
+
+def test_error_behaviour(handle):
+    a = S.CsrMatrix.identity(4)
+    b = S.CsrMatrix.identity(5)
+    with pytest.raises(S.DimensionMismatch):       # the reference panics out-of-bounds (mul_hash.rs:46)
+        a.mul_hash(b, handle=handle)
+    bad = S.CsrMatrix(2, 2, [1.0, 1.0], [0, 1], [0, 1, 2])
+    bad.indices[1] = 9                             # column index >= rows(B): IndexError, not a device fault
+    with pytest.raises(IndexError):
+        bad.mul_hash(S.CsrMatrix.identity(2), handle=handle)
+    L = handle.L
+    assert L.spam_spgemm_numeric(handle.h, None, None, 1) == 6      # SPAM_ESTATE: numeric without symbolic
+    assert L.spam_dok_to_csr_fetch(handle.h, None, None) == 6
+    f32 = S.CsrMatrix.identity(4, dtype=np.float32)
+    with pytest.raises(TypeError):
+        a.mul_hash(f32, handle=handle)
+    # the handle still works after errors
+    c = a.mul_hash(a, handle=handle)
+    assert c.nnz() == 4
+    with pytest.raises(IndexError):
+        S.CsrMatrix.from_triplets(2, 2, [0, 2], [0, 0], np.array([1.0, 1.0]), handle=handle)
+
+
+# ---------------------------------------------------------------------------------------------
+# the named configurations
+# ---------------------------------------------------------------------------------------------
+def test_config1_uniform_10k(oracle, handle):
+    a = G.uniform_random(10_000, 10_000, 10, seed=1)
+    c = gpu_mul(a, a, handle)
+    off, idx, val = check_against_oracle(oracle, a, a, c)
+    assert 990_000 < len(idx) < 1_000_000
+
+
+def test_config2_poisson_full_size(oracle, handle):
+    """C2 at BASELINE.json's full size, device-resident path: counts from SURVEY §8, full comparison
+    against the oracle (it finishes in seconds), and the row-sum identity (A*A)*1 == A*(A*1)."""
+    p = G.poisson2d(2048)
+    A = as_csr_matrix(p)
+    dA = S.DeviceCsr.upload(A, handle)
+    handle.set_timing(True)
+    dC = dA.matmul(dA)
+    st = handle.stats()
+    handle.set_timing(False)
+    assert st["flops"] == 104_783_880 and st["nnz_c"] == 54_484_996
+    assert st["sym_bin_rows"][0] == 4_194_304 and st["num_bin_rows"][0] == 4_194_304
+    c = dC.download()
+    check_against_oracle(oracle, p, p, c, exact_values=True)
+    ones = np.ones(p[0])
+    y1 = c.spmv(ones, handle=handle)
+    y2 = A.spmv(A.spmv(ones, handle=handle), handle=handle)
+    assert np.array_equal(y1, y2)        # small integers: exact in f64
+    dC.free()
+    dA.free()
+
+
+def test_config3_stencil27_reduced(oracle, handle):
+    s = G.stencil27(40)
+    c = gpu_mul(s, s, handle)
+    off, idx, val = check_against_oracle(oracle, s, s, c)
+    assert len(idx) == (5 * 40 - 6) ** 3
+
+
+def test_config4_rmat_reduced(oracle, handle):
+    r = G.rmat(15, 16)
+    handle.set_timing(True)
+    c = gpu_mul(r, r, handle)
+    st = handle.stats()
+    handle.set_timing(False)
+    check_against_oracle(oracle, r, r, c)
+    assert st["sym_bin_rows"][5] > 0 or st["sym_bin_rows"][4] > 0   # power-law rows reach the big bins
+
+
+def test_config5_rectangular_i64_and_dok(oracle, handle):
+    a = G.uniform_random(100_000, 400_000, 8, seed=5, dtype=np.int64, int_range=1 << 15)
+    at = G.transpose(a)
+    c = gpu_mul(a, at, handle)
+    check_against_oracle(oracle, a, at, c)
+    tr, tc, tv = G.triplets_with_rewrites(a, seed=5)
+    got = S.CsrMatrix.from_triplets(a[0], a[1], tr, tc, tv, handle=handle)
+    off, idx, val = oracle.dok_to_csr(a[0], a[1], tr, tc, tv)
+    assert got.invariants()
+    assert np.array_equal(got.offsets, off) and np.array_equal(got.indices, idx) and np.array_equal(got.vals, val)
+
+
+# ---------------------------------------------------------------------------------------------
+# SpMV, DOK -> CSR, device-resident helpers
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", ALL_DTYPES)
+def test_spmv(oracle, handle, dtype):
+    rng = np.random.default_rng(8)
+    for rows, cols, deg in [(1, 1, 1), (500, 300, 3), (2000, 2500, 40), (64, 5000, 900)]:
+        a = random_csr(rng, rows, cols, rng.integers(0, deg + 1, size=rows), dtype=dtype, sorted_rows=False)
+        if np.dtype(dtype).kind == "f":
+            x = rng.uniform(-1, 1, size=cols).astype(dtype)
+        else:
+            x = rng.integers(-50, 50, size=cols).astype(dtype)
+        y = as_csr_matrix(a, False).spmv(x, handle=handle)
+        want = oracle.spmv(rows, cols, a[2], a[3], a[4], x)
+        if np.dtype(dtype).kind == "f":
+            sabs = oracle.spmv(rows, cols, a[2], a[3], np.abs(a[4]), np.abs(x)).astype(np.float64)
+            assert np.all(np.abs(y.astype(np.float64) - want.astype(np.float64)) <= TOL[np.dtype(dtype)] * sabs)
+        else:
+            assert np.array_equal(y, want)
+    with pytest.raises(S.DimensionMismatch):
+        S.CsrMatrix.identity(3).spmv(np.ones(4), handle=handle)
+
+
+@pytest.mark.parametrize("dtype", ALL_DTYPES)
+def test_dok_to_csr(oracle, handle, dtype):
+    rng = np.random.default_rng(21)
+    for rows, cols, n in [(1, 1, 0), (1, 1, 3), (5, 5, 40), (300, 70_000, 20_000), (70_000, 3, 50_000)]:
+        ri = rng.integers(0, rows, n)
+        ci = rng.integers(0, cols, n)
+        v = rng.integers(-2, 3, n).astype(dtype)          # many zeros: deletes and re-inserts
+        got = S.CsrMatrix.from_triplets(rows, cols, ri, ci, v, handle=handle)
+        off, idx, val = oracle.dok_to_csr(rows, cols, ri, ci, v)
+        assert got.invariants()
+        assert np.array_equal(got.offsets, off) and np.array_equal(got.indices, idx)
+        assert np.array_equal(got.vals, val)
+    d = S.DokMatrix.new((4, 4), dtype)
+    d.set_element((3, 1), 2)
+    d.set_element((0, 0), 1)
+    d.set_element((3, 1), 0)
+    d.set_element((2, 2), 5)
+    m = S.CsrMatrix.from_dok(d, handle=handle)
+    assert m.offsets.tolist() == [0, 1, 1, 2, 2] and m.indices.tolist() == [0, 2] and m.to_dok().entries == d.entries
+
+
+def test_rows_to_parts_and_row_slices(oracle, handle):
+    """Multi-GPU plumbing on one GPU: the flop-balanced partition equals rows_to_threads
+    (mul_hash.rs:51-62) and the row-block products concatenate to the full product."""
+    r = G.rmat(13, 12)
+    A = as_csr_matrix(r)
+    dA = S.DeviceCsr.upload(A, handle)
+    full = dA.matmul(dA).download()
+    for parts in (1, 2, 3, 8):
+        starts, total = dA.rows_to_parts(dA, parts)
+        flop, ro = oracle.rows_to_threads(r[0], r[2], r[3], r[2], parts)
+        assert np.array_equal(starts, ro) and total == int(flop.sum())
+        offs, idxs, vals = [np.zeros(1, np.uint64)], [], []
+        for t in range(parts):
+            blk = dA.slice_rows(int(starts[t]), int(starts[t + 1]))
+            c = blk.matmul(dA).download()
+            offs.append(c.offsets[1:] + offs[-1][-1])     # offset-fixed row_ptr shard
+            idxs.append(c.indices)
+            vals.append(c.vals)
+            blk.free()
+        assert np.array_equal(np.concatenate(offs), full.offsets)
+        assert np.array_equal(np.concatenate(idxs), full.indices)
+        assert np.allclose(np.concatenate(vals), full.vals, rtol=1e-13, atol=0)
+    dA.free()
+
+
+def test_scan_sizes_through_dok_row_ptr(oracle, handle):
+    """The look-back scan at awkward lengths (around tile and warp boundaries) via DOK row_ptr."""
+    rng = np.random.default_rng(4)
+    for rows in (1, 2, 31, 33, 2047, 2048, 2049, 4097, 100_003):
+        n = rows * 2
+        ri, ci = rng.integers(0, rows, n), rng.integers(0, 4, n)
+        v = rng.integers(1, 5, n).astype(np.int32)
+        got = S.CsrMatrix.from_triplets(rows, 4, ri, ci, v, handle=handle)
+        off, idx, val = oracle.dok_to_csr(rows, 4, ri, ci, v)
+        assert np.array_equal(got.offsets, off) and np.array_equal(got.indices, idx) and np.array_equal(got.vals, val)
