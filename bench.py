@@ -209,7 +209,12 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     handle = S.Handle(local_rank)
-    handle.set_stream(torch.cuda.current_stream().cuda_stream)
+    # one explicit (non-default) stream for everything: the library's kernels, torch's events and the
+    # NCCL collectives are all ordered on it, so the CUDA events below see the kernels they bracket
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
+    handle.set_stream(stream.cuda_stream)
     L = handle.L
 
     # ---- inputs: rank 0 generates, everyone gets A over NCCL (B = A is replicated) ----

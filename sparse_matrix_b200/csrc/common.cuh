@@ -41,10 +41,19 @@ constexpr u32 SYM_TINY_MAX = 32, SYM_G1_MAX = 256, SYM_G2_MAX = 1024, SYM_G3_MAX
 constexpr u32 NUM_TINY_MAX = 16, NUM_TINY_FLOP_MAX = 128, NUM_G1_MAX = 128, NUM_G2_MAX = 512, NUM_G3_MAX = 2048,
               NUM_G4_MAX = 8192;
 
-__host__ __device__ __forceinline__ int sym_bin_of(u32 f) {
+// Bin 6 "merge": when every row of B is sorted by column (CsrMatrix<T, true>, e.g. anything built by
+// From<DokMatrix>), a short A row is a handful of sorted runs; one thread merges them with the run
+// heads in registers — no table, no sort, output already ordered.
+//   symbolic: len(A row) <= MERGE_K and f <= 64;  numeric: additionally z <= 16 and f <= 128
+constexpr int MERGE_BIN = 6;
+constexpr u32 MERGE_K = 8, MERGE_SYM_FLOP_MAX = 64, MERGE_ZMAX = 16;
+
+__host__ __device__ __forceinline__ int sym_bin_of(u32 f, u32 alen = 0xFFFFFFFFu, bool merge_ok = false) {
+  if (merge_ok && alen <= MERGE_K && f <= MERGE_SYM_FLOP_MAX) return MERGE_BIN;
   return f <= SYM_TINY_MAX ? 0 : f <= SYM_G1_MAX ? 1 : f <= SYM_G2_MAX ? 2 : f <= SYM_G3_MAX ? 3 : f <= SYM_G4_MAX ? 4 : 5;
 }
-__host__ __device__ __forceinline__ int num_bin_of(u32 z, u32 f) {
+__host__ __device__ __forceinline__ int num_bin_of(u32 z, u32 f, u32 alen = 0xFFFFFFFFu, bool merge_ok = false) {
+  if (merge_ok && alen <= MERGE_K && z <= MERGE_ZMAX && f <= NUM_TINY_FLOP_MAX) return MERGE_BIN;
   if (z <= NUM_TINY_MAX) return (f <= NUM_TINY_FLOP_MAX) ? 0 : 1;
   return z <= NUM_G1_MAX ? 1 : z <= NUM_G2_MAX ? 2 : z <= NUM_G3_MAX ? 3 : z <= NUM_G4_MAX ? 4 : 5;
 }
@@ -63,7 +72,9 @@ struct Counters {
   u32 work_a;     // dynamic work counters for the persistent heavy-row kernels
   u32 work_b;
   u32 scan_tile;  // dynamic tile id for the look-back scan
-  u32 pad[2];
+  u32 max_alen;   // longest A row among the rows of the merge bin (picks the head-count template)
+  u32 unsorted;   // set by k_rows_sorted when some row is not strictly increasing
+
 };
 
 struct BinBase { u32 v[NBINS]; };
@@ -129,6 +140,7 @@ struct spam_dcsr {
   u32* idx;   // device
   void* val;  // device
   bool owning;
+  int rows_sorted;  // cached property: -1 unknown, 0 no, 1 every row strictly increasing (IS_SORTED)
 };
 
 struct SpgemmPending;  // state between the two host phases
@@ -182,7 +194,7 @@ int spgemm_numeric_dev(spam_handle* h, SpgemmPending* p, spam_dcsr** c);
 void spgemm_pending_free(spam_handle* h, SpgemmPending* p);
 u64 spgemm_pending_nnz(const SpgemmPending* p);
 const u64* spgemm_pending_cptr(const SpgemmPending* p);
-int flop_count_dev(spam_handle* h, const spam_dcsr* a, const spam_dcsr* b, u32* d_flop, bool do_bins);
+int flop_count_dev(spam_handle* h, const spam_dcsr* a, const spam_dcsr* b, u32* d_flop, bool do_bins, int merge_ok);
 // spmv.cu
 int spmv_dev(spam_handle* h, const spam_dcsr* a, const void* d_x, void* d_y);
 // dok.cu

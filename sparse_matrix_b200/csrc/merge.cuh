@@ -1,0 +1,180 @@
+// merge.cuh — the "merge" bin: SpGEMM rows as a k-way merge of sorted runs, one thread per row.
+//
+// When B's rows are sorted by column (CsrMatrix<T, true>; everything From<DokMatrix> builds,
+// spam_csr/src/lib.rs:315-334), row i of C is the union of the runs  a_ik * B[k,:]  over the entries
+// k of A's row i, each run already ordered.  For short A rows (<= MERGE_K entries) a thread keeps the
+// run heads (position, end, current column) in registers and repeatedly takes the smallest column:
+//   * no hash table, no shared-memory atomics, no per-row sort: the output comes out ordered
+//     (the reference's B2=true branch, mul_hash.rs:164-175);
+//   * runs are visited in A-row storage order and equal columns are folded first-stored-then-added
+//     with separate mul and add, i.e. exactly the reference's accumulation order
+//     (mul_hash.rs:145-162): sums are bit-identical to the reference, floats included.
+// HBM-bound by design: A and the B rows it touches are read once (B mostly from L1/L2 for banded
+// matrices), C is written once through a shared-memory transpose so that each warp stores the
+// contiguous output of its 32 consecutive rows.
+#pragma once
+#include "common.cuh"
+
+namespace {
+
+constexpr u32 INF_COL = 0xFFFFFFFFu;
+
+// Are all rows strictly increasing by column?  (invariant6 with IS_SORTED, lib.rs:69-77)
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_rows_sorted(u64 m, const u64* __restrict__ ptr,
+                                                       const u32* __restrict__ idx, Counters* cnt) {
+  const int lane = threadIdx.x & 31;
+  const u64 row = (u64)blockIdx.x * BLOCK + threadIdx.x;
+  const bool valid = row < m;
+  u64 lo = 0, hi = 0;
+  if (valid) { lo = ptr[row]; hi = ptr[row + 1]; }
+  bool bad = false;
+  if (valid && hi - lo <= 32) {
+    for (u64 e = lo + 1; e < hi; ++e) bad |= idx[e - 1] >= idx[e];
+  }
+  unsigned longmask = __ballot_sync(0xffffffffu, valid && hi - lo > 32);
+  while (longmask) {
+    const int src = __ffs(longmask) - 1;
+    longmask &= longmask - 1;
+    const u64 l = __shfl_sync(0xffffffffu, lo, src), hh = __shfl_sync(0xffffffffu, hi, src);
+    for (u64 e = l + 1 + lane; e < hh; e += 32) bad |= idx[e - 1] >= idx[e];
+  }
+  if (bad) atomicOr(&cnt->unsorted, 1u);
+}
+
+// SYMBOLIC merge: count distinct columns; also histograms the numeric bin of each row so that the
+// separate k_num_bin_count pass is skipped when every row is in this bin.
+template <int K, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_sym_merge(u32 n, const u32* __restrict__ perm,
+                                                     const u64* __restrict__ a_ptr, const u32* __restrict__ a_col,
+                                                     const u64* __restrict__ b_ptr, const u32* __restrict__ b_col,
+                                                     const u32* __restrict__ flop, u32* __restrict__ row_nnz,
+                                                     Counters* cnt) {
+  __shared__ u32 s_hist[NBINS];
+  const int tid = threadIdx.x;
+  if (tid < NBINS) s_hist[tid] = 0;
+  __syncthreads();
+  const u32 i = blockIdx.x * BLOCK + tid;
+  if (i < n) {
+    const u32 row = perm ? perm[i] : i;
+    const u64 alo = a_ptr[row];
+    const u32 k = (u32)(a_ptr[row + 1] - alo);
+    u32 pos[K], end[K], col[K];
+#pragma unroll
+    for (int h = 0; h < K; ++h) {
+      pos[h] = 0; end[h] = 0; col[h] = INF_COL;
+      if (h < k) {
+        const u32 kk = a_col[alo + h];
+        pos[h] = (u32)b_ptr[kk];
+        end[h] = (u32)b_ptr[kk + 1];
+      }
+    }
+#pragma unroll
+    for (int h = 0; h < K; ++h)
+      if (pos[h] < end[h]) col[h] = b_col[pos[h]];
+    u32 z = 0;
+    for (;;) {
+      u32 cmin = col[0];
+#pragma unroll
+      for (int h = 1; h < K; ++h) cmin = min(cmin, col[h]);
+      if (cmin == INF_COL) break;
+      ++z;
+#pragma unroll
+      for (int h = 0; h < K; ++h) {
+        if (col[h] == cmin) {
+          ++pos[h];
+          col[h] = (pos[h] < end[h]) ? b_col[pos[h]] : INF_COL;
+        }
+      }
+    }
+    row_nnz[row] = z;  // mul_hash.rs:95
+    atomicAdd(&s_hist[num_bin_of(z, flop[row], k, true)], 1u);
+  }
+  __syncthreads();
+  if (tid < NBINS && s_hist[tid]) atomicAdd(&cnt->num_bins[tid], s_hist[tid]);
+}
+
+// NUMERIC merge.  Staging is [slot][thread] with a padded stride so the owner's writes (same slot,
+// consecutive threads) and the half-warp read-back (consecutive slots, one thread column) both hit
+// distinct banks.
+template <class V, int K, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_num_merge(u32 n, const u32* __restrict__ perm,
+                                                     const u64* __restrict__ a_ptr, const u32* __restrict__ a_col,
+                                                     const V* __restrict__ a_val, const u64* __restrict__ b_ptr,
+                                                     const u32* __restrict__ b_col, const V* __restrict__ b_val,
+                                                     const u64* __restrict__ c_ptr, u32* __restrict__ c_col,
+                                                     V* __restrict__ c_val) {
+  constexpr int STRIDE = BLOCK + 1;
+  extern __shared__ __align__(16) unsigned char sm_merge[];
+  V* sv = reinterpret_cast<V*>(sm_merge);                 // [MERGE_ZMAX][STRIDE]
+  u32* sk = reinterpret_cast<u32*>(sv + MERGE_ZMAX * STRIDE);  // [MERGE_ZMAX][STRIDE]
+  const int tid = threadIdx.x, lane = tid & 31;
+  const u32 i = blockIdx.x * BLOCK + tid;
+  u64 c0 = 0;
+  u32 z = 0, row = 0;
+  if (i < n) {
+    row = perm ? perm[i] : i;
+    c0 = c_ptr[row];
+    z = (u32)(c_ptr[row + 1] - c0);
+  }
+  if (z > 0) {
+    const u64 alo = a_ptr[row];
+    const u32 k = (u32)(a_ptr[row + 1] - alo);
+    u32 pos[K], end[K], col[K];
+    V av[K];
+#pragma unroll
+    for (int h = 0; h < K; ++h) {
+      pos[h] = 0; end[h] = 0; col[h] = INF_COL; av[h] = Num<V>::zero();
+      if (h < k) {
+        const u32 kk = a_col[alo + h];
+        av[h] = a_val[alo + h];
+        pos[h] = (u32)b_ptr[kk];
+        end[h] = (u32)b_ptr[kk + 1];
+      }
+    }
+#pragma unroll
+    for (int h = 0; h < K; ++h)
+      if (pos[h] < end[h]) col[h] = b_col[pos[h]];
+    u32 t = 0;
+    for (;;) {
+      u32 cmin = col[0];
+#pragma unroll
+      for (int h = 1; h < K; ++h) cmin = min(cmin, col[h]);
+      if (cmin == INF_COL || t >= MERGE_ZMAX) break;
+      V acc = Num<V>::zero();
+      bool first = true;
+#pragma unroll
+      for (int h = 0; h < K; ++h) {  // A-row storage order
+        if (col[h] == cmin) {
+          const V p = Num<V>::mul(av[h], b_val[pos[h]]);
+          acc = first ? p : Num<V>::add(acc, p);  // first product stored, not added to 0
+          first = false;
+          ++pos[h];
+          col[h] = (pos[h] < end[h]) ? b_col[pos[h]] : INF_COL;
+        }
+      }
+      sk[t * STRIDE + tid] = cmin;
+      sv[t * STRIDE + tid] = acc;
+      ++t;
+    }
+  }
+  __syncwarp();
+  // write-back: each half-warp stores one row (<= 16 entries); a warp's 32 rows are consecutive in C
+  // when the bin holds consecutive rows, so the stores of one iteration are contiguous in memory.
+  const int wbase = tid & ~31, half = lane >> 4, s = lane & 15;
+#pragma unroll 4
+  for (int it = 0; it < 16; ++it) {
+    const int src = it * 2 + half;
+    const u32 zr = __shfl_sync(0xffffffffu, z, src);
+    const u64 c0r = __shfl_sync(0xffffffffu, c0, src);
+    if ((u32)s < zr) {
+      c_col[c0r + s] = sk[s * STRIDE + wbase + src];
+      c_val[c0r + s] = sv[s * STRIDE + wbase + src];
+    }
+  }
+}
+
+template <class V, int BLOCK>
+constexpr size_t num_merge_smem() { return (size_t)MERGE_ZMAX * (BLOCK + 1) * (sizeof(V) + 4); }
+
+}  // namespace

@@ -17,6 +17,7 @@
 // global-memory tables for heavy power-law rows.  Everything is integer/byte gather-scatter work
 // bounded by HBM/L2 and shared-memory throughput; no tensor cores.
 #include "common.cuh"
+#include "merge.cuh"
 
 namespace {
 
@@ -73,13 +74,14 @@ __device__ __forceinline__ u32 block_excl_scan_u32(u32 v, u32* s_warp /* >= T/32
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK) k_flop_count(u64 m, u64 b_rows, const u64* __restrict__ a_ptr,
                                                       const u32* __restrict__ a_col, const u64* __restrict__ b_ptr,
-                                                      u32* __restrict__ flop_out, Counters* cnt, int do_bins) {
+                                                      u32* __restrict__ flop_out, Counters* cnt, int do_bins,
+                                                      int merge_ok) {
   __shared__ u32 s_hist[NBINS];
   __shared__ ull s_total;
-  __shared__ u32 s_max;
+  __shared__ u32 s_max, s_maxalen;
   const int tid = threadIdx.x, lane = tid & 31;
   if (tid < NBINS) s_hist[tid] = 0;
-  if (tid == 0) { s_total = 0; s_max = 0; }
+  if (tid == 0) { s_total = 0; s_max = 0; s_maxalen = 0; }
   __syncthreads();
   const u64 row = (u64)blockIdx.x * BLOCK + tid;
   const bool valid = row < m;
@@ -113,8 +115,11 @@ __global__ void __launch_bounds__(BLOCK) k_flop_count(u64 m, u64 b_rows, const u
     const u32 fs = f > 0xFFFFFFFFull ? 0xFFFFFFFFu : (u32)f;  // saturate: still lands in the heavy bin
     flop_out[row] = fs;
     if (do_bins) {
-      atomicAdd(&s_hist[sym_bin_of(fs)], 1u);
-      atomicMax(&s_max, fs);
+      const u32 alen = len > 0xFFFFFFFFull ? 0xFFFFFFFFu : (u32)len;
+      const int bin = sym_bin_of(fs, alen, merge_ok != 0);
+      atomicAdd(&s_hist[bin], 1u);
+      if (merge_ok && alen <= MERGE_K) atomicMax(&s_maxalen, alen);  // bound for both merge bins
+      if (bin != MERGE_BIN) atomicMax(&s_max, fs);
     }
   }
   // block total of f
@@ -127,13 +132,15 @@ __global__ void __launch_bounds__(BLOCK) k_flop_count(u64 m, u64 b_rows, const u
   if (tid == 0) {
     if (s_total) atomicAdd(&cnt->total_flops, s_total);
     if (s_max) atomicMax(&cnt->max_flop, s_max);
+    if (s_maxalen) atomicMax(&cnt->max_alen, s_maxalen);
   }
 }
 
 // histogram of the numeric bins, from (row nnz, flop)
 template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK) k_num_bin_count(u64 m, const u32* __restrict__ row_nnz,
-                                                         const u32* __restrict__ flop, Counters* cnt) {
+__global__ void __launch_bounds__(BLOCK) k_num_bin_count(u64 m, const u64* __restrict__ a_ptr,
+                                                         const u32* __restrict__ row_nnz,
+                                                         const u32* __restrict__ flop, Counters* cnt, int merge_ok) {
   __shared__ u32 s_hist[NBINS];
   __shared__ u32 s_max;
   const int tid = threadIdx.x;
@@ -142,8 +149,11 @@ __global__ void __launch_bounds__(BLOCK) k_num_bin_count(u64 m, const u32* __res
   __syncthreads();
   const u64 row = (u64)blockIdx.x * BLOCK + tid;
   if (row < m) {
-    const u32 z = row_nnz[row];
-    atomicAdd(&s_hist[num_bin_of(z, flop[row])], 1u);
+    const u32 z = row_nnz[row], f = flop[row];
+    const u64 len = a_ptr[row + 1] - a_ptr[row];
+    const u32 alen = len > 0xFFFFFFFFull ? 0xFFFFFFFFu : (u32)len;
+    // rows of the symbolic merge bin were already histogrammed by k_sym_merge
+    if (sym_bin_of(f, alen, merge_ok != 0) != MERGE_BIN) atomicAdd(&s_hist[num_bin_of(z, f, alen, merge_ok != 0)], 1u);
     if (z > NUM_G4_MAX) atomicMax(&s_max, z);
   }
   __syncthreads();
@@ -154,9 +164,10 @@ __global__ void __launch_bounds__(BLOCK) k_num_bin_count(u64 m, const u32* __res
 // scatter row ids into per-bin segments of perm[] (counting sort by bin; a block's rows stay
 // together inside each bin so neighbouring rows still share cache lines of A and B)
 template <int BLOCK, bool NUMERIC>
-__global__ void __launch_bounds__(BLOCK) k_bin_scatter(u64 m, const u32* __restrict__ row_nnz,
+__global__ void __launch_bounds__(BLOCK) k_bin_scatter(u64 m, const u64* __restrict__ a_ptr,
+                                                       const u32* __restrict__ row_nnz,
                                                        const u32* __restrict__ flop, BinBase base, u32* cursors,
-                                                       u32* __restrict__ perm) {
+                                                       u32* __restrict__ perm, int merge_ok) {
   __shared__ u32 s_cnt[NBINS];
   __shared__ u32 s_base[NBINS];
   const int tid = threadIdx.x;
@@ -166,7 +177,9 @@ __global__ void __launch_bounds__(BLOCK) k_bin_scatter(u64 m, const u32* __restr
   int b = -1;
   u32 r = 0;
   if (row < m) {
-    b = NUMERIC ? num_bin_of(row_nnz[row], flop[row]) : sym_bin_of(flop[row]);
+    const u64 len = a_ptr[row + 1] - a_ptr[row];
+    const u32 alen = len > 0xFFFFFFFFull ? 0xFFFFFFFFu : (u32)len;
+    b = NUMERIC ? num_bin_of(row_nnz[row], flop[row], alen, merge_ok != 0) : sym_bin_of(flop[row], alen, merge_ok != 0);
     r = atomicAdd(&s_cnt[b], 1u);
   }
   __syncthreads();
@@ -625,8 +638,8 @@ struct Bins {
   u32* perm;  // device, null when one bin holds every row (identity)
 };
 
-int build_perm(spam_handle* h, u64 m, const u32* counts, bool numeric, const u32* d_row_nnz, const u32* d_flop,
-               Bins* out) {
+int build_perm(spam_handle* h, u64 m, const u32* counts, bool numeric, const u64* d_aptr, const u32* d_row_nnz,
+               const u32* d_flop, int merge_ok, Bins* out) {
   u32 acc = 0;
   bool identity = false;
   for (int b = 0; b < NBINS; ++b) {
@@ -643,9 +656,9 @@ int build_perm(spam_handle* h, u64 m, const u32* counts, bool numeric, const u32
   u32* cursors = numeric ? h->d_cnt->num_cursor : h->d_cnt->sym_cursor;
   const unsigned grid = (unsigned)((m + 255) / 256);
   if (numeric)
-    k_bin_scatter<256, true><<<grid, 256, 0, h->stream>>>(m, d_row_nnz, d_flop, bb, cursors, out->perm);
+    k_bin_scatter<256, true><<<grid, 256, 0, h->stream>>>(m, d_aptr, d_row_nnz, d_flop, bb, cursors, out->perm, merge_ok);
   else
-    k_bin_scatter<256, false><<<grid, 256, 0, h->stream>>>(m, d_row_nnz, d_flop, bb, cursors, out->perm);
+    k_bin_scatter<256, false><<<grid, 256, 0, h->stream>>>(m, d_aptr, d_row_nnz, d_flop, bb, cursors, out->perm, merge_ok);
   count_launch(h);
   CK(cudaGetLastError());
   return SPAM_OK;
@@ -662,7 +675,29 @@ struct SpgemmPending {
   u64 nnz;
   u32 num_counts[NBINS];
   u32 max_nnz;
+  u32 max_alen;   // longest A row in the merge bins
+  int merge_ok;   // B's rows are sorted and nnz(B) < 2^32: the merge bin is in use
 };
+
+namespace {
+
+// Cached per matrix: are all rows strictly increasing by column?  One pass over col_idx the first
+// time a matrix is used as a right-hand side (device matrices are immutable through this API).
+int ensure_rows_sorted(spam_handle* h, const spam_dcsr* b) {
+  if (b->rows_sorted >= 0) return SPAM_OK;
+  spam_dcsr* mb = const_cast<spam_dcsr*>(b);
+  if (b->rows == 0 || b->nnz == 0) { mb->rows_sorted = 1; return SPAM_OK; }
+  CK(cudaMemsetAsync(&h->d_cnt->unsorted, 0, sizeof(u32), h->stream));
+  k_rows_sorted<256><<<(unsigned)((b->rows + 255) / 256), 256, 0, h->stream>>>(b->rows, b->ptr, b->idx, h->d_cnt);
+  count_launch(h);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(&h->h_cnt->unsorted, &h->d_cnt->unsorted, sizeof(u32), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  mb->rows_sorted = h->h_cnt->unsorted ? 0 : 1;
+  return SPAM_OK;
+}
+
+}  // namespace
 
 u64 spgemm_pending_nnz(const SpgemmPending* p) { return p->nnz; }
 const u64* spgemm_pending_cptr(const SpgemmPending* p) { return p->d_cptr; }
@@ -675,11 +710,11 @@ void spgemm_pending_free(spam_handle* h, SpgemmPending* p) {
   delete p;
 }
 
-int flop_count_dev(spam_handle* h, const spam_dcsr* a, const spam_dcsr* b, u32* d_flop, bool do_bins) {
+int flop_count_dev(spam_handle* h, const spam_dcsr* a, const spam_dcsr* b, u32* d_flop, bool do_bins, int merge_ok) {
   const u64 m = a->rows;
   if (m == 0) return SPAM_OK;
   k_flop_count<256><<<(unsigned)((m + 255) / 256), 256, 0, h->stream>>>(m, b->rows, a->ptr, a->idx, b->ptr, d_flop,
-                                                                         h->d_cnt, do_bins ? 1 : 0);
+                                                                         h->d_cnt, do_bins ? 1 : 0, merge_ok);
   count_launch(h);
   CK(cudaGetLastError());
   return SPAM_OK;
@@ -695,8 +730,11 @@ int spgemm_symbolic_dev(spam_handle* h, const spam_dcsr* a, const spam_dcsr* b, 
     return spam_fail(h, SPAM_ECOLS, "dimension >= 2^32-1 (u32::MAX is the empty-slot sentinel)");
 
   h->stats = spam_stats{};
+  CKS(ensure_rows_sorted(h, b));
+  const int merge_ok = (b->rows_sorted == 1 && b->nnz < 0xFFFFFFFFull) ? 1 : 0;
   SpgemmPending* p = new SpgemmPending();
   p->a = a; p->b = b; p->d_flop = nullptr; p->d_row_nnz = nullptr; p->d_cptr = nullptr; p->nnz = 0; p->max_nnz = 0;
+  p->max_alen = 0; p->merge_ok = merge_ok;
   *out = p;
 #define FAIL_FREE(expr) do { int _s = (expr); if (_s != SPAM_OK) { spgemm_pending_free(h, p); *out = nullptr; return _s; } } while (0)
 #define CK_FREE(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { spgemm_pending_free(h, p); *out = nullptr; return spam_fail(h, SPAM_ECUDA, #call, _e); } } while (0)
@@ -706,7 +744,7 @@ int spgemm_symbolic_dev(spam_handle* h, const spam_dcsr* a, const spam_dcsr* b, 
   FAIL_FREE(dev_alloc_t(h, &p->d_cptr, m + 1));
   CK_FREE(cudaMemsetAsync(h->d_cnt, 0, sizeof(Counters), h->stream));
   if (h->timing) CK_FREE(cudaEventRecord(h->ev[0], h->stream));
-  FAIL_FREE(flop_count_dev(h, a, b, p->d_flop, true));
+  FAIL_FREE(flop_count_dev(h, a, b, p->d_flop, true, merge_ok));
   CK_FREE(cudaMemcpyAsync(h->h_cnt, h->d_cnt, sizeof(Counters), cudaMemcpyDeviceToHost, h->stream));
   if (h->timing) CK_FREE(cudaEventRecord(h->ev[1], h->stream));
   CK_FREE(cudaStreamSynchronize(h->stream));
@@ -720,12 +758,25 @@ int spgemm_symbolic_dev(spam_handle* h, const spam_dcsr* a, const spam_dcsr* b, 
 
   // ---- symbolic per bin ----
   Bins sb;
-  FAIL_FREE(build_perm(h, m, c1.sym_bins, false, nullptr, p->d_flop, &sb));
+  FAIL_FREE(build_perm(h, m, c1.sym_bins, false, a->ptr, nullptr, p->d_flop, merge_ok, &sb));
+  p->max_alen = c1.max_alen;
   u32* heavy_tab = nullptr;
   {
     const u64* ap = a->ptr; const u32* ac = a->idx; const u64* bp = b->ptr; const u32* bc = b->idx;
     const u32* fl = p->d_flop; u32* rz = p->d_row_nnz;
     auto seg = [&](int bin) -> const u32* { return sb.perm ? sb.perm + sb.base[bin] : nullptr; };
+    if (sb.count[MERGE_BIN]) {
+      constexpr int BL = 128;
+      const u32 nm = sb.count[MERGE_BIN];
+      const unsigned grid = (nm + BL - 1) / BL;
+      if (c1.max_alen <= 4)
+        k_sym_merge<4, BL><<<grid, BL, 0, h->stream>>>(nm, seg(MERGE_BIN), ap, ac, bp, bc, fl, rz, h->d_cnt);
+      else if (c1.max_alen <= 6)
+        k_sym_merge<6, BL><<<grid, BL, 0, h->stream>>>(nm, seg(MERGE_BIN), ap, ac, bp, bc, fl, rz, h->d_cnt);
+      else
+        k_sym_merge<8, BL><<<grid, BL, 0, h->stream>>>(nm, seg(MERGE_BIN), ap, ac, bp, bc, fl, rz, h->d_cnt);
+      count_launch(h);
+    }
     if (sb.count[0]) {
       constexpr int BL = 128;
       const size_t smem = (size_t)2 * SYM_TINY_MAX * BL * sizeof(u32);
@@ -764,8 +815,9 @@ int spgemm_symbolic_dev(spam_handle* h, const spam_dcsr* a, const spam_dcsr* b, 
   }
   if (h->timing) CK_FREE(cudaEventRecord(h->ev[2], h->stream));
   // ---- numeric bin histogram + row_ptr scan ----
-  if (m) {
-    k_num_bin_count<256><<<(unsigned)((m + 255) / 256), 256, 0, h->stream>>>(m, p->d_row_nnz, p->d_flop, h->d_cnt);
+  if (m && sb.count[MERGE_BIN] != m) {  // the merge kernel histograms its own rows
+    k_num_bin_count<256><<<(unsigned)((m + 255) / 256), 256, 0, h->stream>>>(m, a->ptr, p->d_row_nnz, p->d_flop, h->d_cnt,
+                                                                            merge_ok);
     count_launch(h);
     CK_FREE(cudaGetLastError());
   }
@@ -793,12 +845,26 @@ int numeric_typed(spam_handle* h, SpgemmPending* p, spam_dcsr* c) {
   const spam_dcsr* b = p->b;
   const u64 m = a->rows;
   Bins nb;
-  CKS(build_perm(h, m, p->num_counts, true, p->d_row_nnz, p->d_flop, &nb));
+  CKS(build_perm(h, m, p->num_counts, true, a->ptr, p->d_row_nnz, p->d_flop, p->merge_ok, &nb));
   const u64* ap = a->ptr; const u32* ac = a->idx; const V* av = (const V*)a->val;
   const u64* bp = b->ptr; const u32* bc = b->idx; const V* bv = (const V*)b->val;
   const u64* cp = c->ptr; u32* cc = c->idx; V* cv = (V*)c->val;
   auto seg = [&](int bin) -> const u32* { return nb.perm ? nb.perm + nb.base[bin] : nullptr; };
   const int ws = wshift_for(b, 5);
+  if (nb.count[MERGE_BIN]) {
+    constexpr int BL = 128;
+    constexpr size_t smem = num_merge_smem<V, BL>();
+    const u32 nm = nb.count[MERGE_BIN];
+    const unsigned grid = (nm + BL - 1) / BL;
+    const u32 kmax = p->max_alen;  // longest A row among all rows short enough for a merge bin
+    if (kmax <= 4)
+      k_num_merge<V, 4, BL><<<grid, BL, smem, h->stream>>>(nm, seg(MERGE_BIN), ap, ac, av, bp, bc, bv, cp, cc, cv);
+    else if (kmax <= 6)
+      k_num_merge<V, 6, BL><<<grid, BL, smem, h->stream>>>(nm, seg(MERGE_BIN), ap, ac, av, bp, bc, bv, cp, cc, cv);
+    else
+      k_num_merge<V, 8, BL><<<grid, BL, smem, h->stream>>>(nm, seg(MERGE_BIN), ap, ac, av, bp, bc, bv, cp, cc, cv);
+    count_launch(h);
+  }
   if (nb.count[0]) {
     constexpr int BL = 128;
     constexpr size_t smem = num_tiny_smem<V, BL>();
@@ -849,7 +915,7 @@ int spgemm_numeric_dev(spam_handle* h, SpgemmPending* p, spam_dcsr** cout) {
   *cout = nullptr;
   spam_dcsr* c = new spam_dcsr();
   c->dtype = p->a->dtype; c->rows = p->a->rows; c->cols = p->b->cols; c->nnz = p->nnz;
-  c->ptr = p->d_cptr; c->idx = nullptr; c->val = nullptr; c->owning = true;
+  c->ptr = p->d_cptr; c->idx = nullptr; c->val = nullptr; c->owning = true; c->rows_sorted = 1;
   int st = dev_alloc_t(h, &c->idx, p->nnz ? p->nnz : 1);
   if (st == SPAM_OK) st = dev_alloc(h, &c->val, (p->nnz ? p->nnz : 1) * dtype_size(c->dtype));
   if (st == SPAM_OK && p->nnz) {
