@@ -44,16 +44,17 @@ constexpr u32 NUM_TINY_MAX = 16, NUM_TINY_FLOP_MAX = 128, NUM_G1_MAX = 128, NUM_
 // Bin 6 "merge": when every row of B is sorted by column (CsrMatrix<T, true>, e.g. anything built by
 // From<DokMatrix>), a short A row is a handful of sorted runs; one thread merges them with the run
 // heads in registers — no table, no sort, output already ordered.
-//   symbolic: len(A row) <= MERGE_K and f <= 64;  numeric: additionally z <= 16 and f <= 128
+//   both passes: len(A row) <= MERGE_K and f <= 128
 constexpr int MERGE_BIN = 6;
-constexpr u32 MERGE_K = 8, MERGE_SYM_FLOP_MAX = 64, MERGE_ZMAX = 16;
+constexpr u32 MERGE_K = 8, MERGE_FLOP_MAX = 128;
 
 __host__ __device__ __forceinline__ int sym_bin_of(u32 f, u32 alen = 0xFFFFFFFFu, bool merge_ok = false) {
-  if (merge_ok && alen <= MERGE_K && f <= MERGE_SYM_FLOP_MAX) return MERGE_BIN;
+  if (merge_ok && alen <= MERGE_K && f <= MERGE_FLOP_MAX) return MERGE_BIN;
   return f <= SYM_TINY_MAX ? 0 : f <= SYM_G1_MAX ? 1 : f <= SYM_G2_MAX ? 2 : f <= SYM_G3_MAX ? 3 : f <= SYM_G4_MAX ? 4 : 5;
 }
 __host__ __device__ __forceinline__ int num_bin_of(u32 z, u32 f, u32 alen = 0xFFFFFFFFu, bool merge_ok = false) {
-  if (merge_ok && alen <= MERGE_K && z <= MERGE_ZMAX && f <= NUM_TINY_FLOP_MAX) return MERGE_BIN;
+  (void)z;
+  if (merge_ok && alen <= MERGE_K && f <= MERGE_FLOP_MAX) return MERGE_BIN;
   if (z <= NUM_TINY_MAX) return (f <= NUM_TINY_FLOP_MAX) ? 0 : 1;
   return z <= NUM_G1_MAX ? 1 : z <= NUM_G2_MAX ? 2 : z <= NUM_G3_MAX ? 3 : z <= NUM_G4_MAX ? 4 : 5;
 }

@@ -94,9 +94,21 @@ __global__ void __launch_bounds__(BLOCK) k_sym_merge(u32 n, const u32* __restric
   if (tid < NBINS && s_hist[tid]) atomicAdd(&cnt->num_bins[tid], s_hist[tid]);
 }
 
-// NUMERIC merge.  Staging is [slot][thread] with a padded stride so the owner's writes (same slot,
-// consecutive threads) and the half-warp read-back (consecutive slots, one thread column) both hit
-// distinct banks.
+// NUMERIC merge.  Outputs are staged CH at a time in a small [slot][thread] shared-memory tile and
+// flushed by the whole warp (4 lanes per row, 8 rows per store instruction: each row's 4 values are
+// one full 32-byte sector).  Keeping the tile tiny matters: shared memory is carved out of the same
+// 228 KB as L1, and the run heads re-read B through L1 (with 16-slot staging the L1 hit rate fell
+// to 19% and the kernel became L2-bandwidth bound — profiles/r01_poisson_v1_merge.txt).
+// Tile strides are padded so that the owner's writes and the flush reads are bank-conflict free.
+constexpr int MERGE_CH = 4;
+
+template <class V, int BLOCK>
+struct MergeTile {
+  static constexpr int STRIDE_K = BLOCK + 8;                        // u32 words: (8q + r) mod 32 distinct
+  static constexpr int STRIDE_V = sizeof(V) == 8 ? BLOCK + 4 : BLOCK + 8;  // 8-byte words: (4q + r) mod 16
+  static constexpr size_t bytes = (size_t)MERGE_CH * (STRIDE_V * sizeof(V) + STRIDE_K * 4);
+};
+
 template <class V, int K, int BLOCK>
 __global__ void __launch_bounds__(BLOCK) k_num_merge(u32 n, const u32* __restrict__ perm,
                                                      const u64* __restrict__ a_ptr, const u32* __restrict__ a_col,
@@ -104,10 +116,10 @@ __global__ void __launch_bounds__(BLOCK) k_num_merge(u32 n, const u32* __restric
                                                      const u32* __restrict__ b_col, const V* __restrict__ b_val,
                                                      const u64* __restrict__ c_ptr, u32* __restrict__ c_col,
                                                      V* __restrict__ c_val) {
-  constexpr int STRIDE = BLOCK + 1;
+  using Tile = MergeTile<V, BLOCK>;
   extern __shared__ __align__(16) unsigned char sm_merge[];
-  V* sv = reinterpret_cast<V*>(sm_merge);                 // [MERGE_ZMAX][STRIDE]
-  u32* sk = reinterpret_cast<u32*>(sv + MERGE_ZMAX * STRIDE);  // [MERGE_ZMAX][STRIDE]
+  V* sv = reinterpret_cast<V*>(sm_merge);                               // [MERGE_CH][STRIDE_V]
+  u32* sk = reinterpret_cast<u32*>(sv + MERGE_CH * Tile::STRIDE_V);     // [MERGE_CH][STRIDE_K]
   const int tid = threadIdx.x, lane = tid & 31;
   const u32 i = blockIdx.x * BLOCK + tid;
   u64 c0 = 0;
@@ -117,14 +129,15 @@ __global__ void __launch_bounds__(BLOCK) k_num_merge(u32 n, const u32* __restric
     c0 = c_ptr[row];
     z = (u32)(c_ptr[row + 1] - c0);
   }
+  u32 pos[K], end[K], col[K];
+  V av[K];
+#pragma unroll
+  for (int h = 0; h < K; ++h) { pos[h] = 0; end[h] = 0; col[h] = INF_COL; av[h] = Num<V>::zero(); }
   if (z > 0) {
     const u64 alo = a_ptr[row];
     const u32 k = (u32)(a_ptr[row + 1] - alo);
-    u32 pos[K], end[K], col[K];
-    V av[K];
 #pragma unroll
     for (int h = 0; h < K; ++h) {
-      pos[h] = 0; end[h] = 0; col[h] = INF_COL; av[h] = Num<V>::zero();
       if (h < k) {
         const u32 kk = a_col[alo + h];
         av[h] = a_val[alo + h];
@@ -135,46 +148,49 @@ __global__ void __launch_bounds__(BLOCK) k_num_merge(u32 n, const u32* __restric
 #pragma unroll
     for (int h = 0; h < K; ++h)
       if (pos[h] < end[h]) col[h] = b_col[pos[h]];
-    u32 t = 0;
-    for (;;) {
-      u32 cmin = col[0];
-#pragma unroll
-      for (int h = 1; h < K; ++h) cmin = min(cmin, col[h]);
-      if (cmin == INF_COL || t >= MERGE_ZMAX) break;
-      V acc = Num<V>::zero();
-      bool first = true;
-#pragma unroll
-      for (int h = 0; h < K; ++h) {  // A-row storage order
-        if (col[h] == cmin) {
-          const V p = Num<V>::mul(av[h], b_val[pos[h]]);
-          acc = first ? p : Num<V>::add(acc, p);  // first product stored, not added to 0
-          first = false;
-          ++pos[h];
-          col[h] = (pos[h] < end[h]) ? b_col[pos[h]] : INF_COL;
-        }
-      }
-      sk[t * STRIDE + tid] = cmin;
-      sv[t * STRIDE + tid] = acc;
-      ++t;
-    }
   }
-  __syncwarp();
-  // write-back: each half-warp stores one row (<= 16 entries); a warp's 32 rows are consecutive in C
-  // when the bin holds consecutive rows, so the stores of one iteration are contiguous in memory.
-  const int wbase = tid & ~31, half = lane >> 4, s = lane & 15;
-#pragma unroll 4
-  for (int it = 0; it < 16; ++it) {
-    const int src = it * 2 + half;
-    const u32 zr = __shfl_sync(0xffffffffu, z, src);
-    const u64 c0r = __shfl_sync(0xffffffffu, c0, src);
-    if ((u32)s < zr) {
-      c_col[c0r + s] = sk[s * STRIDE + wbase + src];
-      c_val[c0r + s] = sv[s * STRIDE + wbase + src];
+  const int wbase = tid & ~31, rsub = lane >> 2, q = lane & 3;
+  for (u32 t0 = 0; __any_sync(0xffffffffu, t0 < z); t0 += MERGE_CH) {
+#pragma unroll
+    for (int c = 0; c < MERGE_CH; ++c) {
+      if (t0 + c < z) {
+        u32 cmin = col[0];
+#pragma unroll
+        for (int h = 1; h < K; ++h) cmin = min(cmin, col[h]);
+        V acc = Num<V>::zero();
+        bool first = true;
+#pragma unroll
+        for (int h = 0; h < K; ++h) {  // A-row storage order
+          if (col[h] == cmin && cmin != INF_COL) {
+            const V p = Num<V>::mul(av[h], b_val[pos[h]]);
+            acc = first ? p : Num<V>::add(acc, p);  // first product stored, not added to 0
+            first = false;
+            ++pos[h];
+            col[h] = (pos[h] < end[h]) ? b_col[pos[h]] : INF_COL;
+          }
+        }
+        sk[c * Tile::STRIDE_K + tid] = cmin;
+        sv[c * Tile::STRIDE_V + tid] = acc;
+      }
     }
+    __syncwarp();
+    // flush: lane (rsub, q) stores entry t0+q of the warp's row it*8+rsub
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int src = it * 8 + rsub;
+      const u32 zr = __shfl_sync(0xffffffffu, z, src);
+      const u64 c0r = __shfl_sync(0xffffffffu, c0, src);
+      const u32 tt = t0 + q;
+      if (tt < zr) {
+        c_col[c0r + tt] = sk[q * Tile::STRIDE_K + wbase + src];
+        c_val[c0r + tt] = sv[q * Tile::STRIDE_V + wbase + src];
+      }
+    }
+    __syncwarp();
   }
 }
 
 template <class V, int BLOCK>
-constexpr size_t num_merge_smem() { return (size_t)MERGE_ZMAX * (BLOCK + 1) * (sizeof(V) + 4); }
+constexpr size_t num_merge_smem() { return MergeTile<V, BLOCK>::bytes; }
 
 }  // namespace

@@ -18,6 +18,7 @@
 // bounded by HBM/L2 and shared-memory throughput; no tensor cores.
 #include "common.cuh"
 #include "merge.cuh"
+#include "warp.cuh"
 
 namespace {
 
@@ -245,7 +246,7 @@ __global__ void __launch_bounds__(T) k_sym_group(const u32* __restrict__ perm, c
   if (f == 0) { if (tid == 0) row_nnz[row] = 0; return; }
   u32 cap = table_size_u32(f);
   if (cap > (u32)CAP) cap = CAP;
-  const u32 mask = cap - 1;
+  const u32 mask = cap - 1, shift = 32 - (31 - __clz(cap));
   for (u32 s = tid; s < cap; s += T) keys[s] = EMPTY_KEY;
   __syncthreads();
   volatile u32* vkeys = keys;
@@ -257,7 +258,7 @@ __global__ void __launch_bounds__(T) k_sym_group(const u32* __restrict__ perm, c
     const u64 bl = b_ptr[k], bh = b_ptr[k + 1];
     for (u64 j = bl + lane; j < bh; j += W) {
       const u32 key = b_col[j];
-      u32 s = slot_of(key, mask);
+      u32 s = slot_fib(key, shift);
       for (;;) {
         const u32 cur = vkeys[s];
         if (cur == key) break;
@@ -298,7 +299,7 @@ __global__ void __launch_bounds__(T) k_sym_heavy(u32 n, const u32* __restrict__ 
     const u32 row = perm ? perm[item] : item;
     u32 f = flop[row];
     if (f > b_cols) f = b_cols;  // at most cols(B) distinct keys
-    const u64 cap = 2ull * npow2_u64(f), mask = cap - 1;
+    const u64 cap = 2ull * npow2_u64(f), mask = cap - 1; const int hshift = 64 - (63 - __clzll((long long)cap));
     for (u64 s = tid; s < cap; s += T) __stcg(&keys[s], EMPTY_KEY);
     __syncthreads();
     u32 cnt = 0;
@@ -308,7 +309,7 @@ __global__ void __launch_bounds__(T) k_sym_heavy(u32 n, const u32* __restrict__ 
       const u64 bl = b_ptr[k], bh = b_ptr[k + 1];
       for (u64 j = bl + lane; j < bh; j += W) {
         const u32 key = b_col[j];
-        u64 s = (u64)(key * HASH_SCAL) & mask;
+        u64 s = ((u64)key * 11400714819323198485ull) >> hshift;
         for (;;) {
           const u32 cur = __ldcg(&keys[s]);
           if (cur == key) break;
@@ -475,7 +476,7 @@ __global__ void __launch_bounds__(T) k_num_group(const u32* __restrict__ perm, c
   if (z == 0) return;                              // mul_hash.rs:141-143
   u32 cap = table_size_u32(z);                     // map.rs:49-58
   if (cap > (u32)CAP) cap = CAP;
-  const u32 mask = cap - 1;
+  const u32 mask = cap - 1, shift = 32 - (31 - __clz(cap));
   for (u32 s = tid; s < cap; s += T) { keys[s] = EMPTY_KEY; vals[s] = Num<V>::zero(); }
   __syncthreads();
   volatile u32* vkeys = keys;
@@ -488,7 +489,7 @@ __global__ void __launch_bounds__(T) k_num_group(const u32* __restrict__ perm, c
     for (u64 j = bl + lane; j < bh; j += W) {
       const u32 key = b_col[j];
       const V prod = Num<V>::mul(av, b_val[j]);
-      u32 s = slot_of(key, mask);
+      u32 s = slot_fib(key, shift);
       for (;;) {
         const u32 cur = vkeys[s];
         if (cur != key) {
@@ -556,7 +557,7 @@ __global__ void __launch_bounds__(T) k_num_heavy(u32 n, const u32* __restrict__ 
     const u64 c0 = c_ptr[row];
     const u32 z = (u32)(c_ptr[row + 1] - c0);
     if (z == 0) continue;
-    const u64 cap = 2ull * npow2_u64(z), mask = cap - 1;
+    const u64 cap = 2ull * npow2_u64(z), mask = cap - 1; const int hshift = 64 - (63 - __clzll((long long)cap));
     for (u64 s = tid; s < cap; s += T) { __stcg(&keys[s], EMPTY_KEY); __stcg(&vals[s], Num<V>::zero()); }
     __syncthreads();
     const u64 lo = a_ptr[row], hi = a_ptr[row + 1];
@@ -567,7 +568,7 @@ __global__ void __launch_bounds__(T) k_num_heavy(u32 n, const u32* __restrict__ 
       for (u64 j = bl + lane; j < bh; j += W) {
         const u32 key = b_col[j];
         const V prod = Num<V>::mul(av, b_val[j]);
-        u64 s = (u64)(key * HASH_SCAL) & mask;
+        u64 s = ((u64)key * 11400714819323198485ull) >> hshift;
         for (;;) {
           const u32 cur = __ldcg(&keys[s]);
           if (cur != key) {
@@ -791,8 +792,22 @@ int spgemm_symbolic_dev(spam_handle* h, const spam_dcsr* a, const spam_dcsr* b, 
       count_launch(h);                                                                                   \
     }
     const int ws = wshift_for(b, 5);
-    LAUNCH_SYM(1, 32, 2 * SYM_G1_MAX)
-    LAUNCH_SYM(2, 64, 2 * SYM_G2_MAX)
+#define LAUNCH_SYM_WARP(BIN, CAP)                                                                        \
+    if (sb.count[BIN]) {                                                                                 \
+      constexpr size_t smem = (size_t)WARPS_PER_BLOCK * (CAP) * sizeof(u32);                             \
+      FAIL_FREE(set_smem(h, k_sym_warp<CAP>, smem));                                                     \
+      k_sym_warp<CAP><<<(sb.count[BIN] + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, 32 * WARPS_PER_BLOCK, smem, \
+                        h->stream>>>(sb.count[BIN], seg(BIN), ap, ac, bp, bc, fl, rz, ws);               \
+      count_launch(h);                                                                                   \
+    }
+    if (b->nnz < 0xFFFFFFFFull) {  // the warp kernels keep B offsets in 32 bits
+      LAUNCH_SYM_WARP(1, 2 * SYM_G1_MAX)
+      LAUNCH_SYM_WARP(2, 2 * SYM_G2_MAX)
+    } else {
+      LAUNCH_SYM(1, 32, 2 * SYM_G1_MAX)
+      LAUNCH_SYM(2, 64, 2 * SYM_G2_MAX)
+    }
+#undef LAUNCH_SYM_WARP
     LAUNCH_SYM(3, 256, 2 * SYM_G3_MAX)
     LAUNCH_SYM(4, 1024, 2 * SYM_G4_MAX)
 #undef LAUNCH_SYM
@@ -879,8 +894,24 @@ int numeric_typed(spam_handle* h, SpgemmPending* p, spam_dcsr* c) {
     k_num_group<V, T, CAP><<<nb.count[BIN], T, smem, h->stream>>>(seg(BIN), ap, ac, av, bp, bc, bv, cp, cc, cv, ws); \
     count_launch(h);                                                                                     \
   }
-  LAUNCH_GROUP(1, 32, 2 * NUM_G1_MAX)
-  LAUNCH_GROUP(2, 128, 2 * NUM_G2_MAX)
+#define LAUNCH_NUM_WARP(BIN, CAP)                                                                        \
+  if (nb.count[BIN]) {                                                                                   \
+    constexpr size_t smem = (size_t)WARPS_PER_BLOCK * (CAP) * (sizeof(V) + 4);                           \
+    CKS(set_smem(h, k_num_warp<V, CAP>, smem));                                                          \
+    k_num_warp<V, CAP><<<(nb.count[BIN] + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, 32 * WARPS_PER_BLOCK, smem, \
+                         h->stream>>>(nb.count[BIN], seg(BIN), ap, ac, av, bp, bc, bv, cp, cc, cv, ws,   \
+                                      /* (col << log2(CAP/2)) | slot fits 32 bits? */                    \
+                                      b->cols < (1ull << (32 - (31 - __builtin_clz((unsigned)(CAP) / 2)))) ? 1 : 0); \
+    count_launch(h);                                                                                     \
+  }
+  if (b->nnz < 0xFFFFFFFFull) {
+    LAUNCH_NUM_WARP(1, 2 * NUM_G1_MAX)
+    LAUNCH_NUM_WARP(2, 2 * NUM_G2_MAX)
+  } else {
+    LAUNCH_GROUP(1, 32, 2 * NUM_G1_MAX)
+    LAUNCH_GROUP(2, 128, 2 * NUM_G2_MAX)
+  }
+#undef LAUNCH_NUM_WARP
   LAUNCH_GROUP(3, 512, 2 * NUM_G3_MAX)
   LAUNCH_GROUP(4, 1024, 2 * NUM_G4_MAX)
 #undef LAUNCH_GROUP
