@@ -1,0 +1,55 @@
+// C++ host-mirror test (GPU): the reference's own property test shape
+// (spam_csr/src/tests.rs:356-371: mul_hash == dense DokMatrix product) through include/spam_csr.hpp.
+#include <cstdio>
+#include <random>
+
+#include "../../include/spam_csr.hpp"
+
+template <class T>
+static int run(const char* name, std::mt19937_64& rng) {
+  int fails = 0;
+  for (int it = 0; it < 60; ++it) {
+    const uint64_t l = 1 + rng() % 6, m = 1 + rng() % 6, n = 1 + rng() % 6;
+    spam::DokMatrix<T> da(l, m), db(m, n);
+    for (uint64_t k = rng() % (2 * l * m + 1); k-- > 0;) da.set_element(rng() % l, rng() % m, (T)((int)(rng() % 9) - 4));
+    for (uint64_t k = rng() % (2 * m * n + 1); k-- > 0;) db.set_element(rng() % m, rng() % n, (T)((int)(rng() % 9) - 4));
+    auto a = spam::CsrMatrix<T, true>::from(da);
+    auto b = spam::CsrMatrix<T, true>::from(db);
+    if (!a.invariants() || !b.invariants()) { ++fails; continue; }
+    auto c = a * b;  // impl Mul for &CsrMatrix: CsrMatrix<T, false>
+    auto cs = a.template mul_hash<true>(b);
+    if (!c.invariants() || !cs.invariants()) { ++fails; continue; }
+    // dense DokMatrix product (spam_dok/src/lib.rs:206-233), compared zero-insensitively
+    std::vector<T> want(l * n, T(0)), got(l * n, T(0));
+    for (auto& ea : da.entries())
+      for (auto& eb : db.entries())
+        if (ea.first.second == eb.first.first) want[ea.first.first * n + eb.first.second] += ea.second * eb.second;
+    for (uint64_t r = 0; r < l; ++r)
+      for (uint64_t e = cs.offsets[r]; e < cs.offsets[r + 1]; ++e) got[r * n + cs.indices[e]] = cs.vals[e];
+    if (want != got || c.indices != cs.indices || c.vals != cs.vals) ++fails;
+    // spmv against the same dense data
+    std::vector<T> x(m);
+    for (auto& v : x) v = (T)((int)(rng() % 7) - 3);
+    auto y = a.spmv(x);
+    std::vector<T> yw(l, T(0));
+    for (auto& ea : da.entries()) yw[ea.first.first] += ea.second * x[ea.first.second];
+    if (y != yw) ++fails;
+  }
+  std::printf("%s: %s\n", name, fails ? "FAIL" : "ok");
+  return fails;
+}
+
+int main() {
+  std::mt19937_64 rng(42);
+  int fails = run<double>("f64", rng) + run<float>("f32", rng) + run<int32_t>("i32", rng) + run<int64_t>("i64", rng);
+  // error behaviour: dimension mismatch throws (the reference panics out of bounds, mul_hash.rs:46)
+  bool threw = false;
+  try { auto a = spam::CsrMatrix<double, true>::identity(3); auto b = spam::CsrMatrix<double, true>::identity(4); (void)(a * b); }
+  catch (const std::runtime_error&) { threw = true; }
+  if (!threw) { std::printf("EDIM not raised\n"); ++fails; }
+  bool idx = false;
+  try { spam::DokMatrix<double> d(2, 2); d.set_element(2, 0, 1.0); } catch (const spam::IndexError&) { idx = true; }
+  if (!idx) ++fails;
+  std::printf(fails ? "FAILED\n" : "ALL OK\n");
+  return fails ? 1 : 0;
+}

@@ -368,3 +368,14 @@ def test_scan_sizes_through_dok_row_ptr(oracle, handle):
         got = S.CsrMatrix.from_triplets(rows, 4, ri, ci, v, handle=handle)
         off, idx, val = oracle.dok_to_csr(rows, 4, ri, ci, v)
         assert np.array_equal(got.offsets, off) and np.array_equal(got.indices, idx) and np.array_equal(got.vals, val)
+
+
+def test_cpp_host_mirror():
+    """include/spam_csr.hpp (the C++ stand-in for the vendored spam_csr crate) over the C ABI."""
+    import subprocess
+    exe = os.path.join(os.path.dirname(__file__), "cpp", "test_mirror")
+    if not os.path.exists(exe):
+        import __graft_entry__ as g
+        g.build()
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "ALL OK" in out.stdout, out.stdout + out.stderr
