@@ -15,7 +15,7 @@ fn main() {
         cmd.arg(csrc.join(f));
         println!("cargo:rerun-if-changed={}", csrc.join(f).display());
     }
-    for f in ["common.cuh", "merge.cuh", "warp.cuh"] {
+    for f in ["common.cuh", "merge.cuh", "rowhash.cuh"] {
         println!("cargo:rerun-if-changed={}", csrc.join(f).display());
     }
     assert!(cmd.status().expect("nvcc not found").success(), "nvcc failed");

@@ -239,7 +239,7 @@ int spam_csr_upload(spam_handle* h, int dtype, uint64_t rows, uint64_t cols, uin
   if (rows >= 0xFFFFFFFFull || cols >= 0xFFFFFFFFull) return spam_fail(h, SPAM_ECOLS, "dimension >= 2^32-1");
   CKS(set_device(h));
   spam_dcsr* m = new spam_dcsr();
-  m->dtype = dtype; m->rows = rows; m->cols = cols; m->nnz = nnz; m->owning = true; m->rows_sorted = -1;
+  m->dtype = dtype; m->rows = rows; m->cols = cols; m->nnz = nnz; m->owning = true; m->rows_sorted = -1; m->max_row_len = 0;
   m->ptr = nullptr; m->idx = nullptr; m->val = nullptr;
   u64* tmp = nullptr;
   int st = dev_alloc_t(h, &m->ptr, rows + 1);
@@ -266,7 +266,7 @@ int spam_dcsr_wrap(spam_handle* h, int dtype, uint64_t rows, uint64_t cols, uint
   if (!h || !out || !d_ptr || !valid_dtype(dtype)) return spam_fail(h, SPAM_EINVAL, "bad argument");
   if (rows >= 0xFFFFFFFFull || cols >= 0xFFFFFFFFull) return spam_fail(h, SPAM_ECOLS, "dimension >= 2^32-1");
   spam_dcsr* m = new spam_dcsr();
-  m->dtype = dtype; m->rows = rows; m->cols = cols; m->nnz = nnz; m->owning = false; m->rows_sorted = -1;
+  m->dtype = dtype; m->rows = rows; m->cols = cols; m->nnz = nnz; m->owning = false; m->rows_sorted = -1; m->max_row_len = 0;
   m->ptr = (u64*)d_ptr; m->idx = (u32*)d_idx; m->val = (void*)d_val;
   *out = m;
   return SPAM_OK;
@@ -320,7 +320,7 @@ int spam_dcsr_slice_rows(spam_handle* h, const spam_dcsr* m, uint64_t r0, uint64
   CK(cudaStreamSynchronize(h->stream));
   const u64 nnz = ends[1] - ends[0], rows = r1 - r0;
   spam_dcsr* s = new spam_dcsr();
-  s->dtype = m->dtype; s->rows = rows; s->cols = m->cols; s->nnz = nnz; s->owning = true; s->rows_sorted = m->rows_sorted;
+  s->dtype = m->dtype; s->rows = rows; s->cols = m->cols; s->nnz = nnz; s->owning = true; s->rows_sorted = m->rows_sorted; s->max_row_len = m->max_row_len;
   s->ptr = nullptr; s->idx = nullptr; s->val = nullptr;
   int st = dev_alloc_t(h, &s->ptr, rows + 1);
   if (st == SPAM_OK) st = dev_alloc_t(h, &s->idx, nnz);

@@ -75,6 +75,7 @@ struct Counters {
   u32 scan_tile;  // dynamic tile id for the look-back scan
   u32 max_alen;   // longest A row among the rows of the merge bin (picks the head-count template)
   u32 unsorted;   // set by k_rows_sorted when some row is not strictly increasing
+  u32 max_rowlen; // longest row seen by k_rows_sorted
 
 };
 
@@ -142,6 +143,7 @@ struct spam_dcsr {
   void* val;  // device
   bool owning;
   int rows_sorted;  // cached property: -1 unknown, 0 no, 1 every row strictly increasing (IS_SORTED)
+  u64 max_row_len;  // cached with rows_sorted: longest row (picks DIRECT vs FLAT product enumeration)
 };
 
 struct SpgemmPending;  // state between the two host phases

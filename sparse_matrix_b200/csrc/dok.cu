@@ -216,7 +216,7 @@ int dok_to_csr_dev(spam_handle* h, int dtype, u64 rows, u64 cols, u64 n, const u
   if (n >= 0xFFFFFFFFull) return spam_fail(h, SPAM_EOVERFLOW, "more than 2^32-1 triplets");
   h->stats = spam_stats{};
   spam_dcsr* m = new spam_dcsr();
-  m->dtype = dtype; m->rows = rows; m->cols = cols; m->nnz = 0; m->owning = true; m->rows_sorted = 1;
+  m->dtype = dtype; m->rows = rows; m->cols = cols; m->nnz = 0; m->owning = true; m->rows_sorted = -1; m->max_row_len = 0;
   m->ptr = nullptr; m->idx = nullptr; m->val = nullptr;
   int st;
   switch (dtype) {

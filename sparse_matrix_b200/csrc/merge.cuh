@@ -40,6 +40,11 @@ __global__ void __launch_bounds__(BLOCK) k_rows_sorted(u64 m, const u64* __restr
     for (u64 e = l + 1 + lane; e < hh; e += 32) bad |= idx[e - 1] >= idx[e];
   }
   if (bad) atomicOr(&cnt->unsorted, 1u);
+  u64 len = hi - lo;
+  u32 l32 = len > 0xFFFFFFFFull ? 0xFFFFFFFFu : (u32)len;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) l32 = max(l32, __shfl_xor_sync(0xffffffffu, l32, d));
+  if (lane == 0 && l32) atomicMax(&cnt->max_rowlen, l32);
 }
 
 // SYMBOLIC merge: count distinct columns; also histograms the numeric bin of each row so that the

@@ -18,7 +18,7 @@
 // bounded by HBM/L2 and shared-memory throughput; no tensor cores.
 #include "common.cuh"
 #include "merge.cuh"
-#include "warp.cuh"
+#include "rowhash.cuh"
 
 namespace {
 
@@ -229,53 +229,6 @@ __global__ void __launch_bounds__(BLOCK) k_sym_tiny(u32 n, const u32* __restrict
 }
 
 // ------------------------------------------------------------------------------------------
-// SYMBOLIC, one thread block per row, key table in shared memory (atomicCAS insertion).
-// Sub-groups of W = 2^wshift lanes each take one A entry and stride over that B row, so short
-// B rows still fill the warp.
-// ------------------------------------------------------------------------------------------
-template <int T, int CAP>
-__global__ void __launch_bounds__(T) k_sym_group(const u32* __restrict__ perm, const u64* __restrict__ a_ptr,
-                                                 const u32* __restrict__ a_col, const u64* __restrict__ b_ptr,
-                                                 const u32* __restrict__ b_col, const u32* __restrict__ flop,
-                                                 u32* __restrict__ row_nnz, int wshift) {
-  extern __shared__ u32 keys[];  // [CAP]
-  __shared__ u32 s_warp[32];
-  const int tid = threadIdx.x;
-  const u32 row = perm ? perm[blockIdx.x] : blockIdx.x;
-  const u32 f = flop[row];
-  if (f == 0) { if (tid == 0) row_nnz[row] = 0; return; }
-  u32 cap = table_size_u32(f);
-  if (cap > (u32)CAP) cap = CAP;
-  const u32 mask = cap - 1, shift = 32 - (31 - __clz(cap));
-  for (u32 s = tid; s < cap; s += T) keys[s] = EMPTY_KEY;
-  __syncthreads();
-  volatile u32* vkeys = keys;
-  const int W = 1 << wshift, sub = tid >> wshift, lane = tid & (W - 1), nsub = T >> wshift;
-  u32 cnt = 0;
-  const u64 lo = a_ptr[row], hi = a_ptr[row + 1];
-  for (u64 e = lo + sub; e < hi; e += nsub) {
-    const u32 k = a_col[e];
-    const u64 bl = b_ptr[k], bh = b_ptr[k + 1];
-    for (u64 j = bl + lane; j < bh; j += W) {
-      const u32 key = b_col[j];
-      u32 s = slot_fib(key, shift);
-      for (;;) {
-        const u32 cur = vkeys[s];
-        if (cur == key) break;
-        if (cur == EMPTY_KEY) {
-          const u32 old = atomicCAS(&keys[s], EMPTY_KEY, key);
-          if (old == EMPTY_KEY) { ++cnt; break; }
-          if (old == key) break;
-        }
-        s = (s + 1) & mask;
-      }
-    }
-  }
-  const u32 total = block_reduce_sum_u32<T>(cnt, s_warp);
-  if (tid == 0) row_nnz[row] = total;
-}
-
-// ------------------------------------------------------------------------------------------
 // SYMBOLIC, heavy rows: persistent blocks, one global-memory key table per block, rows handed
 // out through an atomic work counter.
 // ------------------------------------------------------------------------------------------
@@ -454,82 +407,6 @@ __device__ __forceinline__ void block_bitonic_sort(KP keys, VP vals, u32 n2) {
 }
 
 // ------------------------------------------------------------------------------------------
-// NUMERIC, one thread block per row, key+value table in shared memory.
-// accumulate (atomicCAS on the key, atomicAdd on the value) -> compact in place through registers
-// -> bitonic sort by column -> coalesced store.
-// ------------------------------------------------------------------------------------------
-template <class V, int T, int CAP>
-__global__ void __launch_bounds__(T) k_num_group(const u32* __restrict__ perm, const u64* __restrict__ a_ptr,
-                                                 const u32* __restrict__ a_col, const V* __restrict__ a_val,
-                                                 const u64* __restrict__ b_ptr, const u32* __restrict__ b_col,
-                                                 const V* __restrict__ b_val, const u64* __restrict__ c_ptr,
-                                                 u32* __restrict__ c_col, V* __restrict__ c_val, int wshift) {
-  constexpr int ITEMS = CAP / T;
-  extern __shared__ __align__(16) unsigned char sm_raw[];
-  V* vals = reinterpret_cast<V*>(sm_raw);          // [CAP]
-  u32* keys = reinterpret_cast<u32*>(vals + CAP);  // [CAP]
-  u32* s_warp = keys + CAP;                        // [32]
-  const int tid = threadIdx.x;
-  const u32 row = perm ? perm[blockIdx.x] : blockIdx.x;
-  const u64 c0 = c_ptr[row];
-  const u32 z = (u32)(c_ptr[row + 1] - c0);
-  if (z == 0) return;                              // mul_hash.rs:141-143
-  u32 cap = table_size_u32(z);                     // map.rs:49-58
-  if (cap > (u32)CAP) cap = CAP;
-  const u32 mask = cap - 1, shift = 32 - (31 - __clz(cap));
-  for (u32 s = tid; s < cap; s += T) { keys[s] = EMPTY_KEY; vals[s] = Num<V>::zero(); }
-  __syncthreads();
-  volatile u32* vkeys = keys;
-  const int W = 1 << wshift, sub = tid >> wshift, lane = tid & (W - 1), nsub = T >> wshift;
-  const u64 lo = a_ptr[row], hi = a_ptr[row + 1];
-  for (u64 e = lo + sub; e < hi; e += nsub) {
-    const u32 k = a_col[e];
-    const V av = a_val[e];
-    const u64 bl = b_ptr[k], bh = b_ptr[k + 1];
-    for (u64 j = bl + lane; j < bh; j += W) {
-      const u32 key = b_col[j];
-      const V prod = Num<V>::mul(av, b_val[j]);
-      u32 s = slot_fib(key, shift);
-      for (;;) {
-        const u32 cur = vkeys[s];
-        if (cur != key) {
-          if (cur != EMPTY_KEY) { s = (s + 1) & mask; continue; }
-          const u32 old = atomicCAS(&keys[s], EMPTY_KEY, key);
-          if (old != EMPTY_KEY && old != key) { s = (s + 1) & mask; continue; }
-        }
-        Num<V>::atomic_add(&vals[s], prod);
-        break;
-      }
-    }
-  }
-  __syncthreads();
-  // compaction through registers: slots tid, tid+T, ... -> front of the table
-  u32 rk[ITEMS];
-  V rv[ITEMS];
-  u32 mine = 0;
-#pragma unroll
-  for (int it = 0; it < ITEMS; ++it) {
-    const u32 s = it * T + tid;
-    rk[it] = EMPTY_KEY;
-    rv[it] = Num<V>::zero();
-    if (s < cap) { rk[it] = keys[s]; rv[it] = vals[s]; }
-    mine += (rk[it] != EMPTY_KEY) ? 1u : 0u;
-  }
-  u32 total;
-  u32 pos = block_excl_scan_u32<T>(mine, s_warp, &total);  // contains the barrier that ends the reads
-  if (T == 32) __syncwarp();
-#pragma unroll
-  for (int it = 0; it < ITEMS; ++it) {
-    if (rk[it] != EMPTY_KEY) { keys[pos] = rk[it]; vals[pos] = rv[it]; ++pos; }
-  }
-  const u32 n2 = npow2_u32(z);
-  for (u32 s = z + tid; s < n2; s += T) keys[s] = EMPTY_KEY;  // total == z by construction (mul_hash.rs:190)
-  __syncthreads();
-  block_bitonic_sort<T, V>(keys, vals, n2);
-  for (u32 s = tid; s < z; s += T) { c_col[c0 + s] = keys[s]; c_val[c0 + s] = vals[s]; }
-}
-
-// ------------------------------------------------------------------------------------------
 // NUMERIC, heavy rows: persistent blocks, global-memory key+value tables (ld.cg/st.cg: the
 // tables are updated by L2 atomics, so never read them through L1).
 // ------------------------------------------------------------------------------------------
@@ -539,13 +416,15 @@ __global__ void __launch_bounds__(T) k_num_heavy(u32 n, const u32* __restrict__ 
                                                  const u64* __restrict__ b_ptr, const u32* __restrict__ b_col,
                                                  const V* __restrict__ b_val, const u64* __restrict__ c_ptr,
                                                  u32* __restrict__ c_col, V* __restrict__ c_val, u32* key_tables,
-                                                 V* val_tables, u64 table_stride, u32* work, int wshift) {
+                                                 V* val_tables, u64 table_stride, u32* cnt_tables, u32 b_cols,
+                                                 u32* work, int wshift) {
   constexpr int ITEMS = 4;
-  __shared__ u32 s_item;
+  __shared__ u32 s_item, s_maxcnt;
   __shared__ u32 s_warp[32];
   const int tid = threadIdx.x;
   u32* keys = key_tables + (u64)blockIdx.x * table_stride;
   V* vals = val_tables + (u64)blockIdx.x * table_stride;
+  u32* cnt = cnt_tables + (u64)blockIdx.x * (table_stride / 2 + 1);  // [npow2(z) + 1] bucket counters
   const int W = 1 << wshift, sub = tid >> wshift, lane = tid & (W - 1), nsub = T >> wshift;
   for (;;) {
     if (tid == 0) s_item = atomicAdd(work, 1u);
@@ -582,8 +461,59 @@ __global__ void __launch_bounds__(T) k_num_heavy(u32 n, const u32* __restrict__ 
       }
     }
     __syncthreads();
-    // in-place chunked compaction: chunk c is read into registers, barrier, then written at the
-    // running output offset, which never passes the start of the next unread chunk.
+    // drain + sort by column straight into C: count the occupied slots into NB = npow2(z)
+    // order-preserving buckets over the column range, scan, scatter (rank = atomic cursor), then
+    // finish each short bucket with an insertion sort in C.  Falls back to compaction + bitonic
+    // network when some bucket is far longer than average.
+    const u32 NB = npow2_u32(z);
+    {
+      const int lgnb = 31 - __clz(NB);
+      const int rbits = b_cols > 1 ? 32 - __clz(b_cols - 1) : 0;
+      const int bshift = rbits > lgnb ? rbits - lgnb : 0;
+      for (u32 b = tid; b <= NB; b += T) __stcg(&cnt[b], 0u);
+      if (tid == 0) s_maxcnt = 0;
+      __syncthreads();
+      for (u64 s = tid; s < cap; s += T) {
+        const u32 kk = __ldcg(&keys[s]);
+        if (kk != EMPTY_KEY) atomicAdd(&cnt[kk >> bshift], 1u);
+      }
+      __syncthreads();
+      const u32 chunk = (NB + T - 1) / T;
+      const u32 b0 = tid * chunk, b1 = min(NB, b0 + chunk);
+      u32 sum = 0, mx = 0;
+      for (u32 b = b0; b < b1; ++b) { const u32 c = __ldcg(&cnt[b]); sum += c; mx = max(mx, c); }
+      u32 total;
+      u32 runb = block_excl_scan_u32<T>(sum, s_warp, &total);
+      for (u32 b = b0; b < b1; ++b) { const u32 c = __ldcg(&cnt[b]); __stcg(&cnt[b], runb); runb += c; }
+      if (mx) atomicMax(&s_maxcnt, mx);
+      __syncthreads();
+      if (s_maxcnt <= 64) {
+        for (u64 s = tid; s < cap; s += T) {
+          const u32 kk = __ldcg(&keys[s]);
+          if (kk != EMPTY_KEY) {
+            const u32 pos = atomicAdd(&cnt[kk >> bshift], 1u);  // afterwards cnt[b] = end of bucket b
+            c_col[c0 + pos] = kk;
+            c_val[c0 + pos] = __ldcg(&vals[s]);
+          }
+        }
+        __syncthreads();
+        for (u32 b = tid; b < NB; b += T) {
+          const u32 lo_b = b ? __ldcg(&cnt[b - 1]) : 0u, hi_b = __ldcg(&cnt[b]);
+          for (u32 i = lo_b + 1; i < hi_b; ++i) {
+            const u32 k = c_col[c0 + i];
+            const V v = c_val[c0 + i];
+            u32 j = i;
+            while (j > lo_b && c_col[c0 + j - 1] > k) { c_col[c0 + j] = c_col[c0 + j - 1]; c_val[c0 + j] = c_val[c0 + j - 1]; --j; }
+            c_col[c0 + j] = k;
+            c_val[c0 + j] = v;
+          }
+        }
+        __syncthreads();
+        continue;
+      }
+    }
+    // fallback: in-place chunked compaction: chunk c is read into registers, barrier, then written at
+    // the running output offset, which never passes the start of the next unread chunk.
     u32 run = 0;
     for (u64 cbase = 0; cbase < cap; cbase += (u64)T * ITEMS) {
       u32 rk[ITEMS];
@@ -619,6 +549,13 @@ __global__ void __launch_bounds__(T) k_num_heavy(u32 n, const u32* __restrict__ 
 // ------------------------------------------------------------------------------------------
 // host orchestration
 // ------------------------------------------------------------------------------------------
+// One B row per warp batch (DIRECT) pays off when B rows are about a warp long and not skewed (stencils);
+// otherwise the products are flattened over the lanes (FLAT).  Uses the per-matrix cached stats.
+bool direct_enumeration(const spam_dcsr* b) {
+  const double mean = b->rows ? (double)b->nnz / (double)b->rows : 0.0;
+  return mean >= 12.0 && (double)b->max_row_len <= 3.0 * mean + 8.0;
+}
+
 int wshift_for(const spam_dcsr* b, int tmax_shift) {
   const double avg = b->rows ? (double)b->nnz / (double)b->rows : 1.0;
   int ws = 2;  // at least 4 lanes per A entry
@@ -687,14 +624,15 @@ namespace {
 int ensure_rows_sorted(spam_handle* h, const spam_dcsr* b) {
   if (b->rows_sorted >= 0) return SPAM_OK;
   spam_dcsr* mb = const_cast<spam_dcsr*>(b);
-  if (b->rows == 0 || b->nnz == 0) { mb->rows_sorted = 1; return SPAM_OK; }
-  CK(cudaMemsetAsync(&h->d_cnt->unsorted, 0, sizeof(u32), h->stream));
+  if (b->rows == 0 || b->nnz == 0) { mb->rows_sorted = 1; mb->max_row_len = 0; return SPAM_OK; }
+  CK(cudaMemsetAsync(&h->d_cnt->unsorted, 0, 2 * sizeof(u32), h->stream));  // unsorted, max_rowlen
   k_rows_sorted<256><<<(unsigned)((b->rows + 255) / 256), 256, 0, h->stream>>>(b->rows, b->ptr, b->idx, h->d_cnt);
   count_launch(h);
   CK(cudaGetLastError());
-  CK(cudaMemcpyAsync(&h->h_cnt->unsorted, &h->d_cnt->unsorted, sizeof(u32), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(&h->h_cnt->unsorted, &h->d_cnt->unsorted, 2 * sizeof(u32), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   mb->rows_sorted = h->h_cnt->unsorted ? 0 : 1;
+  mb->max_row_len = h->h_cnt->max_rowlen;
   return SPAM_OK;
 }
 
@@ -784,33 +722,26 @@ int spgemm_symbolic_dev(spam_handle* h, const spam_dcsr* a, const spam_dcsr* b, 
       k_sym_tiny<BL><<<(sb.count[0] + BL - 1) / BL, BL, smem, h->stream>>>(sb.count[0], seg(0), ap, ac, bp, bc, fl, rz);
       count_launch(h);
     }
-#define LAUNCH_SYM(BIN, T, CAP)                                                                          \
+#define LAUNCH_SYM_ROW(BIN, NW, CAP, DIRECT)                                                             \
     if (sb.count[BIN]) {                                                                                 \
-      constexpr size_t smem = (size_t)(CAP) * sizeof(u32);                                               \
-      FAIL_FREE(set_smem(h, k_sym_group<T, CAP>, smem));                                                 \
-      k_sym_group<T, CAP><<<sb.count[BIN], T, smem, h->stream>>>(seg(BIN), ap, ac, bp, bc, fl, rz, ws);  \
+      constexpr size_t smem = sym_row_smem<NW, CAP>();                                                   \
+      FAIL_FREE(set_smem(h, k_sym_row<NW, CAP, DIRECT>, smem));                                          \
+      const unsigned grid = NW == 1 ? (sb.count[BIN] + ROWS_PER_BLOCK_W1 - 1) / ROWS_PER_BLOCK_W1 : sb.count[BIN]; \
+      k_sym_row<NW, CAP, DIRECT><<<grid, NW == 1 ? 32 * ROWS_PER_BLOCK_W1 : 32 * NW, smem, h->stream>>>(    \
+          sb.count[BIN], seg(BIN), ap, ac, bp, bc, fl, rz);                                              \
       count_launch(h);                                                                                   \
     }
     const int ws = wshift_for(b, 5);
-#define LAUNCH_SYM_WARP(BIN, CAP)                                                                        \
-    if (sb.count[BIN]) {                                                                                 \
-      constexpr size_t smem = (size_t)WARPS_PER_BLOCK * (CAP) * sizeof(u32);                             \
-      FAIL_FREE(set_smem(h, k_sym_warp<CAP>, smem));                                                     \
-      k_sym_warp<CAP><<<(sb.count[BIN] + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, 32 * WARPS_PER_BLOCK, smem, \
-                        h->stream>>>(sb.count[BIN], seg(BIN), ap, ac, bp, bc, fl, rz, ws);               \
-      count_launch(h);                                                                                   \
-    }
-    if (b->nnz < 0xFFFFFFFFull) {  // the warp kernels keep B offsets in 32 bits
-      LAUNCH_SYM_WARP(1, 2 * SYM_G1_MAX)
-      LAUNCH_SYM_WARP(2, 2 * SYM_G2_MAX)
+    if (direct_enumeration(b)) {
+      LAUNCH_SYM_ROW(1, 1, 2 * SYM_G1_MAX, true)
+      LAUNCH_SYM_ROW(2, 1, 2 * SYM_G2_MAX, true)
     } else {
-      LAUNCH_SYM(1, 32, 2 * SYM_G1_MAX)
-      LAUNCH_SYM(2, 64, 2 * SYM_G2_MAX)
+      LAUNCH_SYM_ROW(1, 1, 2 * SYM_G1_MAX, false)
+      LAUNCH_SYM_ROW(2, 1, 2 * SYM_G2_MAX, false)
     }
-#undef LAUNCH_SYM_WARP
-    LAUNCH_SYM(3, 256, 2 * SYM_G3_MAX)
-    LAUNCH_SYM(4, 1024, 2 * SYM_G4_MAX)
-#undef LAUNCH_SYM
+    LAUNCH_SYM_ROW(3, 8, 2 * SYM_G3_MAX, false)
+    LAUNCH_SYM_ROW(4, 32, 2 * SYM_G4_MAX, false)
+#undef LAUNCH_SYM_ROW
     CK_FREE(cudaGetLastError());
     if (sb.count[5]) {
       const u32 nheavy = sb.count[5];
@@ -887,36 +818,31 @@ int numeric_typed(spam_handle* h, SpgemmPending* p, spam_dcsr* c) {
     k_num_tiny<V, BL><<<(nb.count[0] + BL - 1) / BL, BL, smem, h->stream>>>(nb.count[0], seg(0), ap, ac, av, bp, bc, bv, cp, cc, cv);
     count_launch(h);
   }
-#define LAUNCH_GROUP(BIN, T, CAP)                                                                        \
+#define LAUNCH_NUM_ROW(BIN, NW, CAP, DIRECT)                                                             \
   if (nb.count[BIN]) {                                                                                   \
-    constexpr size_t smem = (size_t)(CAP) * (sizeof(V) + 4) + 32 * 4;                                   \
-    CKS(set_smem(h, k_num_group<V, T, CAP>, smem));                                                      \
-    k_num_group<V, T, CAP><<<nb.count[BIN], T, smem, h->stream>>>(seg(BIN), ap, ac, av, bp, bc, bv, cp, cc, cv, ws); \
+    constexpr size_t smem = num_row_smem<V, NW, CAP>();                                                  \
+    CKS(set_smem(h, k_num_row<V, NW, CAP, DIRECT>, smem));                                               \
+    const unsigned grid = NW == 1 ? (nb.count[BIN] + ROWS_PER_BLOCK_W1 - 1) / ROWS_PER_BLOCK_W1 : nb.count[BIN]; \
+    /* NW = 1 sorts (column << log2(CAP/2)) | index packed in 32 bits when the columns are narrow enough */ \
+    const int pack_ok = b->cols < (1ull << (32 - (31 - __builtin_clz((unsigned)(CAP) / 2)))) ? 1 : 0;   \
+    k_num_row<V, NW, CAP, DIRECT><<<grid, NW == 1 ? 32 * ROWS_PER_BLOCK_W1 : 32 * NW, smem, h->stream>>>(  \
+        nb.count[BIN], seg(BIN), ap, ac, av, bp, bc, bv, cp, cc, cv, pack_ok);                           \
     count_launch(h);                                                                                     \
   }
-#define LAUNCH_NUM_WARP(BIN, CAP)                                                                        \
-  if (nb.count[BIN]) {                                                                                   \
-    constexpr size_t smem = (size_t)WARPS_PER_BLOCK * (CAP) * (sizeof(V) + 4);                           \
-    CKS(set_smem(h, k_num_warp<V, CAP>, smem));                                                          \
-    k_num_warp<V, CAP><<<(nb.count[BIN] + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, 32 * WARPS_PER_BLOCK, smem, \
-                         h->stream>>>(nb.count[BIN], seg(BIN), ap, ac, av, bp, bc, bv, cp, cc, cv, ws,   \
-                                      /* (col << log2(CAP/2)) | slot fits 32 bits? */                    \
-                                      b->cols < (1ull << (32 - (31 - __builtin_clz((unsigned)(CAP) / 2)))) ? 1 : 0); \
-    count_launch(h);                                                                                     \
-  }
-  if (b->nnz < 0xFFFFFFFFull) {
-    LAUNCH_NUM_WARP(1, 2 * NUM_G1_MAX)
-    LAUNCH_NUM_WARP(2, 2 * NUM_G2_MAX)
+  if (direct_enumeration(b)) {
+    LAUNCH_NUM_ROW(1, 1, 2 * NUM_G1_MAX, true)
+    LAUNCH_NUM_ROW(2, 1, 2 * NUM_G2_MAX, true)
   } else {
-    LAUNCH_GROUP(1, 32, 2 * NUM_G1_MAX)
-    LAUNCH_GROUP(2, 128, 2 * NUM_G2_MAX)
+    LAUNCH_NUM_ROW(1, 1, 2 * NUM_G1_MAX, false)
+    LAUNCH_NUM_ROW(2, 1, 2 * NUM_G2_MAX, false)
   }
-#undef LAUNCH_NUM_WARP
-  LAUNCH_GROUP(3, 512, 2 * NUM_G3_MAX)
-  LAUNCH_GROUP(4, 1024, 2 * NUM_G4_MAX)
-#undef LAUNCH_GROUP
+  // team sizes: these kernels are latency-bound (dependent shared-memory and shuffle chains), so the
+  // big-table bins get many warps per row: G4's 224 KB table allows one block per SM, give it 32 warps
+  LAUNCH_NUM_ROW(3, 8, 2 * NUM_G3_MAX, false)
+  LAUNCH_NUM_ROW(4, 32, 2 * NUM_G4_MAX, false)
+#undef LAUNCH_NUM_ROW
   CK(cudaGetLastError());
-  u32* hk = nullptr;
+  u32 *hk = nullptr, *hc = nullptr;
   V* hv = nullptr;
   if (nb.count[5]) {
     u32 zmax = p->max_nnz;
@@ -927,11 +853,13 @@ int numeric_typed(spam_handle* h, SpgemmPending* p, spam_dcsr* c) {
     while (nblk > 1 && nblk * stride * (sizeof(u32) + sizeof(V)) > budget) nblk /= 2;
     CKS(dev_alloc_t(h, &hk, nblk * stride));
     CKS(dev_alloc_t(h, &hv, nblk * stride));
+    CKS(dev_alloc_t(h, &hc, nblk * (stride / 2 + 1)));
     k_num_heavy<V, 1024><<<(unsigned)nblk, 1024, 0, h->stream>>>(nb.count[5], seg(5), ap, ac, av, bp, bc, bv, cp, cc, cv, hk,
-                                                                hv, stride, &h->d_cnt->work_b, ws);
+                                                                hv, stride, hc, (u32)b->cols, &h->d_cnt->work_b, ws);
     count_launch(h);
     CK(cudaGetLastError());
   }
+  if (hc) CKS(dev_free(h, hc));
   if (hk) CKS(dev_free(h, hk));
   if (hv) CKS(dev_free(h, hv));
   if (nb.perm) CKS(dev_free(h, nb.perm));
@@ -946,7 +874,7 @@ int spgemm_numeric_dev(spam_handle* h, SpgemmPending* p, spam_dcsr** cout) {
   *cout = nullptr;
   spam_dcsr* c = new spam_dcsr();
   c->dtype = p->a->dtype; c->rows = p->a->rows; c->cols = p->b->cols; c->nnz = p->nnz;
-  c->ptr = p->d_cptr; c->idx = nullptr; c->val = nullptr; c->owning = true; c->rows_sorted = 1;
+  c->ptr = p->d_cptr; c->idx = nullptr; c->val = nullptr; c->owning = true; c->rows_sorted = -1; c->max_row_len = 0;  // stats are taken lazily if C becomes a right-hand side
   int st = dev_alloc_t(h, &c->idx, p->nnz ? p->nnz : 1);
   if (st == SPAM_OK) st = dev_alloc(h, &c->val, (p->nnz ? p->nnz : 1) * dtype_size(c->dtype));
   if (st == SPAM_OK && p->nnz) {
