@@ -99,6 +99,113 @@ __global__ void __launch_bounds__(BLOCK) k_sym_merge(u32 n, const u32* __restric
   if (tid < NBINS && s_hist[tid]) atomicAdd(&cnt->num_bins[tid], s_hist[tid]);
 }
 
+// FUSED flop count + symbolic merge (used when B's rows are sorted): one pass over A instead of two.
+// Every row gets its flop count (rows_to_threads, mul_hash.rs:39-50) and its symbolic bin; rows that
+// qualify for the merge bin (len(A row) <= K <= MERGE_K, flop <= MERGE_FLOP_MAX) are counted on the
+// spot — the B row extents just loaded for the flop count are exactly the run heads the merge needs.
+// For stencil-like matrices every row qualifies and no other symbolic kernel runs.
+template <int K, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_flop_sym_merge(u64 m, u64 b_rows, const u64* __restrict__ a_ptr,
+                                                          const u32* __restrict__ a_col,
+                                                          const u64* __restrict__ b_ptr,
+                                                          const u32* __restrict__ b_col, u32* __restrict__ flop_out,
+                                                          u32* __restrict__ row_nnz, Counters* cnt) {
+  __shared__ u32 s_sym[NBINS], s_num[NBINS];
+  __shared__ ull s_total;
+  __shared__ u32 s_max;
+  const int tid = threadIdx.x, lane = tid & 31;
+  if (tid < NBINS) { s_sym[tid] = 0; s_num[tid] = 0; }
+  if (tid == 0) { s_total = 0; s_max = 0; }
+  __syncthreads();
+  const u64 row = (u64)blockIdx.x * BLOCK + tid;
+  const bool valid = row < m;
+  u64 lo = 0, hi = 0;
+  if (valid) { lo = a_ptr[row]; hi = a_ptr[row + 1]; }
+  const u64 len = hi - lo;
+  u64 f = 0;
+  bool bad = false, merged = false;
+  if (valid && len <= (u64)K) {
+    u32 pos[K], end[K], col[K];
+#pragma unroll
+    for (int h = 0; h < K; ++h) {
+      pos[h] = 0; end[h] = 0; col[h] = INF_COL;
+      if ((u64)h < len) {
+        const u32 kk = a_col[lo + h];
+        if (kk < b_rows) { pos[h] = (u32)b_ptr[kk]; end[h] = (u32)b_ptr[kk + 1]; } else bad = true;
+      }
+      f += end[h] - pos[h];
+    }
+    if (f <= MERGE_FLOP_MAX) {
+      merged = true;
+#pragma unroll
+      for (int h = 0; h < K; ++h)
+        if (pos[h] < end[h]) col[h] = b_col[pos[h]];
+      u32 z = 0;
+      for (;;) {
+        u32 cmin = col[0];
+#pragma unroll
+        for (int h = 1; h < K; ++h) cmin = min(cmin, col[h]);
+        if (cmin == INF_COL) break;
+        ++z;
+#pragma unroll
+        for (int h = 0; h < K; ++h) {
+          if (col[h] == cmin) {
+            ++pos[h];
+            col[h] = (pos[h] < end[h]) ? b_col[pos[h]] : INF_COL;
+          }
+        }
+      }
+      row_nnz[row] = z;  // mul_hash.rs:95
+      atomicAdd(&s_num[MERGE_BIN], 1u);
+    }
+  } else if (valid && len <= 32) {
+    for (u64 e = lo; e < hi; ++e) {
+      const u32 kk = a_col[e];
+      if (kk < b_rows) f += b_ptr[kk + 1] - b_ptr[kk]; else bad = true;
+    }
+  }
+  unsigned longmask = __ballot_sync(0xffffffffu, valid && len > 32);
+  while (longmask) {
+    const int src = __ffs(longmask) - 1;
+    longmask &= longmask - 1;
+    const u64 l = __shfl_sync(0xffffffffu, lo, src), hh = __shfl_sync(0xffffffffu, hi, src);
+    u64 part = 0;
+    for (u64 e = l + lane; e < hh; e += 32) {
+      const u32 kk = a_col[e];
+      if (kk < b_rows) part += b_ptr[kk + 1] - b_ptr[kk]; else bad = true;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+    if (lane == src) f = part;
+  }
+  if (bad) atomicOr(&cnt->error, 1u);
+  if (valid) {
+    const u32 fs = f > 0xFFFFFFFFull ? 0xFFFFFFFFu : (u32)f;
+    flop_out[row] = fs;
+    if (merged) {
+      atomicAdd(&s_sym[MERGE_BIN], 1u);
+    } else {
+      // a row with len <= MERGE_K but len > K cannot occur: K >= min(MERGE_K, longest row of A)
+      const u32 alen = len > 0xFFFFFFFFull ? 0xFFFFFFFFu : (u32)len;
+      atomicAdd(&s_sym[sym_bin_of(fs, alen, false)], 1u);
+      atomicMax(&s_max, fs);
+    }
+  }
+  u64 t = f;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) t += __shfl_xor_sync(0xffffffffu, t, d);
+  if (lane == 0 && t) atomicAdd(&s_total, (ull)t);
+  __syncthreads();
+  if (tid < NBINS) {
+    if (s_sym[tid]) atomicAdd(&cnt->sym_bins[tid], s_sym[tid]);
+    if (s_num[tid]) atomicAdd(&cnt->num_bins[tid], s_num[tid]);
+  }
+  if (tid == 0) {
+    if (s_total) atomicAdd(&cnt->total_flops, s_total);
+    if (s_max) atomicMax(&cnt->max_flop, s_max);
+  }
+}
+
 // NUMERIC merge.  Outputs are staged CH at a time in a small [slot][thread] shared-memory tile and
 // flushed by the whole warp (4 lanes per row, 8 rows per store instruction: each row's 4 values are
 // one full 32-byte sector).  Keeping the tile tiny matters: shared memory is carved out of the same

@@ -683,9 +683,33 @@ int spgemm_symbolic_dev(spam_handle* h, const spam_dcsr* a, const spam_dcsr* b, 
   FAIL_FREE(dev_alloc_t(h, &p->d_cptr, m + 1));
   CK_FREE(cudaMemsetAsync(h->d_cnt, 0, sizeof(Counters), h->stream));
   if (h->timing) CK_FREE(cudaEventRecord(h->ev[0], h->stream));
-  FAIL_FREE(flop_count_dev(h, a, b, p->d_flop, true, merge_ok));
+  bool fused = false;
+  if (merge_ok && m) {
+    // B sorted: flop count and the merge-bin symbolic pass in ONE kernel, then a speculative scan —
+    // when every row is in the merge bin (stencils) that scan is final and the product needs a
+    // single host sync before the numeric pass.
+    if (a != b) FAIL_FREE(ensure_rows_sorted(h, a));  // only for A's longest row (cached with the matrix)
+    const u64 amax = a->max_row_len;
+    const u32 kk = amax <= 4 ? 4 : amax <= 6 ? 6 : 8;
+    p->max_alen = kk;
+    const unsigned grid = (unsigned)((m + 127) / 128);
+    if (kk == 4)
+      k_flop_sym_merge<4, 128><<<grid, 128, 0, h->stream>>>(m, b->rows, a->ptr, a->idx, b->ptr, b->idx, p->d_flop, p->d_row_nnz, h->d_cnt);
+    else if (kk == 6)
+      k_flop_sym_merge<6, 128><<<grid, 128, 0, h->stream>>>(m, b->rows, a->ptr, a->idx, b->ptr, b->idx, p->d_flop, p->d_row_nnz, h->d_cnt);
+    else
+      k_flop_sym_merge<8, 128><<<grid, 128, 0, h->stream>>>(m, b->rows, a->ptr, a->idx, b->ptr, b->idx, p->d_flop, p->d_row_nnz, h->d_cnt);
+    count_launch(h);
+    CK_FREE(cudaGetLastError());
+    if (h->timing) { CK_FREE(cudaEventRecord(h->ev[1], h->stream)); CK_FREE(cudaEventRecord(h->ev[2], h->stream)); }
+    FAIL_FREE(scan_u32_to_u64(h, p->d_row_nnz, p->d_cptr, m, &h->d_cnt->total_nnz));
+    fused = true;
+  } else {
+    FAIL_FREE(flop_count_dev(h, a, b, p->d_flop, true, merge_ok));
+    if (h->timing) CK_FREE(cudaEventRecord(h->ev[1], h->stream));
+  }
   CK_FREE(cudaMemcpyAsync(h->h_cnt, h->d_cnt, sizeof(Counters), cudaMemcpyDeviceToHost, h->stream));
-  if (h->timing) CK_FREE(cudaEventRecord(h->ev[1], h->stream));
+  if (fused && h->timing) CK_FREE(cudaEventRecord(h->ev[3], h->stream));
   CK_FREE(cudaStreamSynchronize(h->stream));
   const Counters c1 = *h->h_cnt;
   if (c1.error & 1u) {
@@ -694,17 +718,24 @@ int spgemm_symbolic_dev(spam_handle* h, const spam_dcsr* a, const spam_dcsr* b, 
   }
   h->stats.flops = c1.total_flops;
   for (int i = 0; i < NBINS; ++i) h->stats.sym_bin_rows[i] = c1.sym_bins[i];
+  if (fused && c1.sym_bins[MERGE_BIN] == m) {  // every row merged: the speculative scan stands
+    p->nnz = c1.total_nnz;
+    p->max_nnz = 0;
+    for (int i = 0; i < NBINS; ++i) { p->num_counts[i] = c1.num_bins[i]; h->stats.num_bin_rows[i] = c1.num_bins[i]; }
+    h->stats.nnz_c = p->nnz;
+    return SPAM_OK;
+  }
 
   // ---- symbolic per bin ----
   Bins sb;
   FAIL_FREE(build_perm(h, m, c1.sym_bins, false, a->ptr, nullptr, p->d_flop, merge_ok, &sb));
-  p->max_alen = c1.max_alen;
+  if (!fused) p->max_alen = c1.max_alen;
   u32* heavy_tab = nullptr;
   {
     const u64* ap = a->ptr; const u32* ac = a->idx; const u64* bp = b->ptr; const u32* bc = b->idx;
     const u32* fl = p->d_flop; u32* rz = p->d_row_nnz;
     auto seg = [&](int bin) -> const u32* { return sb.perm ? sb.perm + sb.base[bin] : nullptr; };
-    if (sb.count[MERGE_BIN]) {
+    if (sb.count[MERGE_BIN] && !fused) {
       constexpr int BL = 128;
       const u32 nm = sb.count[MERGE_BIN];
       const unsigned grid = (nm + BL - 1) / BL;
