@@ -148,6 +148,7 @@ int spam_cuda_create(spam_handle** out, int device) {
   spam_handle* h = new (std::nothrow) spam_handle();
   if (!h) return SPAM_ENOMEM;
   h->device = device; h->timing = false; h->pending = nullptr; h->dok_pending = nullptr;
+  h->scan_ws = nullptr; h->scan_ws_cap = 0;
   h->d_cnt = nullptr; h->h_cnt = nullptr; h->own_stream = nullptr; h->stream = nullptr;
   h->stats = spam_stats{};
   for (auto& e : h->ev) e = nullptr;
@@ -184,6 +185,7 @@ int spam_cuda_destroy(spam_handle* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   drop_spgemm_state(h);
   drop_dok_state(h);
+  if (h->scan_ws) { dev_free(h, h->scan_ws); h->scan_ws = nullptr; }
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (auto& e : h->ev) if (e) cudaEventDestroy(e);
   if (h->d_cnt) cudaFree(h->d_cnt);

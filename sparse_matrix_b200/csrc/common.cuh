@@ -162,6 +162,8 @@ struct spam_handle {
   void* pending;             // SpgemmHostState* (api.cu) between the two host phases
   DokPending* dok_pending;
   cudaEvent_t ev[6];
+  u64* scan_ws;      // look-back scan tile states + tile counter (grow-only, stream-ordered reuse)
+  u64 scan_ws_cap;   // in u64 words
 };
 
 static inline size_t dtype_size(int dt) { return (dt == SPAM_F32 || dt == SPAM_I32) ? 4 : 8; }

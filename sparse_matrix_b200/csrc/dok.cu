@@ -56,42 +56,53 @@ __global__ void __launch_bounds__(RS_T) k_radix_hist(const u64* __restrict__ key
 __global__ void __launch_bounds__(RS_T) k_radix_scatter(const u64* __restrict__ keys_in, const u32* __restrict__ pay_in,
                                                         u64* __restrict__ keys_out, u32* __restrict__ pay_out, u64 n,
                                                         int shift, const u64* __restrict__ offs, u32 nblocks) {
+  // Each warp owns a contiguous 512-key slice of the tile and ranks it alone: per-warp digit counters in
+  // shared memory, __match_any_sync for the rank inside a 32-key round, no block barrier inside the
+  // loop (the first version synchronised the block three times per round and ran 70x off the roofline).
+  // Two block barriers in total: one before the per-digit prefix over warps, one after.
   __shared__ u32 s_cnt[RS_T / 32][RADIX];
-  __shared__ u32 s_run[RADIX];
+  __shared__ u64 s_off[RADIX];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  s_run[tid] = 0;
 #pragma unroll
   for (int w = 0; w < RS_T / 32; ++w) s_cnt[w][tid] = 0;
   __syncthreads();
-  const u64 base = (u64)blockIdx.x * RS_TILE;
-  const u64 my_off = offs[(u64)tid * nblocks + blockIdx.x];  // global base of digit `tid` for this block
-  __shared__ u64 s_off[RADIX];
-  s_off[tid] = my_off;
-  __syncthreads();
-  for (int r = 0; r < RS_ITEMS; ++r) {
-    const u64 i = base + (u64)r * RS_T + tid;
-    const bool valid = i < n;
-    u64 key = 0;
-    u32 pay = 0;
-    if (valid) { key = keys_in[i]; pay = pay_in[i]; }
-    const u32 d = valid ? (u32)((key >> shift) & (RADIX - 1)) : (u32)RADIX;
-    const unsigned peers = __match_any_sync(0xffffffffu, d);
-    const u32 rank_w = __popc(peers & ((1u << lane) - 1u));
-    if (valid && rank_w == 0) s_cnt[wid][d] = __popc(peers);
-    __syncthreads();
-    if (valid) {
-      u32 pre = s_run[d];
-      for (int w = 0; w < wid; ++w) pre += s_cnt[w][d];
-      const u64 pos = s_off[d] + pre + rank_w;
-      keys_out[pos] = key;
-      pay_out[pos] = pay;
-    }
-    __syncthreads();
-    u32 s = 0;
+  const u64 wbase = (u64)blockIdx.x * RS_TILE + (u64)wid * (32 * RS_ITEMS);
+  u64 key[RS_ITEMS];
+  u32 pay[RS_ITEMS], rank[RS_ITEMS];
 #pragma unroll
-    for (int w = 0; w < RS_T / 32; ++w) { s += s_cnt[w][tid]; s_cnt[w][tid] = 0; }
-    s_run[tid] += s;
-    __syncthreads();
+  for (int r = 0; r < RS_ITEMS; ++r) {
+    const u64 i = wbase + (u64)r * 32 + lane;
+    const bool valid = i < n;
+    key[r] = 0; pay[r] = 0;
+    if (valid) { key[r] = keys_in[i]; pay[r] = pay_in[i]; }
+  }
+#pragma unroll
+  for (int r = 0; r < RS_ITEMS; ++r) {
+    const bool valid = wbase + (u64)r * 32 + lane < n;
+    const u32 d = valid ? (u32)((key[r] >> shift) & (RADIX - 1)) : (u32)RADIX;
+    const unsigned peers = __match_any_sync(0xffffffffu, d);
+    const u32 before = valid ? s_cnt[wid][d] : 0u;
+    rank[r] = before + __popc(peers & ((1u << lane) - 1u));
+    __syncwarp();
+    if (valid && (__ffs(peers) - 1) == lane) s_cnt[wid][d] = before + __popc(peers);
+    __syncwarp();
+  }
+  __syncthreads();
+  {
+    u32 run = 0;  // thread `tid` = digit: exclusive prefix of the warps' counts
+#pragma unroll
+    for (int w = 0; w < RS_T / 32; ++w) { const u32 t = s_cnt[w][tid]; s_cnt[w][tid] = run; run += t; }
+    s_off[tid] = offs[(u64)tid * nblocks + blockIdx.x];  // global base of digit `tid` for this block
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < RS_ITEMS; ++r) {
+    if (wbase + (u64)r * 32 + lane < n) {
+      const u32 d = (u32)((key[r] >> shift) & (RADIX - 1));
+      const u64 pos = s_off[d] + s_cnt[wid][d] + rank[r];
+      keys_out[pos] = key[r];
+      pay_out[pos] = pay[r];
+    }
   }
 }
 

@@ -207,17 +207,19 @@ __global__ void __launch_bounds__(BLOCK) k_flop_sym_merge(u64 m, u64 b_rows, con
 }
 
 // NUMERIC merge.  Outputs are staged CH at a time in a small [slot][thread] shared-memory tile and
-// flushed by the whole warp (4 lanes per row, 8 rows per store instruction: each row's 4 values are
-// one full 32-byte sector).  Keeping the tile tiny matters: shared memory is carved out of the same
-// 228 KB as L1, and the run heads re-read B through L1 (with 16-slot staging the L1 hit rate fell
-// to 19% and the kernel became L2-bandwidth bound — profiles/r01_poisson_v1_merge.txt).
+// flushed by the whole warp (8 lanes per row, 4 rows per store instruction: a row's 8 columns are one
+// full 32-byte sector, its 8 values two).  Keeping the tile small matters: shared memory is carved
+// out of the same 228 KB as L1, and the run heads re-read B through L1 (with 16-slot staging the L1
+// hit rate fell to 19% and the kernel became L2-bandwidth bound — profiles/r01_poisson_v1_merge.txt);
+// with 4-slot staging the half-sector column stores were written back early by L2 (DRAM writes 773 MB
+// for a 654 MB result — profiles/r01_poisson_v2_fused.txt).
 // Tile strides are padded so that the owner's writes and the flush reads are bank-conflict free.
-constexpr int MERGE_CH = 4;
+constexpr int MERGE_CH = 8;
 
 template <class V, int BLOCK>
 struct MergeTile {
-  static constexpr int STRIDE_K = BLOCK + 8;                        // u32 words: (8q + r) mod 32 distinct
-  static constexpr int STRIDE_V = sizeof(V) == 8 ? BLOCK + 4 : BLOCK + 8;  // 8-byte words: (4q + r) mod 16
+  static constexpr int STRIDE_K = BLOCK + 4;                        // u32 words: (4q + r) mod 32 distinct
+  static constexpr int STRIDE_V = sizeof(V) == 8 ? BLOCK + 2 : BLOCK + 4;  // 8-byte words: (2q + r) mod 16
   static constexpr size_t bytes = (size_t)MERGE_CH * (STRIDE_V * sizeof(V) + STRIDE_K * 4);
 };
 
@@ -261,7 +263,7 @@ __global__ void __launch_bounds__(BLOCK) k_num_merge(u32 n, const u32* __restric
     for (int h = 0; h < K; ++h)
       if (pos[h] < end[h]) col[h] = b_col[pos[h]];
   }
-  const int wbase = tid & ~31, rsub = lane >> 2, q = lane & 3;
+  const int wbase = tid & ~31, rsub = lane >> 3, q = lane & 7;
   for (u32 t0 = 0; __any_sync(0xffffffffu, t0 < z); t0 += MERGE_CH) {
 #pragma unroll
     for (int c = 0; c < MERGE_CH; ++c) {
@@ -286,10 +288,10 @@ __global__ void __launch_bounds__(BLOCK) k_num_merge(u32 n, const u32* __restric
       }
     }
     __syncwarp();
-    // flush: lane (rsub, q) stores entry t0+q of the warp's row it*8+rsub
+    // flush: lane (rsub, q) stores entry t0+q of the warp's row it*4+rsub
 #pragma unroll
-    for (int it = 0; it < 4; ++it) {
-      const int src = it * 8 + rsub;
+    for (int it = 0; it < 8; ++it) {
+      const int src = it * 4 + rsub;
       const u32 zr = __shfl_sync(0xffffffffu, z, src);
       const u64 c0r = __shfl_sync(0xffffffffu, c0, src);
       const u32 tt = t0 + q;

@@ -119,13 +119,22 @@ int scan_u32_to_u64(spam_handle* h, const u32* in, u64* out, u64 n, ull* d_total
     return SPAM_OK;
   }
   const u64 tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
-  u64* state = nullptr;
-  CKS(dev_alloc_t(h, &state, tiles));
-  CK(cudaMemsetAsync(state, 0, tiles * sizeof(u64), h->stream));
-  CK(cudaMemsetAsync(&h->d_cnt->scan_tile, 0, sizeof(u32), h->stream));
-  k_scan_lookback<<<(unsigned)tiles, SCAN_T, 0, h->stream>>>(in, out, n, state, &h->d_cnt->scan_tile, d_total);
+  // tile states + the tile counter live in one grow-only buffer owned by the handle: one memset, no
+  // allocation per scan (the DOK->CSR build runs eight scans per call)
+  if (h->scan_ws_cap < tiles + 1) {
+    if (h->scan_ws) CKS(dev_free(h, h->scan_ws));
+    h->scan_ws = nullptr;
+    h->scan_ws_cap = 0;
+    u64* ws = nullptr;
+    CKS(dev_alloc_t(h, &ws, 2 * tiles + 1));
+    h->scan_ws = ws;
+    h->scan_ws_cap = 2 * tiles + 1;
+  }
+  u64* state = h->scan_ws;
+  CK(cudaMemsetAsync(state, 0, (tiles + 1) * sizeof(u64), h->stream));
+  u32* tile_counter = reinterpret_cast<u32*>(state + tiles);
+  k_scan_lookback<<<(unsigned)tiles, SCAN_T, 0, h->stream>>>(in, out, n, state, tile_counter, d_total);
   count_launch(h);
   CK(cudaGetLastError());
-  CKS(dev_free(h, state));
   return SPAM_OK;
 }
