@@ -375,7 +375,8 @@ def main():
         if my_bytes is not None and ms_num > 0:
             ach = my_bytes / (ms_num / 1e3) / 1e9
             line["roofline"] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                                "traffic": traffic, "kernel": "numeric pass (k_num_tiny for Poisson)",
+                                "traffic": traffic,
+                                "kernel": "numeric pass (k_num_merge<double,6,128> on Poisson: one launch per step)",
                                 "kernel_ms": ms_num, "peak_source": peak_src,
                                 "pipeline_frac": line["hbm_gbs_pipeline"] / peak}
         else:

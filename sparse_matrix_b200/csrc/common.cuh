@@ -24,20 +24,20 @@ constexpr int NBINS = 8;
 // ---- row bins ---------------------------------------------------------------------------
 // Symbolic bins by flop f (intermediate products of the row).  The table must hold up to
 // min(f, cols(B)) distinct keys at load <= 1/2 (linprobe sizing rule, set.rs:38-43).
-//   0 tiny   f <= 32      thread-per-row, 64-slot private smem table
-//   1 G1     f <= 256     32-thread block,   512-key smem table
-//   2 G2     f <= 1024    64-thread block,   2048-key
-//   3 G3     f <= 4096    256-thread block,  8192-key
-//   4 G4     f <= 16384   1024-thread block, 32768-key
-//   5 heavy  f  > 16384   global-memory table, persistent 1024-thread blocks
+//   0 tiny   f <= 32      thread-per-row, 64-slot private smem table          (k_sym_tiny)
+//   1 G1     f <= 256     one warp per row,  512-key smem table              (k_sym_row<1,..>)
+//   2 G2     f <= 1024    one warp per row,  2048-key
+//   3 G3     f <= 4096    8 warps per row,   8192-key                        (k_sym_row<8,..>)
+//   4 G4     f <= 16384   32 warps per row,  32768-key                       (k_sym_row<32,..>)
+//   5 heavy  f  > 16384   global-memory table, persistent 1024-thread blocks (k_sym_heavy)
 constexpr u32 SYM_TINY_MAX = 32, SYM_G1_MAX = 256, SYM_G2_MAX = 1024, SYM_G3_MAX = 4096, SYM_G4_MAX = 16384;
 // Numeric bins by row nnz z (table = max(16, 2*npow2(z)) slots of key+value, map.rs:49-58).
 //   0 tiny   z <= 16 and f <= 128   thread-per-row (sequential, reference accumulation order)
-//   1 G1     z <= 128    32-thread block,   256 slots
-//   2 G2     z <= 512    128-thread block,  1024 slots
-//   3 G3     z <= 2048   512-thread block,  4096 slots
-//   4 G4     z <= 8192   1024-thread block, 16384 slots (192 KB smem for 8-byte values)
-//   5 heavy  z  > 8192   global-memory table
+//   1 G1     z <= 128    one warp per row,  256 slots   (k_num_row<V,1,..>: no atomics for values)
+//   2 G2     z <= 512    one warp per row,  1024 slots
+//   3 G3     z <= 2048   8 warps per row,   4096 slots  (k_num_row<V,8,..>: atomicAdd, bucket drain)
+//   4 G4     z <= 8192   32 warps per row,  16384 slots (192 KB + 32 KB of bucket counters)
+//   5 heavy  z  > 8192   global-memory table            (k_num_heavy)
 constexpr u32 NUM_TINY_MAX = 16, NUM_TINY_FLOP_MAX = 128, NUM_G1_MAX = 128, NUM_G2_MAX = 512, NUM_G3_MAX = 2048,
               NUM_G4_MAX = 8192;
 

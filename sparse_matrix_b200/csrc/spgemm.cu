@@ -9,13 +9,14 @@
 //                                               B2=true branch (:164-175): per-row sort by column
 //
 // Hash design = linprobe (linprobe/src/{lib,set,map}.rs): open addressing, linear probing,
-// hash = key*107 mod 2^32, table = max(16, 2*npow2(n)) slots, u32::MAX = empty.
+// table = max(16, 2*npow2(n)) slots, u32::MAX = empty; hash = key*107 (exact) in the thread-per-row
+// kernels, high bits of a Fibonacci hash elsewhere (rowhash.cuh explains why).
 //
-// Bins (common.cuh): thread-per-row private smem tables for tiny rows (sequential insertion in the
-// reference's own order => float sums bit-identical to the reference for those rows), one thread
-// block per row with a shared-memory table for medium rows, and persistent blocks with
-// global-memory tables for heavy power-law rows.  Everything is integer/byte gather-scatter work
-// bounded by HBM/L2 and shared-memory throughput; no tensor cores.
+// Bins (common.cuh): k-way merge of sorted runs for short rows when B is sorted (merge.cuh),
+// thread-per-row private smem tables for tiny rows of unsorted inputs (this file), one warp or a
+// team of warps per row with a shared-memory table for medium rows (rowhash.cuh), and persistent
+// blocks with global-memory tables for heavy power-law rows (this file).  Everything is integer/byte
+// gather-scatter work bounded by HBM/L2 and shared-memory throughput; no tensor cores.
 #include "common.cuh"
 #include "merge.cuh"
 #include "rowhash.cuh"
