@@ -61,8 +61,9 @@ typedef struct spam_stats {
   uint64_t kernel_launches; /* number of kernels this library launched for the last call */
   uint64_t bytes_h2d, bytes_d2h;
   float ms_flop, ms_symbolic, ms_scan, ms_numeric, ms_total; /* CUDA-event times; 0 when timing disabled */
-  uint32_t sym_bin_rows[8]; /* rows per symbolic bin (by flop) */
-  uint32_t num_bin_rows[8]; /* rows per numeric bin (by nnz) */
+  /* rows per bin: 0 tiny, 1..8 hash bins (one per power of two), 9 heavy (global table), 10 merge */
+  uint32_t sym_bin_rows[16]; /* symbolic pass, binned by intermediate products */
+  uint32_t num_bin_rows[16]; /* numeric pass, binned by row nnz of C */
 } spam_stats;
 
 /* ---- lifecycle --------------------------------------------------------------------- */

@@ -33,7 +33,10 @@ class SpamStats(C.Structure):
     _fields_ = [("flops", C.c_uint64), ("nnz_c", C.c_uint64), ("kernel_launches", C.c_uint64),
                 ("bytes_h2d", C.c_uint64), ("bytes_d2h", C.c_uint64), ("ms_flop", C.c_float),
                 ("ms_symbolic", C.c_float), ("ms_scan", C.c_float), ("ms_numeric", C.c_float),
-                ("ms_total", C.c_float), ("sym_bin_rows", C.c_uint32 * 8), ("num_bin_rows", C.c_uint32 * 8)]
+                ("ms_total", C.c_float), ("sym_bin_rows", C.c_uint32 * 16), ("num_bin_rows", C.c_uint32 * 16)]
+
+
+TINY_BIN, HEAVY_BIN, MERGE_BIN = 0, 9, 10   # indices into sym_bin_rows / num_bin_rows; 1..8 = hash bins
 
 
 class SpamError(RuntimeError):

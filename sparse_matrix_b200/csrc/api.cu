@@ -119,7 +119,7 @@ void finish_timing(spam_handle* h) {
 
 extern "C" {
 
-int spam_cuda_abi_version(void) { return 1; }
+int spam_cuda_abi_version(void) { return 2; }  // 2: spam_stats bin arrays grew to 16 entries
 
 const char* spam_strerror(int s) {
   switch (s) {

@@ -19,44 +19,45 @@ constexpr u32 EMPTY_KEY = 0xFFFFFFFFu;  // linprobe/src/set.rs:45
 constexpr u32 HASH_SCAL = 107u;         // linprobe/src/lib.rs:13
 constexpr u32 MIN_TABLE = 16u;          // linprobe/src/lib.rs:14
 
-constexpr int NBINS = 8;
+constexpr int NBINS = 12;
 
 // ---- row bins ---------------------------------------------------------------------------
-// Symbolic bins by flop f (intermediate products of the row).  The table must hold up to
-// min(f, cols(B)) distinct keys at load <= 1/2 (linprobe sizing rule, set.rs:38-43).
-//   0 tiny   f <= 32      thread-per-row, 64-slot private smem table          (k_sym_tiny)
-//   1 G1     f <= 256     one warp per row,  512-key smem table              (k_sym_row<1,..>)
-//   2 G2     f <= 1024    one warp per row,  2048-key
-//   3 G3     f <= 4096    8 warps per row,   8192-key                        (k_sym_row<8,..>)
-//   4 G4     f <= 16384   32 warps per row,  32768-key                       (k_sym_row<32,..>)
-//   5 heavy  f  > 16384   global-memory table, persistent 1024-thread blocks (k_sym_heavy)
-constexpr u32 SYM_TINY_MAX = 32, SYM_G1_MAX = 256, SYM_G2_MAX = 1024, SYM_G3_MAX = 4096, SYM_G4_MAX = 16384;
-// Numeric bins by row nnz z (table = max(16, 2*npow2(z)) slots of key+value, map.rs:49-58).
-//   0 tiny   z <= 16 and f <= 128   thread-per-row (sequential, reference accumulation order)
-//   1 G1     z <= 128    one warp per row,  256 slots   (k_num_row<V,1,..>: no atomics for values)
-//   2 G2     z <= 512    one warp per row,  1024 slots
-//   3 G3     z <= 2048   8 warps per row,   4096 slots  (k_num_row<V,8,..>: atomicAdd, bucket drain)
-//   4 G4     z <= 8192   32 warps per row,  16384 slots (192 KB + 32 KB of bucket counters)
-//   5 heavy  z  > 8192   global-memory table            (k_num_heavy)
-constexpr u32 NUM_TINY_MAX = 16, NUM_TINY_FLOP_MAX = 128, NUM_G1_MAX = 128, NUM_G2_MAX = 512, NUM_G3_MAX = 2048,
-              NUM_G4_MAX = 8192;
-
-// Bin 6 "merge": when every row of B is sorted by column (CsrMatrix<T, true>, e.g. anything built by
-// From<DokMatrix>), a short A row is a handful of sorted runs; one thread merges them with the run
-// heads in registers — no table, no sort, output already ordered.
-//   both passes: len(A row) <= MERGE_K and f <= 128
-constexpr int MERGE_BIN = 6;
+// One hash bin per power of two, so a row's shared-memory table is at most 2x what linprobe's rule
+// max(16, 2*npow2(n)) gives it: the team kernels are occupancy-bound (profiles/r01_rmat18_v1_rowhash.txt),
+// and a bin that lumps z = 513..2048 together makes every row pay for a 4096-slot table.
+//   0        tiny   f <= 32 / (z <= 16 and f <= 128)   thread-per-row private table (k_*_tiny)
+//   1..8     hash   symbolic bin b: f <= 64 << b  (128 .. 16384), table 128 << b keys
+//                   numeric  bin b: z <= 32 << b  (64 .. 8192),   table 64 << b (key, value) slots
+//                   one warp per row while the table is <= 12 KB, then teams of 4 .. 32 warps (k_*_row)
+//   9        heavy  above: global-memory table, persistent 1024-thread blocks (k_*_heavy)
+//   10       merge  B sorted, len(A row) <= MERGE_K, f <= 128: k-way merge of sorted runs (merge.cuh)
+constexpr int NHASH = 8, HEAVY_BIN = 9, MERGE_BIN = 10;
+constexpr u32 SYM_TINY_MAX = 32, NUM_TINY_MAX = 16, NUM_TINY_FLOP_MAX = 128;
+constexpr u32 SYM_HASH_FMAX = 64u << NHASH, NUM_HASH_ZMAX = 32u << NHASH;
 constexpr u32 MERGE_K = 8, MERGE_FLOP_MAX = 128;
 
+__host__ __device__ __forceinline__ int ceil_log2_u32(u32 x) {  // x >= 1
+#ifdef __CUDA_ARCH__
+  return x <= 1 ? 0 : 32 - __clz(x - 1);
+#else
+  int l = 0;
+  while ((1ull << l) < x) ++l;
+  return l;
+#endif
+}
 __host__ __device__ __forceinline__ int sym_bin_of(u32 f, u32 alen = 0xFFFFFFFFu, bool merge_ok = false) {
   if (merge_ok && alen <= MERGE_K && f <= MERGE_FLOP_MAX) return MERGE_BIN;
-  return f <= SYM_TINY_MAX ? 0 : f <= SYM_G1_MAX ? 1 : f <= SYM_G2_MAX ? 2 : f <= SYM_G3_MAX ? 3 : f <= SYM_G4_MAX ? 4 : 5;
+  if (f <= SYM_TINY_MAX) return 0;
+  if (f > SYM_HASH_FMAX) return HEAVY_BIN;
+  const int b = ceil_log2_u32(f) - 6;  // smallest b with f <= 64 << b
+  return b < 1 ? 1 : b;
 }
 __host__ __device__ __forceinline__ int num_bin_of(u32 z, u32 f, u32 alen = 0xFFFFFFFFu, bool merge_ok = false) {
-  (void)z;
   if (merge_ok && alen <= MERGE_K && f <= MERGE_FLOP_MAX) return MERGE_BIN;
-  if (z <= NUM_TINY_MAX) return (f <= NUM_TINY_FLOP_MAX) ? 0 : 1;
-  return z <= NUM_G1_MAX ? 1 : z <= NUM_G2_MAX ? 2 : z <= NUM_G3_MAX ? 3 : z <= NUM_G4_MAX ? 4 : 5;
+  if (z <= NUM_TINY_MAX && f <= NUM_TINY_FLOP_MAX) return 0;
+  if (z > NUM_HASH_ZMAX) return HEAVY_BIN;
+  const int b = ceil_log2_u32(z < 1 ? 1 : z) - 5;  // smallest b with z <= 32 << b
+  return b < 1 ? 1 : b;
 }
 
 // ---- device counters block (one per handle, zeroed per product) ---------------------------

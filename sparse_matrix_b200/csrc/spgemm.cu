@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(BLOCK) k_num_bin_count(u64 m, const u64* __res
     const u32 alen = len > 0xFFFFFFFFull ? 0xFFFFFFFFu : (u32)len;
     // rows of the symbolic merge bin were already histogrammed by k_sym_merge
     if (sym_bin_of(f, alen, merge_ok != 0) != MERGE_BIN) atomicAdd(&s_hist[num_bin_of(z, f, alen, merge_ok != 0)], 1u);
-    if (z > NUM_G4_MAX) atomicMax(&s_max, z);
+    if (z > NUM_HASH_ZMAX) atomicMax(&s_max, z);
   }
   __syncthreads();
   if (tid < NBINS && s_hist[tid]) atomicAdd(&cnt->num_bins[tid], s_hist[tid]);
@@ -764,19 +764,26 @@ int spgemm_symbolic_dev(spam_handle* h, const spam_dcsr* a, const spam_dcsr* b, 
       count_launch(h);                                                                                   \
     }
     const int ws = wshift_for(b, 5);
+    // symbolic hash bin b: f <= 64 << b, table 128 << b keys (4 B each)
     if (direct_enumeration(b)) {
-      LAUNCH_SYM_ROW(1, 1, 2 * SYM_G1_MAX, true)
-      LAUNCH_SYM_ROW(2, 1, 2 * SYM_G2_MAX, true)
+      LAUNCH_SYM_ROW(1, 1, 256, true)
+      LAUNCH_SYM_ROW(2, 1, 512, true)
+      LAUNCH_SYM_ROW(3, 1, 1024, true)
+      LAUNCH_SYM_ROW(4, 1, 2048, true)
     } else {
-      LAUNCH_SYM_ROW(1, 1, 2 * SYM_G1_MAX, false)
-      LAUNCH_SYM_ROW(2, 1, 2 * SYM_G2_MAX, false)
+      LAUNCH_SYM_ROW(1, 1, 256, false)
+      LAUNCH_SYM_ROW(2, 1, 512, false)
+      LAUNCH_SYM_ROW(3, 1, 1024, false)
+      LAUNCH_SYM_ROW(4, 1, 2048, false)
     }
-    LAUNCH_SYM_ROW(3, 8, 2 * SYM_G3_MAX, false)
-    LAUNCH_SYM_ROW(4, 32, 2 * SYM_G4_MAX, false)
+    LAUNCH_SYM_ROW(5, 4, 4096, false)
+    LAUNCH_SYM_ROW(6, 8, 8192, false)
+    LAUNCH_SYM_ROW(7, 16, 16384, false)
+    LAUNCH_SYM_ROW(8, 32, 32768, false)
 #undef LAUNCH_SYM_ROW
     CK_FREE(cudaGetLastError());
-    if (sb.count[5]) {
-      const u32 nheavy = sb.count[5];
+    if (sb.count[HEAVY_BIN]) {
+      const u32 nheavy = sb.count[HEAVY_BIN];
       u32 fmax = c1.max_flop;
       if (fmax > (u32)b->cols) fmax = (u32)b->cols;
       const u64 stride = 2ull * npow2_u64(fmax);
@@ -785,7 +792,7 @@ int spgemm_symbolic_dev(spam_handle* h, const spam_dcsr* a, const spam_dcsr* b, 
       const u64 budget = 8ull << 30;
       while (nblk > 1 && nblk * stride * sizeof(u32) > budget) nblk /= 2;
       FAIL_FREE(dev_alloc_t(h, &heavy_tab, nblk * stride));
-      k_sym_heavy<1024><<<(unsigned)nblk, 1024, 0, h->stream>>>(nheavy, seg(5), ap, ac, bp, bc, fl, rz, heavy_tab, stride,
+      k_sym_heavy<1024><<<(unsigned)nblk, 1024, 0, h->stream>>>(nheavy, seg(HEAVY_BIN), ap, ac, bp, bc, fl, rz, heavy_tab, stride,
                                                                 (u32)b->cols, &h->d_cnt->work_a, ws);
       count_launch(h);
       CK_FREE(cudaGetLastError());
@@ -861,32 +868,39 @@ int numeric_typed(spam_handle* h, SpgemmPending* p, spam_dcsr* c) {
         nb.count[BIN], seg(BIN), ap, ac, av, bp, bc, bv, cp, cc, cv, pack_ok);                           \
     count_launch(h);                                                                                     \
   }
+  // numeric hash bin b: z <= 32 << b, table 64 << b (key, value) slots
   if (direct_enumeration(b)) {
-    LAUNCH_NUM_ROW(1, 1, 2 * NUM_G1_MAX, true)
-    LAUNCH_NUM_ROW(2, 1, 2 * NUM_G2_MAX, true)
+    LAUNCH_NUM_ROW(1, 1, 128, true)
+    LAUNCH_NUM_ROW(2, 1, 256, true)
+    LAUNCH_NUM_ROW(3, 1, 512, true)
+    LAUNCH_NUM_ROW(4, 1, 1024, true)
   } else {
-    LAUNCH_NUM_ROW(1, 1, 2 * NUM_G1_MAX, false)
-    LAUNCH_NUM_ROW(2, 1, 2 * NUM_G2_MAX, false)
+    LAUNCH_NUM_ROW(1, 1, 128, false)
+    LAUNCH_NUM_ROW(2, 1, 256, false)
+    LAUNCH_NUM_ROW(3, 1, 512, false)
+    LAUNCH_NUM_ROW(4, 1, 1024, false)
   }
   // team sizes: these kernels are latency-bound (dependent shared-memory and shuffle chains), so the
   // big-table bins get many warps per row: G4's 224 KB table allows one block per SM, give it 32 warps
-  LAUNCH_NUM_ROW(3, 8, 2 * NUM_G3_MAX, false)
-  LAUNCH_NUM_ROW(4, 32, 2 * NUM_G4_MAX, false)
+  LAUNCH_NUM_ROW(5, 4, 2048, false)
+  LAUNCH_NUM_ROW(6, 8, 4096, false)
+  LAUNCH_NUM_ROW(7, 16, 8192, false)
+  LAUNCH_NUM_ROW(8, 32, 16384, false)
 #undef LAUNCH_NUM_ROW
   CK(cudaGetLastError());
   u32 *hk = nullptr, *hc = nullptr;
   V* hv = nullptr;
-  if (nb.count[5]) {
+  if (nb.count[HEAVY_BIN]) {
     u32 zmax = p->max_nnz;
     const u64 stride = 2ull * npow2_u64(zmax);
     u64 nblk = (u64)h->num_sms * 2;
-    if (nblk > nb.count[5]) nblk = nb.count[5];
+    if (nblk > nb.count[HEAVY_BIN]) nblk = nb.count[HEAVY_BIN];
     const u64 budget = 16ull << 30;
     while (nblk > 1 && nblk * stride * (sizeof(u32) + sizeof(V)) > budget) nblk /= 2;
     CKS(dev_alloc_t(h, &hk, nblk * stride));
     CKS(dev_alloc_t(h, &hv, nblk * stride));
     CKS(dev_alloc_t(h, &hc, nblk * (stride / 2 + 1)));
-    k_num_heavy<V, 1024><<<(unsigned)nblk, 1024, 0, h->stream>>>(nb.count[5], seg(5), ap, ac, av, bp, bc, bv, cp, cc, cv, hk,
+    k_num_heavy<V, 1024><<<(unsigned)nblk, 1024, 0, h->stream>>>(nb.count[HEAVY_BIN], seg(HEAVY_BIN), ap, ac, av, bp, bc, bv, cp, cc, cv, hk,
                                                                 hv, stride, hc, (u32)b->cols, &h->d_cnt->work_b, ws);
     count_launch(h);
     CK(cudaGetLastError());

@@ -19,6 +19,7 @@ pytestmark = pytest.mark.gpu
 
 GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "linprobe_kat.json")))
 ALL_DTYPES = [np.float64, np.float32, np.int32, np.int64]
+MERGE, HEAVY = S._lib.MERGE_BIN, S._lib.HEAVY_BIN
 
 
 def gpu_mul(a, b, handle, sorted_output=True):
@@ -108,8 +109,9 @@ def test_every_bin_is_exercised(oracle, handle, dtype):
     c = gpu_mul(a, b, handle)
     st = handle.stats()
     handle.set_timing(False)
-    assert all(x > 0 for x in st["sym_bin_rows"][:6]), st["sym_bin_rows"]
-    assert all(x > 0 for x in st["num_bin_rows"][:6]), st["num_bin_rows"]
+    # bins 0 (tiny), 1..8 (one hash bin per power of two), 9 (heavy, global-memory table)
+    assert all(x > 0 for x in st["sym_bin_rows"][:10]), st["sym_bin_rows"]
+    assert all(x > 0 for x in st["num_bin_rows"][:10]), st["num_bin_rows"]
     off, idx, val = check_against_oracle(oracle, a, b, c)
     assert st["nnz_c"] == len(idx) and st["flops"] == G.spgemm_counts(a, b)[0] and st["kernel_launches"] >= 10
     # many duplicates: few distinct columns but a large flop count (numeric bin chosen by nnz, not flop)
@@ -128,7 +130,7 @@ def test_tiny_rows_are_bit_identical_for_floats(oracle, handle):
         handle.set_timing(True)
         c = gpu_mul(p, p, handle)                       # sorted rows: the merge bin
         st = handle.stats()
-        assert st["sym_bin_rows"][6] == p[0] and st["num_bin_rows"][6] == p[0]
+        assert st["sym_bin_rows"][MERGE] == p[0] and st["num_bin_rows"][MERGE] == p[0]
         check_against_oracle(oracle, p, p, c, exact_values=True)
         # same matrix with every row shuffled (CsrMatrix<T,false>): the private-hash-table bin
         off, idx, val = p[2], p[3].copy(), p[4].copy()
@@ -159,9 +161,9 @@ def test_merge_bin_mixed_with_other_bins(oracle, handle):
         c = gpu_mul(a, b, handle)
         st = handle.stats()
         handle.set_timing(False)
-        assert st["sym_bin_rows"][6] > 0 and st["num_bin_rows"][6] > 0
+        assert st["sym_bin_rows"][MERGE] > 0 and st["num_bin_rows"][MERGE] > 0
         if kmax == 40:
-            assert st["sym_bin_rows"][1] > 0 and st["num_bin_rows"][1] > 0
+            assert sum(st["sym_bin_rows"][1:9]) > 0 and sum(st["num_bin_rows"][1:9]) > 0
         check_against_oracle(oracle, a, b, c)
 
 
@@ -247,7 +249,7 @@ def test_config2_poisson_full_size(oracle, handle):
     st = handle.stats()
     handle.set_timing(False)
     assert st["flops"] == 104_783_880 and st["nnz_c"] == 54_484_996
-    assert st["sym_bin_rows"][6] == 4_194_304 and st["num_bin_rows"][6] == 4_194_304   # sorted B: merge bin
+    assert st["sym_bin_rows"][MERGE] == 4_194_304 and st["num_bin_rows"][MERGE] == 4_194_304   # sorted B: merge bin
     c = dC.download()
     check_against_oracle(oracle, p, p, c, exact_values=True)
     ones = np.ones(p[0])
@@ -272,7 +274,7 @@ def test_config4_rmat_reduced(oracle, handle):
     st = handle.stats()
     handle.set_timing(False)
     check_against_oracle(oracle, r, r, c)
-    assert st["sym_bin_rows"][5] > 0 or st["sym_bin_rows"][4] > 0   # power-law rows reach the big bins
+    assert st["sym_bin_rows"][HEAVY] > 0 or st["sym_bin_rows"][8] > 0 or st["sym_bin_rows"][7] > 0   # power-law rows reach the big bins
 
 
 def test_config5_rectangular_i64_and_dok(oracle, handle):
