@@ -309,6 +309,58 @@ __device__ __forceinline__ void warp_bitonic_sort(u32 kbase, u32 vbase, u32 n2, 
 }
 
 // ------------------------------------------------------------------------------------------------
+// finishing the order-preserving buckets of the team drain (entries already sit in C, bucket by bucket)
+// ------------------------------------------------------------------------------------------------
+constexpr u32 SMALL_BUCKET_MAX = 8;    // up to here: insertion sort by one thread
+constexpr u32 BIG_BUCKET_MAX = 256;    // up to here: rank sort by one warp; beyond: whole-row bitonic fallback
+constexpr int BIG_QUEUE = 128;         // long buckets queued per row (overflow falls back to insertion sort)
+
+template <class V>
+__device__ __forceinline__ void insertion_sort_bucket(u32* __restrict__ c_col, V* __restrict__ c_val, u64 c0, u32 lo_b,
+                                                      u32 hi_b) {
+  for (u32 i = lo_b + 1; i < hi_b; ++i) {
+    const u32 k = c_col[c0 + i];
+    const V v = c_val[c0 + i];
+    u32 j = i;
+    while (j > lo_b && c_col[c0 + j - 1] > k) { c_col[c0 + j] = c_col[c0 + j - 1]; c_val[c0 + j] = c_val[c0 + j - 1]; --j; }
+    c_col[c0 + j] = k;
+    c_val[c0 + j] = v;
+  }
+}
+
+// n <= BIG_BUCKET_MAX distinct keys at c_col[base..base+n): each lane holds up to 8, counts for each how
+// many keys of the bucket are smaller (keys broadcast by shuffle), then stores it at its rank.
+template <class V>
+__device__ __forceinline__ void rank_sort_bucket_warp(u32* __restrict__ c_col, V* __restrict__ c_val, u64 base, u32 n,
+                                                      int lane) {
+  constexpr int R = BIG_BUCKET_MAX / 32;
+  u32 k[R], rank[R];
+  V v[R];
+  const int rounds = (int)((n + 31) / 32);
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const u32 i = lane + 32 * r;
+    k[r] = 0xFFFFFFFFu; rank[r] = 0; v[r] = V();
+    if (i < n) { k[r] = c_col[base + i]; v[r] = c_val[base + i]; }
+  }
+#pragma unroll
+  for (int rr = 0; rr < R; ++rr) {
+    if (rr < rounds) {
+      for (int src = 0; src < 32; ++src) {
+        const u32 ko = __shfl_sync(FULL, k[rr], src);
+#pragma unroll
+        for (int r = 0; r < R; ++r) rank[r] += (ko < k[r]) ? 1u : 0u;  // padding keys are never smaller
+      }
+    }
+  }
+  __syncwarp();
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    if (lane + 32 * r < n) { c_col[base + rank[r]] = k[r]; c_val[base + rank[r]] = v[r]; }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // NUMERIC (mul_hash.rs:105-201)
 // ------------------------------------------------------------------------------------------------
 // NW = 1, DIRECT: the lanes of a batch hold distinct columns -> distinct slots: plain read-modify-write
@@ -360,6 +412,7 @@ k_num_row(u32 n, const u32* __restrict__ perm, const u64* __restrict__ a_ptr, co
   extern __shared__ __align__(16) unsigned char sm_num_raw[];
   __shared__ u32 s_warp[32];
   __shared__ u32 s_kmin, s_kmax, s_maxcnt;
+  __shared__ u32 s_big[NW == 1 ? 1 : BIG_QUEUE];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const u32 item = NW == 1 ? blockIdx.x * RPB + wid : blockIdx.x;
   if (item >= n) return;
@@ -526,7 +579,7 @@ k_num_row(u32 n, const u32* __restrict__ perm, const u64* __restrict__ a_ptr, co
     if (mx) atomicMax(&s_maxcnt, mx);
   }
   __syncthreads();
-  if (s_maxcnt <= 64) {
+  if (s_maxcnt <= BIG_BUCKET_MAX) {
     for (u32 s = rt; s < cap; s += TT) {
       const u32 kk = keys[s];
       if (kk != EMPTY_KEY) {
@@ -535,17 +588,24 @@ k_num_row(u32 n, const u32* __restrict__ perm, const u64* __restrict__ a_ptr, co
         c_val[c0 + pos] = vals[s];
       }
     }
+    if (threadIdx.x == 0) s_kmax = 0;  // reused: number of long buckets queued for the warps
     __syncthreads();
+    // short buckets: one thread each; long ones (power-law columns crowd the low end of the range) are
+    // queued and rank-sorted by a whole warp
     for (u32 b = rt; b < NB; b += TT) {
       const u32 lo_b = b ? cnt[b - 1] : 0u, hi_b = cnt[b];
-      for (u32 i = lo_b + 1; i < hi_b; ++i) {
-        const u32 k = c_col[c0 + i];
-        const V v = c_val[c0 + i];
-        u32 j = i;
-        while (j > lo_b && c_col[c0 + j - 1] > k) { c_col[c0 + j] = c_col[c0 + j - 1]; c_val[c0 + j] = c_val[c0 + j - 1]; --j; }
-        c_col[c0 + j] = k;
-        c_val[c0 + j] = v;
+      if (hi_b - lo_b > SMALL_BUCKET_MAX) {
+        const u32 q = atomicAdd(&s_kmax, 1u);
+        if (q < BIG_QUEUE) { s_big[q] = b; continue; }
       }
+      insertion_sort_bucket<V>(c_col, c_val, c0, lo_b, hi_b);
+    }
+    __syncthreads();
+    const u32 nbig = min(s_kmax, (u32)BIG_QUEUE);
+    for (u32 q = rw; q < nbig; q += NW) {
+      const u32 b = s_big[q];
+      const u32 lo_b = b ? cnt[b - 1] : 0u, hi_b = cnt[b];
+      rank_sort_bucket_warp<V>(c_col, c_val, c0 + lo_b, hi_b - lo_b, lane);
     }
   } else {
     // pathological column distribution: compact in shared memory and run the bitonic network

@@ -420,8 +420,10 @@ __global__ void __launch_bounds__(T) k_num_heavy(u32 n, const u32* __restrict__ 
                                                  V* val_tables, u64 table_stride, u32* cnt_tables, u32 b_cols,
                                                  u32* work, int wshift) {
   constexpr int ITEMS = 4;
-  __shared__ u32 s_item, s_maxcnt;
+  constexpr int HEAVY_QUEUE = 2048;  // long buckets queued per heavy row
+  __shared__ u32 s_item, s_maxcnt, s_nbig;
   __shared__ u32 s_warp[32];
+  __shared__ u32 s_big[HEAVY_QUEUE];
   const int tid = threadIdx.x;
   u32* keys = key_tables + (u64)blockIdx.x * table_stride;
   V* vals = val_tables + (u64)blockIdx.x * table_stride;
@@ -488,7 +490,7 @@ __global__ void __launch_bounds__(T) k_num_heavy(u32 n, const u32* __restrict__ 
       for (u32 b = b0; b < b1; ++b) { const u32 c = __ldcg(&cnt[b]); __stcg(&cnt[b], runb); runb += c; }
       if (mx) atomicMax(&s_maxcnt, mx);
       __syncthreads();
-      if (s_maxcnt <= 64) {
+      if (s_maxcnt <= BIG_BUCKET_MAX) {
         for (u64 s = tid; s < cap; s += T) {
           const u32 kk = __ldcg(&keys[s]);
           if (kk != EMPTY_KEY) {
@@ -497,17 +499,22 @@ __global__ void __launch_bounds__(T) k_num_heavy(u32 n, const u32* __restrict__ 
             c_val[c0 + pos] = __ldcg(&vals[s]);
           }
         }
+        if (tid == 0) s_nbig = 0;
         __syncthreads();
         for (u32 b = tid; b < NB; b += T) {
           const u32 lo_b = b ? __ldcg(&cnt[b - 1]) : 0u, hi_b = __ldcg(&cnt[b]);
-          for (u32 i = lo_b + 1; i < hi_b; ++i) {
-            const u32 k = c_col[c0 + i];
-            const V v = c_val[c0 + i];
-            u32 j = i;
-            while (j > lo_b && c_col[c0 + j - 1] > k) { c_col[c0 + j] = c_col[c0 + j - 1]; c_val[c0 + j] = c_val[c0 + j - 1]; --j; }
-            c_col[c0 + j] = k;
-            c_val[c0 + j] = v;
+          if (hi_b - lo_b > SMALL_BUCKET_MAX) {
+            const u32 q = atomicAdd(&s_nbig, 1u);
+            if (q < (u32)HEAVY_QUEUE) { s_big[q] = b; continue; }
           }
+          insertion_sort_bucket<V>(c_col, c_val, c0, lo_b, hi_b);
+        }
+        __syncthreads();
+        const u32 nbig = min(s_nbig, (u32)HEAVY_QUEUE);
+        for (u32 q = tid >> 5; q < nbig; q += T / 32) {
+          const u32 b = s_big[q];
+          const u32 lo_b = b ? __ldcg(&cnt[b - 1]) : 0u, hi_b = __ldcg(&cnt[b]);
+          rank_sort_bucket_warp<V>(c_col, c_val, c0 + lo_b, hi_b - lo_b, tid & 31);
         }
         __syncthreads();
         continue;
