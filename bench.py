@@ -38,6 +38,7 @@ WORKLOAD_DESC = {
     "stencil96": "3-D 27-point stencil 96^3 (0.88M rows), A*A, f64  [reduced configs[2]]",
     "rmat22": "R-MAT(0.45,0.15,0.15,0.25) scale 22 ef 16, A*A, f64  [BASELINE configs[3]]",
     "rmat18": "R-MAT(0.45,0.15,0.15,0.25) scale 18 ef 16, A*A, f64  [reduced configs[3]]",
+    "rmat20": "R-MAT(0.45,0.15,0.15,0.25) scale 20 ef 16, A*A, f64  [reduced configs[3]]",
 }
 
 
@@ -55,6 +56,8 @@ def make_workload(name):
         return G.rmat(22)
     if name == "rmat18":
         return G.rmat(18)
+    if name == "rmat20":
+        return G.rmat(20)
     raise SystemExit(f"unknown workload {name}")
 
 

@@ -315,6 +315,52 @@ constexpr u32 SMALL_BUCKET_MAX = 8;    // up to here: insertion sort by one thre
 constexpr u32 BIG_BUCKET_MAX = 256;    // up to here: rank sort by one warp; beyond: whole-row bitonic fallback
 constexpr int BIG_QUEUE = 128;         // long buckets queued per row (overflow falls back to insertion sort)
 
+// A short bucket (2..8 entries) sorted by one thread IN REGISTERS: all loads issued at once, an odd-even
+// transposition network with static indices, stores back.  The first version insertion-sorted in global
+// memory: a chain of dependent L2 loads that was 38% of the team kernel's instructions and a third of its
+// stall samples on R-MAT (profiles/r01_rmat20_v2_finebins.txt).
+template <class V, int N>
+__device__ __forceinline__ void sort_bucket_regs(u32* __restrict__ c_col, V* __restrict__ c_val, u64 base, u32 n) {
+  u32 k[N];
+  V v[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    k[i] = 0xFFFFFFFFu; v[i] = V();
+    if ((u32)i < n) { k[i] = c_col[base + i]; v[i] = c_val[base + i]; }
+  }
+#pragma unroll
+  for (int round = 0; round < N; ++round) {
+#pragma unroll
+    for (int i = round & 1; i + 1 < N; i += 2) {
+      if (k[i] > k[i + 1]) {
+        const u32 tk = k[i]; k[i] = k[i + 1]; k[i + 1] = tk;
+        const V tv = v[i]; v[i] = v[i + 1]; v[i + 1] = tv;
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+    if ((u32)i < n) { c_col[base + i] = k[i]; c_val[base + i] = v[i]; }
+}
+
+template <class V>
+__device__ __forceinline__ void sort_small_bucket(u32* __restrict__ c_col, V* __restrict__ c_val, u64 c0, u32 lo_b, u32 hi_b) {
+  const u32 n = hi_b - lo_b;
+  if (n < 2) return;
+  if (n == 2) {
+    const u32 k0 = c_col[c0 + lo_b], k1 = c_col[c0 + lo_b + 1];
+    if (k0 > k1) {
+      const V v0 = c_val[c0 + lo_b], v1 = c_val[c0 + lo_b + 1];
+      c_col[c0 + lo_b] = k1; c_col[c0 + lo_b + 1] = k0;
+      c_val[c0 + lo_b] = v1; c_val[c0 + lo_b + 1] = v0;
+    }
+  } else if (n <= 4) {
+    sort_bucket_regs<V, 4>(c_col, c_val, c0 + lo_b, n);
+  } else {
+    sort_bucket_regs<V, 8>(c_col, c_val, c0 + lo_b, n);
+  }
+}
+
 template <class V>
 __device__ __forceinline__ void insertion_sort_bucket(u32* __restrict__ c_col, V* __restrict__ c_val, u64 c0, u32 lo_b,
                                                       u32 hi_b) {
@@ -398,6 +444,12 @@ __device__ __forceinline__ void accumulate_fold(u32 kbase, u32 vbase, u32 mask, 
   if (leader) SV<V>::st(va, acc);
   __syncwarp();
 }
+
+// team kernels: number of drain buckets (CAP while that does not cost a resident block, else CAP/2)
+template <class V, int NW, int CAP>
+struct NumRowCfg {
+  static constexpr int NBMAX = CAP <= 4096 ? CAP : CAP / 2;
+};
 
 template <class V, int NW, int CAP, bool DIRECT>
 __global__ void __launch_bounds__(NW == 1 ? 32 * ROWS_PER_BLOCK_W1 : 32 * NW)
@@ -544,7 +596,8 @@ k_num_row(u32 n, const u32* __restrict__ perm, const u64* __restrict__ a_ptr, co
   // ---- NW > 1: bucket drain straight into C --------------------------------------------------
   __syncthreads();
   if (threadIdx.x == 0) { s_kmin = 0xFFFFFFFFu; s_kmax = 0; s_maxcnt = 0; }
-  const u32 NB = npow2_u32(z);
+  // 2*npow2(z) buckets (about one entry per two buckets) where the counter array fits, else npow2(z)
+  const u32 NB = NumRowCfg<V, NW, CAP>::NBMAX == CAP ? cap : npow2_u32(z);
   for (u32 b = rt; b <= NB; b += TT) cnt[b] = 0;
   __syncthreads();
 #pragma unroll
@@ -596,9 +649,10 @@ k_num_row(u32 n, const u32* __restrict__ perm, const u64* __restrict__ a_ptr, co
       const u32 lo_b = b ? cnt[b - 1] : 0u, hi_b = cnt[b];
       if (hi_b - lo_b > SMALL_BUCKET_MAX) {
         const u32 q = atomicAdd(&s_kmax, 1u);
-        if (q < BIG_QUEUE) { s_big[q] = b; continue; }
+        if (q < BIG_QUEUE) s_big[q] = b; else insertion_sort_bucket<V>(c_col, c_val, c0, lo_b, hi_b);
+        continue;
       }
-      insertion_sort_bucket<V>(c_col, c_val, c0, lo_b, hi_b);
+      sort_small_bucket<V>(c_col, c_val, c0, lo_b, hi_b);
     }
     __syncthreads();
     const u32 nbig = min(s_kmax, (u32)BIG_QUEUE);
@@ -645,7 +699,8 @@ k_num_row(u32 n, const u32* __restrict__ perm, const u64* __restrict__ a_ptr, co
 
 template <class V, int NW, int CAP>
 constexpr size_t num_row_smem() {
-  return NW == 1 ? (size_t)ROWS_PER_BLOCK_W1 * CAP * (sizeof(V) + 4) : (size_t)CAP * (sizeof(V) + 4) + (CAP / 2 + 1) * 4;
+  return NW == 1 ? (size_t)ROWS_PER_BLOCK_W1 * CAP * (sizeof(V) + 4)
+                 : (size_t)CAP * (sizeof(V) + 4) + (size_t)(NumRowCfg<V, NW, CAP>::NBMAX + 1) * 4;
 }
 
 }  // namespace

@@ -505,9 +505,10 @@ __global__ void __launch_bounds__(T) k_num_heavy(u32 n, const u32* __restrict__ 
           const u32 lo_b = b ? __ldcg(&cnt[b - 1]) : 0u, hi_b = __ldcg(&cnt[b]);
           if (hi_b - lo_b > SMALL_BUCKET_MAX) {
             const u32 q = atomicAdd(&s_nbig, 1u);
-            if (q < (u32)HEAVY_QUEUE) { s_big[q] = b; continue; }
+            if (q < (u32)HEAVY_QUEUE) s_big[q] = b; else insertion_sort_bucket<V>(c_col, c_val, c0, lo_b, hi_b);
+            continue;
           }
-          insertion_sort_bucket<V>(c_col, c_val, c0, lo_b, hi_b);
+          sort_small_bucket<V>(c_col, c_val, c0, lo_b, hi_b);
         }
         __syncthreads();
         const u32 nbig = min(s_nbig, (u32)HEAVY_QUEUE);
