@@ -24,26 +24,30 @@ from oracle import pyoracle as O  # noqa: E402
 from sparse_matrix_b200 import generators as G  # noqa: E402
 
 
+_H = None
+
+
 def timed(fn, stream, reps=20, warm=3):
+    """ms per call: `reps` back-to-back calls on the handle's own stream between two stream syncs (host
+    clock; the calls are asynchronous apart from the library's own syncs, so this is device time plus the
+    launch gaps a caller would see)."""
     for _ in range(warm):
         fn()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
+    _H.synchronize()
+    t0 = time.perf_counter()
     for _ in range(reps):
         fn()
-    e1.record(stream)
-    torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / reps
+    _H.synchronize()
+    return (time.perf_counter() - t0) * 1e3 / reps
 
 
 def main():
     which = sys.argv[1:] or ["spmv", "dok", "rect"]
     dev = torch.device("cuda", 0)
-    stream = torch.cuda.Stream(device=dev)
-    torch.cuda.set_stream(stream)
-    h = S.Handle(0)
-    h.set_stream(stream.cuda_stream)
+    stream = None
+    h = S.Handle(0)   # the handle's own non-blocking stream
+    global _H
+    _H = h
     L = h.L
     peak, src = measured_peak()
 
@@ -55,7 +59,9 @@ def main():
         x = rng.uniform(-1, 1, size=p[1])
         dx = torch.from_numpy(x).to(dev)
         dy = torch.empty(p[0], dtype=torch.float64, device=dev)
+        torch.cuda.synchronize()
         ms = timed(lambda: S._lib.check(h.h, L.spam_spmv_dev(h.h, dA.p, C.c_void_p(dx.data_ptr()), C.c_void_p(dy.data_ptr()))), stream)
+        h.synchronize()
         y = dy.cpu().numpy()
         t0 = time.perf_counter()
         want = O.spmv(p[0], p[1], p[2], p[3], p[4], x)
@@ -77,6 +83,7 @@ def main():
         d_r = torch.from_numpy(tr.view(np.int64)).to(dev)
         d_c = torch.from_numpy(tc.view(np.int64)).to(dev)
         d_v = torch.from_numpy(tv).to(dev)
+        torch.cuda.synchronize()
         outs = []
 
         def run():

@@ -201,6 +201,8 @@ void spgemm_pending_free(spam_handle* h, SpgemmPending* p);
 u64 spgemm_pending_nnz(const SpgemmPending* p);
 const u64* spgemm_pending_cptr(const SpgemmPending* p);
 int flop_count_dev(spam_handle* h, const spam_dcsr* a, const spam_dcsr* b, u32* d_flop, bool do_bins, int merge_ok);
+// cached per-matrix properties (rows sorted? longest row), one pass over col_idx on first use
+int ensure_matrix_stats(spam_handle* h, const spam_dcsr* m);
 // spmv.cu
 int spmv_dev(spam_handle* h, const spam_dcsr* a, const void* d_x, void* d_y);
 // dok.cu

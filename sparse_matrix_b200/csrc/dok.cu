@@ -151,13 +151,10 @@ unsigned grid_for(const spam_handle* h, u64 n) {
 }
 
 // stable LSD radix sort of (key, payload) on `keybits` low bits; result may end in either buffer
-int radix_sort_pairs(spam_handle* h, u64 n, int keybits, u64*& k0, u32*& p0, u64*& k1, u32*& p1) {
+int radix_sort_pairs(spam_handle* h, u64 n, int keybits, u64*& k0, u32*& p0, u64*& k1, u32*& p1, u32* hist,
+                     u64* offs) {
   if (n == 0) return SPAM_OK;
   const u32 nblocks = (u32)((n + RS_TILE - 1) / RS_TILE);
-  u32* hist = nullptr;
-  u64* offs = nullptr;
-  CKS(dev_alloc_t(h, &hist, (u64)RADIX * nblocks));
-  CKS(dev_alloc_t(h, &offs, (u64)RADIX * nblocks + 1));
   for (int shift = 0; shift < keybits; shift += 8) {
     k_radix_hist<<<nblocks, RS_T, 0, h->stream>>>(k0, n, shift, hist, nblocks);
     count_launch(h);
@@ -169,23 +166,29 @@ int radix_sort_pairs(spam_handle* h, u64 n, int keybits, u64*& k0, u32*& p0, u64
     u64* tk = k0; k0 = k1; k1 = tk;
     u32* tp = p0; p0 = p1; p1 = tp;
   }
-  CKS(dev_free(h, hist));
-  CKS(dev_free(h, offs));
   return SPAM_OK;
 }
 
 template <class V>
 int dok_typed(spam_handle* h, u64 rows, u64 cols, u64 n, const u64* d_r, const u64* d_c, const V* d_v, spam_dcsr* out) {
   const int cbits = bits_for(cols), rbits = bits_for(rows);
-  u64 *k0 = nullptr, *k1 = nullptr, *pos = nullptr;
-  u32 *p0 = nullptr, *p1 = nullptr, *flags = nullptr, *row_cnt = nullptr;
-  CKS(dev_alloc_t(h, &k0, n));
-  CKS(dev_alloc_t(h, &k1, n));
-  CKS(dev_alloc_t(h, &p0, n));
-  CKS(dev_alloc_t(h, &p1, n));
-  CKS(dev_alloc_t(h, &flags, n));
-  CKS(dev_alloc_t(h, &pos, n + 1));
-  CKS(dev_alloc_t(h, &row_cnt, rows));
+  // one workspace allocation, carved up (allocator calls were a visible part of this ~1.5 ms routine)
+  const u64 nblocks = (n + RS_TILE - 1) / RS_TILE;
+  auto al = [](u64 bytes) { return (bytes + 255) & ~255ull; };
+  const u64 sz_k = al(n * 8), sz_pos = al((n + 1) * 8), sz_p = al(n * 4), sz_rc = al(rows * 4),
+            sz_hist = al((u64)RADIX * nblocks * 4), sz_offs = al(((u64)RADIX * nblocks + 1) * 8);
+  char* ws = nullptr;
+  CKS(dev_alloc(h, (void**)&ws, 2 * sz_k + sz_pos + 3 * sz_p + sz_rc + sz_hist + sz_offs));
+  char* cur = ws;
+  u64* k0 = (u64*)cur; cur += sz_k;
+  u64* k1 = (u64*)cur; cur += sz_k;
+  u64* pos = (u64*)cur; cur += sz_pos;
+  u64* offs = (u64*)cur; cur += sz_offs;
+  u32* p0 = (u32*)cur; cur += sz_p;
+  u32* p1 = (u32*)cur; cur += sz_p;
+  u32* flags = (u32*)cur; cur += sz_p;
+  u32* row_cnt = (u32*)cur; cur += sz_rc;
+  u32* hist = (u32*)cur;
   CKS(dev_alloc_t(h, &out->ptr, rows + 1));
   CK(cudaMemsetAsync(h->d_cnt, 0, sizeof(Counters), h->stream));
   CK(cudaMemsetAsync(row_cnt, 0, rows * sizeof(u32), h->stream));
@@ -193,7 +196,7 @@ int dok_typed(spam_handle* h, u64 rows, u64 cols, u64 n, const u64* d_r, const u
     k_make_keys<<<grid_for(h, n), 256, 0, h->stream>>>(n, rows, cols, cbits, d_r, d_c, k0, p0, h->d_cnt);
     count_launch(h);
     CK(cudaGetLastError());
-    CKS(radix_sort_pairs(h, n, cbits + rbits, k0, p0, k1, p1));
+    CKS(radix_sort_pairs(h, n, cbits + rbits, k0, p0, k1, p1, hist, offs));
     k_mark_last<V><<<grid_for(h, n), 256, 0, h->stream>>>(n, cbits, k0, p0, d_v, flags, row_cnt);
     count_launch(h);
     CK(cudaGetLastError());
@@ -215,8 +218,7 @@ int dok_typed(spam_handle* h, u64 rows, u64 cols, u64 n, const u64* d_r, const u
       if (e != cudaSuccess) st = spam_fail(h, SPAM_ECUDA, "k_emit", e);
     }
   }
-  dev_free(h, k0); dev_free(h, k1); dev_free(h, p0); dev_free(h, p1);
-  dev_free(h, flags); dev_free(h, pos); dev_free(h, row_cnt);
+  dev_free(h, ws);
   return st;
 }
 

@@ -658,6 +658,8 @@ void spgemm_pending_free(spam_handle* h, SpgemmPending* p) {
   delete p;
 }
 
+int ensure_matrix_stats(spam_handle* h, const spam_dcsr* m) { return ensure_rows_sorted(h, m); }
+
 int flop_count_dev(spam_handle* h, const spam_dcsr* a, const spam_dcsr* b, u32* d_flop, bool do_bins, int merge_ok) {
   const u64 m = a->rows;
   if (m == 0) return SPAM_OK;
