@@ -42,10 +42,22 @@ WORKLOAD_DESC = {
 }
 
 
-def make_workload(name):
+def resolve_scaling(args):
+    """`strong`: the named matrix, rows split over the ranks (BASELINE configs[2], [3]: "row-partitioned
+    1/2/4/8 B200").  `weak`: every rank owns one unit of the named workload — for Poisson (configs[1], a
+    1-GPU configuration) a 2048 x 2048 block of lines of a 2048 x (2048 N) grid, B = the whole matrix
+    replicated; per-GPU work is fixed as N grows.  `auto` = weak for poisson2048, strong otherwise."""
+    if args.scaling != "auto":
+        if args.scaling == "weak" and args.workload != "poisson2048":
+            raise SystemExit("--scaling weak is defined for poisson2048 only")
+        return args.scaling
+    return "weak" if (args.workload == "poisson2048" and args.gpus > 1) else "strong"
+
+
+def make_workload(name, units=1):
     from sparse_matrix_b200 import generators as G
     if name == "poisson2048":
-        return G.poisson2d(2048)
+        return G.poisson2d(2048, ny=2048 * units)
     if name == "uniform10k":
         return G.uniform_random(10_000, 10_000, 10, seed=1)
     if name == "stencil160":
@@ -155,7 +167,8 @@ class DevArray:
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    mat = make_workload(args.workload)
+    scaling = resolve_scaling(args)
+    mat = make_workload(args.workload, args.gpus if scaling == "weak" else 1)
     from oracle import pyoracle as O
     O.build()
     a = (mat[0], mat[1], np.ascontiguousarray(mat[2], np.uint64), np.ascontiguousarray(mat[3], np.uint64), mat[4])
@@ -170,8 +183,8 @@ def run_reference(args, rank, world):
     val = 2.0 * flops / (ms / 1e3) / 1e9
     line = {"impl": "reference", "metric": "spgemm_gflops", "value": val, "unit": "GFLOP/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": args.workload, "desc": WORKLOAD_DESC[args.workload]},
+            "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "desc": WORKLOAD_DESC[args.workload], "rows": int(mat[0])},
             "cpu_baseline": {"value": val, "unit": "GFLOP/s", "cores": O.hardware_threads(), "kind": "port",
                              "sample": "full workload A*A per step; C++ restatement of spam_csr::mul_hash "
                                        "(the Rust reference cannot be built: no cargo/rustc in the image)"},
@@ -186,6 +199,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--workload", default="poisson2048", choices=sorted(WORKLOAD_DESC))
+    ap.add_argument("--scaling", default="auto", choices=["auto", "strong", "weak"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -222,8 +236,9 @@ def main():
 
     # ---- inputs: rank 0 generates, everyone gets A over NCCL (B = A is replicated) ----
     t_bcast = 0.0
+    scaling = resolve_scaling(args)
     if world == 1 or rank == 0:
-        mat = make_workload(args.workload)
+        mat = make_workload(args.workload, world if scaling == "weak" else 1)
         rows, cols = mat[0], mat[1]
         h_ptr = torch.from_numpy(np.ascontiguousarray(mat[2]).view(np.int64))
         h_idx = torch.from_numpy(np.ascontiguousarray(mat[3]).astype(np.uint32).view(np.int32))
@@ -260,7 +275,7 @@ def main():
         # reported as partition_ms.  Each rank's product still does its own flop count / binning per step.
         torch.cuda.synchronize()
         tp0 = time.perf_counter()
-        starts, total = dA.rows_to_parts(dA, world)
+        starts, total = dA.rows_to_parts(dA, world, balance="cost")
         blk = dA.slice_rows(int(starts[rank]), int(starts[rank + 1]))
         handle.synchronize()
         partition_ms = (time.perf_counter() - tp0) * 1e3
@@ -317,9 +332,12 @@ def main():
     ms_step = ev0.elapsed_time(ev1) / args.steps
     if world > 1:
         t = torch.tensor([ms_step], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_step = float(t.item())
+        per_rank = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(per_rank, t)
+        rank_ms = [round(float(x.item()), 4) for x in per_rank]
+        ms_step = max(rank_ms)
     flops, nnz_c = st["flops"], st["nnz_c"]
+    local_nnz_c = nnz_c
     if world > 1:
         t = torch.tensor([flops, nnz_c, launches], dtype=torch.int64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
@@ -345,20 +363,25 @@ def main():
     gflops = 2.0 * flops / (ms_step / 1e3) / 1e9
 
     line = {"metric": "spgemm_gflops", "value": gflops, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": scaling,
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": args.workload, "desc": WORKLOAD_DESC[args.workload], "rows": rows, "nnz_a": nnz_a,
                        "products": flops, "nnz_c": nnz_c, "algorithmic_bytes": bytes_alg,
                        "l2": "no flush: per-step working set (A + C, %.2f GB) exceeds the 126 MB L2" %
                              ((nnz_a * 12 + nnz_c * 12 + rows * 16) / 1e9),
                        "sharding": "single GPU" if world == 1 else
-                                   f"A pre-sharded in flop-balanced row blocks over {world} ranks (partition + slice "
+                                   f"A pre-sharded in device-cost-balanced row blocks (spam_rows_to_parts_cost) over {world} ranks (partition + slice "
                                    f"{partition_ms:.2f} ms, untimed set-up), B replicated (NCCL broadcast "
                                    f"{t_bcast * 1e3:.1f} ms, untimed), C left row-sharded in `value`; `gathered` adds "
                                    f"the all-gather-v"},
             "gpu_launches": launches,
             "hbm_gbs_pipeline": bytes_alg / (ms_step / 1e3) / 1e9,
             "phases_ms": {k: v / args.steps for k, v in phase.items()}}
+    if world > 1:
+        line["rank_ms"] = rank_ms      # each rank's own device time per step: the load balance of the partition
+        if scaling == "weak":
+            line["config"]["weak_unit"] = ("one 2048 x 2048 block of grid lines (4.19M rows of A) per GPU; the matrix is "
+                                           f"the Poisson operator on a 2048 x {2048 * world} grid, B = all of it, replicated")
     if gathered_ms is not None:
         line["gathered"] = {"ms_per_step": gathered_ms, "value": 2.0 * flops / (gathered_ms / 1e3) / 1e9,
                             "unit": "GFLOP/s", "note": "same step plus all-gather-v of row_ptr/col_idx/val so every "
@@ -389,42 +412,83 @@ def main():
                                 "peak_source": peak_src + f" x {world} GPUs"}
         line["clocks"] = clocks
 
-    # ---- e2e: the reference-facing two-phase C ABI with pinned HOST buffers, N=1 only ----
-    if world == 1 and not args.no_e2e:
+    # ---- e2e: the reference-facing two-phase C ABI with pinned HOST buffers.  At N > 1 every rank is a
+    # host caller multiplying ITS row block of A (host memory) by all of B (host memory): both are uploaded
+    # and the C shard is downloaded inside the timed region; time = max over ranks.
+    do_e2e = not args.no_e2e
+    if do_e2e and world > 1:
+        # bound pinned host memory: skip (and say so) when the box cannot hold every rank's buffers
+        need = world * ((rows + 1) * 8 + nnz_a * 16) + (rows + 1) * 16 + nnz_a * 16 + nnz_c * 16
+        try:
+            avail = int([l for l in open("/proc/meminfo") if l.startswith("MemAvailable")][0].split()[1]) * 1024
+        except Exception:
+            avail = 0
+        flag = torch.tensor([1 if need * 3 > avail else 0], dtype=torch.int64, device=dev)
+        dist.broadcast(flag, src=0)     # one decision for every rank (the e2e steps are bracketed by barriers)
+        if int(flag.item()):
+            do_e2e = False
+            if rank == 0:
+                line["e2e_skipped"] = f"pinned host buffers for {world} ranks need {need / 1e9:.1f} GB, MemAvailable {avail / 1e9:.1f} GB"
+    if do_e2e:
         keep = []
         try:
-            p_ptr = pinned_array(L, rows + 1, np.uint64, keep); p_ptr[:] = mat[2]
-            p_idx = pinned_array(L, nnz_a, np.uint64, keep); p_idx[:] = mat[3]
-            p_val = pinned_array(L, nnz_a, np.float64, keep); p_val[:] = mat[4]
-            c_ptr = pinned_array(L, rows + 1, np.uint64, keep)
-            c_idx = pinned_array(L, nnz_c, np.uint64, keep)
-            c_val = pinned_array(L, nnz_c, np.float64, keep)
+            if world == 1:
+                hb_ptr, hb_idx, hb_val = mat[2], mat[3], mat[4]
+                a_rows, a_nnz = rows, nnz_a
+            else:
+                hb_ptr = d_ptr.cpu().numpy().view(np.uint64)
+                hb_idx = d_idx.cpu().numpy().view(np.uint32)
+                hb_val = d_val.cpu().numpy()
+                r0, r1 = int(starts[rank]), int(starts[rank + 1])
+                a_rows = r1 - r0
+                e0_, e1_ = int(hb_ptr[r0]), int(hb_ptr[r1])
+                a_nnz = e1_ - e0_
+            p_ptr = pinned_array(L, rows + 1, np.uint64, keep); p_ptr[:] = hb_ptr
+            p_idx = pinned_array(L, nnz_a, np.uint64, keep); p_idx[:] = hb_idx
+            p_val = pinned_array(L, nnz_a, np.float64, keep); p_val[:] = hb_val
+            if world == 1:
+                pa_ptr, pa_idx, pa_val = p_ptr, p_idx, p_val     # A aliases B: the library uploads it once
+            else:
+                pa_ptr = pinned_array(L, a_rows + 1, np.uint64, keep); pa_ptr[:] = hb_ptr[r0:r1 + 1] - hb_ptr[r0]
+                pa_idx = pinned_array(L, a_nnz, np.uint64, keep); pa_idx[:] = hb_idx[e0_:e1_]
+                pa_val = pinned_array(L, a_nnz, np.float64, keep); pa_val[:] = hb_val[e0_:e1_]
+            c_ptr = pinned_array(L, a_rows + 1, np.uint64, keep)
+            c_idx = pinned_array(L, local_nnz_c, np.uint64, keep)
+            c_val = pinned_array(L, local_nnz_c, np.float64, keep)
 
             def e2e_step():
                 nz = C.c_uint64()
-                S._lib.check(handle.h, L.spam_spgemm_symbolic(handle.h, 1, rows, cols, S._lib.ptr(p_ptr),
-                                                              S._lib.ptr(p_idx), S._lib.ptr(p_val), rows, cols,
+                S._lib.check(handle.h, L.spam_spgemm_symbolic(handle.h, 1, a_rows, cols, S._lib.ptr(pa_ptr),
+                                                              S._lib.ptr(pa_idx), S._lib.ptr(pa_val), rows, cols,
                                                               S._lib.ptr(p_ptr), S._lib.ptr(p_idx), S._lib.ptr(p_val),
                                                               S._lib.ptr(c_ptr), C.byref(nz)))
-                assert nz.value == nnz_c
+                assert nz.value == local_nnz_c
                 S._lib.check(handle.h, L.spam_spgemm_numeric(handle.h, S._lib.ptr(c_idx), S._lib.ptr(c_val), 1))
 
             for _ in range(2):
                 e2e_step()
-            torch.cuda.synchronize()
+            sync_all()
             k = max(3, min(args.steps, 10))
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             for _ in range(k):
                 e2e_step()
             e1.record()
-            torch.cuda.synchronize()
+            sync_all()
             ms_e2e = e0.elapsed_time(e1) / k
+            h2d = (a_rows + 1) * 8 + a_nnz * 16 + (0 if world == 1 else (rows + 1) * 8 + nnz_a * 16)
+            d2h = (a_rows + 1) * 8 + local_nnz_c * 16
+            if world > 1:
+                t = torch.tensor([ms_e2e, -ms_e2e, h2d, d2h], dtype=torch.float64, device=dev)
+                tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+                dist.all_reduce(t, op=dist.ReduceOp.SUM)
+                ms_e2e, h2d, d2h = float(tmax[0].item()), int(t[2].item()), int(t[3].item())
             line["e2e"] = {"value": 2.0 * flops / (ms_e2e / 1e3) / 1e9, "unit": "GFLOP/s",
-                           "h2d_bytes_per_step": int((rows + 1) * 8 + nnz_a * 16),
-                           "d2h_bytes_per_step": int((rows + 1) * 8 + nnz_c * 16), "ms_per_step": ms_e2e,
-                           "api": "spam_spgemm_symbolic + spam_spgemm_numeric (host u64 indices, pinned buffers; "
-                                  "A aliases B so it is uploaded once)"}
+                           "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e,
+                           "api": "spam_spgemm_symbolic + spam_spgemm_numeric (host u64 indices, pinned buffers; " +
+                                  ("A aliases B so it is uploaded once)" if world == 1 else
+                                   "every rank uploads its row block of A and all of B, downloads its shard of C; "
+                                   "bytes summed over ranks, time = max over ranks)")}
         finally:
             for p in keep:
                 L.spam_host_free(p)

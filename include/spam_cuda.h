@@ -132,6 +132,15 @@ int spam_dok_to_csr_dev(spam_handle* h, int dtype, uint64_t rows, uint64_t cols,
 int spam_rows_to_parts(spam_handle* h, const spam_dcsr* a, const spam_dcsr* b, uint32_t parts,
                        uint64_t* row_starts /* parts+1, host */, uint64_t* total_flops);
 
+/* Same formula on a per-row device-time estimate instead of the raw product count:
+ * cost_i = flop_i * w(flop_i), w = measured time per product of the kernel that rows of that size take
+ * on B200 (team and global-table rows cost 2-4x more per product than one-warp rows).  The reference
+ * balances CPU threads whose cost per product is flat; across GPUs a power-law matrix puts all the
+ * heavy rows into the first block (R-MAT 22 over 8 GPUs: balance 0.78 by flops).
+ * Equivalent to spam_rows_to_parts (up to rounding) when every row is in the same size class (stencils). */
+int spam_rows_to_parts_cost(spam_handle* h, const spam_dcsr* a, const spam_dcsr* b, uint32_t parts,
+                            uint64_t* row_starts /* parts+1, host */, uint64_t* total_flops);
+
 /* add `offset` to every entry of a device u64 array (offset-fixing a rank's row_ptr shard before the
  * all-gather-v); n entries */
 int spam_offset_u64(spam_handle* h, void* d_ptr_u64, uint64_t n, uint64_t offset);

@@ -25,7 +25,7 @@ EXPORTS = [
     "spam_host_free", "spam_spgemm_symbolic", "spam_spgemm_numeric", "spam_spmv", "spam_dok_to_csr",
     "spam_dok_to_csr_fetch", "spam_csr_upload", "spam_dcsr_wrap", "spam_dcsr_info", "spam_dcsr_download",
     "spam_dcsr_free", "spam_dcsr_slice_rows", "spam_spgemm_dev", "spam_spmv_dev", "spam_dok_to_csr_dev",
-    "spam_rows_to_parts", "spam_offset_u64",
+    "spam_rows_to_parts", "spam_rows_to_parts_cost", "spam_offset_u64",
 ]
 
 
@@ -90,6 +90,7 @@ def load():
     L.spam_spmv_dev.argtypes = [vp, vp, vp, vp]
     L.spam_dok_to_csr_dev.argtypes = [vp, i32, u64, u64, u64, vp, vp, vp, C.POINTER(vp)]
     L.spam_rows_to_parts.argtypes = [vp, vp, vp, C.c_uint32, vp, C.POINTER(u64)]
+    L.spam_rows_to_parts_cost.argtypes = [vp, vp, vp, C.c_uint32, vp, C.POINTER(u64)]
     L.spam_offset_u64.argtypes = [vp, vp, u64, u64]
     for name in EXPORTS:
         fn = getattr(L, name)

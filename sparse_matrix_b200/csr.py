@@ -135,11 +135,15 @@ class DeviceCsr:
         check(self.handle.h, self.handle.L.spam_dcsr_slice_rows(self.handle.h, self.p, r0, r1, C.byref(out)))
         return DeviceCsr(self.handle, out)
 
-    def rows_to_parts(self, rhs: "DeviceCsr", parts: int) -> Tuple[np.ndarray, int]:
+    def rows_to_parts(self, rhs: "DeviceCsr", parts: int, balance: str = "flops") -> Tuple[np.ndarray, int]:
+        """Contiguous row blocks by the rows_to_threads formula (mul_hash.rs:51-62), balanced on the raw
+        product counts (`flops`, the reference's rule) or on the device-time estimate (`cost`)."""
+        if balance not in ("flops", "cost"):
+            raise ValueError("balance must be 'flops' or 'cost'")
         starts = np.zeros(parts + 1, dtype=np.uint64)
         total = C.c_uint64()
-        check(self.handle.h, self.handle.L.spam_rows_to_parts(self.handle.h, self.p, rhs.p, parts, ptr(starts),
-                                                              C.byref(total)))
+        fn = self.handle.L.spam_rows_to_parts if balance == "flops" else self.handle.L.spam_rows_to_parts_cost
+        check(self.handle.h, fn(self.handle.h, self.p, rhs.p, parts, ptr(starts), C.byref(total)))
         return starts, total.value
 
     def free(self):

@@ -64,6 +64,31 @@ __global__ void k_partition_points(const u64* __restrict__ ps, u64 m, u32 parts,
   out[t] = lo - 1;  // ps[0] = 0 <= bound so lo >= 1
 }
 
+// Device-time cost of a row of C as a function of its intermediate-product count f (and the length of its
+// A row, which decides the merge bin): f x a per-product weight in 1/16 units.  The weights are the measured
+// time per product of the kernel that takes rows of that size on B200 (symbolic + numeric, R-MAT scale 22,
+// profiles/r01_rmat22_v3_balance.txt): one-warp hash rows are cheapest, team rows pay shared-memory
+// atomics and the bucket sort, global-table rows pay L2 atomics.  Shard times predicted by this table
+// are within 2% of the measured ones.
+__device__ __forceinline__ u32 row_cost_q(u32 f, u64 alen) {
+  u32 w;
+  if (f <= 128) w = 16;           // merge / tiny / smallest hash bin
+  else if (f <= 256) w = 10;
+  else if (f <= 512) w = 13;
+  else if (f <= 1024) w = 18;
+  else if (f <= 4096) w = 20;
+  else if (f <= 8192) w = 25;
+  else w = 44;                    // 32-warp team rows and the global-table bin
+  (void)alen;
+  const u64 c = (u64)f * w;
+  return c > 0xFFFFFFFFull ? 0xFFFFFFFFu : (u32)c;
+}
+
+__global__ void __launch_bounds__(256) k_flop_to_cost(u32* __restrict__ flop, const u64* __restrict__ a_ptr, u64 m) {
+  const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < m) flop[i] = row_cost_q(flop[i], a_ptr[i + 1] - a_ptr[i]);
+}
+
 __global__ void __launch_bounds__(256) k_rebase_ptr(const u64* __restrict__ in, u64* __restrict__ out, u64 n) {
   const u64 base = in[0];
   const u64 stride = (u64)gridDim.x * blockDim.x;
@@ -119,7 +144,7 @@ void finish_timing(spam_handle* h) {
 
 extern "C" {
 
-int spam_cuda_abi_version(void) { return 2; }  // 2: spam_stats bin arrays grew to 16 entries
+int spam_cuda_abi_version(void) { return 3; }  // 2: spam_stats bin arrays grew to 16 entries; 3: spam_rows_to_parts_cost
 
 const char* spam_strerror(int s) {
   switch (s) {
@@ -491,8 +516,8 @@ int spam_dok_to_csr_fetch(spam_handle* h, uint64_t* c_idx, void* c_val) {
 
 /* ---------------- multi-GPU helpers ---------------- */
 
-int spam_rows_to_parts(spam_handle* h, const spam_dcsr* a, const spam_dcsr* b, uint32_t parts, uint64_t* row_starts,
-                       uint64_t* total_flops) {
+static int rows_to_parts_impl(spam_handle* h, const spam_dcsr* a, const spam_dcsr* b, uint32_t parts,
+                              uint64_t* row_starts, uint64_t* total_flops, bool by_cost) {
   if (!h || !a || !b || !row_starts || parts == 0) return spam_fail(h, SPAM_EINVAL, "bad argument");
   if (a->cols != b->rows) return spam_fail(h, SPAM_EDIM, "A.cols != B.rows");
   CKS(set_device(h));
@@ -504,6 +529,11 @@ int spam_rows_to_parts(spam_handle* h, const spam_dcsr* a, const spam_dcsr* b, u
   CKS(dev_alloc_t(h, &d_out, (u64)parts + 1));
   CK(cudaMemsetAsync(h->d_cnt, 0, sizeof(Counters), h->stream));
   CKS(flop_count_dev(h, a, b, flop, false, 0));
+  if (by_cost && m) {
+    k_flop_to_cost<<<(unsigned)((m + 255) / 256), 256, 0, h->stream>>>(flop, a->ptr, m);
+    count_launch(h);
+    CK(cudaGetLastError());
+  }
   CKS(scan_u32_to_u64(h, flop, ps, m, nullptr));
   k_partition_points<<<(parts + 1 + 127) / 128, 128, 0, h->stream>>>(ps, m, parts, d_out);
   count_launch(h);
@@ -515,6 +545,16 @@ int spam_rows_to_parts(spam_handle* h, const spam_dcsr* a, const spam_dcsr* b, u
   if (h->h_cnt->error & 1u) return spam_fail(h, SPAM_EINDEX, "a column index of A is >= rows(B)");
   if (total_flops) *total_flops = h->h_cnt->total_flops;
   return SPAM_OK;
+}
+
+int spam_rows_to_parts(spam_handle* h, const spam_dcsr* a, const spam_dcsr* b, uint32_t parts, uint64_t* row_starts,
+                       uint64_t* total_flops) {
+  return rows_to_parts_impl(h, a, b, parts, row_starts, total_flops, false);
+}
+
+int spam_rows_to_parts_cost(spam_handle* h, const spam_dcsr* a, const spam_dcsr* b, uint32_t parts,
+                            uint64_t* row_starts, uint64_t* total_flops) {
+  return rows_to_parts_impl(h, a, b, parts, row_starts, total_flops, true);
 }
 
 int spam_offset_u64(spam_handle* h, void* d_ptr_u64, uint64_t n, uint64_t offset) {

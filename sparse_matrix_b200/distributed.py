@@ -33,6 +33,14 @@ def partition_rows_from_flops(flop_per_row: np.ndarray, parts: int) -> np.ndarra
     return np.asarray(starts, dtype=np.uint64)
 
 
+def row_cost(flop_per_row: np.ndarray) -> np.ndarray:
+    """Host mirror of the device-time estimate behind spam_rows_to_parts_cost (api.cu row_cost_q):
+    products x a per-product weight (1/16 units) that depends on the size class of the row."""
+    f = flop_per_row.astype(np.uint64)
+    w = np.select([f <= 128, f <= 256, f <= 512, f <= 1024, f <= 4096, f <= 8192], [16, 10, 13, 18, 20, 25], 44)
+    return np.minimum(f * w.astype(np.uint64), np.uint64(0xFFFFFFFF))
+
+
 def replicate(tensors: Sequence[torch.Tensor], src: int = 0) -> float:
     """Broadcast the CSR arrays of B (and A) from `src` to every rank.  Returns seconds (host clock
     around a device sync; setup cost, reported separately from the product)."""

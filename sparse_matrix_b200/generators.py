@@ -38,13 +38,15 @@ def uniform_random(rows: int, cols: int, per_row: int, seed: int = 1, dtype=np.f
     return _csr_from_sorted_keys(rows, cols, keys, v)
 
 
-def poisson2d(n: int, dtype=np.float64):
-    """C2: 5-point Laplacian on an n x n grid, row-major, diagonal 4, off-diagonals -1, sorted columns."""
-    m = n * n
+def poisson2d(n: int, dtype=np.float64, ny: int | None = None):
+    """C2: 5-point Laplacian on an n x n grid (ny lines of n points when `ny` is given), row-major,
+    diagonal 4, off-diagonals -1, sorted columns."""
+    ny = n if ny is None else ny
+    m = n * ny
     i = np.arange(m, dtype=np.int64)
     y, x = i // n, i % n
     cand = np.stack([i - n, i - 1, i, i + 1, i + n], axis=1)
-    ok = np.stack([y > 0, x > 0, np.ones(m, bool), x < n - 1, y < n - 1], axis=1)
+    ok = np.stack([y > 0, x > 0, np.ones(m, bool), x < n - 1, y < ny - 1], axis=1)
     v = np.broadcast_to(np.array([-1, -1, 4, -1, -1], dtype=dtype), (m, 5))
     offsets = np.zeros(m + 1, dtype=np.uint64)
     np.cumsum(ok.sum(axis=1), out=offsets[1:])

@@ -96,3 +96,23 @@ def test_partition_edge_cases(oracle):
         b_off = np.concatenate([[0], np.cumsum(flops)]).astype(np.uint64)
         f, ro = oracle.rows_to_threads(n, a_off, a_idx, b_off, parts)
         assert np.array_equal(f, flops) and np.array_equal(ro, starts)
+
+
+def test_cost_balanced_partition_host_mirror():
+    """spam_rows_to_parts_cost's host mirror: cost = products x a weight between 10 and 44 sixteenths, uniform
+    rows give the flop partition, and on a power-law flop vector the heaviest block holds fewer products."""
+    from sparse_matrix_b200 import distributed as D
+    f = np.arange(0, 40_000, 7, dtype=np.uint64)
+    c = D.row_cost(f)
+    assert c[0] == 0 and np.all(c >= 10 * f) and np.all(c <= 44 * f)
+    assert D.row_cost(np.array([2**31], np.uint64))[0] == 0xFFFFFFFF       # saturates like the device u32
+    uni = np.full(1000, 25, np.uint64)
+    assert np.array_equal(D.partition_rows_from_flops(uni, 8), D.partition_rows_from_flops(D.row_cost(uni), 8))
+    rng = np.random.default_rng(3)
+    pl = np.sort((rng.pareto(1.2, 50_000) * 60).astype(np.uint64) + 1)[::-1].copy()   # heavy rows first, like R-MAT
+    by_f = D.partition_rows_from_flops(pl, 8).astype(np.int64)
+    by_c = D.partition_rows_from_flops(D.row_cost(pl), 8).astype(np.int64)
+    assert by_c[1] < by_f[1]                         # the first (heaviest) block shrinks
+    cost = D.row_cost(pl).astype(np.float64)
+    blocks = lambda st: np.array([cost[st[i]:st[i + 1]].sum() for i in range(8)])
+    assert blocks(by_c).max() <= blocks(by_f).max()

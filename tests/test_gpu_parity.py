@@ -12,6 +12,7 @@ import numpy as np
 import pytest
 
 import sparse_matrix_b200 as S
+from sparse_matrix_b200 import distributed as D
 from sparse_matrix_b200 import generators as G
 from util import TOL, as_csr_matrix, check_against_oracle, random_csr
 
@@ -345,6 +346,9 @@ def test_rows_to_parts_and_row_slices(oracle, handle):
         starts, total = dA.rows_to_parts(dA, parts)
         flop, ro = oracle.rows_to_threads(r[0], r[2], r[3], r[2], parts)
         assert np.array_equal(starts, ro) and total == int(flop.sum())
+        # the device-time-balanced variant: same formula on cost_i = flop_i * w(flop_i)
+        cstarts, ctotal = dA.rows_to_parts(dA, parts, balance="cost")
+        assert np.array_equal(cstarts, D.partition_rows_from_flops(D.row_cost(flop), parts)) and ctotal == total
         offs, idxs, vals = [np.zeros(1, np.uint64)], [], []
         for t in range(parts):
             blk = dA.slice_rows(int(starts[t]), int(starts[t + 1]))
