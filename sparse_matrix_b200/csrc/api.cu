@@ -89,6 +89,33 @@ __global__ void __launch_bounds__(256) k_flop_to_cost(u32* __restrict__ flop, co
   if (i < m) flop[i] = row_cost_q(flop[i], a_ptr[i + 1] - a_ptr[i]);
 }
 
+// Column range of A (= the rows of B the product can touch): max into work_b, min as max(~col) into work_a,
+// both zeroed by the caller.
+__global__ void __launch_bounds__(256) k_col_range(const u32* __restrict__ idx, u64 nnz, Counters* cnt) {
+  u32 mx = 0, nmn = 0;
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < nnz; i += stride) {
+    const u32 c = idx[i];
+    mx = max(mx, c);
+    nmn = max(nmn, ~c);
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+    nmn = max(nmn, __shfl_xor_sync(0xffffffffu, nmn, d));
+  }
+  if ((threadIdx.x & 31) == 0) { atomicMax(&cnt->work_b, mx); atomicMax(&cnt->work_a, nmn); }
+}
+
+// row_ptr of a matrix of which only rows [r0, r1) were uploaded (entries r0..r1 of the host array sit at
+// ptr[r0..r1], still absolute): rebase them and make every other row empty.
+__global__ void __launch_bounds__(256) k_window_ptr(u64* __restrict__ ptr, u64 n_entries, u64 r0, u64 r1, u64 base,
+                                                    u64 nnz_w) {
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_entries; i += stride)
+    ptr[i] = i < r0 ? 0 : (i > r1 ? nnz_w : ptr[i] - base);
+}
+
 __global__ void __launch_bounds__(256) k_rebase_ptr(const u64* __restrict__ in, u64* __restrict__ out, u64 n) {
   const u64 base = in[0];
   const u64 stride = (u64)gridDim.x * blockDim.x;
@@ -288,6 +315,63 @@ int spam_csr_upload(spam_handle* h, int dtype, uint64_t rows, uint64_t cols, uin
   return SPAM_OK;
 }
 
+// Upload only rows [r0, r1) of a host CSR matrix; the device matrix keeps its full shape with every
+// other row empty.  Used for B when A references a narrow band of its rows (a row block of a banded
+// matrix times the whole matrix: each GPU of a row-sharded product needs only its halo of B).
+static int upload_csr_window(spam_handle* h, int dtype, u64 rows, u64 cols, const u64* ptr, const u64* idx,
+                             const void* val, u64 r0, u64 r1, spam_dcsr** out) {
+  *out = nullptr;
+  if (rows >= 0xFFFFFFFFull || cols >= 0xFFFFFFFFull) return spam_fail(h, SPAM_ECOLS, "dimension >= 2^32-1");
+  const u64 base = ptr[r0], nnz_w = ptr[r1] - base;
+  const size_t es = dtype_size(dtype);
+  spam_dcsr* m = new spam_dcsr();
+  m->dtype = dtype; m->rows = rows; m->cols = cols; m->nnz = nnz_w; m->owning = true; m->rows_sorted = -1; m->max_row_len = 0;
+  m->ptr = nullptr; m->idx = nullptr; m->val = nullptr;
+  u64* tmp = nullptr;
+  int st = dev_alloc_t(h, &m->ptr, rows + 1);
+  if (st == SPAM_OK) st = dev_alloc_t(h, &m->idx, nnz_w);
+  if (st == SPAM_OK) st = dev_alloc(h, &m->val, nnz_w * es);
+  if (st == SPAM_OK) st = dev_alloc_t(h, &tmp, nnz_w);
+  cudaError_t e = cudaSuccess;
+  if (st == SPAM_OK) {
+    e = cudaMemcpyAsync(m->ptr + r0, ptr + r0, (r1 - r0 + 1) * sizeof(u64), cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess && nnz_w) e = cudaMemcpyAsync(tmp, idx + base, nnz_w * sizeof(u64), cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess && nnz_w)
+      e = cudaMemcpyAsync(m->val, (const char*)val + base * es, nnz_w * es, cudaMemcpyHostToDevice, h->stream);
+    if (e != cudaSuccess) st = spam_fail(h, SPAM_ECUDA, "cudaMemcpyAsync H2D", e);
+  }
+  if (st == SPAM_OK) {
+    const u64 nb = (rows + 1 + 255) / 256;
+    k_window_ptr<<<(unsigned)(nb > 2048 ? 2048 : nb), 256, 0, h->stream>>>(m->ptr, rows + 1, r0, r1, base, nnz_w);
+    count_launch(h);
+    if ((e = cudaGetLastError()) != cudaSuccess) st = spam_fail(h, SPAM_ECUDA, "k_window_ptr", e);
+  }
+  if (st == SPAM_OK) st = narrow_u64_to_u32(h, tmp, m->idx, nnz_w);
+  dev_free(h, tmp);
+  if (st != SPAM_OK) { free_dcsr(h, m); return st; }
+  h->stats.bytes_h2d += (r1 - r0 + 1) * 8 + nnz_w * (8 + es);
+  *out = m;
+  return SPAM_OK;
+}
+
+// Rows of B that A's columns reference: [*r0, *r1).  One small kernel + one sync.
+static int referenced_rows(spam_handle* h, const spam_dcsr* a, u64 b_rows, u64* r0, u64* r1) {
+  *r0 = 0; *r1 = 0;
+  if (a->nnz == 0) return SPAM_OK;
+  CK(cudaMemsetAsync(h->d_cnt, 0, sizeof(Counters), h->stream));
+  const u64 nb = (a->nnz + 255) / 256;
+  k_col_range<<<(unsigned)(nb > 1184 ? 1184 : nb), 256, 0, h->stream>>>(a->idx, a->nnz, h->d_cnt);
+  count_launch(h);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(h->h_cnt, h->d_cnt, sizeof(Counters), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  const u64 cmin = (u32)~h->h_cnt->work_a, cmax = h->h_cnt->work_b;
+  *r0 = cmin < b_rows ? cmin : b_rows;
+  *r1 = cmax + 1 < b_rows ? cmax + 1 : b_rows;  // an out-of-range column is reported by the flop count (SPAM_EINDEX)
+  if (*r1 < *r0) *r1 = *r0;
+  return SPAM_OK;
+}
+
 int spam_dcsr_wrap(spam_handle* h, int dtype, uint64_t rows, uint64_t cols, uint64_t nnz, const void* d_ptr,
                    const void* d_idx, const void* d_val, spam_dcsr** out) {
   if (!h || !out || !d_ptr || !valid_dtype(dtype)) return spam_fail(h, SPAM_EINVAL, "bad argument");
@@ -397,8 +481,18 @@ int spam_spgemm_symbolic(spam_handle* h, int dtype, uint64_t a_rows, uint64_t a_
   int st = spam_csr_upload(h, dtype, a_rows, a_cols, a_nnz, a_ptr, a_idx, a_val, &s->a);
   const bool alias = (b_ptr == a_ptr && b_idx == a_idx && b_val == a_val && b_rows == a_rows && b_cols == a_cols);
   if (st == SPAM_OK) {
-    if (alias) s->b = s->a;
-    else st = spam_csr_upload(h, dtype, b_rows, b_cols, b_nnz, b_ptr, b_idx, b_val, &s->b);
+    if (alias) {
+      s->b = s->a;
+    } else {
+      // A touches rows [r0, r1) of B only: when that is a narrow band (a row block of a banded matrix), upload
+      // just the band over PCIe
+      u64 r0 = 0, r1 = b_rows;
+      st = referenced_rows(h, s->a, b_rows, &r0, &r1);
+      if (st == SPAM_OK) {
+        if ((r1 - r0) < b_rows - b_rows / 8) st = upload_csr_window(h, dtype, b_rows, b_cols, b_ptr, b_idx, b_val, r0, r1, &s->b);
+        else st = spam_csr_upload(h, dtype, b_rows, b_cols, b_nnz, b_ptr, b_idx, b_val, &s->b);
+      }
+    }
   }
   const u64 h2d = h->stats.bytes_h2d;
   (void)keep;

@@ -364,6 +364,31 @@ def test_rows_to_parts_and_row_slices(oracle, handle):
     dA.free()
 
 
+def test_host_path_uploads_only_the_referenced_band_of_b(oracle, handle):
+    """A row block of a banded matrix times the whole matrix through the host C ABI: only the rows of B that
+    A's columns reference travel over PCIe (the other rows are empty on the device), the product is the same."""
+    p = G.poisson2d(64)
+    full = as_csr_matrix(p)
+    for r0, r1 in ((640, 1280), (0, 64), (4000, 4096), (100, 101)):
+        lo, hi = int(p[2][r0]), int(p[2][r1])
+        a = (r1 - r0, p[1], (p[2][r0:r1 + 1] - p[2][r0]).astype(np.uint64), p[3][lo:hi].copy(), p[4][lo:hi].copy())
+        c = as_csr_matrix(a).mul_hash(full, sorted_output=True, handle=handle)
+        check_against_oracle(oracle, a, p, c, exact_values=True)     # merge bin: bit-identical floats
+        h2d = handle.stats()["bytes_h2d"]
+        whole_b = (p[0] + 1) * 8 + len(p[3]) * 16
+        assert h2d < 0.5 * whole_b, (h2d, whole_b)
+    # a block that references (almost) every row of B takes the plain upload
+    a = random_csr(np.random.default_rng(5), 50, p[0], np.full(50, 40), dtype=np.float64)
+    c = as_csr_matrix(a).mul_hash(full, sorted_output=True, handle=handle)
+    check_against_oracle(oracle, a, p, c)
+    assert handle.stats()["bytes_h2d"] > (p[0] + 1) * 8 + len(p[3]) * 16
+    # A with no entries at all, and A whose only column is the last row of B
+    e = S.CsrMatrix.new((3, p[0])).mul_hash(full, sorted_output=True, handle=handle)
+    assert e.nnz() == 0 and e.offsets.tolist() == [0, 0, 0, 0]
+    a = (2, p[0], np.array([0, 1, 1], np.uint64), np.array([p[0] - 1], np.uint64), np.array([2.0]))
+    check_against_oracle(oracle, a, p, as_csr_matrix(a).mul_hash(full, sorted_output=True, handle=handle), exact_values=True)
+
+
 def test_scan_sizes_through_dok_row_ptr(oracle, handle):
     """The look-back scan at awkward lengths (around tile and warp boundaries) via DOK row_ptr."""
     rng = np.random.default_rng(4)
