@@ -11,6 +11,7 @@
 
 #include "../../include/spam_cuda.h"
 
+typedef uint16_t u16;
 typedef uint32_t u32;
 typedef uint64_t u64;
 typedef unsigned long long ull;

@@ -21,8 +21,9 @@
 //  * SORT.  The B2 = true branch (mul_hash.rs:164-175) as a shared-memory bitonic network was as expensive
 //    as the accumulation (NW = 1) or 85% of the kernel (block per row on R-MAT).  NW = 1: (column, index)
 //    packed in one u32 and sorted in registers by warp shuffles.  NW > 1: occupied slots are counted into
-//    npow2(z) order-preserving buckets over the row's column range, scanned, scattered straight into C,
-//    and each short bucket is finished by insertion sort.
+//    order-preserving buckets over the row's column range, scanned, their slot indices scattered bucket by
+//    bucket inside shared memory, and every entry then ranks itself among the 1-2 entries of its bucket
+//    and stores (key, value) at its final place in C (one nearly coalesced pass over C).
 //  * SHARED MEMORY THROUGH EXPLICIT 32-BIT SHARED ADDRESSES (ld/st/atom.shared): with generic pointers
 //    the compiler re-derived the shared window (S2R SR_CgaCtaId + LEA) in every loop iteration.
 #pragma once
@@ -445,11 +446,13 @@ __device__ __forceinline__ void accumulate_fold(u32 kbase, u32 vbase, u32 mask, 
   __syncwarp();
 }
 
-// team kernels: number of drain buckets (CAP while that does not cost a resident block, else CAP/2)
+// team kernels: number of drain buckets, as many as fit without costing a resident block
+// (per block: table CAP * (4 + sizeof V), counters (NBMAX + 1) * 4, ord CAP/2 * 2 bytes)
 template <class V, int NW, int CAP>
 struct NumRowCfg {
-  static constexpr int NBMAX = CAP <= 4096 ? CAP : CAP / 2;
+  static constexpr int NBMAX = CAP == 4096 ? CAP : (CAP <= 2048 ? CAP / 2 : CAP / 4);
 };
+constexpr u32 RANK_BUCKET_MAX = 512;  // longest bucket ranked by counting; beyond: whole-row bitonic fallback
 
 template <class V, int NW, int CAP, bool DIRECT>
 __global__ void __launch_bounds__(NW == 1 ? 32 * ROWS_PER_BLOCK_W1 : 32 * NW)
@@ -464,7 +467,6 @@ k_num_row(u32 n, const u32* __restrict__ perm, const u64* __restrict__ a_ptr, co
   extern __shared__ __align__(16) unsigned char sm_num_raw[];
   __shared__ u32 s_warp[32];
   __shared__ u32 s_kmin, s_kmax, s_maxcnt;
-  __shared__ u32 s_big[NW == 1 ? 1 : BIG_QUEUE];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const u32 item = NW == 1 ? blockIdx.x * RPB + wid : blockIdx.x;
   if (item >= n) return;
@@ -481,6 +483,10 @@ k_num_row(u32 n, const u32* __restrict__ perm, const u64* __restrict__ a_ptr, co
   if (cap > (u32)CAP) cap = CAP;
   const u32 mask = cap - 1, shift = 32 - (31 - __clz(cap));
   for (u32 s = rt; s < cap; s += TT) { sts32(kbase + 4u * s, EMPTY_KEY); if (NW > 1) vals[s] = Num<V>::zero(); }
+  if (NW > 1) {
+    for (u32 b = rt; b <= (u32)NumRowCfg<V, NW, CAP>::NBMAX; b += TT) cnt[b] = 0;  // drain bucket counters
+    if (threadIdx.x == 0) { s_kmin = 0xFFFFFFFFu; s_kmax = 0; s_maxcnt = 0; }
+  }
   if (NW == 1) __syncwarp(); else __syncthreads();
 
   const u64 lo = a_ptr[row], hi = a_ptr[row + 1];
@@ -593,13 +599,16 @@ k_num_row(u32 n, const u32* __restrict__ perm, const u64* __restrict__ a_ptr, co
     return;
   }
 
-  // ---- NW > 1: bucket drain straight into C --------------------------------------------------
+  // ---- NW > 1: order-preserving bucket drain -------------------------------------------------
+  // The occupied slots are counted into NB buckets over the row's own column range, the counts scanned,
+  // and the SLOT INDICES scattered bucket by bucket into `ord` (shared memory).  Then every entry finds its
+  // rank inside its bucket by counting the smaller keys of that bucket (mostly 1-2 entries) and stores
+  // (key, value) at its final position in C.  C is written once, nearly coalesced; nothing is sorted in
+  // global memory (the previous version scattered into C and re-sorted the buckets there: 60% of the
+  // kernel's instructions and two thirds of its stall samples, profiles/r01_rmat20_v3_team_drain.txt).
   __syncthreads();
-  if (threadIdx.x == 0) { s_kmin = 0xFFFFFFFFu; s_kmax = 0; s_maxcnt = 0; }
-  // 2*npow2(z) buckets (about one entry per two buckets) where the counter array fits, else npow2(z)
-  const u32 NB = NumRowCfg<V, NW, CAP>::NBMAX == CAP ? cap : npow2_u32(z);
-  for (u32 b = rt; b <= NB; b += TT) cnt[b] = 0;
-  __syncthreads();
+  const u32 NB = min(cap, (u32)NumRowCfg<V, NW, CAP>::NBMAX);
+  u16* ord = reinterpret_cast<u16*>(cnt + NumRowCfg<V, NW, CAP>::NBMAX + 1);  // [CAP/2] slot index of the i-th entry
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) {
     kmin = min(kmin, __shfl_xor_sync(FULL, kmin, d));
@@ -613,7 +622,7 @@ k_num_row(u32 n, const u32* __restrict__ perm, const u64* __restrict__ a_ptr, co
   const int rbits = range ? 32 - __clz(range) : 0;
   const int bshift = rbits > lgnb ? rbits - lgnb : 0;
   for (u32 s = rt; s < cap; s += TT) {
-    const u32 kk = keys[s];
+    const u32 kk = lds32(kbase + 4u * s);
     if (kk != EMPTY_KEY) atomicAdd(&cnt[(kk - kmin) >> bshift], 1u);
   }
   __syncthreads();
@@ -624,42 +633,39 @@ k_num_row(u32 n, const u32* __restrict__ perm, const u64* __restrict__ a_ptr, co
     for (u32 b = b0; b < b1; ++b) { const u32 cc = cnt[b]; sum += cc; mx = max(mx, cc); }
     const u32 x = warp_incl_scan_u32(sum, lane);
     if (lane == 31) s_warp[wid] = x;
+    mx = max(mx, __shfl_xor_sync(FULL, mx, 16));
+    mx = max(mx, __shfl_xor_sync(FULL, mx, 8));
+    mx = max(mx, __shfl_xor_sync(FULL, mx, 4));
+    mx = max(mx, __shfl_xor_sync(FULL, mx, 2));
+    mx = max(mx, __shfl_xor_sync(FULL, mx, 1));
+    if (lane == 0 && mx) atomicMax(&s_maxcnt, mx);
     __syncthreads();
     u32 woff = 0;
     for (int w = 0; w < wid; ++w) woff += s_warp[w];
     u32 runb = woff + x - sum;
     for (u32 b = b0; b < b1; ++b) { const u32 cc = cnt[b]; cnt[b] = runb; runb += cc; }
-    if (mx) atomicMax(&s_maxcnt, mx);
   }
   __syncthreads();
-  if (s_maxcnt <= BIG_BUCKET_MAX) {
+  if (s_maxcnt <= RANK_BUCKET_MAX) {
     for (u32 s = rt; s < cap; s += TT) {
-      const u32 kk = keys[s];
+      const u32 kk = lds32(kbase + 4u * s);
       if (kk != EMPTY_KEY) {
         const u32 pos = atomicAdd(&cnt[(kk - kmin) >> bshift], 1u);  // afterwards cnt[b] = end of bucket b
-        c_col[c0 + pos] = kk;
-        c_val[c0 + pos] = vals[s];
+        ord[pos] = (u16)s;
       }
     }
-    if (threadIdx.x == 0) s_kmax = 0;  // reused: number of long buckets queued for the warps
     __syncthreads();
-    // short buckets: one thread each; long ones (power-law columns crowd the low end of the range) are
-    // queued and rank-sorted by a whole warp
-    for (u32 b = rt; b < NB; b += TT) {
+    for (u32 p = rt; p < z; p += TT) {
+      const u32 s = ord[p];
+      const u32 kk = lds32(kbase + 4u * s);
+      const u32 b = (kk - kmin) >> bshift;
       const u32 lo_b = b ? cnt[b - 1] : 0u, hi_b = cnt[b];
-      if (hi_b - lo_b > SMALL_BUCKET_MAX) {
-        const u32 q = atomicAdd(&s_kmax, 1u);
-        if (q < BIG_QUEUE) s_big[q] = b; else insertion_sort_bucket<V>(c_col, c_val, c0, lo_b, hi_b);
-        continue;
+      u32 rank = 0;
+      if (hi_b - lo_b > 1) {
+        for (u32 j = lo_b; j < hi_b; ++j) rank += (lds32(kbase + 4u * (u32)ord[j]) < kk) ? 1u : 0u;
       }
-      sort_small_bucket<V>(c_col, c_val, c0, lo_b, hi_b);
-    }
-    __syncthreads();
-    const u32 nbig = min(s_kmax, (u32)BIG_QUEUE);
-    for (u32 q = rw; q < nbig; q += NW) {
-      const u32 b = s_big[q];
-      const u32 lo_b = b ? cnt[b - 1] : 0u, hi_b = cnt[b];
-      rank_sort_bucket_warp<V>(c_col, c_val, c0 + lo_b, hi_b - lo_b, lane);
+      c_col[c0 + lo_b + rank] = kk;
+      c_val[c0 + lo_b + rank] = SV<V>::ld(vbase + SZ * s);
     }
   } else {
     // pathological column distribution: compact in shared memory and run the bitonic network
@@ -700,7 +706,7 @@ k_num_row(u32 n, const u32* __restrict__ perm, const u64* __restrict__ a_ptr, co
 template <class V, int NW, int CAP>
 constexpr size_t num_row_smem() {
   return NW == 1 ? (size_t)ROWS_PER_BLOCK_W1 * CAP * (sizeof(V) + 4)
-                 : (size_t)CAP * (sizeof(V) + 4) + (size_t)(NumRowCfg<V, NW, CAP>::NBMAX + 1) * 4;
+                 : (size_t)CAP * (sizeof(V) + 4) + (size_t)(NumRowCfg<V, NW, CAP>::NBMAX + 1) * 4 + (size_t)CAP;
 }
 
 }  // namespace
