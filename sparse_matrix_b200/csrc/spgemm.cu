@@ -417,18 +417,18 @@ __global__ void __launch_bounds__(T) k_num_heavy(u32 n, const u32* __restrict__ 
                                                  const u64* __restrict__ b_ptr, const u32* __restrict__ b_col,
                                                  const V* __restrict__ b_val, const u64* __restrict__ c_ptr,
                                                  u32* __restrict__ c_col, V* __restrict__ c_val, u32* key_tables,
-                                                 V* val_tables, u64 table_stride, u32* cnt_tables, u32 b_cols,
-                                                 u32* work, int wshift) {
+                                                 V* val_tables, u64 table_stride, u32* cnt_tables, u32* ord_tables,
+                                                 u32 b_cols, u32* work) {
   constexpr int ITEMS = 4;
-  constexpr int HEAVY_QUEUE = 2048;  // long buckets queued per heavy row
-  __shared__ u32 s_item, s_maxcnt, s_nbig;
+  constexpr u32 HEAVY_RANK_MAX = 2048;  // longest bucket ranked by counting; beyond: bitonic fallback
+  __shared__ u32 s_item, s_maxcnt;
   __shared__ u32 s_warp[32];
-  __shared__ u32 s_big[HEAVY_QUEUE];
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, wid = tid >> 5, ln = tid & 31;
   u32* keys = key_tables + (u64)blockIdx.x * table_stride;
   V* vals = val_tables + (u64)blockIdx.x * table_stride;
   u32* cnt = cnt_tables + (u64)blockIdx.x * (table_stride / 2 + 1);  // [npow2(z) + 1] bucket counters
-  const int W = 1 << wshift, sub = tid >> wshift, lane = tid & (W - 1), nsub = T >> wshift;
+  u32* okey = ord_tables + (u64)blockIdx.x * table_stride;           // [z] keys in bucket order
+  u32* ord = okey + table_stride / 2;                                // [z] their table slots
   for (;;) {
     if (tid == 0) s_item = atomicAdd(work, 1u);
     __syncthreads();
@@ -440,42 +440,47 @@ __global__ void __launch_bounds__(T) k_num_heavy(u32 n, const u32* __restrict__ 
     const u32 z = (u32)(c_ptr[row + 1] - c0);
     if (z == 0) continue;
     const u64 cap = 2ull * npow2_u64(z), mask = cap - 1; const int hshift = 64 - (63 - __clzll((long long)cap));
+    const u32 NB = npow2_u32(z);
     for (u64 s = tid; s < cap; s += T) { __stcg(&keys[s], EMPTY_KEY); __stcg(&vals[s], Num<V>::zero()); }
+    for (u32 b = tid; b <= NB; b += T) __stcg(&cnt[b], 0u);
+    if (tid == 0) s_maxcnt = 0;
     __syncthreads();
+    // FLAT enumeration (rowhash.cuh): the products of 32 A entries are spread evenly over the block's lanes,
+    // whatever the B row lengths (a sub-warp per A entry left a quarter of the kernel waiting at the
+    // barrier below for the warps that drew the hub rows: profiles/r01_rmat20_v3_team_drain.txt)
     const u64 lo = a_ptr[row], hi = a_ptr[row + 1];
-    for (u64 e = lo + sub; e < hi; e += nsub) {
-      const u32 k = a_col[e];
-      const V av = a_val[e];
-      const u64 bl = b_ptr[k], bh = b_ptr[k + 1];
-      for (u64 j = bl + lane; j < bh; j += W) {
-        const u32 key = b_col[j];
-        const V prod = Num<V>::mul(av, b_val[j]);
-        u64 s = ((u64)key * 11400714819323198485ull) >> hshift;
-        for (;;) {
-          const u32 cur = __ldcg(&keys[s]);
-          if (cur != key) {
-            if (cur != EMPTY_KEY) { s = (s + 1) & mask; continue; }
-            const u32 old = atomicCAS(&keys[s], EMPTY_KEY, key);
-            if (old != EMPTY_KEY && old != key) { s = (s + 1) & mask; continue; }
+    for (u64 ec = lo; ec < hi; ec += 32) {
+      const AChunk<V> c = load_chunk<V, true, true>(ec, hi, ln, a_col, a_val, b_ptr);
+      for (u32 p0 = 32u * wid; p0 < c.total; p0 += T) {
+        u64 addr;
+        V av;
+        locate<V, true>(c, p0 + ln, addr, av);
+        if (p0 + ln < c.total) {
+          const u32 key = b_col[addr];
+          const V prod = Num<V>::mul(av, b_val[addr]);
+          u64 s = ((u64)key * 11400714819323198485ull) >> hshift;
+          for (;;) {
+            const u32 cur = __ldcg(&keys[s]);
+            if (cur != key) {
+              if (cur != EMPTY_KEY) { s = (s + 1) & mask; continue; }
+              const u32 old = atomicCAS(&keys[s], EMPTY_KEY, key);
+              if (old != EMPTY_KEY && old != key) { s = (s + 1) & mask; continue; }
+            }
+            Num<V>::atomic_add(&vals[s], prod);
+            break;
           }
-          Num<V>::atomic_add(&vals[s], prod);
-          break;
         }
       }
     }
     __syncthreads();
-    // drain + sort by column straight into C: count the occupied slots into NB = npow2(z)
-    // order-preserving buckets over the column range, scan, scatter (rank = atomic cursor), then
-    // finish each short bucket with an insertion sort in C.  Falls back to compaction + bitonic
-    // network when some bucket is far longer than average.
-    const u32 NB = npow2_u32(z);
+    // drain, sorted by column: count the occupied slots into NB = npow2(z) order-preserving buckets over the
+    // column range, scan, scatter (key, slot) bucket by bucket into scratch, then every entry ranks itself
+    // inside its bucket and stores (key, value) at its final place in C: one coalesced pass over C.
+    // Falls back to compaction + bitonic network when some bucket is far longer than average.
     {
       const int lgnb = 31 - __clz(NB);
       const int rbits = b_cols > 1 ? 32 - __clz(b_cols - 1) : 0;
       const int bshift = rbits > lgnb ? rbits - lgnb : 0;
-      for (u32 b = tid; b <= NB; b += T) __stcg(&cnt[b], 0u);
-      if (tid == 0) s_maxcnt = 0;
-      __syncthreads();
       for (u64 s = tid; s < cap; s += T) {
         const u32 kk = __ldcg(&keys[s]);
         if (kk != EMPTY_KEY) atomicAdd(&cnt[kk >> bshift], 1u);
@@ -490,32 +495,26 @@ __global__ void __launch_bounds__(T) k_num_heavy(u32 n, const u32* __restrict__ 
       for (u32 b = b0; b < b1; ++b) { const u32 c = __ldcg(&cnt[b]); __stcg(&cnt[b], runb); runb += c; }
       if (mx) atomicMax(&s_maxcnt, mx);
       __syncthreads();
-      if (s_maxcnt <= BIG_BUCKET_MAX) {
+      if (s_maxcnt <= HEAVY_RANK_MAX) {
         for (u64 s = tid; s < cap; s += T) {
           const u32 kk = __ldcg(&keys[s]);
           if (kk != EMPTY_KEY) {
             const u32 pos = atomicAdd(&cnt[kk >> bshift], 1u);  // afterwards cnt[b] = end of bucket b
-            c_col[c0 + pos] = kk;
-            c_val[c0 + pos] = __ldcg(&vals[s]);
+            __stcg(&okey[pos], kk);
+            __stcg(&ord[pos], (u32)s);
           }
         }
-        if (tid == 0) s_nbig = 0;
         __syncthreads();
-        for (u32 b = tid; b < NB; b += T) {
+        for (u32 p = tid; p < z; p += T) {
+          const u32 kk = __ldcg(&okey[p]);
+          const u32 b = kk >> bshift;
           const u32 lo_b = b ? __ldcg(&cnt[b - 1]) : 0u, hi_b = __ldcg(&cnt[b]);
-          if (hi_b - lo_b > SMALL_BUCKET_MAX) {
-            const u32 q = atomicAdd(&s_nbig, 1u);
-            if (q < (u32)HEAVY_QUEUE) s_big[q] = b; else insertion_sort_bucket<V>(c_col, c_val, c0, lo_b, hi_b);
-            continue;
+          u32 rank = 0;
+          if (hi_b - lo_b > 1) {
+            for (u32 j = lo_b; j < hi_b; ++j) rank += (__ldcg(&okey[j]) < kk) ? 1u : 0u;
           }
-          sort_small_bucket<V>(c_col, c_val, c0, lo_b, hi_b);
-        }
-        __syncthreads();
-        const u32 nbig = min(s_nbig, (u32)HEAVY_QUEUE);
-        for (u32 q = tid >> 5; q < nbig; q += T / 32) {
-          const u32 b = s_big[q];
-          const u32 lo_b = b ? __ldcg(&cnt[b - 1]) : 0u, hi_b = __ldcg(&cnt[b]);
-          rank_sort_bucket_warp<V>(c_col, c_val, c0 + lo_b, hi_b - lo_b, tid & 31);
+          c_col[c0 + lo_b + rank] = kk;
+          c_val[c0 + lo_b + rank] = __ldcg(&vals[__ldcg(&ord[p])]);
         }
         __syncthreads();
         continue;
@@ -845,7 +844,6 @@ int numeric_typed(spam_handle* h, SpgemmPending* p, spam_dcsr* c) {
   const u64* bp = b->ptr; const u32* bc = b->idx; const V* bv = (const V*)b->val;
   const u64* cp = c->ptr; u32* cc = c->idx; V* cv = (V*)c->val;
   auto seg = [&](int bin) -> const u32* { return nb.perm ? nb.perm + nb.base[bin] : nullptr; };
-  const int ws = wshift_for(b, 5);
   if (nb.count[MERGE_BIN]) {
     constexpr int BL = 128;
     constexpr size_t smem = num_merge_smem<V, BL>();
@@ -898,7 +896,7 @@ int numeric_typed(spam_handle* h, SpgemmPending* p, spam_dcsr* c) {
   LAUNCH_NUM_ROW(8, 32, 16384, false)
 #undef LAUNCH_NUM_ROW
   CK(cudaGetLastError());
-  u32 *hk = nullptr, *hc = nullptr;
+  u32 *hk = nullptr, *hc = nullptr, *ho = nullptr;
   V* hv = nullptr;
   if (nb.count[HEAVY_BIN]) {
     u32 zmax = p->max_nnz;
@@ -906,15 +904,18 @@ int numeric_typed(spam_handle* h, SpgemmPending* p, spam_dcsr* c) {
     u64 nblk = (u64)h->num_sms * 2;
     if (nblk > nb.count[HEAVY_BIN]) nblk = nb.count[HEAVY_BIN];
     const u64 budget = 16ull << 30;
-    while (nblk > 1 && nblk * stride * (sizeof(u32) + sizeof(V)) > budget) nblk /= 2;
+    // per block: keys + values (stride each), bucket counters (stride/2), bucket-ordered keys + slots (stride)
+    while (nblk > 1 && nblk * stride * (2 * sizeof(u32) + sizeof(V) + 2) > budget) nblk /= 2;
     CKS(dev_alloc_t(h, &hk, nblk * stride));
     CKS(dev_alloc_t(h, &hv, nblk * stride));
     CKS(dev_alloc_t(h, &hc, nblk * (stride / 2 + 1)));
+    CKS(dev_alloc_t(h, &ho, nblk * stride));
     k_num_heavy<V, 1024><<<(unsigned)nblk, 1024, 0, h->stream>>>(nb.count[HEAVY_BIN], seg(HEAVY_BIN), ap, ac, av, bp, bc, bv, cp, cc, cv, hk,
-                                                                hv, stride, hc, (u32)b->cols, &h->d_cnt->work_b, ws);
+                                                                hv, stride, hc, ho, (u32)b->cols, &h->d_cnt->work_b);
     count_launch(h);
     CK(cudaGetLastError());
   }
+  if (ho) CKS(dev_free(h, ho));
   if (hc) CKS(dev_free(h, hc));
   if (hk) CKS(dev_free(h, hk));
   if (hv) CKS(dev_free(h, hv));
