@@ -783,7 +783,7 @@ int spgemm_symbolic_dev(spam_handle* h, const spam_dcsr* a, const spam_dcsr* b, 
       LAUNCH_SYM_ROW(1, 1, 256, false)
       LAUNCH_SYM_ROW(2, 1, 512, false)
       LAUNCH_SYM_ROW(3, 1, 1024, false)
-      LAUNCH_SYM_ROW(4, 1, 2048, false)
+      LAUNCH_SYM_ROW(4, 4, 2048, false)  // 4 rows x 8 KB per block left 28 warps per SM; a team per row runs 64
     }
     LAUNCH_SYM_ROW(5, 4, 4096, false)
     LAUNCH_SYM_ROW(6, 8, 8192, false)
@@ -886,13 +886,15 @@ int numeric_typed(spam_handle* h, SpgemmPending* p, spam_dcsr* c) {
     LAUNCH_NUM_ROW(1, 1, 128, false)
     LAUNCH_NUM_ROW(2, 1, 256, false)
     LAUNCH_NUM_ROW(3, 1, 512, false)
-    LAUNCH_NUM_ROW(4, 1, 1024, false)
+    // z in (256, 512]: one warp per row leaves 16 warps per SM (4 rows x 12 KB per block); a 4-warp team with the
+    // bucket drain runs 48
+    LAUNCH_NUM_ROW(4, 4, 1024, false)
   }
   // team sizes: these kernels are latency-bound (dependent shared-memory and shuffle chains), so the
   // big-table bins get many warps per row: G4's 224 KB table allows one block per SM, give it 32 warps
-  LAUNCH_NUM_ROW(5, 4, 2048, false)
-  LAUNCH_NUM_ROW(6, 8, 4096, false)
-  LAUNCH_NUM_ROW(7, 16, 8192, false)
+  LAUNCH_NUM_ROW(5, 8, 2048, false)
+  LAUNCH_NUM_ROW(6, 16, 4096, false)
+  LAUNCH_NUM_ROW(7, 24, 8192, false)
   LAUNCH_NUM_ROW(8, 32, 16384, false)
 #undef LAUNCH_NUM_ROW
   CK(cudaGetLastError());

@@ -5,6 +5,8 @@ Every generator returns a csr.CsrMatrix-compatible tuple (rows, cols, offsets u6
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 
 
@@ -79,19 +81,38 @@ def stencil27(n: int, dtype=np.float64):
 def rmat(scale: int, edge_factor: int = 16, abcd=(0.45, 0.15, 0.15, 0.25), seed: int = 42, dtype=np.float64):
     """C4: R-MAT power-law graph, 2^scale rows, duplicates merged.  Default skew is the milder
     (0.45, 0.15, 0.15, 0.25): Graph500's (0.57, 0.19, 0.19, 0.05) makes A*A infeasible."""
-    rng = np.random.Generator(np.random.PCG64(seed))
     n = 1 << scale
     ne = edge_factor * n
     a, b, c, _ = abcd
-    r = np.zeros(ne, dtype=np.uint64)
-    col = np.zeros(ne, dtype=np.uint64)
-    for _level in range(scale):
-        u = rng.random(ne)
-        rbit = (u >= a + b).astype(np.uint64)
-        cbit = (((u >= a) & (u < a + b)) | (u >= a + b + c)).astype(np.uint64)
-        r = (r << np.uint64(1)) | rbit
-        col = (col << np.uint64(1)) | cbit
-    keys = np.unique(r * np.uint64(n) + col)
+
+    # Level l of edge e uses draw number l * ne + e of the PCG64 stream (one draw per double), so edge chunks
+    # can be generated independently (cache-resident, one thread each) and still give the same matrix as one
+    # pass per level over all the edges.
+    def chunk(e0, e1):
+        r = np.zeros(e1 - e0, dtype=np.uint64)
+        col = np.zeros(e1 - e0, dtype=np.uint64)
+        for level in range(scale):
+            bg = np.random.PCG64(seed)
+            bg.advance(level * ne + e0)
+            u = np.random.Generator(bg).random(e1 - e0)
+            rbit = (u >= a + b).astype(np.uint64)
+            cbit = (((u >= a) & (u < a + b)) | (u >= a + b + c)).astype(np.uint64)
+            r = (r << np.uint64(1)) | rbit
+            col = (col << np.uint64(1)) | cbit
+        return r * np.uint64(n) + col
+
+    step = 1 << 18
+    spans = [(e0, min(ne, e0 + step)) for e0 in range(0, ne, step)]
+    if len(spans) > 1:
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=min(32, os.cpu_count() or 1)) as ex:
+            parts = list(ex.map(lambda sp: chunk(*sp), spans))
+        allkeys = np.concatenate(parts)
+    else:
+        allkeys = chunk(0, ne)
+    rng = np.random.Generator(np.random.PCG64(seed))
+    rng.bit_generator.advance(scale * ne)
+    keys = np.unique(allkeys)
     v = _nonzero_uniform(rng, keys.shape[0], dtype)
     return _csr_from_sorted_keys(n, n, keys, v)
 
