@@ -204,12 +204,16 @@ int spam_cuda_create(spam_handle** out, int device) {
   h->d_cnt = nullptr; h->h_cnt = nullptr; h->own_stream = nullptr; h->stream = nullptr;
   h->stats = spam_stats{};
   for (auto& e : h->ev) e = nullptr;
+  for (auto& s : h->lane) s = nullptr;
+  for (auto& e : h->lane_ev) e = nullptr;
   cudaError_t e = cudaSetDevice(device);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
   h->stream = h->own_stream;
   if (e == cudaSuccess) e = cudaMalloc((void**)&h->d_cnt, sizeof(Counters));
   if (e == cudaSuccess) e = cudaHostAlloc((void**)&h->h_cnt, sizeof(Counters), cudaHostAllocDefault);
   for (int i = 0; i < 6 && e == cudaSuccess; ++i) e = cudaEventCreate(&h->ev[i]);
+  for (int i = 0; i < 3 && e == cudaSuccess; ++i) e = cudaStreamCreateWithFlags(&h->lane[i], cudaStreamNonBlocking);
+  for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&h->lane_ev[i], cudaEventDisableTiming);
   cudaDeviceProp prop;
   if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, device);
   if (e == cudaSuccess) {
@@ -240,6 +244,8 @@ int spam_cuda_destroy(spam_handle* h) {
   if (h->scan_ws) { dev_free(h, h->scan_ws); h->scan_ws = nullptr; }
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+  for (auto& s : h->lane) if (s) { cudaStreamSynchronize(s); cudaStreamDestroy(s); }
+  for (auto& e : h->lane_ev) if (e) cudaEventDestroy(e);
   if (h->d_cnt) cudaFree(h->d_cnt);
   if (h->h_cnt) cudaFreeHost(h->h_cnt);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);

@@ -6,6 +6,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include <string>
 
@@ -164,6 +165,10 @@ struct spam_handle {
   void* pending;             // SpgemmHostState* (api.cu) between the two host phases
   DokPending* dok_pending;
   cudaEvent_t ev[6];
+  // side lanes: the per-bin kernels of one product touch disjoint rows, so they are spread over the main
+  // stream and NLANES-1 internal streams (fork/join by events) and the tail of one bin overlaps the next
+  cudaStream_t lane[3];
+  cudaEvent_t lane_ev[4];  // [0] fork, [1..3] join
   u64* scan_ws;      // look-back scan tile states + tile counter (grow-only, stream-ordered reuse)
   u64 scan_ws_cap;   // in u64 words
 };
@@ -191,6 +196,35 @@ template <class T>
 static inline int dev_alloc_t(spam_handle* h, T** p, size_t n) { return dev_alloc(h, (void**)p, n * sizeof(T)); }
 
 static inline void count_launch(spam_handle* h, u64 n = 1) { h->stats.kernel_launches += n; }
+
+// fork: the side lanes wait for everything queued on the main stream so far; join: the main stream waits
+// for everything queued on the side lanes.
+static inline cudaError_t lanes_fork(spam_handle* h) {
+  cudaError_t e = cudaEventRecord(h->lane_ev[0], h->stream);
+  for (int i = 0; i < 3 && e == cudaSuccess; ++i) e = cudaStreamWaitEvent(h->lane[i], h->lane_ev[0], 0);
+  return e;
+}
+static inline cudaError_t lanes_join(spam_handle* h) {
+  cudaError_t e = cudaSuccess;
+  for (int i = 0; i < 3 && e == cudaSuccess; ++i) {
+    e = cudaEventRecord(h->lane_ev[1 + i], h->lane[i]);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(h->stream, h->lane_ev[1 + i], 0);
+  }
+  return e;
+}
+// stream of row bin `bin`: the team bins go to the side lanes, the rest stays on the main stream.  The
+// global-table (heavy) kernels always run alone, after the join: overlapping them with the team kernels cost
+// 10% of the whole product on R-MAT 22 (their L2 atomics and the teams' B gathers fight over L2).
+static inline cudaStream_t lane_of(spam_handle* h, int bin) {
+  const char* e = getenv("SPAM_LANES");
+  if (e && e[0] == '0') return h->stream;
+  switch (bin) {
+    case 8: case 5: return h->lane[0];
+    case 7: case 4: return h->lane[1];
+    case 6: return h->lane[2];
+    default: return h->stream;
+  }
+}
 
 // ---- entry points implemented across the .cu files ---------------------------------------------
 // scan.cu : exclusive scan of u32 counts into u64 offsets (out has n+1 entries), decoupled look-back

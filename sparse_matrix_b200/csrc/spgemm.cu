@@ -426,7 +426,7 @@ __global__ void __launch_bounds__(T) k_num_heavy(u32 n, const u32* __restrict__ 
   const int tid = threadIdx.x, wid = tid >> 5, ln = tid & 31;
   u32* keys = key_tables + (u64)blockIdx.x * table_stride;
   V* vals = val_tables + (u64)blockIdx.x * table_stride;
-  u32* cnt = cnt_tables + (u64)blockIdx.x * (table_stride / 2 + 1);  // [npow2(z) + 1] bucket counters
+  u32* cnt = cnt_tables + (u64)blockIdx.x * (table_stride / 2 + 4);  // [npow2(z) + 1] bucket counters, 16 B aligned
   u32* okey = ord_tables + (u64)blockIdx.x * table_stride;           // [z] keys in bucket order
   u32* ord = okey + table_stride / 2;                                // [z] their table slots
   for (;;) {
@@ -481,40 +481,81 @@ __global__ void __launch_bounds__(T) k_num_heavy(u32 n, const u32* __restrict__ 
       const int lgnb = 31 - __clz(NB);
       const int rbits = b_cols > 1 ? 32 - __clz(b_cols - 1) : 0;
       const int bshift = rbits > lgnb ? rbits - lgnb : 0;
-      for (u64 s = tid; s < cap; s += T) {
-        const u32 kk = __ldcg(&keys[s]);
-        if (kk != EMPTY_KEY) atomicAdd(&cnt[kk >> bshift], 1u);
+      // every loop below keeps U independent L2 requests in flight per thread: with one request at a time a
+      // heavy row costs ~0.35 ms of pure L2 latency, a fixed price every shard of a partitioned product pays
+      constexpr int U = 4;
+      for (u64 s0 = tid; s0 < cap; s0 += (u64)U * T) {
+        u32 kk[U];
+#pragma unroll
+        for (int i = 0; i < U; ++i) { const u64 s = s0 + (u64)i * T; kk[i] = s < cap ? __ldcg(&keys[s]) : EMPTY_KEY; }
+#pragma unroll
+        for (int i = 0; i < U; ++i) if (kk[i] != EMPTY_KEY) atomicAdd(&cnt[kk[i] >> bshift], 1u);
       }
       __syncthreads();
-      const u32 chunk = (NB + T - 1) / T;
-      const u32 b0 = tid * chunk, b1 = min(NB, b0 + chunk);
+      // NB = npow2(z) >= 16384 here (z > 8192): each thread scans a multiple of four consecutive counters
+      const u32 chunk = NB / T;
+      const u32 b0 = tid * chunk, b1 = b0 + chunk;
       u32 sum = 0, mx = 0;
-      for (u32 b = b0; b < b1; ++b) { const u32 c = __ldcg(&cnt[b]); sum += c; mx = max(mx, c); }
+      for (u32 b = b0; b < b1; b += 4) {
+        const uint4 c = __ldcg(reinterpret_cast<const uint4*>(&cnt[b]));
+        sum += c.x + c.y + c.z + c.w;
+        mx = max(max(mx, max(c.x, c.y)), max(c.z, c.w));
+      }
       u32 total;
       u32 runb = block_excl_scan_u32<T>(sum, s_warp, &total);
-      for (u32 b = b0; b < b1; ++b) { const u32 c = __ldcg(&cnt[b]); __stcg(&cnt[b], runb); runb += c; }
+      for (u32 b = b0; b < b1; b += 4) {
+        const uint4 c = __ldcg(reinterpret_cast<const uint4*>(&cnt[b]));
+        uint4 o;
+        o.x = runb; o.y = o.x + c.x; o.z = o.y + c.y; o.w = o.z + c.z;
+        runb = o.w + c.w;
+        __stcg(reinterpret_cast<uint4*>(&cnt[b]), o);
+      }
       if (mx) atomicMax(&s_maxcnt, mx);
       __syncthreads();
       if (s_maxcnt <= HEAVY_RANK_MAX) {
-        for (u64 s = tid; s < cap; s += T) {
-          const u32 kk = __ldcg(&keys[s]);
-          if (kk != EMPTY_KEY) {
-            const u32 pos = atomicAdd(&cnt[kk >> bshift], 1u);  // afterwards cnt[b] = end of bucket b
-            __stcg(&okey[pos], kk);
-            __stcg(&ord[pos], (u32)s);
-          }
+        for (u64 s0 = tid; s0 < cap; s0 += (u64)U * T) {
+          u32 kk[U], pos[U];
+#pragma unroll
+          for (int i = 0; i < U; ++i) { const u64 s = s0 + (u64)i * T; kk[i] = s < cap ? __ldcg(&keys[s]) : EMPTY_KEY; }
+#pragma unroll
+          for (int i = 0; i < U; ++i)
+            if (kk[i] != EMPTY_KEY) pos[i] = atomicAdd(&cnt[kk[i] >> bshift], 1u);  // afterwards cnt[b] = end of bucket b
+#pragma unroll
+          for (int i = 0; i < U; ++i)
+            if (kk[i] != EMPTY_KEY) { __stcg(&okey[pos[i]], kk[i]); __stcg(&ord[pos[i]], (u32)(s0 + (u64)i * T)); }
         }
         __syncthreads();
-        for (u32 p = tid; p < z; p += T) {
-          const u32 kk = __ldcg(&okey[p]);
-          const u32 b = kk >> bshift;
-          const u32 lo_b = b ? __ldcg(&cnt[b - 1]) : 0u, hi_b = __ldcg(&cnt[b]);
-          u32 rank = 0;
-          if (hi_b - lo_b > 1) {
-            for (u32 j = lo_b; j < hi_b; ++j) rank += (__ldcg(&okey[j]) < kk) ? 1u : 0u;
+        for (u32 p0 = tid; p0 < z; p0 += U * T) {
+          u32 kk[U], lo_b[U], hi_b[U], slot[U];
+          V val[U];
+#pragma unroll
+          for (int i = 0; i < U; ++i) {
+            const u32 p = p0 + i * T;
+            kk[i] = 0; slot[i] = 0;
+            if (p < z) { kk[i] = __ldcg(&okey[p]); slot[i] = __ldcg(&ord[p]); }
           }
-          c_col[c0 + lo_b + rank] = kk;
-          c_val[c0 + lo_b + rank] = __ldcg(&vals[__ldcg(&ord[p])]);
+#pragma unroll
+          for (int i = 0; i < U; ++i) {
+            const u32 bkt = kk[i] >> bshift;
+            lo_b[i] = 0; hi_b[i] = 0; val[i] = Num<V>::zero();
+            if (p0 + i * T < z) {
+              lo_b[i] = bkt ? __ldcg(&cnt[bkt - 1]) : 0u;
+              hi_b[i] = __ldcg(&cnt[bkt]);
+              val[i] = __ldcg(&vals[slot[i]]);
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < U; ++i) {
+            if (p0 + i * T < z) {
+              u32 rank = 0;
+              if (hi_b[i] - lo_b[i] > 1) {
+#pragma unroll 4
+                for (u32 j = lo_b[i]; j < hi_b[i]; ++j) rank += (__ldcg(&okey[j]) < kk[i]) ? 1u : 0u;
+              }
+              c_col[c0 + lo_b[i] + rank] = kk[i];
+              c_val[c0 + lo_b[i] + rank] = val[i];
+            }
+          }
         }
         __syncthreads();
         continue;
@@ -745,6 +786,48 @@ int spgemm_symbolic_dev(spam_handle* h, const spam_dcsr* a, const spam_dcsr* b, 
     const u64* ap = a->ptr; const u32* ac = a->idx; const u64* bp = b->ptr; const u32* bc = b->idx;
     const u32* fl = p->d_flop; u32* rz = p->d_row_nnz;
     auto seg = [&](int bin) -> const u32* { return sb.perm ? sb.perm + sb.base[bin] : nullptr; };
+    // bins 4.. run on the side lanes (disjoint rows); the heavy bin runs alone after the join
+    const int ws = wshift_for(b, 5);
+    bool side = false;
+    for (int bin = 4; bin <= NHASH; ++bin) side = side || sb.count[bin] != 0;
+    u64 heavy_nblk = 0, heavy_stride = 0;
+    if (sb.count[HEAVY_BIN]) {
+      u32 fmax = c1.max_flop;
+      if (fmax > (u32)b->cols) fmax = (u32)b->cols;
+      heavy_stride = 2ull * npow2_u64(fmax);
+      heavy_nblk = (u64)h->num_sms * 2;
+      if (heavy_nblk > sb.count[HEAVY_BIN]) heavy_nblk = sb.count[HEAVY_BIN];
+      const u64 budget = 8ull << 30;
+      while (heavy_nblk > 1 && heavy_nblk * heavy_stride * sizeof(u32) > budget) heavy_nblk /= 2;
+      FAIL_FREE(dev_alloc_t(h, &heavy_tab, heavy_nblk * heavy_stride));
+    }
+    if (side) CK_FREE(lanes_fork(h));
+#define LAUNCH_SYM_ROW(BIN, NW, CAP, DIRECT)                                                             \
+    if (sb.count[BIN]) {                                                                                 \
+      constexpr size_t smem = sym_row_smem<NW, CAP>();                                                   \
+      FAIL_FREE(set_smem(h, k_sym_row<NW, CAP, DIRECT>, smem));                                          \
+      const unsigned grid = NW == 1 ? (sb.count[BIN] + ROWS_PER_BLOCK_W1 - 1) / ROWS_PER_BLOCK_W1 : sb.count[BIN]; \
+      k_sym_row<NW, CAP, DIRECT><<<grid, NW == 1 ? 32 * ROWS_PER_BLOCK_W1 : 32 * NW, smem, lane_of(h, BIN)>>>( \
+          sb.count[BIN], seg(BIN), ap, ac, bp, bc, fl, rz);                                              \
+      count_launch(h);                                                                                   \
+    }
+    // symbolic hash bin b: f <= 64 << b, table 128 << b keys (4 B each); expensive bins first
+    LAUNCH_SYM_ROW(8, 32, 32768, false)
+    LAUNCH_SYM_ROW(7, 16, 16384, false)
+    LAUNCH_SYM_ROW(6, 8, 8192, false)
+    LAUNCH_SYM_ROW(5, 4, 4096, false)
+    if (direct_enumeration(b)) {
+      LAUNCH_SYM_ROW(1, 1, 256, true)
+      LAUNCH_SYM_ROW(2, 1, 512, true)
+      LAUNCH_SYM_ROW(3, 1, 1024, true)
+      LAUNCH_SYM_ROW(4, 1, 2048, true)
+    } else {
+      LAUNCH_SYM_ROW(1, 1, 256, false)
+      LAUNCH_SYM_ROW(2, 1, 512, false)
+      LAUNCH_SYM_ROW(3, 1, 1024, false)
+      LAUNCH_SYM_ROW(4, 4, 2048, false)  // 4 rows x 8 KB per block left 28 warps per SM; a team per row runs 64
+    }
+#undef LAUNCH_SYM_ROW
     if (sb.count[MERGE_BIN] && !fused) {
       constexpr int BL = 128;
       const u32 nm = sb.count[MERGE_BIN];
@@ -763,46 +846,12 @@ int spgemm_symbolic_dev(spam_handle* h, const spam_dcsr* a, const spam_dcsr* b, 
       k_sym_tiny<BL><<<(sb.count[0] + BL - 1) / BL, BL, smem, h->stream>>>(sb.count[0], seg(0), ap, ac, bp, bc, fl, rz);
       count_launch(h);
     }
-#define LAUNCH_SYM_ROW(BIN, NW, CAP, DIRECT)                                                             \
-    if (sb.count[BIN]) {                                                                                 \
-      constexpr size_t smem = sym_row_smem<NW, CAP>();                                                   \
-      FAIL_FREE(set_smem(h, k_sym_row<NW, CAP, DIRECT>, smem));                                          \
-      const unsigned grid = NW == 1 ? (sb.count[BIN] + ROWS_PER_BLOCK_W1 - 1) / ROWS_PER_BLOCK_W1 : sb.count[BIN]; \
-      k_sym_row<NW, CAP, DIRECT><<<grid, NW == 1 ? 32 * ROWS_PER_BLOCK_W1 : 32 * NW, smem, h->stream>>>(    \
-          sb.count[BIN], seg(BIN), ap, ac, bp, bc, fl, rz);                                              \
-      count_launch(h);                                                                                   \
-    }
-    const int ws = wshift_for(b, 5);
-    // symbolic hash bin b: f <= 64 << b, table 128 << b keys (4 B each)
-    if (direct_enumeration(b)) {
-      LAUNCH_SYM_ROW(1, 1, 256, true)
-      LAUNCH_SYM_ROW(2, 1, 512, true)
-      LAUNCH_SYM_ROW(3, 1, 1024, true)
-      LAUNCH_SYM_ROW(4, 1, 2048, true)
-    } else {
-      LAUNCH_SYM_ROW(1, 1, 256, false)
-      LAUNCH_SYM_ROW(2, 1, 512, false)
-      LAUNCH_SYM_ROW(3, 1, 1024, false)
-      LAUNCH_SYM_ROW(4, 4, 2048, false)  // 4 rows x 8 KB per block left 28 warps per SM; a team per row runs 64
-    }
-    LAUNCH_SYM_ROW(5, 4, 4096, false)
-    LAUNCH_SYM_ROW(6, 8, 8192, false)
-    LAUNCH_SYM_ROW(7, 16, 16384, false)
-    LAUNCH_SYM_ROW(8, 32, 32768, false)
-#undef LAUNCH_SYM_ROW
     CK_FREE(cudaGetLastError());
+    if (side) CK_FREE(lanes_join(h));
     if (sb.count[HEAVY_BIN]) {
-      const u32 nheavy = sb.count[HEAVY_BIN];
-      u32 fmax = c1.max_flop;
-      if (fmax > (u32)b->cols) fmax = (u32)b->cols;
-      const u64 stride = 2ull * npow2_u64(fmax);
-      u64 nblk = (u64)h->num_sms * 2;
-      if (nblk > nheavy) nblk = nheavy;
-      const u64 budget = 8ull << 30;
-      while (nblk > 1 && nblk * stride * sizeof(u32) > budget) nblk /= 2;
-      FAIL_FREE(dev_alloc_t(h, &heavy_tab, nblk * stride));
-      k_sym_heavy<1024><<<(unsigned)nblk, 1024, 0, h->stream>>>(nheavy, seg(HEAVY_BIN), ap, ac, bp, bc, fl, rz, heavy_tab, stride,
-                                                                (u32)b->cols, &h->d_cnt->work_a, ws);
+      k_sym_heavy<1024><<<(unsigned)heavy_nblk, 1024, 0, h->stream>>>(sb.count[HEAVY_BIN], seg(HEAVY_BIN), ap, ac, bp, bc, fl,
+                                                                                 rz, heavy_tab, heavy_stride, (u32)b->cols,
+                                                                                 &h->d_cnt->work_a, ws);
       count_launch(h);
       CK_FREE(cudaGetLastError());
     }
@@ -844,6 +893,58 @@ int numeric_typed(spam_handle* h, SpgemmPending* p, spam_dcsr* c) {
   const u64* bp = b->ptr; const u32* bc = b->idx; const V* bv = (const V*)b->val;
   const u64* cp = c->ptr; u32* cc = c->idx; V* cv = (V*)c->val;
   auto seg = [&](int bin) -> const u32* { return nb.perm ? nb.perm + nb.base[bin] : nullptr; };
+#define LAUNCH_NUM_ROW(BIN, NW, CAP, DIRECT)                                                             \
+  if (nb.count[BIN]) {                                                                                   \
+    constexpr size_t smem = num_row_smem<V, NW, CAP>();                                                  \
+    CKS(set_smem(h, k_num_row<V, NW, CAP, DIRECT>, smem));                                               \
+    const unsigned grid = NW == 1 ? (nb.count[BIN] + ROWS_PER_BLOCK_W1 - 1) / ROWS_PER_BLOCK_W1 : nb.count[BIN]; \
+    /* NW = 1 sorts (column << log2(CAP/2)) | index packed in 32 bits when the columns are narrow enough */ \
+    const int pack_ok = b->cols < (1ull << (32 - (31 - __builtin_clz((unsigned)(CAP) / 2)))) ? 1 : 0;   \
+    k_num_row<V, NW, CAP, DIRECT><<<grid, NW == 1 ? 32 * ROWS_PER_BLOCK_W1 : 32 * NW, smem, lane_of(h, BIN)>>>( \
+        nb.count[BIN], seg(BIN), ap, ac, av, bp, bc, bv, cp, cc, cv, pack_ok);                           \
+    count_launch(h);                                                                                     \
+  }
+  // The bins touch disjoint rows of C.  The team bins (largest first) go to the side lanes so that the tail of
+  // one (a few blocks still on their last rows) overlaps the next; the heavy bin runs alone at the end.
+  bool side = false;
+  for (int bin = 4; bin <= NHASH; ++bin) side = side || nb.count[bin] != 0;
+  u32 *hk = nullptr, *hc = nullptr, *ho = nullptr;
+  V* hv = nullptr;
+  u64 heavy_nblk = 0, heavy_stride = 0;
+  if (nb.count[HEAVY_BIN]) {
+    u32 zmax = p->max_nnz;
+    heavy_stride = 2ull * npow2_u64(zmax);
+    heavy_nblk = (u64)h->num_sms * 2;
+    if (heavy_nblk > nb.count[HEAVY_BIN]) heavy_nblk = nb.count[HEAVY_BIN];
+    const u64 budget = 16ull << 30;
+    // per block: keys + values (stride each), bucket counters (stride/2), bucket-ordered keys + slots (stride)
+    while (heavy_nblk > 1 && heavy_nblk * heavy_stride * (2 * sizeof(u32) + sizeof(V) + 2) > budget) heavy_nblk /= 2;
+    CKS(dev_alloc_t(h, &hk, heavy_nblk * heavy_stride));
+    CKS(dev_alloc_t(h, &hv, heavy_nblk * heavy_stride));
+    CKS(dev_alloc_t(h, &hc, heavy_nblk * (heavy_stride / 2 + 4)));
+    CKS(dev_alloc_t(h, &ho, heavy_nblk * heavy_stride));
+  }
+  if (side) CK(lanes_fork(h));
+  // numeric hash bin b: z <= 32 << b, table 64 << b (key, value) slots.  Team sizes: these kernels are
+  // latency-bound (dependent shared-memory and shuffle chains), so the big-table bins get many warps per row
+  LAUNCH_NUM_ROW(8, 32, 16384, false)
+  LAUNCH_NUM_ROW(7, 24, 8192, false)
+  LAUNCH_NUM_ROW(6, 16, 4096, false)
+  LAUNCH_NUM_ROW(5, 8, 2048, false)
+  if (direct_enumeration(b)) {
+    LAUNCH_NUM_ROW(4, 1, 1024, true)
+    LAUNCH_NUM_ROW(3, 1, 512, true)
+    LAUNCH_NUM_ROW(2, 1, 256, true)
+    LAUNCH_NUM_ROW(1, 1, 128, true)
+  } else {
+    // z in (256, 512]: one warp per row leaves 16 warps per SM (4 rows x 12 KB per block); a 4-warp team with the
+    // bucket drain runs 48
+    LAUNCH_NUM_ROW(4, 4, 1024, false)
+    LAUNCH_NUM_ROW(3, 1, 512, false)
+    LAUNCH_NUM_ROW(2, 1, 256, false)
+    LAUNCH_NUM_ROW(1, 1, 128, false)
+  }
+#undef LAUNCH_NUM_ROW
   if (nb.count[MERGE_BIN]) {
     constexpr int BL = 128;
     constexpr size_t smem = num_merge_smem<V, BL>();
@@ -865,55 +966,12 @@ int numeric_typed(spam_handle* h, SpgemmPending* p, spam_dcsr* c) {
     k_num_tiny<V, BL><<<(nb.count[0] + BL - 1) / BL, BL, smem, h->stream>>>(nb.count[0], seg(0), ap, ac, av, bp, bc, bv, cp, cc, cv);
     count_launch(h);
   }
-#define LAUNCH_NUM_ROW(BIN, NW, CAP, DIRECT)                                                             \
-  if (nb.count[BIN]) {                                                                                   \
-    constexpr size_t smem = num_row_smem<V, NW, CAP>();                                                  \
-    CKS(set_smem(h, k_num_row<V, NW, CAP, DIRECT>, smem));                                               \
-    const unsigned grid = NW == 1 ? (nb.count[BIN] + ROWS_PER_BLOCK_W1 - 1) / ROWS_PER_BLOCK_W1 : nb.count[BIN]; \
-    /* NW = 1 sorts (column << log2(CAP/2)) | index packed in 32 bits when the columns are narrow enough */ \
-    const int pack_ok = b->cols < (1ull << (32 - (31 - __builtin_clz((unsigned)(CAP) / 2)))) ? 1 : 0;   \
-    k_num_row<V, NW, CAP, DIRECT><<<grid, NW == 1 ? 32 * ROWS_PER_BLOCK_W1 : 32 * NW, smem, h->stream>>>(  \
-        nb.count[BIN], seg(BIN), ap, ac, av, bp, bc, bv, cp, cc, cv, pack_ok);                           \
-    count_launch(h);                                                                                     \
-  }
-  // numeric hash bin b: z <= 32 << b, table 64 << b (key, value) slots
-  if (direct_enumeration(b)) {
-    LAUNCH_NUM_ROW(1, 1, 128, true)
-    LAUNCH_NUM_ROW(2, 1, 256, true)
-    LAUNCH_NUM_ROW(3, 1, 512, true)
-    LAUNCH_NUM_ROW(4, 1, 1024, true)
-  } else {
-    LAUNCH_NUM_ROW(1, 1, 128, false)
-    LAUNCH_NUM_ROW(2, 1, 256, false)
-    LAUNCH_NUM_ROW(3, 1, 512, false)
-    // z in (256, 512]: one warp per row leaves 16 warps per SM (4 rows x 12 KB per block); a 4-warp team with the
-    // bucket drain runs 48
-    LAUNCH_NUM_ROW(4, 4, 1024, false)
-  }
-  // team sizes: these kernels are latency-bound (dependent shared-memory and shuffle chains), so the
-  // big-table bins get many warps per row: G4's 224 KB table allows one block per SM, give it 32 warps
-  LAUNCH_NUM_ROW(5, 8, 2048, false)
-  LAUNCH_NUM_ROW(6, 16, 4096, false)
-  LAUNCH_NUM_ROW(7, 24, 8192, false)
-  LAUNCH_NUM_ROW(8, 32, 16384, false)
-#undef LAUNCH_NUM_ROW
   CK(cudaGetLastError());
-  u32 *hk = nullptr, *hc = nullptr, *ho = nullptr;
-  V* hv = nullptr;
+  if (side) CK(lanes_join(h));
   if (nb.count[HEAVY_BIN]) {
-    u32 zmax = p->max_nnz;
-    const u64 stride = 2ull * npow2_u64(zmax);
-    u64 nblk = (u64)h->num_sms * 2;
-    if (nblk > nb.count[HEAVY_BIN]) nblk = nb.count[HEAVY_BIN];
-    const u64 budget = 16ull << 30;
-    // per block: keys + values (stride each), bucket counters (stride/2), bucket-ordered keys + slots (stride)
-    while (nblk > 1 && nblk * stride * (2 * sizeof(u32) + sizeof(V) + 2) > budget) nblk /= 2;
-    CKS(dev_alloc_t(h, &hk, nblk * stride));
-    CKS(dev_alloc_t(h, &hv, nblk * stride));
-    CKS(dev_alloc_t(h, &hc, nblk * (stride / 2 + 1)));
-    CKS(dev_alloc_t(h, &ho, nblk * stride));
-    k_num_heavy<V, 1024><<<(unsigned)nblk, 1024, 0, h->stream>>>(nb.count[HEAVY_BIN], seg(HEAVY_BIN), ap, ac, av, bp, bc, bv, cp, cc, cv, hk,
-                                                                hv, stride, hc, ho, (u32)b->cols, &h->d_cnt->work_b);
+    k_num_heavy<V, 1024><<<(unsigned)heavy_nblk, 1024, 0, h->stream>>>(nb.count[HEAVY_BIN], seg(HEAVY_BIN), ap, ac, av, bp, bc, bv,
+                                                                                  cp, cc, cv, hk, hv, heavy_stride, hc, ho,
+                                                                                  (u32)b->cols, &h->d_cnt->work_b);
     count_launch(h);
     CK(cudaGetLastError());
   }
