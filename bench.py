@@ -476,8 +476,10 @@ def main():
             e1.record()
             sync_all()
             ms_e2e = e0.elapsed_time(e1) / k
-            h2d = (a_rows + 1) * 8 + a_nnz * 16 + (0 if world == 1 else (rows + 1) * 8 + nnz_a * 16)
-            d2h = (a_rows + 1) * 8 + local_nnz_c * 16
+            # bytes actually moved over PCIe by the last step, as counted by the library (at N > 1 only the band
+            # of B that this rank's rows of A reference is uploaded)
+            st_e2e = handle.stats()
+            h2d, d2h = int(st_e2e["bytes_h2d"]), int(st_e2e["bytes_d2h"])
             if world > 1:
                 t = torch.tensor([ms_e2e, -ms_e2e, h2d, d2h], dtype=torch.float64, device=dev)
                 tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -487,7 +489,7 @@ def main():
                            "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e,
                            "api": "spam_spgemm_symbolic + spam_spgemm_numeric (host u64 indices, pinned buffers; " +
                                   ("A aliases B so it is uploaded once)" if world == 1 else
-                                   "every rank uploads its row block of A and all of B, downloads its shard of C; "
+                                   "every rank uploads its row block of A and the rows of B it references, downloads its shard of C; "
                                    "bytes summed over ranks, time = max over ranks)")}
         finally:
             for p in keep:

@@ -64,21 +64,16 @@ __global__ void k_partition_points(const u64* __restrict__ ps, u64 m, u32 parts,
   out[t] = lo - 1;  // ps[0] = 0 <= bound so lo >= 1
 }
 
-// Device-time cost of a row of C as a function of its intermediate-product count f (and the length of its
-// A row, which decides the merge bin): f x a per-product weight in 1/16 units.  The weights are the measured
-// time per product of the kernel that takes rows of that size on B200 (symbolic + numeric, R-MAT scale 22,
-// profiles/r01_rmat22_v3_balance.txt): one-warp hash rows are cheapest, team rows pay shared-memory
-// atomics and the bucket sort, global-table rows pay L2 atomics.  Shard times predicted by this table
-// are within 2% of the measured ones.
+// Device-time cost of a row of C as a function of its intermediate-product count f: f x a per-product
+// weight in 1/16 units, fitted to the measured times of 48 row blocks of R-MAT scale 22 on B200
+// (profiles/r01_rmat22_v3_balance.txt): every shared-memory bin costs about 30 ps per product (the merge
+// bin slightly more: random gathers of short B rows), rows of the global-table bin about 120 ps (L2
+// atomics).  Shard times predicted by this table are within 3% (rms) of the measured ones.
 __device__ __forceinline__ u32 row_cost_q(u32 f, u64 alen) {
   u32 w;
-  if (f <= 128) w = 16;           // merge / tiny / smallest hash bin
-  else if (f <= 256) w = 10;
-  else if (f <= 512) w = 13;
-  else if (f <= 1024) w = 18;
-  else if (f <= 4096) w = 20;
-  else if (f <= 8192) w = 25;
-  else w = 44;                    // 32-warp team rows and the global-table bin
+  if (f <= 128) w = 18;           // merge / tiny
+  else if (f <= 8192) w = 16;     // one-warp and team hash bins
+  else w = 64;                    // global-table bin
   (void)alen;
   const u64 c = (u64)f * w;
   return c > 0xFFFFFFFFull ? 0xFFFFFFFFu : (u32)c;

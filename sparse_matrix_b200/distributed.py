@@ -37,7 +37,7 @@ def row_cost(flop_per_row: np.ndarray) -> np.ndarray:
     """Host mirror of the device-time estimate behind spam_rows_to_parts_cost (api.cu row_cost_q):
     products x a per-product weight (1/16 units) that depends on the size class of the row."""
     f = flop_per_row.astype(np.uint64)
-    w = np.select([f <= 128, f <= 256, f <= 512, f <= 1024, f <= 4096, f <= 8192], [16, 10, 13, 18, 20, 25], 44)
+    w = np.select([f <= 128, f <= 8192], [18, 16], 64)
     return np.minimum(f * w.astype(np.uint64), np.uint64(0xFFFFFFFF))
 
 
