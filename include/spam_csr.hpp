@@ -143,6 +143,16 @@ class CsrMatrix {
     return y;
   }
 
+  // Matrix::transpose (spam_csr/src/lib.rs:256-264); rows of the result are sorted by column
+  CsrMatrix<T, true> transpose(Handle& h = Handle::thread_default()) const {
+    CsrMatrix<T, true> t(cols, rows);
+    t.indices.resize(indices.size());
+    t.vals.resize(vals.size());
+    h.check(spam_csr_transpose(h.get(), device_scalar<T>::dtype, rows, cols, offsets.data(), indices.data(), vals.data(),
+                               t.offsets.data(), t.indices.data(), t.vals.data()));
+    return t;
+  }
+
   // impl From<DokMatrix<T>> for CsrMatrix<T, true>; from_triplets replays a set_element stream
   static CsrMatrix<T, true> from_triplets(uint64_t r, uint64_t c, const std::vector<uint64_t>& tr,
                                           const std::vector<uint64_t>& tc, const std::vector<T>& tv,

@@ -119,6 +119,16 @@ int spam_dcsr_free(spam_handle* h, spam_dcsr* m);
 /* rows [r0, r1) of m as a new owning matrix with row_ptr rebased to 0 (the per-rank A block) */
 int spam_dcsr_slice_rows(spam_handle* h, const spam_dcsr* m, uint64_t r0, uint64_t r1, spam_dcsr** out);
 
+/* Transpose.  Replaces `Matrix::transpose` of CsrMatrix, spam_csr/src/lib.rs:256-264 (an O(rows*cols)
+ * loop of set_element calls in the reference; for matrices without explicit zeros the same result as
+ * DokMatrix::transpose, spam_dok/src/lib.rs:178-188, followed by From<DokMatrix>): every stored entry
+ * (i, j, v) — explicit zeros included, CsrMatrix::set_element stores them — becomes (j, i, v); rows of the result are sorted by column whatever the order inside
+ * the input's rows.  Device: *out is a new owning matrix.  Host: t_ptr has cols+1 entries, t_idx / t_val
+ * have nnz = ptr[rows] entries (the caller knows all sizes up front, so one phase). */
+int spam_dcsr_transpose(spam_handle* h, const spam_dcsr* m, spam_dcsr** out);
+int spam_csr_transpose(spam_handle* h, int dtype, uint64_t rows, uint64_t cols, const uint64_t* ptr,
+                       const uint64_t* idx, const void* val, uint64_t* t_ptr, uint64_t* t_idx, void* t_val);
+
 /* C = A * B, all on the device; *c is a new owning matrix (stream-ordered allocation). */
 int spam_spgemm_dev(spam_handle* h, const spam_dcsr* a, const spam_dcsr* b, spam_dcsr** c);
 int spam_spmv_dev(spam_handle* h, const spam_dcsr* a, const void* d_x, void* d_y);

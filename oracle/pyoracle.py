@@ -41,6 +41,7 @@ def lib():
         L.oracle_dok_to_csr.restype = C.c_int
         L.oracle_dok_dense_mul.restype = C.c_int
         L.oracle_spmv.restype = C.c_int
+        L.oracle_transpose.restype = C.c_int
         L.oracle_table_size_for.restype = C.c_uint64
         L.oracle_table_size_for.argtypes = [C.c_uint64]
         L.oracle_hash.restype = C.c_uint64
@@ -160,6 +161,25 @@ def dok_to_csr(rows, cols, ri, ci, vals):
         raise RuntimeError(f"oracle_dok_to_csr rc={rc}")
     n = nnz.value
     return _take(c_off.value, rows + 1, np.uint64), _take(c_idx.value, n, np.uint64), _take(c_val.value, n, vals.dtype)
+
+
+def transpose(mat, literal: bool = False):
+    """CsrMatrix::transpose (lib.rs:256-264): (offsets, indices, vals) of the cols x rows result.  `literal`
+    runs the reference's own (j, i) double loop (small inputs only)."""
+    L = lib()
+    rows, cols, off, idx, val = mat
+    off, idx, val = _u64(off), _u64(idx), np.ascontiguousarray(val)
+    nnz = int(off[rows])
+    t_off = np.zeros(cols + 1, np.uint64)
+    t_idx = np.zeros(nnz, np.uint64)
+    t_val = np.zeros(nnz, val.dtype)
+    rc = L.oracle_transpose(C.c_int(DT[val.dtype]), C.c_uint64(rows), C.c_uint64(cols), _ptr(off), _ptr(idx), _ptr(val),
+                            C.c_int(1 if literal else 0), _ptr(t_off), _ptr(t_idx), _ptr(t_val))
+    if rc == 4:
+        raise IndexError("IndexError")
+    if rc != 0:
+        raise RuntimeError(f"oracle_transpose rc={rc}")
+    return t_off, t_idx, t_val
 
 
 def dok_dense_mul(a: np.ndarray, b: np.ndarray) -> np.ndarray:

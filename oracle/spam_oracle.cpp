@@ -456,6 +456,57 @@ int oracle_dok_to_csr(int dtype, uint64_t rows, uint64_t cols, uint64_t n, const
   });
 }
 
+// Matrix::transpose of CsrMatrix (spam_csr/src/lib.rs:256-264):
+//   for (j, i) in iproduct!(0..cols, 0..rows) {
+//     if let Some(t) = self.set_element((i, j), T::zero()).unwrap() { new.set_element((j, i), t).unwrap(); } }
+// set_element on a stored entry swaps the value in and returns the old one, explicit zeros included
+// (lib.rs:213-226, 238-242); on a missing entry it inserts the zero into `self` (which is consumed, so
+// that is unobservable) and returns None.  new.set_element((j, i), t) finds no entry and inserts at the end
+// of row j in both the sorted and the unsorted branch because i only grows (lib.rs:227-236, 243-252).
+// `literal` = exactly those loops (O(cols * nnz), tests only); otherwise the equivalent stable counting
+// sort by column.  Outputs are caller-allocated: t_off[cols+1], t_idx[nnz], t_val[nnz].
+int oracle_transpose(int dtype, uint64_t rows, uint64_t cols, const uint64_t* off, const uint64_t* idx, const void* val,
+                     int literal, uint64_t* t_off, uint64_t* t_idx, void* t_val) {
+  return dispatch(dtype, [&](auto tag) {
+    using T = decltype(tag);
+    const T* v = (const T*)val;
+    T* tv = (T*)t_val;
+    if (literal) {
+      u64 out = 0;
+      t_off[0] = 0;
+      for (u64 j = 0; j < cols; ++j) {
+        for (u64 i = 0; i < rows; ++i) {
+          for (u64 e = off[i]; e < off[i + 1]; ++e) {
+            if (idx[e] == j) {  // first match: binary_search / position on distinct columns
+              t_idx[out] = i;
+              tv[out] = v[e];
+              ++out;
+              break;
+            }
+          }
+        }
+        t_off[j + 1] = out;
+      }
+      return 0;
+    }
+    std::vector<u64> cnt(cols + 1, 0);
+    for (u64 e = 0; e < off[rows]; ++e) {
+      if (idx[e] >= cols) return 4;
+      ++cnt[idx[e] + 1];
+    }
+    for (u64 j = 0; j < cols; ++j) cnt[j + 1] += cnt[j];
+    std::memcpy(t_off, cnt.data(), (cols + 1) * sizeof(u64));
+    for (u64 i = 0; i < rows; ++i) {
+      for (u64 e = off[i]; e < off[i + 1]; ++e) {
+        const u64 p = cnt[idx[e]]++;
+        t_idx[p] = i;
+        tv[p] = v[e];
+      }
+    }
+    return 0;
+  });
+}
+
 int oracle_dok_dense_mul(int dtype, uint64_t l, uint64_t m, uint64_t n, const void* a, const void* b, void* c) {
   return dispatch(dtype, [&](auto tag) {
     using T = decltype(tag);

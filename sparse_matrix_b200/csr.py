@@ -130,6 +130,12 @@ class DeviceCsr:
         check(self.handle.h, self.handle.L.spam_spgemm_dev(self.handle.h, self.p, rhs.p, C.byref(out)))
         return DeviceCsr(self.handle, out)
 
+    def transpose(self) -> "DeviceCsr":
+        """Matrix::transpose (spam_csr/src/lib.rs:256-264) on the device; rows of the result are sorted."""
+        out = C.c_void_p()
+        check(self.handle.h, self.handle.L.spam_dcsr_transpose(self.handle.h, self.p, C.byref(out)))
+        return DeviceCsr(self.handle, out)
+
     def slice_rows(self, r0: int, r1: int) -> "DeviceCsr":
         out = C.c_void_p()
         check(self.handle.h, self.handle.L.spam_dcsr_slice_rows(self.handle.h, self.p, r0, r1, C.byref(out)))
@@ -310,6 +316,19 @@ class CsrMatrix:
         return self.mul_hash(rhs, sorted_output=False)
 
     __matmul__ = __mul__
+
+    def transpose(self, handle: Optional[Handle] = None) -> "CsrMatrix":
+        """Matrix::transpose (spam_csr/src/lib.rs:256-264): every stored entry (i, j, v), explicit zeros
+        included, becomes (j, i, v); the result's rows are sorted by column."""
+        handle = handle or get_handle()
+        nnz = self.nnz()
+        t_ptr = np.empty(self.cols_ + 1, dtype=np.uint64)
+        t_idx = np.empty(nnz, dtype=np.uint64)
+        t_val = np.empty(nnz, dtype=self.vals.dtype)
+        check(handle.h, handle.L.spam_csr_transpose(handle.h, _dtype_code(self.vals.dtype), self.rows_, self.cols_,
+                                                    ptr(self.offsets), ptr(self.indices), ptr(self.vals), ptr(t_ptr),
+                                                    ptr(t_idx), ptr(t_val)))
+        return CsrMatrix(self.cols_, self.rows_, t_val, t_idx, t_ptr, is_sorted=True)
 
     def spmv(self, x, handle: Optional[Handle] = None) -> np.ndarray:
         x = np.ascontiguousarray(x, dtype=self.vals.dtype)

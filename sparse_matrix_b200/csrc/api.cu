@@ -453,6 +453,34 @@ int spam_dcsr_slice_rows(spam_handle* h, const spam_dcsr* m, uint64_t r0, uint64
   return SPAM_OK;
 }
 
+/* ---------------- transpose ---------------- */
+
+int spam_dcsr_transpose(spam_handle* h, const spam_dcsr* m, spam_dcsr** out) {
+  if (!h || !m || !out) return spam_fail(h, SPAM_EINVAL, "null argument");
+  CKS(set_device(h));
+  return transpose_dev(h, m, out);
+}
+
+int spam_csr_transpose(spam_handle* h, int dtype, uint64_t rows, uint64_t cols, const uint64_t* ptr, const uint64_t* idx,
+                       const void* val, uint64_t* t_ptr, uint64_t* t_idx, void* t_val) {
+  if (!h || !ptr || !t_ptr || !valid_dtype(dtype)) return spam_fail(h, SPAM_EINVAL, "bad argument");
+  const u64 nnz = ptr[rows];
+  if (nnz && (!idx || !val || !t_idx || !t_val)) return spam_fail(h, SPAM_EINVAL, "null buffer");
+  CKS(set_device(h));
+  spam_dcsr *a = nullptr, *t = nullptr;
+  h->stats = spam_stats{};
+  CKS(spam_csr_upload(h, dtype, rows, cols, nnz, ptr, idx, val, &a));
+  const u64 h2d = h->stats.bytes_h2d;
+  int st = transpose_dev(h, a, &t);  // resets stats
+  if (st == SPAM_OK) {
+    h->stats.bytes_h2d = h2d;
+    st = spam_dcsr_download(h, t, t_ptr, t_idx, t_val);
+  }
+  free_dcsr(h, t);
+  free_dcsr(h, a);
+  return st;
+}
+
 /* ---------------- SpGEMM ---------------- */
 
 int spam_spgemm_dev(spam_handle* h, const spam_dcsr* a, const spam_dcsr* b, spam_dcsr** c) {

@@ -243,6 +243,7 @@ int spmv_dev(spam_handle* h, const spam_dcsr* a, const void* d_x, void* d_y);
 // dok.cu
 int dok_to_csr_dev(spam_handle* h, int dtype, u64 rows, u64 cols, u64 n, const u64* d_r, const u64* d_c,
                    const void* d_v, spam_dcsr** out);
+int transpose_dev(spam_handle* h, const spam_dcsr* a, spam_dcsr** out);
 // convert.cu : index width conversion at the host boundary
 int narrow_u64_to_u32(spam_handle* h, const u64* in, u32* out, u64 n);
 int widen_u32_to_u64(spam_handle* h, const u32* in, u64* out, u64 n);

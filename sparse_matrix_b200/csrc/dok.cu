@@ -222,7 +222,120 @@ int dok_typed(spam_handle* h, u64 rows, u64 cols, u64 n, const u64* d_r, const u
   return st;
 }
 
+// ---- CSR transpose ------------------------------------------------------------
+// Reference: `fn transpose` spam_csr/src/lib.rs:256-264 walks (j, i) over cols x rows and moves every stored
+// entry (i, j) — explicit zeros included: CsrMatrix::set_element stores a zero like any value,
+// lib.rs:213-253 — to (j, i) of the new matrix, appending in increasing i.  So row j of the result lists
+// the rows i of A that hold column j in increasing i, whatever the order inside A's rows: a STABLE sort of
+// the entries by column.  Here: key = column, payload = entry position, the same LSD radix sort as above
+// on the column bits only, then one gather.
+__global__ void __launch_bounds__(256) k_transpose_keys(u64 m, u64 cols, const u64* __restrict__ ptr,
+                                                        const u32* __restrict__ idx, u64* __restrict__ keys,
+                                                        u32* __restrict__ pay, u32* __restrict__ erow,
+                                                        u32* __restrict__ col_cnt, Counters* cnt) {
+  const int lane = threadIdx.x & 31;
+  const u64 row = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = row < m;
+  u64 lo = 0, hi = 0;
+  if (valid) { lo = ptr[row]; hi = ptr[row + 1]; }
+  bool bad = false;
+  if (valid && hi - lo <= 32) {
+    for (u64 e = lo; e < hi; ++e) {
+      const u32 c = idx[e];
+      if (c < cols) atomicAdd(&col_cnt[c], 1u); else bad = true;
+      keys[e] = c < cols ? c : 0; pay[e] = (u32)e; erow[e] = (u32)row;
+    }
+  }
+  unsigned longmask = __ballot_sync(0xffffffffu, valid && hi - lo > 32);  // long rows: the whole warp helps
+  while (longmask) {
+    const int src = __ffs(longmask) - 1;
+    longmask &= longmask - 1;
+    const u64 l = __shfl_sync(0xffffffffu, lo, src), hh = __shfl_sync(0xffffffffu, hi, src);
+    const u32 rr = (u32)__shfl_sync(0xffffffffu, row, src);
+    for (u64 e = l + lane; e < hh; e += 32) {
+      const u32 c = idx[e];
+      if (c < cols) atomicAdd(&col_cnt[c], 1u); else bad = true;
+      keys[e] = c < cols ? c : 0; pay[e] = (u32)e; erow[e] = rr;
+    }
+  }
+  if (bad) atomicOr(&cnt->error, 2u);
+}
+
+template <class W>  // W = uint32_t / uint64_t: values are moved, never interpreted
+__global__ void __launch_bounds__(256) k_transpose_emit(u64 n, const u32* __restrict__ pay, const u32* __restrict__ erow,
+                                                        const W* __restrict__ val, u32* __restrict__ t_idx,
+                                                        W* __restrict__ t_val) {
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const u32 e = pay[i];
+    t_idx[i] = erow[e];
+    t_val[i] = val[e];
+  }
+}
+
 }  // namespace
+
+int transpose_dev(spam_handle* h, const spam_dcsr* a, spam_dcsr** out) {
+  *out = nullptr;
+  const u64 m = a->rows, n = a->nnz, tc = a->cols;
+  if (n >= 0xFFFFFFFFull) return spam_fail(h, SPAM_EOVERFLOW, "more than 2^32-1 entries");
+  h->stats = spam_stats{};
+  spam_dcsr* t = new spam_dcsr();
+  t->dtype = a->dtype; t->rows = a->cols; t->cols = a->rows; t->nnz = n; t->owning = true;
+  t->rows_sorted = 1; t->max_row_len = 0;  // rows come out strictly increasing (one entry per (i, j))
+  t->ptr = nullptr; t->idx = nullptr; t->val = nullptr;
+  const size_t es = dtype_size(a->dtype);
+  const u64 nblocks = (n + RS_TILE - 1) / RS_TILE;
+  auto al = [](u64 bytes) { return (bytes + 255) & ~255ull; };
+  const u64 sz_k = al(n * 8), sz_p = al(n * 4), sz_cc = al(tc * 4), sz_hist = al((u64)RADIX * nblocks * 4),
+            sz_offs = al(((u64)RADIX * nblocks + 1) * 8);
+  char* ws = nullptr;
+  int st = dev_alloc(h, (void**)&ws, 2 * sz_k + 3 * sz_p + sz_cc + sz_hist + sz_offs);
+  if (st == SPAM_OK) st = dev_alloc_t(h, &t->ptr, tc + 1);
+  if (st == SPAM_OK) st = dev_alloc_t(h, &t->idx, n);
+  if (st == SPAM_OK) st = dev_alloc(h, &t->val, n * es);
+  auto fail = [&](int s) {
+    dev_free(h, ws); dev_free(h, t->ptr); dev_free(h, t->idx); dev_free(h, t->val);
+    delete t;
+    return s;
+  };
+  if (st != SPAM_OK) return fail(st);
+  char* cur = ws;
+  u64* k0 = (u64*)cur; cur += sz_k;
+  u64* k1 = (u64*)cur; cur += sz_k;
+  u64* offs = (u64*)cur; cur += sz_offs;
+  u32* p0 = (u32*)cur; cur += sz_p;
+  u32* p1 = (u32*)cur; cur += sz_p;
+  u32* erow = (u32*)cur; cur += sz_p;
+  u32* col_cnt = (u32*)cur; cur += sz_cc;
+  u32* hist = (u32*)cur;
+  cudaError_t e = cudaMemsetAsync(h->d_cnt, 0, sizeof(Counters), h->stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(col_cnt, 0, tc * sizeof(u32), h->stream);
+  if (e != cudaSuccess) return fail(spam_fail(h, SPAM_ECUDA, "cudaMemsetAsync", e));
+  if (m) {
+    k_transpose_keys<<<(unsigned)((m + 255) / 256), 256, 0, h->stream>>>(m, tc, a->ptr, a->idx, k0, p0, erow, col_cnt, h->d_cnt);
+    count_launch(h);
+    if ((e = cudaGetLastError()) != cudaSuccess) return fail(spam_fail(h, SPAM_ECUDA, "k_transpose_keys", e));
+  }
+  st = radix_sort_pairs(h, n, bits_for(tc), k0, p0, k1, p1, hist, offs);
+  if (st == SPAM_OK) st = scan_u32_to_u64(h, col_cnt, t->ptr, tc, nullptr);
+  if (st != SPAM_OK) return fail(st);
+  if (n) {
+    if (es == 4)
+      k_transpose_emit<uint32_t><<<grid_for(h, n), 256, 0, h->stream>>>(n, p0, erow, (const uint32_t*)a->val, t->idx, (uint32_t*)t->val);
+    else
+      k_transpose_emit<uint64_t><<<grid_for(h, n), 256, 0, h->stream>>>(n, p0, erow, (const uint64_t*)a->val, t->idx, (uint64_t*)t->val);
+    count_launch(h);
+    if ((e = cudaGetLastError()) != cudaSuccess) return fail(spam_fail(h, SPAM_ECUDA, "k_transpose_emit", e));
+  }
+  e = cudaMemcpyAsync(h->h_cnt, h->d_cnt, sizeof(Counters), cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  if (e != cudaSuccess) return fail(spam_fail(h, SPAM_ECUDA, "transpose sync", e));
+  if (h->h_cnt->error & 2u) return fail(spam_fail(h, SPAM_EINDEX, "a column index is >= cols"));
+  dev_free(h, ws);
+  *out = t;
+  return SPAM_OK;
+}
 
 int dok_to_csr_dev(spam_handle* h, int dtype, u64 rows, u64 cols, u64 n, const u64* d_r, const u64* d_c,
                    const void* d_v, spam_dcsr** out) {

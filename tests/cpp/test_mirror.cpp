@@ -34,6 +34,14 @@ static int run(const char* name, std::mt19937_64& rng) {
     std::vector<T> yw(l, T(0));
     for (auto& ea : da.entries()) yw[ea.first.first] += ea.second * x[ea.first.second];
     if (y != yw) ++fails;
+    // transpose (lib.rs:256-264) against the DOK transpose (spam_dok/src/lib.rs:178-188): entry (i, j) -> (j, i)
+    auto t = a.transpose();
+    if (!t.invariants() || t.rows != m || t.cols != l || t.indices.size() != a.indices.size()) { ++fails; continue; }
+    std::vector<T> dt(m * l, T(0)), dw(m * l, T(0));
+    for (uint64_t r = 0; r < m; ++r)
+      for (uint64_t e = t.offsets[r]; e < t.offsets[r + 1]; ++e) dt[r * l + t.indices[e]] = t.vals[e];
+    for (auto& ea : da.entries()) dw[ea.first.second * l + ea.first.first] = ea.second;
+    if (dt != dw) ++fails;
   }
   std::printf("%s: %s\n", name, fails ? "FAIL" : "ok");
   return fails;

@@ -389,6 +389,38 @@ def test_host_path_uploads_only_the_referenced_band_of_b(oracle, handle):
     check_against_oracle(oracle, a, p, as_csr_matrix(a).mul_hash(full, sorted_output=True, handle=handle), exact_values=True)
 
 
+@pytest.mark.parametrize("dtype", ALL_DTYPES)
+def test_transpose(oracle, handle, dtype):
+    """Matrix::transpose of CsrMatrix (lib.rs:256-264) through the host C ABI and on the device: bit-exact
+    against the oracle (values are moved, never recomputed), explicit zeros kept, unsorted input rows,
+    rows longer than a warp, empty rows and columns, a single element."""
+    rng = np.random.default_rng(21)
+    cases = [(1, 1, 1, True), (9, 4, 3, True), (4, 900, 300, False), (700, 6, 5, False), (300, 300, 0, True),
+             (2000, 1500, 24, False), (64, 5000, 100, True)]
+    for rows, cols, deg, srt in cases:
+        a = random_csr(rng, rows, cols, rng.integers(0, deg + 1, size=rows), dtype=dtype, sorted_rows=srt, zero_frac=0.1)
+        want = oracle.transpose(a)
+        A = as_csr_matrix(a)
+        got = A.transpose(handle=handle)
+        assert (got.rows(), got.cols()) == (cols, rows) and got.invariants()
+        assert np.array_equal(got.offsets, want[0]) and np.array_equal(got.indices, want[1])
+        assert np.array_equal(got.vals.view(np.uint8), want[2].view(np.uint8))
+        dA = S.DeviceCsr.upload(A, handle)
+        dT = dA.transpose()
+        dev = dT.download()
+        assert np.array_equal(dev.offsets, want[0]) and np.array_equal(dev.indices, want[1])
+        assert np.array_equal(dev.vals.view(np.uint8), want[2].view(np.uint8))
+        # the transposed matrix is a valid right-hand side: A * A^T against the oracle (C5's shape of product)
+        if rows * deg and rows <= 2000:
+            c = dA.matmul(dT).download()
+            check_against_oracle(oracle, a, (cols, rows) + want, c)
+        dT.free(); dA.free()
+    bad = S.CsrMatrix(2, 2, np.array([1, 1], dtype=dtype), [0, 1], [0, 1, 2])
+    bad.indices[1] = 7
+    with pytest.raises(IndexError):
+        bad.transpose(handle=handle)
+
+
 def test_scan_sizes_through_dok_row_ptr(oracle, handle):
     """The look-back scan at awkward lengths (around tile and warp boundaries) via DOK row_ptr."""
     rng = np.random.default_rng(4)

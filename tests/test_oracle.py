@@ -293,3 +293,35 @@ def test_spmv_is_mul_hash_with_column_vector(oracle):
     rows = np.repeat(np.arange(80), np.diff(off).astype(np.int64))
     dense[rows] = val
     assert np.array_equal(dense, y)   # bit-identical: same order, same unfused arithmetic
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.int32])
+@pytest.mark.parametrize("sorted_rows", [True, False])
+def test_transpose_literal_loops_equal_stable_column_sort(oracle, dtype, sorted_rows):
+    """CsrMatrix::transpose (lib.rs:256-264): the reference's own (j, i) double loop of set_element calls
+    against the stable counting sort the GPU path is checked with; explicit zeros are kept; an independent
+    check against scipy; (A^T)^T is A with sorted rows."""
+    rng = np.random.default_rng(11)
+    for rows, cols, deg in ((1, 1, 1), (7, 3, 2), (5, 40, 9), (40, 5, 4), (33, 33, 0), (24, 31, 12)):
+        a = random_csr(rng, rows, cols, rng.integers(0, deg + 1, size=rows), dtype=dtype, sorted_rows=sorted_rows,
+                       zero_frac=0.2)
+        lit = oracle.transpose(a, literal=True)
+        fast = oracle.transpose(a)
+        for x, y in zip(lit, fast):
+            assert np.array_equal(x, y)
+        t_off, t_idx, t_val = fast
+        assert int(t_off[-1]) == len(a[3]) and len(t_off) == cols + 1                  # zeros kept
+        for j in range(cols):
+            seg = t_idx[int(t_off[j]):int(t_off[j + 1])]
+            assert np.all(np.diff(seg.astype(np.int64)) > 0)                          # rows sorted
+        # structure through scipy on a zero-free copy of the values (scipy would be free to drop zeros)
+        ones = np.arange(1, len(a[3]) + 1, dtype=np.float64)
+        m = sp.csr_matrix((ones, a[3].astype(np.int64), a[2].astype(np.int64)), shape=(rows, cols)).T.tocsr()
+        m.sort_indices()
+        assert np.array_equal(m.indptr, t_off.astype(np.int64)) and np.array_equal(m.indices, t_idx.astype(np.int64))
+        assert np.array_equal(a[4][(m.data - 1).astype(np.int64)], t_val)
+        back = oracle.transpose((cols, rows) + fast)
+        srt = oracle.transpose((cols, rows) + oracle.transpose(a))                     # = A with sorted rows
+        assert np.array_equal(back[0], a[2]) and np.array_equal(back[0], srt[0])
+        if sorted_rows:
+            assert np.array_equal(back[1], a[3]) and np.array_equal(back[2], a[4])
