@@ -25,6 +25,9 @@ extern "C" {
     pub fn spam_dok_to_csr(h: *mut spam_handle, dtype: c_int, rows: u64, cols: u64, n: u64, tri_rows: *const u64,
         tri_cols: *const u64, tri_vals: *const c_void, c_ptr: *mut u64, c_nnz: *mut u64) -> c_int;
     pub fn spam_dok_to_csr_fetch(h: *mut spam_handle, c_idx: *mut u64, c_val: *mut c_void) -> c_int;
+    /// `Matrix::transpose` of `CsrMatrix` (spam_csr/src/lib.rs:256-264); t_ptr: cols+1, t_idx/t_val: nnz entries
+    pub fn spam_csr_transpose(h: *mut spam_handle, dtype: c_int, rows: u64, cols: u64, ptr: *const u64, idx: *const u64,
+        val: *const c_void, t_ptr: *mut u64, t_idx: *mut u64, t_val: *mut c_void) -> c_int;
 }
 
 /// Element types the device serves.  `Wrapping<i32/i64>` are `repr(transparent)` and map to I32/I64.
