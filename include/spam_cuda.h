@@ -74,6 +74,11 @@ int spam_cuda_set_stream(spam_handle* h, void* cuda_stream);
 /* enable per-phase event timing into spam_stats (adds event records, no syncs beyond the API's own) */
 int spam_cuda_set_timing(spam_handle* h, int enabled);
 int spam_cuda_get_stats(spam_handle* h, spam_stats* out); /* syncs on the last product when timing is on */
+/* Running totals of the CUDA-event phase times (flop, symbolic, scan, numeric, total; ms) over the products
+ * completed since the last reset, and their count.  With timing enabled every product records its phase
+ * events into one of two event sets; a set is read back after the next host synchronisation that covers it,
+ * so a loop of products can be timed per phase without any extra synchronisation inside the loop. */
+int spam_cuda_get_phase_totals(spam_handle* h, double* ms5 /* 5 entries */, uint64_t* products, int reset);
 int spam_cuda_synchronize(spam_handle* h);
 const char* spam_strerror(int status);
 const char* spam_last_error(const spam_handle* h);

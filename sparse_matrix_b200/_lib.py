@@ -21,7 +21,7 @@ STATUS_NAMES = {0: "SPAM_OK", 1: "SPAM_EINVAL", 2: "SPAM_EDIM", 3: "SPAM_ECOLS",
 # every symbol include/spam_cuda.h declares (tests check the .so exports each of them)
 EXPORTS = [
     "spam_cuda_create", "spam_cuda_destroy", "spam_cuda_set_stream", "spam_cuda_set_timing", "spam_cuda_get_stats",
-    "spam_cuda_synchronize", "spam_strerror", "spam_last_error", "spam_cuda_abi_version", "spam_host_alloc",
+    "spam_cuda_synchronize", "spam_cuda_get_phase_totals", "spam_strerror", "spam_last_error", "spam_cuda_abi_version", "spam_host_alloc",
     "spam_host_free", "spam_spgemm_symbolic", "spam_spgemm_numeric", "spam_spmv", "spam_dok_to_csr",
     "spam_dok_to_csr_fetch", "spam_csr_upload", "spam_dcsr_wrap", "spam_dcsr_info", "spam_dcsr_download",
     "spam_dcsr_free", "spam_dcsr_slice_rows", "spam_dcsr_transpose", "spam_csr_transpose", "spam_spgemm_dev", "spam_spmv_dev", "spam_dok_to_csr_dev",
@@ -72,6 +72,7 @@ def load():
     L.spam_cuda_set_timing.argtypes = [vp, i32]
     L.spam_cuda_get_stats.argtypes = [vp, C.POINTER(SpamStats)]
     L.spam_cuda_synchronize.argtypes = [vp]
+    L.spam_cuda_get_phase_totals.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(u64), i32]
     L.spam_host_alloc.argtypes = [C.POINTER(vp), u64]
     L.spam_host_free.argtypes = [vp]
     L.spam_spgemm_symbolic.argtypes = [vp, i32, u64, u64, vp, vp, vp, u64, u64, vp, vp, vp, vp, C.POINTER(u64)]

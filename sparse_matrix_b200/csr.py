@@ -68,6 +68,18 @@ class Handle:
                 "num_bin_rows": list(s.num_bin_rows)}
 
 
+def _phase_totals(self, reset: bool = False) -> dict:
+    """Sums of the per-phase CUDA-event times (ms) over the products finished since the last reset."""
+    ms = (C.c_double * 5)()
+    n = C.c_uint64()
+    check(self.h, self.L.spam_cuda_get_phase_totals(self.h, ms, C.byref(n), 1 if reset else 0))
+    return {"ms_flop": ms[0], "ms_symbolic": ms[1], "ms_scan": ms[2], "ms_numeric": ms[3], "ms_total": ms[4],
+            "products": n.value}
+
+
+Handle.phase_totals = _phase_totals
+
+
 def get_handle(device: int = 0) -> Handle:
     h = _handles.get(device)
     if h is None or h.h is None:

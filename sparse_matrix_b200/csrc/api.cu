@@ -151,22 +151,45 @@ void drop_dok_state(spam_handle* h) {
 
 int valid_dtype(int dt) { return dt == SPAM_F32 || dt == SPAM_F64 || dt == SPAM_I32 || dt == SPAM_I64; }
 
-void finish_timing(spam_handle* h) {
-  if (!h->timing || !h->stats.kernel_launches) return;
-  if (cudaEventSynchronize(h->ev[4]) != cudaSuccess) return;
-  float t;
-  if (cudaEventElapsedTime(&t, h->ev[0], h->ev[1]) == cudaSuccess) h->stats.ms_flop = t;
-  if (cudaEventElapsedTime(&t, h->ev[1], h->ev[2]) == cudaSuccess) h->stats.ms_symbolic = t;
-  if (cudaEventElapsedTime(&t, h->ev[2], h->ev[3]) == cudaSuccess) h->stats.ms_scan = t;
-  if (cudaEventElapsedTime(&t, h->ev[3], h->ev[4]) == cudaSuccess) h->stats.ms_numeric = t;
-  if (cudaEventElapsedTime(&t, h->ev[0], h->ev[4]) == cudaSuccess) h->stats.ms_total = t;
+}  // namespace
+
+void timing_begin_product(spam_handle* h) {
+  if (!h->timing) return;
+  const int other = h->ev_cur ^ 1;
+  if (h->ev_pending[other]) {  // never harvested (no sync covered it yet): wait for it rather than lose it
+    if (cudaEventSynchronize(h->evs[other][4]) == cudaSuccess) timing_harvest(h, other);
+    h->ev_pending[other] = false;
+  }
+  h->ev_cur = other;
+  h->ev = h->evs[other];
 }
 
-}  // namespace
+void timing_harvest(spam_handle* h, int set) {
+  if (!h->ev_pending[set]) return;
+  h->ev_pending[set] = false;
+  cudaEvent_t* e = h->evs[set];
+  float t[5];
+  if (cudaEventElapsedTime(&t[0], e[0], e[1]) != cudaSuccess || cudaEventElapsedTime(&t[1], e[1], e[2]) != cudaSuccess ||
+      cudaEventElapsedTime(&t[2], e[2], e[3]) != cudaSuccess || cudaEventElapsedTime(&t[3], e[3], e[4]) != cudaSuccess ||
+      cudaEventElapsedTime(&t[4], e[0], e[4]) != cudaSuccess) {
+    cudaGetLastError();
+    return;
+  }
+  h->stats.ms_flop = t[0]; h->stats.ms_symbolic = t[1]; h->stats.ms_scan = t[2]; h->stats.ms_numeric = t[3];
+  h->stats.ms_total = t[4];
+  for (int i = 0; i < 5; ++i) h->acc_ms[i] += t[i];
+  h->acc_n += 1;
+}
+
+void finish_timing(spam_handle* h) {
+  if (!h->timing || !h->ev_pending[h->ev_cur]) return;
+  if (cudaEventSynchronize(h->ev[4]) != cudaSuccess) return;
+  timing_harvest(h, h->ev_cur);
+}
 
 extern "C" {
 
-int spam_cuda_abi_version(void) { return 3; }  // 2: spam_stats bin arrays grew to 16 entries; 3: spam_rows_to_parts_cost
+int spam_cuda_abi_version(void) { return 4; }  // 2: spam_stats bin arrays grew to 16 entries; 3: spam_rows_to_parts_cost; 4: transpose, phase totals
 
 const char* spam_strerror(int s) {
   switch (s) {
@@ -198,7 +221,10 @@ int spam_cuda_create(spam_handle** out, int device) {
   h->scan_ws = nullptr; h->scan_ws_cap = 0;
   h->d_cnt = nullptr; h->h_cnt = nullptr; h->own_stream = nullptr; h->stream = nullptr;
   h->stats = spam_stats{};
-  for (auto& e : h->ev) e = nullptr;
+  for (auto& set : h->evs) for (auto& e : set) e = nullptr;
+  h->ev = h->evs[0]; h->ev_cur = 0; h->ev_pending[0] = h->ev_pending[1] = false;
+  for (auto& a : h->acc_ms) a = 0.0;
+  h->acc_n = 0;
   for (auto& s : h->lane) s = nullptr;
   for (auto& e : h->lane_ev) e = nullptr;
   cudaError_t e = cudaSetDevice(device);
@@ -206,7 +232,7 @@ int spam_cuda_create(spam_handle** out, int device) {
   h->stream = h->own_stream;
   if (e == cudaSuccess) e = cudaMalloc((void**)&h->d_cnt, sizeof(Counters));
   if (e == cudaSuccess) e = cudaHostAlloc((void**)&h->h_cnt, sizeof(Counters), cudaHostAllocDefault);
-  for (int i = 0; i < 6 && e == cudaSuccess; ++i) e = cudaEventCreate(&h->ev[i]);
+  for (int i = 0; i < 12 && e == cudaSuccess; ++i) e = cudaEventCreate(&h->evs[i / 6][i % 6]);
   for (int i = 0; i < 3 && e == cudaSuccess; ++i) e = cudaStreamCreateWithFlags(&h->lane[i], cudaStreamNonBlocking);
   for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&h->lane_ev[i], cudaEventDisableTiming);
   cudaDeviceProp prop;
@@ -238,7 +264,7 @@ int spam_cuda_destroy(spam_handle* h) {
   drop_dok_state(h);
   if (h->scan_ws) { dev_free(h, h->scan_ws); h->scan_ws = nullptr; }
   if (h->stream) cudaStreamSynchronize(h->stream);
-  for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+  for (auto& set : h->evs) for (auto& e : set) if (e) cudaEventDestroy(e);
   for (auto& s : h->lane) if (s) { cudaStreamSynchronize(s); cudaStreamDestroy(s); }
   for (auto& e : h->lane_ev) if (e) cudaEventDestroy(e);
   if (h->d_cnt) cudaFree(h->d_cnt);
@@ -264,6 +290,20 @@ int spam_cuda_get_stats(spam_handle* h, spam_stats* out) {
   if (!h || !out) return SPAM_EINVAL;
   finish_timing(h);
   *out = h->stats;
+  return SPAM_OK;
+}
+
+int spam_cuda_get_phase_totals(spam_handle* h, double* ms5, uint64_t* products, int reset) {
+  if (!h) return SPAM_EINVAL;
+  finish_timing(h);
+  if (h->ev_pending[h->ev_cur ^ 1] && cudaEventSynchronize(h->evs[h->ev_cur ^ 1][4]) == cudaSuccess)
+    timing_harvest(h, h->ev_cur ^ 1);
+  if (ms5) for (int i = 0; i < 5; ++i) ms5[i] = h->acc_ms[i];
+  if (products) *products = h->acc_n;
+  if (reset) {
+    for (auto& a : h->acc_ms) a = 0.0;
+    h->acc_n = 0;
+  }
   return SPAM_OK;
 }
 

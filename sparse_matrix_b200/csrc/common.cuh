@@ -164,7 +164,15 @@ struct spam_handle {
   int max_smem_optin;
   void* pending;             // SpgemmHostState* (api.cu) between the two host phases
   DokPending* dok_pending;
-  cudaEvent_t ev[6];
+  // phase events, two sets: a product records into one set while the previous product's set is still
+  // un-harvested; a set is harvested (elapsed times -> stats + running totals) after the next host sync
+  // that covers it, so per-phase timing adds no synchronisation of its own
+  cudaEvent_t evs[2][6];
+  cudaEvent_t* ev;       // = evs[ev_cur]
+  int ev_cur;
+  bool ev_pending[2];
+  double acc_ms[5];      // flop, symbolic, scan, numeric, total over the harvested products
+  u64 acc_n;
   // side lanes: the per-bin kernels of one product touch disjoint rows, so they are spread over the main
   // stream and NLANES-1 internal streams (fork/join by events) and the tail of one bin overlaps the next
   cudaStream_t lane[3];
@@ -225,6 +233,11 @@ static inline cudaStream_t lane_of(spam_handle* h, int bin) {
     default: return h->stream;
   }
 }
+
+// api.cu : phase-event bookkeeping
+void timing_begin_product(spam_handle* h);          // switch to the other event set
+void timing_harvest(spam_handle* h, int set);       // events of `set` are known complete
+void finish_timing(spam_handle* h);                 // wait for the current set, harvest it
 
 // ---- entry points implemented across the .cu files ---------------------------------------------
 // scan.cu : exclusive scan of u32 counts into u64 offsets (out has n+1 entries), decoupled look-back

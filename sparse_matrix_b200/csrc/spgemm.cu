@@ -733,6 +733,7 @@ int spgemm_symbolic_dev(spam_handle* h, const spam_dcsr* a, const spam_dcsr* b, 
   FAIL_FREE(dev_alloc_t(h, &p->d_row_nnz, m));
   FAIL_FREE(dev_alloc_t(h, &p->d_cptr, m + 1));
   CK_FREE(cudaMemsetAsync(h->d_cnt, 0, sizeof(Counters), h->stream));
+  timing_begin_product(h);
   if (h->timing) CK_FREE(cudaEventRecord(h->ev[0], h->stream));
   bool fused = false;
   if (merge_ok && m) {
@@ -762,6 +763,8 @@ int spgemm_symbolic_dev(spam_handle* h, const spam_dcsr* a, const spam_dcsr* b, 
   CK_FREE(cudaMemcpyAsync(h->h_cnt, h->d_cnt, sizeof(Counters), cudaMemcpyDeviceToHost, h->stream));
   if (fused && h->timing) CK_FREE(cudaEventRecord(h->ev[3], h->stream));
   CK_FREE(cudaStreamSynchronize(h->stream));
+  // (the previous product finished before this sync: its phase events are read back at the end of the numeric
+  // phase, while the GPU is busy, not here where it would wait for the host)
   const Counters c1 = *h->h_cnt;
   if (c1.error & 1u) {
     spgemm_pending_free(h, p); *out = nullptr;
@@ -1006,6 +1009,10 @@ int spgemm_numeric_dev(spam_handle* h, SpgemmPending* p, spam_dcsr** cout) {
   if (st == SPAM_OK && h->timing) {
     cudaError_t e = cudaEventRecord(h->ev[4], h->stream);
     if (e != cudaSuccess) st = spam_fail(h, SPAM_ECUDA, "cudaEventRecord", e);
+    else {
+      h->ev_pending[h->ev_cur] = true;
+      timing_harvest(h, h->ev_cur ^ 1);  // previous product: complete since this product's symbolic sync
+    }
   }
   if (st != SPAM_OK) {
     dev_free(h, c->idx); dev_free(h, c->val);
