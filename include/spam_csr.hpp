@@ -143,6 +143,22 @@ class CsrMatrix {
     return y;
   }
 
+  // impl Add / Sub for CsrMatrix -> apply_elementwise (spam_csr/src/lib.rs:83-149, 276-290)
+  CsrMatrix<T, IS_SORTED> ewise(const CsrMatrix<T, IS_SORTED>& rhs, int op, Handle& h = Handle::thread_default()) const {
+    if (rows != rhs.rows || cols != rhs.cols) throw std::runtime_error("matrices must have identical dimensions");
+    CsrMatrix<T, IS_SORTED> c(rows, cols);
+    uint64_t nnz = 0;
+    h.check(spam_csr_ewise(h.get(), op | (IS_SORTED ? 0 : 2), device_scalar<T>::dtype, rows, cols, offsets.data(),
+                           indices.data(), vals.data(), rhs.offsets.data(), rhs.indices.data(), rhs.vals.data(),
+                           c.offsets.data(), &nnz));
+    c.indices.resize(nnz);
+    c.vals.resize(nnz);
+    h.check(spam_csr_ewise_fetch(h.get(), c.indices.data(), c.vals.data()));
+    return c;
+  }
+  CsrMatrix<T, IS_SORTED> operator+(const CsrMatrix<T, IS_SORTED>& rhs) const { return ewise(rhs, 0); }
+  CsrMatrix<T, IS_SORTED> operator-(const CsrMatrix<T, IS_SORTED>& rhs) const { return ewise(rhs, 1); }
+
   // Matrix::transpose (spam_csr/src/lib.rs:256-264); rows of the result are sorted by column
   CsrMatrix<T, true> transpose(Handle& h = Handle::thread_default()) const {
     CsrMatrix<T, true> t(cols, rows);

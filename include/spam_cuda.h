@@ -127,12 +127,27 @@ int spam_dcsr_slice_rows(spam_handle* h, const spam_dcsr* m, uint64_t r0, uint64
 /* Transpose.  Replaces `Matrix::transpose` of CsrMatrix, spam_csr/src/lib.rs:256-264 (an O(rows*cols)
  * loop of set_element calls in the reference; for matrices without explicit zeros the same result as
  * DokMatrix::transpose, spam_dok/src/lib.rs:178-188, followed by From<DokMatrix>): every stored entry
- * (i, j, v) — explicit zeros included, CsrMatrix::set_element stores them — becomes (j, i, v); rows of the result are sorted by column whatever the order inside
- * the input's rows.  Device: *out is a new owning matrix.  Host: t_ptr has cols+1 entries, t_idx / t_val
- * have nnz = ptr[rows] entries (the caller knows all sizes up front, so one phase). */
+ * (i, j, v) — explicit zeros included, CsrMatrix::set_element stores them — becomes (j, i, v); rows of
+ * the result are sorted by column whatever the order inside the input's rows.  Device: *out is a new
+ * owning matrix.  Host: t_ptr has cols+1 entries, t_idx / t_val have nnz = ptr[rows] entries (the caller
+ * knows all sizes up front, so one phase). */
 int spam_dcsr_transpose(spam_handle* h, const spam_dcsr* m, spam_dcsr** out);
 int spam_csr_transpose(spam_handle* h, int dtype, uint64_t rows, uint64_t cols, const uint64_t* ptr,
                        const uint64_t* idx, const void* val, uint64_t* t_ptr, uint64_t* t_idx, void* t_val);
+
+/* Elementwise C = A + B (op 0) or A - B (op 1).  Replaces `impl Add / Sub for CsrMatrix` ->
+ * `apply_elementwise`, spam_csr/src/lib.rs:83-149, 276-290: per row the union of the two column sets; a column
+ * in both rows gives f(t1, t2), in one row f(t, 0) or f(0, t); nothing is filtered (cancellation zeros stay);
+ * rows of the result are sorted by column (the reference's unsorted branch iterates a std HashMap, whose
+ * order is unspecified).  `op | 2` applies the IS_SORTED = false branch's rule for entries only in the left
+ * operand (kept as they are instead of f(t, 0), lib.rs:119-137; differs only for t = -0.0 under add).
+ * SPAM_EDIM when the shapes differ (the reference asserts, lib.rs:87-91).
+ * Host path in two phases like DOK -> CSR: phase 1 writes c_ptr[rows+1] and *c_nnz, phase 2 fills. */
+int spam_dcsr_ewise(spam_handle* h, int op, const spam_dcsr* a, const spam_dcsr* b, spam_dcsr** out);
+int spam_csr_ewise(spam_handle* h, int op, int dtype, uint64_t rows, uint64_t cols, const uint64_t* a_ptr,
+                   const uint64_t* a_idx, const void* a_val, const uint64_t* b_ptr, const uint64_t* b_idx,
+                   const void* b_val, uint64_t* c_ptr, uint64_t* c_nnz);
+int spam_csr_ewise_fetch(spam_handle* h, uint64_t* c_idx, void* c_val);
 
 /* C = A * B, all on the device; *c is a new owning matrix (stream-ordered allocation). */
 int spam_spgemm_dev(spam_handle* h, const spam_dcsr* a, const spam_dcsr* b, spam_dcsr** c);

@@ -42,6 +42,7 @@ def lib():
         L.oracle_dok_dense_mul.restype = C.c_int
         L.oracle_spmv.restype = C.c_int
         L.oracle_transpose.restype = C.c_int
+        L.oracle_ewise.restype = C.c_int
         L.oracle_table_size_for.restype = C.c_uint64
         L.oracle_table_size_for.argtypes = [C.c_uint64]
         L.oracle_hash.restype = C.c_uint64
@@ -180,6 +181,28 @@ def transpose(mat, literal: bool = False):
     if rc != 0:
         raise RuntimeError(f"oracle_transpose rc={rc}")
     return t_off, t_idx, t_val
+
+
+def ewise(a, b, op: str = "add", is_sorted: bool = True):
+    """impl Add / Sub for CsrMatrix (apply_elementwise, lib.rs:83-149): (offsets, indices, vals) of a op b.
+    `is_sorted` is the operands' IS_SORTED const generic (selects the merge-join or the HashMap branch)."""
+    L = lib()
+    ar, ac, a_off, a_idx, a_val = a
+    br, bc, b_off, b_idx, b_val = b
+    a_off, a_idx, a_val = _u64(a_off), _u64(a_idx), np.ascontiguousarray(a_val)
+    b_off, b_idx, b_val = _u64(b_off), _u64(b_idx), np.ascontiguousarray(b_val, dtype=a_val.dtype)
+    c_off, c_idx, c_val = C.c_void_p(), C.c_void_p(), C.c_void_p()
+    nnz = C.c_uint64()
+    rc = L.oracle_ewise(C.c_int(DT[a_val.dtype]), C.c_int({"add": 0, "sub": 1}[op]), C.c_int(1 if is_sorted else 0),
+                        C.c_uint64(ar), C.c_uint64(ac), C.c_uint64(br), C.c_uint64(bc), _ptr(a_off), _ptr(a_idx),
+                        _ptr(a_val), _ptr(b_off), _ptr(b_idx), _ptr(b_val), C.byref(c_off), C.byref(c_idx),
+                        C.byref(c_val), C.byref(nnz))
+    if rc == 2:
+        raise ValueError("matrices must have identical dimensions")
+    if rc != 0:
+        raise RuntimeError(f"oracle_ewise rc={rc}")
+    n = nnz.value
+    return _take(c_off.value, ar + 1, np.uint64), _take(c_idx.value, n, np.uint64), _take(c_val.value, n, a_val.dtype)
 
 
 def dok_dense_mul(a: np.ndarray, b: np.ndarray) -> np.ndarray:

@@ -507,6 +507,73 @@ int oracle_transpose(int dtype, uint64_t rows, uint64_t cols, const uint64_t* of
   });
 }
 
+// impl Add / Sub for CsrMatrix -> apply_elementwise (spam_csr/src/lib.rs:83-149, 276-290).
+//   IS_SORTED = true  (lib.rs:102-118): merge_join_by on the column of the two rows;
+//       Both -> f(t1, t2), Left -> f(t, 0), Right -> f(0, t); output in column order.
+//   IS_SORTED = false (lib.rs:119-137): the left row goes into a std HashMap; every right entry does
+//       entry = f(entry-or-zero, t); entries only in the left row keep their value untouched.  The map's
+//       iteration order is unspecified (RandomState), so this restatement emits the row sorted by column.
+// op: 0 add, 1 sub (wrapping for integers, like the device scalar types).  No entry is ever dropped.
+// Outputs are malloc'ed; free with oracle_free.  rc 2: shapes differ (the reference asserts, lib.rs:87-91).
+int oracle_ewise(int dtype, int op, int is_sorted, uint64_t rows, uint64_t a_cols, uint64_t b_rows, uint64_t b_cols,
+                 const uint64_t* a_off, const uint64_t* a_idx, const void* a_val, const uint64_t* b_off,
+                 const uint64_t* b_idx, const void* b_val, uint64_t** c_off, uint64_t** c_idx, void** c_val,
+                 uint64_t* c_nnz) {
+  if (rows != b_rows || a_cols != b_cols) return 2;
+  return dispatch(dtype, [&](auto tag) {
+    using T = decltype(tag);
+    const T* av = (const T*)a_val;
+    const T* bv = (const T*)b_val;
+    auto f = [op](T x, T y) -> T {
+      if constexpr (std::is_integral<T>::value) {
+        using U = typename std::make_unsigned<T>::type;
+        return (T)(op == 0 ? (U)((U)x + (U)y) : (U)((U)x - (U)y));
+      } else {
+        return op == 0 ? x + y : x - y;
+      }
+    };
+    std::vector<u64> off(rows + 1, 0), idx;
+    std::vector<T> val;
+    for (u64 r = 0; r < rows; ++r) {
+      std::vector<std::pair<u64, T>> left, right, out;
+      for (u64 e = a_off[r]; e < a_off[r + 1]; ++e) left.emplace_back(a_idx[e], av[e]);
+      for (u64 e = b_off[r]; e < b_off[r + 1]; ++e) right.emplace_back(b_idx[e], bv[e]);
+      if (is_sorted) {
+        size_t i = 0, j = 0;
+        while (i < left.size() || j < right.size()) {
+          if (j == right.size() || (i < left.size() && left[i].first < right[j].first)) {
+            out.emplace_back(left[i].first, f(left[i].second, T(0))); ++i;
+          } else if (i == left.size() || right[j].first < left[i].first) {
+            out.emplace_back(right[j].first, f(T(0), right[j].second)); ++j;
+          } else {
+            out.emplace_back(left[i].first, f(left[i].second, right[j].second)); ++i; ++j;
+          }
+        }
+      } else {
+        std::map<u64, T> row;  // ordered stand-in for the HashMap: only the iteration order differs
+        for (auto& p : left) row[p.first] = p.second;  // collect(): a later duplicate key would replace
+        for (auto& p : right) {
+          auto it = row.find(p.first);
+          if (it == row.end()) it = row.emplace(p.first, T(0)).first;
+          it->second = f(it->second, p.second);
+        }
+        for (auto& p : row) out.emplace_back(p.first, p.second);
+      }
+      for (auto& p : out) { idx.push_back(p.first); val.push_back(p.second); }
+      off[r + 1] = idx.size();
+    }
+    *c_nnz = idx.size();
+    *c_off = (u64*)std::malloc((rows + 1) * sizeof(u64));
+    *c_idx = (u64*)std::malloc(std::max<size_t>(1, idx.size()) * sizeof(u64));
+    T* cv = (T*)std::malloc(std::max<size_t>(1, val.size()) * sizeof(T));
+    std::memcpy(*c_off, off.data(), (rows + 1) * sizeof(u64));
+    if (!idx.empty()) std::memcpy(*c_idx, idx.data(), idx.size() * sizeof(u64));
+    if (!val.empty()) std::memcpy(cv, val.data(), val.size() * sizeof(T));
+    *c_val = cv;
+    return 0;
+  });
+}
+
 int oracle_dok_dense_mul(int dtype, uint64_t l, uint64_t m, uint64_t n, const void* a, const void* b, void* c) {
   return dispatch(dtype, [&](auto tag) {
     using T = decltype(tag);

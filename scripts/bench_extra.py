@@ -42,7 +42,7 @@ def timed(fn, stream, reps=20, warm=3):
 
 
 def main():
-    which = sys.argv[1:] or ["spmv", "dok", "rect"]
+    which = sys.argv[1:] or ["spmv", "ewise", "dok", "rect"]
     dev = torch.device("cuda", 0)
     stream = None
     h = S.Handle(0)   # the handle's own non-blocking stream
@@ -73,6 +73,35 @@ def main():
                           "algorithmic_bytes": by, "gbs": by / ms / 1e6, "frac_of_measured_peak": by / ms / 1e6 / peak,
                           "peak_source": src, "parity_ok": ok, "cpu_oracle_ms_1thread": cpu_ms}), flush=True)
         dA.free()
+
+    if "ewise" in which:
+        # C = A*A + A on the Poisson matrix (the add on either side of a product)
+        p = G.poisson2d(2048)
+        A = S.CsrMatrix(p[0], p[1], p[4], p[3], p[2])
+        dA = S.DeviceCsr.upload(A, h)
+        dB = dA.matmul(dA)
+        outs = []
+
+        def run_add():
+            outs.append(dB.add(dA))
+            if len(outs) > 1:
+                outs.pop(0).free()
+        ms = timed(run_add, stream, reps=10)
+        got = outs[-1].download()
+        b_host = dB.download()
+        t0 = time.perf_counter()
+        want = O.ewise((p[0], p[1], b_host.offsets, b_host.indices, b_host.vals), p, "add", True)
+        cpu_ms = (time.perf_counter() - t0) * 1e3
+        ok = bool(np.array_equal(got.offsets, want[0]) and np.array_equal(got.indices, want[1]) and
+                  np.array_equal(got.vals, want[2]))
+        nb, na, nc = b_host.nnz(), len(p[3]), got.nnz()
+        by = (na + nb + nc) * 12 + 3 * (p[0] + 1) * 8      # read A and B once, write C once (count pass not credited)
+        print(json.dumps({"op": "ewise_add", "workload": "poisson2048 f64: A*A + A", "nnz_a": na, "nnz_b": nb, "nnz_c": nc,
+                          "ms": ms, "algorithmic_bytes": by, "gbs": by / ms / 1e6, "frac_of_measured_peak": by / ms / 1e6 / peak,
+                          "parity_ok": ok, "cpu_oracle_ms_1thread": cpu_ms}), flush=True)
+        for d in outs:
+            d.free()
+        dB.free(); dA.free()
 
     if "dok" in which or "rect" in which:
         a = G.uniform_random(1_000_000, 4_000_000, 8, seed=5, dtype=np.int64, int_range=1 << 15)

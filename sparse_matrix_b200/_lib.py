@@ -25,7 +25,8 @@ EXPORTS = [
     "spam_host_free", "spam_spgemm_symbolic", "spam_spgemm_numeric", "spam_spmv", "spam_dok_to_csr",
     "spam_dok_to_csr_fetch", "spam_csr_upload", "spam_dcsr_wrap", "spam_dcsr_info", "spam_dcsr_download",
     "spam_dcsr_free", "spam_dcsr_slice_rows", "spam_dcsr_transpose", "spam_csr_transpose", "spam_spgemm_dev", "spam_spmv_dev", "spam_dok_to_csr_dev",
-    "spam_rows_to_parts", "spam_rows_to_parts_cost", "spam_offset_u64",
+    "spam_rows_to_parts", "spam_rows_to_parts_cost", "spam_offset_u64", "spam_dcsr_ewise", "spam_csr_ewise",
+    "spam_csr_ewise_fetch",
 ]
 
 
@@ -87,6 +88,9 @@ def load():
     L.spam_dcsr_download.argtypes = [vp, vp, vp, vp, vp]
     L.spam_dcsr_free.argtypes = [vp, vp]
     L.spam_dcsr_slice_rows.argtypes = [vp, vp, u64, u64, C.POINTER(vp)]
+    L.spam_dcsr_ewise.argtypes = [vp, i32, vp, vp, C.POINTER(vp)]
+    L.spam_csr_ewise.argtypes = [vp, i32, i32, u64, u64, vp, vp, vp, vp, vp, vp, vp, C.POINTER(u64)]
+    L.spam_csr_ewise_fetch.argtypes = [vp, vp, vp]
     L.spam_dcsr_transpose.argtypes = [vp, vp, C.POINTER(vp)]
     L.spam_csr_transpose.argtypes = [vp, i32, u64, u64, vp, vp, vp, vp, vp, vp]
     L.spam_spgemm_dev.argtypes = [vp, vp, vp, C.POINTER(vp)]

@@ -142,6 +142,17 @@ class DeviceCsr:
         check(self.handle.h, self.handle.L.spam_spgemm_dev(self.handle.h, self.p, rhs.p, C.byref(out)))
         return DeviceCsr(self.handle, out)
 
+    def add(self, rhs: "DeviceCsr") -> "DeviceCsr":
+        """impl Add for CsrMatrix (apply_elementwise, lib.rs:83-149) on the device."""
+        out = C.c_void_p()
+        check(self.handle.h, self.handle.L.spam_dcsr_ewise(self.handle.h, 0, self.p, rhs.p, C.byref(out)))
+        return DeviceCsr(self.handle, out)
+
+    def sub(self, rhs: "DeviceCsr") -> "DeviceCsr":
+        out = C.c_void_p()
+        check(self.handle.h, self.handle.L.spam_dcsr_ewise(self.handle.h, 1, self.p, rhs.p, C.byref(out)))
+        return DeviceCsr(self.handle, out)
+
     def transpose(self) -> "DeviceCsr":
         """Matrix::transpose (spam_csr/src/lib.rs:256-264) on the device; rows of the result are sorted."""
         out = C.c_void_p()
@@ -328,6 +339,40 @@ class CsrMatrix:
         return self.mul_hash(rhs, sorted_output=False)
 
     __matmul__ = __mul__
+
+    # ---- elementwise add / sub (impl Add / Sub -> apply_elementwise, lib.rs:83-149, 276-290) ----
+    def _ewise(self, rhs: "CsrMatrix", op: int, handle: Optional[Handle]) -> "CsrMatrix":
+        if self.vals.dtype != rhs.vals.dtype:
+            raise TypeError("operand element types differ")
+        if (self.rows_, self.cols_) != (rhs.rows_, rhs.cols_):
+            raise _lib.DimensionMismatch(2, "matrices must have identical dimensions")   # assert_eq!, lib.rs:87-91
+        handle = handle or get_handle()
+        L, h = handle.L, handle.h
+        c_ptr = np.empty(self.rows_ + 1, dtype=np.uint64)
+        nnz = C.c_uint64()
+        same = rhs is self
+        if not self.is_sorted:
+            op |= 2    # IS_SORTED = false: entries only in the left operand are kept untouched (lib.rs:119-137)
+        check(h, L.spam_csr_ewise(h, op, _dtype_code(self.vals.dtype), self.rows_, self.cols_, ptr(self.offsets),
+                                  ptr(self.indices), ptr(self.vals), ptr(self.offsets if same else rhs.offsets),
+                                  ptr(self.indices if same else rhs.indices), ptr(self.vals if same else rhs.vals),
+                                  ptr(c_ptr), C.byref(nnz)))
+        c_idx = np.empty(nnz.value, dtype=np.uint64)
+        c_val = np.empty(nnz.value, dtype=self.vals.dtype)
+        check(h, L.spam_csr_ewise_fetch(h, ptr(c_idx), ptr(c_val)))
+        return CsrMatrix(self.rows_, self.cols_, c_val, c_idx, c_ptr, is_sorted=self.is_sorted)
+
+    def add(self, rhs: "CsrMatrix", handle: Optional[Handle] = None) -> "CsrMatrix":
+        return self._ewise(rhs, 0, handle)
+
+    def sub(self, rhs: "CsrMatrix", handle: Optional[Handle] = None) -> "CsrMatrix":
+        return self._ewise(rhs, 1, handle)
+
+    def __add__(self, rhs: "CsrMatrix") -> "CsrMatrix":
+        return self._ewise(rhs, 0, None)
+
+    def __sub__(self, rhs: "CsrMatrix") -> "CsrMatrix":
+        return self._ewise(rhs, 1, None)
 
     def transpose(self, handle: Optional[Handle] = None) -> "CsrMatrix":
         """Matrix::transpose (spam_csr/src/lib.rs:256-264): every stored entry (i, j, v), explicit zeros

@@ -677,6 +677,44 @@ int spam_dok_to_csr_fetch(spam_handle* h, uint64_t* c_idx, void* c_val) {
   return st;
 }
 
+/* ---------------- elementwise add / sub ---------------- */
+
+int spam_dcsr_ewise(spam_handle* h, int op, const spam_dcsr* a, const spam_dcsr* b, spam_dcsr** out) {
+  if (!h || !a || !b || !out) return spam_fail(h, SPAM_EINVAL, "null argument");
+  CKS(set_device(h));
+  return ewise_dev(h, op, a, b, out);
+}
+
+// host path, two phases like DOK -> CSR (the result size is known only after the count): phase 1 writes
+// c_ptr and *c_nnz and parks the result on the device, spam_csr_ewise_fetch downloads it
+int spam_csr_ewise(spam_handle* h, int op, int dtype, uint64_t rows, uint64_t cols, const uint64_t* a_ptr,
+                   const uint64_t* a_idx, const void* a_val, const uint64_t* b_ptr, const uint64_t* b_idx,
+                   const void* b_val, uint64_t* c_ptr, uint64_t* c_nnz) {
+  if (!h || !a_ptr || !b_ptr || !c_ptr || !c_nnz || !valid_dtype(dtype)) return spam_fail(h, SPAM_EINVAL, "bad argument");
+  CKS(set_device(h));
+  drop_dok_state(h);
+  spam_dcsr *a = nullptr, *b = nullptr, *c = nullptr;
+  h->stats = spam_stats{};
+  CKS(spam_csr_upload(h, dtype, rows, cols, a_ptr[rows], a_ptr, a_idx, a_val, &a));
+  const bool alias = (b_ptr == a_ptr && b_idx == a_idx && b_val == a_val);
+  int st = SPAM_OK;
+  if (alias) b = a; else st = spam_csr_upload(h, dtype, rows, cols, b_ptr[rows], b_ptr, b_idx, b_val, &b);
+  const u64 h2d = h->stats.bytes_h2d;
+  if (st == SPAM_OK) st = ewise_dev(h, op, a, b, &c);  // resets stats
+  if (st == SPAM_OK) {
+    h->stats.bytes_h2d = h2d;
+    st = spam_dcsr_download(h, c, c_ptr, nullptr, nullptr);
+  }
+  if (b != a) free_dcsr(h, b);
+  free_dcsr(h, a);
+  if (st != SPAM_OK) { free_dcsr(h, c); return st; }
+  *c_nnz = c->nnz;
+  h->dok_pending = new DokPending{c};
+  return SPAM_OK;
+}
+
+int spam_csr_ewise_fetch(spam_handle* h, uint64_t* c_idx, void* c_val) { return spam_dok_to_csr_fetch(h, c_idx, c_val); }
+
 /* ---------------- multi-GPU helpers ---------------- */
 
 static int rows_to_parts_impl(spam_handle* h, const spam_dcsr* a, const spam_dcsr* b, uint32_t parts,

@@ -90,12 +90,14 @@ template <class T> struct Num;
 template <> struct Num<float> {
   static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
   static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+  static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
   static __device__ __forceinline__ void atomic_add(float* p, float v) { atomicAdd(p, v); }
   static __device__ __forceinline__ float zero() { return 0.f; }
 };
 template <> struct Num<double> {
   static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
   static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+  static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
   static __device__ __forceinline__ void atomic_add(double* p, double v) { atomicAdd(p, v); }
   static __device__ __forceinline__ double zero() { return 0.0; }
 };
@@ -103,12 +105,14 @@ template <> struct Num<double> {
 template <> struct Num<int32_t> {
   static __device__ __forceinline__ int32_t mul(int32_t a, int32_t b) { return (int32_t)((u32)a * (u32)b); }
   static __device__ __forceinline__ int32_t add(int32_t a, int32_t b) { return (int32_t)((u32)a + (u32)b); }
+  static __device__ __forceinline__ int32_t sub(int32_t a, int32_t b) { return (int32_t)((u32)a - (u32)b); }
   static __device__ __forceinline__ void atomic_add(int32_t* p, int32_t v) { atomicAdd((u32*)p, (u32)v); }
   static __device__ __forceinline__ int32_t zero() { return 0; }
 };
 template <> struct Num<int64_t> {
   static __device__ __forceinline__ int64_t mul(int64_t a, int64_t b) { return (int64_t)((u64)a * (u64)b); }
   static __device__ __forceinline__ int64_t add(int64_t a, int64_t b) { return (int64_t)((u64)a + (u64)b); }
+  static __device__ __forceinline__ int64_t sub(int64_t a, int64_t b) { return (int64_t)((u64)a - (u64)b); }
   static __device__ __forceinline__ void atomic_add(int64_t* p, int64_t v) { atomicAdd((ull*)p, (ull)v); }
   static __device__ __forceinline__ int64_t zero() { return 0; }
 };
@@ -257,6 +261,8 @@ int spmv_dev(spam_handle* h, const spam_dcsr* a, const void* d_x, void* d_y);
 int dok_to_csr_dev(spam_handle* h, int dtype, u64 rows, u64 cols, u64 n, const u64* d_r, const u64* d_c,
                    const void* d_v, spam_dcsr** out);
 int transpose_dev(spam_handle* h, const spam_dcsr* a, spam_dcsr** out);
+// ewise.cu : C = A + B (op 0) / A - B (op 1)
+int ewise_dev(spam_handle* h, int op, const spam_dcsr* a, const spam_dcsr* b, spam_dcsr** out);
 // convert.cu : index width conversion at the host boundary
 int narrow_u64_to_u32(spam_handle* h, const u64* in, u32* out, u64 n);
 int widen_u32_to_u64(spam_handle* h, const u32* in, u64* out, u64 n);

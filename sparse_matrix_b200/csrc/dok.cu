@@ -282,7 +282,7 @@ int transpose_dev(spam_handle* h, const spam_dcsr* a, spam_dcsr** out) {
   h->stats = spam_stats{};
   spam_dcsr* t = new spam_dcsr();
   t->dtype = a->dtype; t->rows = a->cols; t->cols = a->rows; t->nnz = n; t->owning = true;
-  t->rows_sorted = 1; t->max_row_len = 0;  // rows come out strictly increasing (one entry per (i, j))
+  t->rows_sorted = -1; t->max_row_len = 0;  // sorted by construction; the cached stats (longest row) are taken lazily
   t->ptr = nullptr; t->idx = nullptr; t->val = nullptr;
   const size_t es = dtype_size(a->dtype);
   const u64 nblocks = (n + RS_TILE - 1) / RS_TILE;

@@ -1,0 +1,170 @@
+// ewise.cu — elementwise C = A + B / A - B on the device.
+//
+// Replaces `impl Add / Sub for CsrMatrix` -> `apply_elementwise` (spam_csr/src/lib.rs:83-149, 276-290).
+// IS_SORTED branch of the reference: per row, a merge-join of the two sorted column lists; a column in both
+// rows gives f(t1, t2), only in the left row f(t, 0), only in the right row f(0, t) (lib.rs:112-116).  Nothing
+// is filtered: cancellation zeros and explicit zeros stay (there is no is_zero test in apply_elementwise).
+// The unsorted branch (lib.rs:119-137) collects the left row into a std HashMap and folds the right row in:
+// same columns, f(t1, t2) and f(0, t) as above, but an entry only in the left row keeps its value t
+// untouched (for f = add that differs from f(t, 0) exactly when t is -0.0).  Its iteration order is
+// unspecified (RandomState), so rows sorted by column are a valid result for both branches.  `op` bit 1
+// selects the unsorted branch's rule for left-only entries.
+//
+// Two passes like the product: count the union per row, look-back scan (scan.cu), fill.  One thread per row:
+// HBM-bound on stencil-like matrices (reads A and B once, writes C once); rows whose columns are not sorted
+// are first put in order by two transposes (dok.cu).
+#include "common.cuh"
+
+namespace {
+
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_ewise_count(u64 m, const u64* __restrict__ ap, const u32* __restrict__ ac,
+                                                       const u64* __restrict__ bp, const u32* __restrict__ bc,
+                                                       u32* __restrict__ row_nnz) {
+  const u64 row = (u64)blockIdx.x * BLOCK + threadIdx.x;
+  if (row >= m) return;
+  u64 i = ap[row], j = bp[row];
+  const u64 ie = ap[row + 1], je = bp[row + 1];
+  u32 z = 0;
+  while (i < ie && j < je) {
+    const u32 ca = ac[i], cb = bc[j];
+    i += ca <= cb ? 1 : 0;
+    j += cb <= ca ? 1 : 0;
+    ++z;
+  }
+  row_nnz[row] = z + (u32)(ie - i) + (u32)(je - j);
+}
+
+// OP 0: f = t1 + t2, OP 1: f = t1 - t2; the one-sided cases still go through f with a zero operand
+// (lib.rs:114-115), so -0.0 + 0.0 = +0.0 comes out as in the reference.
+template <class V, int OP>
+__device__ __forceinline__ V apply(V x, V y) {
+  if (OP == 0) return Num<V>::add(x, y);
+  return Num<V>::sub(x, y);
+}
+
+template <class V, int OP, bool KEEP_LEFT, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_ewise_fill(u64 m, const u64* __restrict__ ap, const u32* __restrict__ ac,
+                                                      const V* __restrict__ av, const u64* __restrict__ bp,
+                                                      const u32* __restrict__ bc, const V* __restrict__ bv,
+                                                      const u64* __restrict__ cp, u32* __restrict__ cc,
+                                                      V* __restrict__ cv) {
+  const u64 row = (u64)blockIdx.x * BLOCK + threadIdx.x;
+  if (row >= m) return;
+  u64 i = ap[row], j = bp[row], o = cp[row];
+  const u64 ie = ap[row + 1], je = bp[row + 1];
+  const V zero = Num<V>::zero();
+  while (i < ie && j < je) {
+    const u32 ca = ac[i], cb = bc[j];
+    if (ca == cb) {
+      cc[o] = ca; cv[o] = apply<V, OP>(av[i], bv[j]); ++i; ++j;
+    } else if (ca < cb) {
+      cc[o] = ca; cv[o] = KEEP_LEFT ? av[i] : apply<V, OP>(av[i], zero); ++i;
+    } else {
+      cc[o] = cb; cv[o] = apply<V, OP>(zero, bv[j]); ++j;
+    }
+    ++o;
+  }
+  for (; i < ie; ++i, ++o) { cc[o] = ac[i]; cv[o] = KEEP_LEFT ? av[i] : apply<V, OP>(av[i], zero); }
+  for (; j < je; ++j, ++o) { cc[o] = bc[j]; cv[o] = apply<V, OP>(zero, bv[j]); }
+}
+
+template <class V>
+int fill_typed(spam_handle* h, int op, const spam_dcsr* a, const spam_dcsr* b, spam_dcsr* c) {
+  constexpr int BL = 128;
+  const unsigned grid = (unsigned)((a->rows + BL - 1) / BL);
+#define EW_LAUNCH(OP, KEEP)                                                                                          \
+  k_ewise_fill<V, OP, KEEP, BL><<<grid, BL, 0, h->stream>>>(a->rows, a->ptr, a->idx, (const V*)a->val, b->ptr, b->idx, \
+                                                            (const V*)b->val, c->ptr, c->idx, (V*)c->val)
+  switch (op) {
+    case 0: EW_LAUNCH(0, false); break;
+    case 1: EW_LAUNCH(1, false); break;
+    case 2: EW_LAUNCH(0, true); break;
+    default: EW_LAUNCH(1, true); break;
+  }
+#undef EW_LAUNCH
+  count_launch(h);
+  CK(cudaGetLastError());
+  return SPAM_OK;
+}
+
+void free_owned(spam_handle* h, spam_dcsr* m) {
+  if (!m) return;
+  dev_free(h, m->ptr); dev_free(h, m->idx); dev_free(h, m->val);
+  delete m;
+}
+
+// rows sorted by column: the matrix itself, or a sorted copy made by two transposes (*tmp owns it)
+int sorted_view(spam_handle* h, const spam_dcsr* m, const spam_dcsr** view, spam_dcsr** tmp) {
+  *tmp = nullptr;
+  *view = m;
+  CKS(ensure_matrix_stats(h, m));
+  if (m->rows_sorted == 1) return SPAM_OK;
+  spam_dcsr* t = nullptr;
+  CKS(transpose_dev(h, m, &t));
+  spam_dcsr* tt = nullptr;
+  const int st = transpose_dev(h, t, &tt);
+  free_owned(h, t);
+  if (st != SPAM_OK) return st;
+  *tmp = tt;
+  *view = tt;
+  return SPAM_OK;
+}
+
+}  // namespace
+
+int ewise_dev(spam_handle* h, int op, const spam_dcsr* a_in, const spam_dcsr* b_in, spam_dcsr** out) {
+  *out = nullptr;
+  if (op < 0 || op > 3) return spam_fail(h, SPAM_EINVAL, "op must be 0 (add), 1 (sub), optionally | 2 (IS_SORTED = false rule)");
+  // lib.rs:87-91: assert_eq!((self.rows, self.cols), (rhs.rows, rhs.cols))
+  if (a_in->rows != b_in->rows || a_in->cols != b_in->cols) return spam_fail(h, SPAM_EDIM, "matrices must have identical dimensions");
+  if (a_in->dtype != b_in->dtype) return spam_fail(h, SPAM_EDTYPE, "operand dtypes differ");
+  const spam_dcsr *a = nullptr, *b = nullptr;
+  spam_dcsr *ta = nullptr, *tb = nullptr;
+  int st = sorted_view(h, a_in, &a, &ta);
+  if (st == SPAM_OK) st = (b_in == a_in) ? (b = a, SPAM_OK) : sorted_view(h, b_in, &b, &tb);
+  if (st != SPAM_OK) { free_owned(h, ta); free_owned(h, tb); return st; }
+  h->stats = spam_stats{};
+  const u64 m = a->rows;
+  spam_dcsr* c = new spam_dcsr();
+  c->dtype = a->dtype; c->rows = m; c->cols = a->cols; c->nnz = 0; c->owning = true; c->rows_sorted = -1; c->max_row_len = 0;  // stats taken lazily if C becomes an operand
+  c->ptr = nullptr; c->idx = nullptr; c->val = nullptr;
+  u32* row_nnz = nullptr;
+  auto fail = [&](int s) {
+    dev_free(h, row_nnz);
+    free_owned(h, c); free_owned(h, ta); free_owned(h, tb);
+    return s;
+  };
+  st = dev_alloc_t(h, &row_nnz, m);
+  if (st == SPAM_OK) st = dev_alloc_t(h, &c->ptr, m + 1);
+  if (st != SPAM_OK) return fail(st);
+  cudaError_t e = cudaMemsetAsync(h->d_cnt, 0, sizeof(Counters), h->stream);
+  if (e != cudaSuccess) return fail(spam_fail(h, SPAM_ECUDA, "cudaMemsetAsync", e));
+  constexpr int BL = 128;
+  k_ewise_count<BL><<<(unsigned)((m + BL - 1) / BL), BL, 0, h->stream>>>(m, a->ptr, a->idx, b->ptr, b->idx, row_nnz);
+  count_launch(h);
+  if ((e = cudaGetLastError()) != cudaSuccess) return fail(spam_fail(h, SPAM_ECUDA, "k_ewise_count", e));
+  st = scan_u32_to_u64(h, row_nnz, c->ptr, m, &h->d_cnt->total_nnz);
+  if (st != SPAM_OK) return fail(st);
+  e = cudaMemcpyAsync(h->h_cnt, h->d_cnt, sizeof(Counters), cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  if (e != cudaSuccess) return fail(spam_fail(h, SPAM_ECUDA, "ewise sync", e));
+  c->nnz = h->h_cnt->total_nnz;
+  st = dev_alloc_t(h, &c->idx, c->nnz);
+  if (st == SPAM_OK) st = dev_alloc(h, &c->val, c->nnz * dtype_size(c->dtype));
+  if (st == SPAM_OK && c->nnz) {
+    switch (c->dtype) {
+      case SPAM_F32: st = fill_typed<float>(h, op, a, b, c); break;
+      case SPAM_F64: st = fill_typed<double>(h, op, a, b, c); break;
+      case SPAM_I32: st = fill_typed<int32_t>(h, op, a, b, c); break;
+      case SPAM_I64: st = fill_typed<int64_t>(h, op, a, b, c); break;
+      default: st = spam_fail(h, SPAM_EINVAL, "bad dtype");
+    }
+  }
+  if (st != SPAM_OK) return fail(st);
+  dev_free(h, row_nnz);
+  free_owned(h, ta); free_owned(h, tb);
+  h->stats.nnz_c = c->nnz;
+  *out = c;
+  return SPAM_OK;
+}

@@ -42,6 +42,22 @@ static int run(const char* name, std::mt19937_64& rng) {
       for (uint64_t e = t.offsets[r]; e < t.offsets[r + 1]; ++e) dt[r * l + t.indices[e]] = t.vals[e];
     for (auto& ea : da.entries()) dw[ea.first.second * l + ea.first.first] = ea.second;
     if (dt != dw) ++fails;
+    // add / sub (apply_elementwise, lib.rs:83-149; the reference's test: tests.rs:334-354): a second l x m
+    // operand, compared through the dense DOK sums
+    spam::DokMatrix<T> da2(l, m);
+    for (uint64_t k = rng() % (2 * l * m + 1); k-- > 0;) da2.set_element(rng() % l, rng() % m, (T)((int)(rng() % 9) - 4));
+    auto a2 = spam::CsrMatrix<T, true>::from(da2);
+    auto s = a + a2;
+    auto d = a - a2;
+    if (!s.invariants() || !d.invariants()) { ++fails; continue; }
+    std::vector<T> ws(l * m, T(0)), wd(l * m, T(0)), gs(l * m, T(0)), gd(l * m, T(0));
+    for (auto& ea : da.entries()) { ws[ea.first.first * m + ea.first.second] += ea.second; wd[ea.first.first * m + ea.first.second] += ea.second; }
+    for (auto& ea : da2.entries()) { ws[ea.first.first * m + ea.first.second] += ea.second; wd[ea.first.first * m + ea.first.second] -= ea.second; }
+    for (uint64_t r = 0; r < l; ++r) {
+      for (uint64_t e = s.offsets[r]; e < s.offsets[r + 1]; ++e) gs[r * m + s.indices[e]] = s.vals[e];
+      for (uint64_t e = d.offsets[r]; e < d.offsets[r + 1]; ++e) gd[r * m + d.indices[e]] = d.vals[e];
+    }
+    if (ws != gs || wd != gd) ++fails;
   }
   std::printf("%s: %s\n", name, fails ? "FAIL" : "ok");
   return fails;

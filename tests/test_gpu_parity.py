@@ -421,6 +421,54 @@ def test_transpose(oracle, handle, dtype):
         bad.transpose(handle=handle)
 
 
+@pytest.mark.parametrize("dtype", ALL_DTYPES)
+@pytest.mark.parametrize("op", ["add", "sub"])
+def test_elementwise_add_sub(oracle, handle, dtype, op):
+    """impl Add / Sub for CsrMatrix (apply_elementwise, lib.rs:83-149) through the host C ABI and on the device:
+    bit-exact against the oracle (one rounding per entry, integers wrap), the union pattern with cancellation
+    and explicit zeros kept, unsorted operands (put in order by two transposes), A op A, shape mismatch."""
+    rng = np.random.default_rng(31)
+    info = np.iinfo(dtype) if np.dtype(dtype).kind == "i" else None
+    for rows, cols, deg, srt in ((1, 1, 1, True), (40, 30, 6, True), (3000, 2500, 20, True), (500, 700, 90, False),
+                                 (64, 64, 0, True)):
+        a = random_csr(rng, rows, cols, rng.integers(0, deg + 1, size=rows), dtype=dtype, sorted_rows=srt, zero_frac=0.1,
+                       int_range=(info.max // 2 + 7) if info else 50)
+        b = random_csr(rng, rows, cols, rng.integers(0, deg + 1, size=rows), dtype=dtype, sorted_rows=srt, zero_frac=0.1,
+                       int_range=(info.max // 2 + 7) if info else 50)
+        want = oracle.ewise(a, b, op, srt)
+        A, B = as_csr_matrix(a, is_sorted=srt), as_csr_matrix(b, is_sorted=srt)
+        got = A.add(B, handle=handle) if op == "add" else A.sub(B, handle=handle)
+        assert (got.rows(), got.cols()) == (rows, cols)
+        assert np.array_equal(got.offsets, want[0]) and np.array_equal(got.indices, want[1])
+        assert np.array_equal(got.vals.view(np.uint8), want[2].view(np.uint8))
+        dA, dB = S.DeviceCsr.upload(A, handle), S.DeviceCsr.upload(B, handle)
+        dC = dA.add(dB) if op == "add" else dA.sub(dB)
+        dev = dC.download()
+        # the device entry point applies the IS_SORTED = true rule to the operands' rows put in column order
+        sa = a if srt else (rows, cols) + oracle.transpose((cols, rows) + oracle.transpose(a))
+        sb = b if srt else (rows, cols) + oracle.transpose((cols, rows) + oracle.transpose(b))
+        wsorted = oracle.ewise(sa, sb, op, True)
+        assert np.array_equal(dev.offsets, wsorted[0]) and np.array_equal(dev.indices, wsorted[1])
+        assert np.array_equal(dev.vals, wsorted[2])
+        # A op A: add doubles, sub leaves the pattern full of cancellation zeros
+        dS = dA.add(dA) if op == "add" else dA.sub(dA)
+        same = dS.download()
+        wself = oracle.ewise(sa, sa, op, True)
+        assert np.array_equal(same.offsets, wself[0]) and np.array_equal(same.indices, wself[1])
+        assert np.array_equal(same.vals, wself[2]) and same.nnz() == len(a[3])
+        for d in (dA, dB, dC, dS):
+            d.free()
+    # left-only -0.0 under add: +0.0 with IS_SORTED = true, kept with IS_SORTED = false (lib.rs:114 vs 119-137)
+    if np.dtype(dtype).kind == "f":
+        a = S.CsrMatrix(1, 2, np.array([-0.0], dtype), [0], [0, 1])
+        b = S.CsrMatrix(1, 2, np.array([2.0], dtype), [1], [0, 1])
+        assert not np.signbit(a.add(b, handle=handle).vals[0])
+        a.is_sorted = False
+        assert np.signbit(a.add(b, handle=handle).vals[0])
+    with pytest.raises(S.DimensionMismatch):
+        S.CsrMatrix.identity(3, dtype=dtype).add(S.CsrMatrix.identity(4, dtype=dtype), handle=handle)
+
+
 def test_scan_sizes_through_dok_row_ptr(oracle, handle):
     """The look-back scan at awkward lengths (around tile and warp boundaries) via DOK row_ptr."""
     rng = np.random.default_rng(4)

@@ -325,3 +325,40 @@ def test_transpose_literal_loops_equal_stable_column_sort(oracle, dtype, sorted_
         assert np.array_equal(back[0], a[2]) and np.array_equal(back[0], srt[0])
         if sorted_rows:
             assert np.array_equal(back[1], a[3]) and np.array_equal(back[2], a[4])
+
+
+@pytest.mark.parametrize("op", ["add", "sub"])
+def test_elementwise_matches_dense_and_keeps_zeros(oracle, op):
+    """apply_elementwise (lib.rs:83-149): against dense numpy on the union pattern; cancellation zeros and
+    explicit zeros stay; the IS_SORTED = false branch gives the same entries except that a -0.0 only in the
+    left operand keeps its sign under add; i8 wraps (the reference's test type, tests.rs:334-354)."""
+    rng = np.random.default_rng(17)
+    for dtype in (np.float64, np.int32, np.int8):
+        for rows, cols, deg in ((1, 1, 1), (6, 9, 4), (30, 17, 8), (12, 40, 0)):
+            a = random_csr(rng, rows, cols, rng.integers(0, deg + 1, size=rows), dtype=dtype, zero_frac=0.15)
+            b = random_csr(rng, rows, cols, rng.integers(0, deg + 1, size=rows), dtype=dtype, zero_frac=0.15)
+            off, idx, val = oracle.ewise(a, b, op, True)
+            da, db = np.zeros((rows, cols), dtype), np.zeros((rows, cols), dtype)
+            pat = np.zeros((rows, cols), bool)
+            for m, d in ((a, da), (b, db)):
+                for r in range(rows):
+                    for e in range(int(m[2][r]), int(m[2][r + 1])):
+                        d[r, int(m[3][e])] = m[4][e]
+                        pat[r, int(m[3][e])] = True
+            with np.errstate(over="ignore"):
+                want = (da + db) if op == "add" else (da - db)
+            assert int(off[-1]) == int(pat.sum())                      # the union pattern, nothing dropped
+            for r in range(rows):
+                seg = idx[int(off[r]):int(off[r + 1])].astype(np.int64)
+                assert np.array_equal(seg, np.nonzero(pat[r])[0])      # sorted by column
+                assert np.array_equal(val[int(off[r]):int(off[r + 1])], want[r, seg])
+            # unsorted branch on row-shuffled operands: same entries
+            off2, idx2, val2 = oracle.ewise(a, b, op, False)
+            assert np.array_equal(off, off2) and np.array_equal(idx, idx2) and np.array_equal(val, val2)
+    # the one observable difference between the branches: left-only -0.0 under add
+    a = (1, 2, [0, 1], [0], np.array([-0.0]))
+    b = (1, 2, [0, 1], [1], np.array([2.0]))
+    assert np.signbit(oracle.ewise(a, b, "add", False)[2][0]) and not np.signbit(oracle.ewise(a, b, "add", True)[2][0])
+    assert np.signbit(oracle.ewise(a, b, "sub", True)[2][0])
+    with pytest.raises(ValueError):
+        oracle.ewise(a, (2, 2, [0, 0, 0], [], np.array([])), "add")
