@@ -196,4 +196,21 @@ CsrMatrix<T, false> operator*(const CsrMatrix<T, B>& a, const CsrMatrix<T, B>& b
   return a.template mul_hash<false>(b);
 }
 
+// parse_matrix_market (spam_dok/src/lib.rs:282-478) followed by CsrMatrix::from(dok): T = int64_t for
+// `integer` files (MatrixType::Integer), double for `real` ones (MatrixType::Real); anything else throws.
+template <class T>
+CsrMatrix<T, true> from_matrix_market(const std::string& text, Handle& h = Handle::thread_default()) {
+  static_assert(std::is_same<T, int64_t>::value || std::is_same<T, double>::value, "MatrixType::Integer is i64, Real is f64");
+  spam_mm mm;
+  const int st = spam_mm_parse(text.data(), text.size(), &mm);
+  if (st == SPAM_EINDEX) throw IndexError();
+  if (st != SPAM_OK) throw std::runtime_error(std::string("FromMatrixMarketError: ") + mm.err);
+  if (mm.kind != device_scalar<T>::dtype) { spam_mm_free(&mm); throw std::runtime_error("entry type of the file differs from T"); }
+  std::vector<uint64_t> tr(mm.tri_rows, mm.tri_rows + mm.n), tc(mm.tri_cols, mm.tri_cols + mm.n);
+  std::vector<T> tv((const T*)mm.tri_vals, (const T*)mm.tri_vals + mm.n);
+  const uint64_t rows = mm.rows, cols = mm.cols;
+  spam_mm_free(&mm);
+  return CsrMatrix<T, true>::from_triplets(rows, cols, tr, tc, tv, h);
+}
+
 }  // namespace spam

@@ -111,6 +111,27 @@ int spam_dok_to_csr(spam_handle* h, int dtype, uint64_t rows, uint64_t cols, uin
                     uint64_t* c_nnz);
 int spam_dok_to_csr_fetch(spam_handle* h, uint64_t* c_idx, void* c_val);
 
+/* MatrixMarket coordinate text -> triplet stream (host code, no device needed).  Restates the grammar of
+ * `parse_matrix_market`, spam_dok/src/lib.rs:282-478: integer -> kind SPAM_I64, real -> SPAM_F64; general or
+ * symmetric (both (r, c) and (c, r) are emitted); 1-based indices; zeros skipped; entry lines are read until the
+ * first line that does not match, the rest is ignored; the declared entry count is not used.  Feed the triplets
+ * to spam_dok_to_csr (a later duplicate replaces an earlier one, as in the reference's BTreeMap::insert) to
+ * get what `CsrMatrix::from(dok)` gives.  SPAM_EINVAL: grammar error; SPAM_EDTYPE: complex / pattern /
+ * skew-symmetric / hermitian; SPAM_EDIM: a zero dimension (HasZeroDimension); SPAM_EINDEX: index 0.
+ * tri_rows / tri_cols / tri_vals are malloc'ed: release with spam_mm_free. */
+typedef struct spam_mm {
+  int kind;                  /* SPAM_I64 or SPAM_F64 */
+  uint64_t rows, cols;
+  uint64_t declared_entries; /* third number of the size line */
+  uint64_t n;                /* triplets produced */
+  uint64_t* tri_rows;
+  uint64_t* tri_cols;
+  void* tri_vals;            /* n values of 8 bytes (int64_t or double) */
+  char err[96];
+} spam_mm;
+int spam_mm_parse(const char* text, uint64_t len, spam_mm* out);
+void spam_mm_free(spam_mm* m);
+
 /* ---- device-resident path (benchmarks, multi-GPU, chained products) ---------------------- */
 int spam_csr_upload(spam_handle* h, int dtype, uint64_t rows, uint64_t cols, uint64_t nnz, const uint64_t* ptr,
                     const uint64_t* idx, const void* val, spam_dcsr** out);

@@ -26,7 +26,7 @@ EXPORTS = [
     "spam_dok_to_csr_fetch", "spam_csr_upload", "spam_dcsr_wrap", "spam_dcsr_info", "spam_dcsr_download",
     "spam_dcsr_free", "spam_dcsr_slice_rows", "spam_dcsr_transpose", "spam_csr_transpose", "spam_spgemm_dev", "spam_spmv_dev", "spam_dok_to_csr_dev",
     "spam_rows_to_parts", "spam_rows_to_parts_cost", "spam_offset_u64", "spam_dcsr_ewise", "spam_csr_ewise",
-    "spam_csr_ewise_fetch",
+    "spam_csr_ewise_fetch", "spam_mm_parse", "spam_mm_free",
 ]
 
 
@@ -101,7 +101,7 @@ def load():
     L.spam_offset_u64.argtypes = [vp, vp, u64, u64]
     for name in EXPORTS:
         fn = getattr(L, name)
-        if name not in ("spam_strerror", "spam_last_error"):
+        if name not in ("spam_strerror", "spam_last_error", "spam_mm_free"):
             fn.restype = C.c_int
     _lib = L
     return L

@@ -8,7 +8,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libspam_cuda.so")
-SOURCES = ["api.cu", "spgemm.cu", "scan.cu", "convert.cu", "spmv.cu", "dok.cu", "ewise.cu"]
+SOURCES = ["api.cu", "spgemm.cu", "scan.cu", "convert.cu", "spmv.cu", "dok.cu", "ewise.cu", "mm.cu"]
 HEADERS = [os.path.join(CSRC, f) for f in ("common.cuh", "merge.cuh", "rowhash.cuh")] + [
     os.path.join(os.path.dirname(HERE), "include", "spam_cuda.h")]
 

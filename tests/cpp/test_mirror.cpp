@@ -74,6 +74,18 @@ int main() {
   bool idx = false;
   try { spam::DokMatrix<double> d(2, 2); d.set_element(2, 0, 1.0); } catch (const spam::IndexError&) { idx = true; }
   if (!idx) ++fails;
+  // MatrixMarket ingest: symmetric integer file -> CsrMatrix<i64, true> (parse_matrix_market + From<DokMatrix>)
+  {
+    auto m = spam::from_matrix_market<int64_t>(
+        "%%MatrixMarket matrix coordinate integer symmetric\n% c\n3 3 3\n1 1 4\n2 1 -1\n3 3 0\n3 2 7\n");
+    const std::vector<uint64_t> off{0, 2, 4, 5}, idx2{0, 1, 0, 2, 1};
+    const std::vector<int64_t> val{4, -1, -1, 7, 7};
+    if (!m.invariants() || m.offsets != off || m.indices != idx2 || m.vals != val) { std::printf("matrix market mismatch\n"); ++fails; }
+    bool threw2 = false;
+    try { (void)spam::from_matrix_market<double>("%%MatrixMarket matrix coordinate pattern general\n2 2 0\n"); }
+    catch (const std::runtime_error&) { threw2 = true; }
+    if (!threw2) ++fails;
+  }
   std::printf(fails ? "FAILED\n" : "ALL OK\n");
   return fails ? 1 : 0;
 }
