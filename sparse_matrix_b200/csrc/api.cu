@@ -189,7 +189,7 @@ void finish_timing(spam_handle* h) {
 
 extern "C" {
 
-int spam_cuda_abi_version(void) { return 4; }  // 2: spam_stats bin arrays grew to 16 entries; 3: spam_rows_to_parts_cost; 4: transpose, phase totals
+int spam_cuda_abi_version(void) { return 5; }  // 2: 16-entry bin arrays; 3: spam_rows_to_parts_cost; 4: transpose, phase totals; 5: ewise, spam_mm_parse
 
 const char* spam_strerror(int s) {
   switch (s) {
