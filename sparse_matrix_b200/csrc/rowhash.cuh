@@ -32,6 +32,7 @@
 namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
+constexpr u32 SYM_REDO = 0xFFFFFFFFu;  // row_nnz marker: the optimistic symbolic table overflowed, redo the row
 constexpr int ROWS_PER_BLOCK_W1 = 4;  // NW = 1: four independent warps (rows) per 128-thread block
 
 __device__ __forceinline__ u32 slot_fib(u32 key, u32 shift) { return (key * 2654435769u) >> shift; }
@@ -138,7 +139,13 @@ template <int NW, int CAP, bool DIRECT>
 __global__ void __launch_bounds__(NW == 1 ? 32 * ROWS_PER_BLOCK_W1 : 32 * NW)
 k_sym_row(u32 n, const u32* __restrict__ perm, const u64* __restrict__ a_ptr, const u32* __restrict__ a_col,
           const u64* __restrict__ b_ptr, const u32* __restrict__ b_col, const u32* __restrict__ flop,
-          u32* __restrict__ row_nnz) {
+          u32* __restrict__ row_nnz, int mode) {
+  // mode 0: the table is sized from the row's product count f (linprobe's rule, an upper bound on the distinct
+  //         columns).
+  // mode 1 (DIRECT only): OPTIMISTIC — all CAP keys whatever f is.  High-compression rows (27-point stencil:
+  //         f = 729, 125 distinct) fit a table a quarter of the size f asks for, which doubles the resident
+  //         warps; a row that passes CAP/2 distinct columns gives up and leaves SYM_REDO in row_nnz.
+  // mode 2: only the rows that gave up (row_nnz == SYM_REDO), with the full-size table.
   static_assert(!DIRECT || NW == 1, "DIRECT enumeration is a single-warp mode");
   extern __shared__ u32 sm_sym_keys[];
   __shared__ u32 s_total;
@@ -147,12 +154,14 @@ k_sym_row(u32 n, const u32* __restrict__ perm, const u64* __restrict__ a_ptr, co
   if (item >= n) return;  // NW == 1: the warp leaves alone (no block barrier below); NW > 1: whole block
   const u32 row = perm ? perm[item] : item;
   const u32 f = flop[row];
+  if (mode == 2 && row_nnz[row] != SYM_REDO) return;
   if (f == 0) { if (threadIdx.x % (32 * NW) == 0) row_nnz[row] = 0; return; }
   const u32 kbase = smem_addr(sm_sym_keys + (NW == 1 ? wid * CAP : 0));
   const int rw = NW == 1 ? 0 : wid;       // warp index inside the row's team
   const int rt = rw * 32 + lane;          // thread index inside the team
   u32 cap = table_size_u32(f);
   if (cap > (u32)CAP) cap = CAP;
+  const bool optimistic = DIRECT && mode == 1;
   const u32 mask = cap - 1, shift = 32 - (31 - __clz(cap));
   for (u32 s = rt; s < cap; s += 32 * NW) sts32(kbase + 4u * s, EMPTY_KEY);
   if (NW > 1 && threadIdx.x == 0) s_total = 0;
@@ -187,6 +196,18 @@ k_sym_row(u32 n, const u32* __restrict__ perm, const u64* __restrict__ a_ptr, co
           u32 s = slot_fib(key, shift);
           probe_insert(kbase, mask, key, active, s, fresh);
           cnt += fresh ? 1u : 0u;
+          if (optimistic && __any_sync(FULL, fresh)) {  // a long B row can add many keys: check per batch
+            u32 tot = cnt;
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) tot += __shfl_xor_sync(FULL, tot, d);
+            if (tot > cap / 2) { if (lane == 0) row_nnz[row] = SYM_REDO; return; }
+          }
+        }
+        if (optimistic) {  // at most 32 new keys since the last check: the table never fills up
+          u32 tot = cnt;
+#pragma unroll
+          for (int d = 16; d > 0; d >>= 1) tot += __shfl_xor_sync(FULL, tot, d);
+          if (tot > cap / 2) { if (lane == 0) row_nnz[row] = SYM_REDO; return; }
         }
       }
     } else {

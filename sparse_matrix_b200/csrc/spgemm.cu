@@ -805,13 +805,14 @@ int spgemm_symbolic_dev(spam_handle* h, const spam_dcsr* a, const spam_dcsr* b, 
       FAIL_FREE(dev_alloc_t(h, &heavy_tab, heavy_nblk * heavy_stride));
     }
     if (side) CK_FREE(lanes_fork(h));
+#define SYM_MODE 0
 #define LAUNCH_SYM_ROW(BIN, NW, CAP, DIRECT)                                                             \
     if (sb.count[BIN]) {                                                                                 \
       constexpr size_t smem = sym_row_smem<NW, CAP>();                                                   \
       FAIL_FREE(set_smem(h, k_sym_row<NW, CAP, DIRECT>, smem));                                          \
       const unsigned grid = NW == 1 ? (sb.count[BIN] + ROWS_PER_BLOCK_W1 - 1) / ROWS_PER_BLOCK_W1 : sb.count[BIN]; \
       k_sym_row<NW, CAP, DIRECT><<<grid, NW == 1 ? 32 * ROWS_PER_BLOCK_W1 : 32 * NW, smem, lane_of(h, BIN)>>>( \
-          sb.count[BIN], seg(BIN), ap, ac, bp, bc, fl, rz);                                              \
+          sb.count[BIN], seg(BIN), ap, ac, bp, bc, fl, rz, SYM_MODE);                                    \
       count_launch(h);                                                                                   \
     }
     // symbolic hash bin b: f <= 64 << b, table 128 << b keys (4 B each); expensive bins first
@@ -823,7 +824,17 @@ int spgemm_symbolic_dev(spam_handle* h, const spam_dcsr* a, const spam_dcsr* b, 
       LAUNCH_SYM_ROW(1, 1, 256, true)
       LAUNCH_SYM_ROW(2, 1, 512, true)
       LAUNCH_SYM_ROW(3, 1, 1024, true)
+      // f in (512, 1024]: the table f asks for (8 KB per row) leaves 28 warps per SM.  Regular matrices compress
+      // well (27-point stencil: 729 products, 125 columns): try a 512-key table first, redo the rows that
+      // pass 256 distinct columns with the full-size one (same stream, so the order holds).
+#undef SYM_MODE
+#define SYM_MODE 1
+      LAUNCH_SYM_ROW(4, 1, 512, true)
+#undef SYM_MODE
+#define SYM_MODE 2
       LAUNCH_SYM_ROW(4, 1, 2048, true)
+#undef SYM_MODE
+#define SYM_MODE 0
     } else {
       LAUNCH_SYM_ROW(1, 1, 256, false)
       LAUNCH_SYM_ROW(2, 1, 512, false)
@@ -831,6 +842,7 @@ int spgemm_symbolic_dev(spam_handle* h, const spam_dcsr* a, const spam_dcsr* b, 
       LAUNCH_SYM_ROW(4, 4, 2048, false)  // 4 rows x 8 KB per block left 28 warps per SM; a team per row runs 64
     }
 #undef LAUNCH_SYM_ROW
+#undef SYM_MODE
     if (sb.count[MERGE_BIN] && !fused) {
       constexpr int BL = 128;
       const u32 nm = sb.count[MERGE_BIN];
