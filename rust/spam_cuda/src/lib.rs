@@ -28,6 +28,29 @@ extern "C" {
     /// `Matrix::transpose` of `CsrMatrix` (spam_csr/src/lib.rs:256-264); t_ptr: cols+1, t_idx/t_val: nnz entries
     pub fn spam_csr_transpose(h: *mut spam_handle, dtype: c_int, rows: u64, cols: u64, ptr: *const u64, idx: *const u64,
         val: *const c_void, t_ptr: *mut u64, t_idx: *mut u64, t_val: *mut c_void) -> c_int;
+    /// `impl Add / Sub for CsrMatrix` -> apply_elementwise (spam_csr/src/lib.rs:83-149): op 0 add, 1 sub, `| 2` for
+    /// IS_SORTED = false operands; phase 1 writes c_ptr[rows+1] and *c_nnz, spam_csr_ewise_fetch fills idx / val
+    pub fn spam_csr_ewise(h: *mut spam_handle, op: c_int, dtype: c_int, rows: u64, cols: u64, a_ptr: *const u64,
+        a_idx: *const u64, a_val: *const c_void, b_ptr: *const u64, b_idx: *const u64, b_val: *const c_void,
+        c_ptr: *mut u64, c_nnz: *mut u64) -> c_int;
+    pub fn spam_csr_ewise_fetch(h: *mut spam_handle, c_idx: *mut u64, c_val: *mut c_void) -> c_int;
+    /// parse_matrix_market (spam_dok/src/lib.rs:282-478) as a triplet stream for spam_dok_to_csr
+    pub fn spam_mm_parse(text: *const c_char, len: u64, out: *mut spam_mm) -> c_int;
+    pub fn spam_mm_free(m: *mut spam_mm);
+}
+
+/// Mirror of `struct spam_mm` (include/spam_cuda.h).
+#[repr(C)]
+pub struct spam_mm {
+    pub kind: c_int,
+    pub rows: u64,
+    pub cols: u64,
+    pub declared_entries: u64,
+    pub n: u64,
+    pub tri_rows: *mut u64,
+    pub tri_cols: *mut u64,
+    pub tri_vals: *mut c_void,
+    pub err: [c_char; 96],
 }
 
 /// Element types the device serves.  `Wrapping<i32/i64>` are `repr(transparent)` and map to I32/I64.

@@ -362,3 +362,38 @@ def test_elementwise_matches_dense_and_keeps_zeros(oracle, op):
     assert np.signbit(oracle.ewise(a, b, "sub", True)[2][0])
     with pytest.raises(ValueError):
         oracle.ewise(a, (2, 2, [0, 0, 0], [], np.array([])), "add")
+
+
+@settings(max_examples=40, deadline=None)
+@given(seed=st.integers(0, 2**31 - 1), rows=st.integers(1, 9), inner=st.integers(1, 9), cols=st.integers(1, 9))
+def test_algebraic_identities_between_the_restatements(oracle, seed, rows, inner, cols):
+    """Cross-checks between the independent restatements (integers, so everything is exact):
+    (A B)^T = B^T A^T,  (A + B)^T = A^T + B^T,  (A + B) - B has A's values on the union pattern,
+    A (B + C) = A B + A C as dense matrices (patterns may differ by explicit zeros)."""
+    rng = np.random.default_rng(seed)
+
+    def dense(m):
+        r, c, off, idx, val = m
+        d = np.zeros((r, c), np.int64)
+        for i in range(r):
+            for e in range(int(off[i]), int(off[i + 1])):
+                d[i, int(idx[e])] = val[e]
+        return d
+    a = random_csr(rng, rows, inner, rng.integers(0, inner + 1, size=rows), dtype=np.int64, int_range=9)
+    b = random_csr(rng, inner, cols, rng.integers(0, cols + 1, size=inner), dtype=np.int64, int_range=9)
+    c = random_csr(rng, inner, cols, rng.integers(0, cols + 1, size=inner), dtype=np.int64, int_range=9)
+    T = lambda m: (m[1], m[0]) + oracle.transpose(m)
+    ab = (rows, cols) + oracle.mul_hash(a, b, True)
+    btat = (cols, rows) + oracle.mul_hash(T(b), T(a), True)
+    abt = T(ab)
+    assert np.array_equal(abt[2], btat[2]) and np.array_equal(abt[3], btat[3]) and np.array_equal(abt[4], btat[4])
+    bc = (inner, cols) + oracle.ewise(b, c, "add", True)
+    lhs = T(bc)
+    rhs = oracle.ewise(T(b), T(c), "add", True)
+    assert all(np.array_equal(x, y) for x, y in zip(lhs[2:], rhs))
+    back = oracle.ewise(bc, c, "sub", True)
+    assert np.array_equal(back[0], bc[2]) and np.array_equal(back[1], bc[3])            # union pattern kept
+    assert np.array_equal(dense((inner, cols) + back), dense(b))
+    left = dense((rows, cols) + oracle.mul_hash(a, bc, True))
+    right = dense((rows, cols) + oracle.ewise(ab, (rows, cols) + oracle.mul_hash(a, c, True), "add", True))
+    assert np.array_equal(left, right)
