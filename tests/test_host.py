@@ -54,6 +54,15 @@ def test_no_cpu_fallback_without_device():
         a.mul_hash(a)
     with pytest.raises(S.SpamError):
         a.spmv(np.ones(4))
+    with pytest.raises(S.SpamError):
+        a.transpose()
+    with pytest.raises(S.SpamError):
+        a + a
+    with pytest.raises(S.SpamError):
+        S.CsrMatrix.from_triplets(2, 2, [0], [1], np.array([1.0]))
+    # the MatrixMarket parser is host code and works without a device; building the matrix does not
+    kind, r, c, tr, tc, tv = S.parse_matrix_market("%%MatrixMarket matrix coordinate real general\n2 2 1\n1 2 3.5\n")
+    assert (kind, r, c, tr.tolist(), tc.tolist(), tv.tolist()) == ("real", 2, 2, [0], [1], [3.5])
 
 
 def test_product_package_never_imports_the_oracle():
