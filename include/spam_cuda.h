@@ -26,6 +26,13 @@
  *     reference panics where we return an error (mul_hash.rs:47-48, lib.rs:270).
  *   - A handle owns one CUDA stream + workspace and is NOT thread-safe; use one handle
  *     per thread.  There is no CPU fallback: without a CUDA device spam_cuda_create fails.
+ *   - Deviation from the reference: rows, cols and the number of entries of an operand must be
+ *     < 2^32-1 (the reference only bounds the right-hand side's columns, mul_hash.rs:12): row ids
+ *     are u32 on the device (row permutations, per-row counters).  nnz(C) and the product count
+ *     are 64-bit.  Larger shapes return SPAM_ECOLS.
+ *   - Operands are validated once per matrix on the device (row_ptr monotone from 0 to nnz,
+ *     columns < cols: invariants 3, 4, 5, 7 of spam_csr/src/lib.rs:47-81): SPAM_EINVAL /
+ *     SPAM_EINDEX where the reference would panic, never a device fault.
  */
 #ifndef SPAM_CUDA_H
 #define SPAM_CUDA_H
@@ -64,6 +71,15 @@ typedef struct spam_stats {
   /* rows per bin: 0 tiny, 1..8 hash bins (one per power of two), 9 heavy (global table), 10 merge */
   uint32_t sym_bin_rows[16]; /* symbolic pass, binned by intermediate products */
   uint32_t num_bin_rows[16]; /* numeric pass, binned by row nnz of C */
+  /* How often the rarely taken code paths ran in the last call (tests assert that they are exercised):
+   * [0] one-warp rows sorted by the shared-memory bitonic network (columns too wide to pack with an index),
+   * [1] team rows whose bucket drain overflowed (compaction + block-wide bitonic network),
+   * [2] global-table rows whose bucket drain overflowed (global-memory bitonic network),
+   * [3] rows the bucket-sort (ESC) bins handed back to the global-table kernel,
+   * [4] DOK->CSR / transpose path of the last build: 1 = counting sort by row (short segments),
+   *     2 = LSD radix sort (some row or column holds more than 32 entries),
+   * [5..7] reserved. */
+  uint32_t fallbacks[8];
 } spam_stats;
 
 /* ---- lifecycle --------------------------------------------------------------------- */
@@ -144,6 +160,10 @@ int spam_dcsr_download(spam_handle* h, const spam_dcsr* m, uint64_t* ptr, uint64
 int spam_dcsr_free(spam_handle* h, spam_dcsr* m);
 /* rows [r0, r1) of m as a new owning matrix with row_ptr rebased to 0 (the per-rank A block) */
 int spam_dcsr_slice_rows(spam_handle* h, const spam_dcsr* m, uint64_t r0, uint64_t r1, spam_dcsr** out);
+
+/* rows rows[0..n) of m (host array of row indices, any order, repeats allowed) as a new owning matrix:
+ * how a caller pulls a sample of rows of a large device-resident product back to the host */
+int spam_dcsr_select_rows(spam_handle* h, const spam_dcsr* m, const uint64_t* rows, uint64_t n, spam_dcsr** out);
 
 /* Transpose.  Replaces `Matrix::transpose` of CsrMatrix, spam_csr/src/lib.rs:256-264 (an O(rows*cols)
  * loop of set_element calls in the reference; for matrices without explicit zeros the same result as

@@ -11,13 +11,19 @@ fn main() {
     let mut cmd = Command::new(nvcc);
     cmd.args(["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-shared", "-o"])
         .arg(&so);
-    for f in ["api.cu", "spgemm.cu", "scan.cu", "convert.cu", "spmv.cu", "dok.cu"] {
-        cmd.arg(csrc.join(f));
-        println!("cargo:rerun-if-changed={}", csrc.join(f).display());
+    // every .cu of the directory, like sparse_matrix_b200/build.py (its SOURCES list is checked against the
+    // directory by tests/test_host.py); headers only trigger rebuilds
+    let mut sources: Vec<PathBuf> = std::fs::read_dir(&csrc).expect("SPAM_CUDA_CSRC is not a directory")
+        .filter_map(|e| e.ok().map(|e| e.path())).collect();
+    sources.sort();
+    for f in &sources {
+        match f.extension().and_then(|e| e.to_str()) {
+            Some("cu") => { cmd.arg(f); println!("cargo:rerun-if-changed={}", f.display()); }
+            Some("cuh") => println!("cargo:rerun-if-changed={}", f.display()),
+            _ => {}
+        }
     }
-    for f in ["common.cuh", "merge.cuh", "rowhash.cuh"] {
-        println!("cargo:rerun-if-changed={}", csrc.join(f).display());
-    }
+    cmd.args(["-lpthread", "-ldl"]);
     assert!(cmd.status().expect("nvcc not found").success(), "nvcc failed");
     println!("cargo:rustc-link-search=native={}", out.display());
     println!("cargo:rustc-link-lib=dylib=spam_cuda");

@@ -24,7 +24,7 @@ EXPORTS = [
     "spam_cuda_synchronize", "spam_cuda_get_phase_totals", "spam_strerror", "spam_last_error", "spam_cuda_abi_version", "spam_host_alloc",
     "spam_host_free", "spam_spgemm_symbolic", "spam_spgemm_numeric", "spam_spmv", "spam_dok_to_csr",
     "spam_dok_to_csr_fetch", "spam_csr_upload", "spam_dcsr_wrap", "spam_dcsr_info", "spam_dcsr_download",
-    "spam_dcsr_free", "spam_dcsr_slice_rows", "spam_dcsr_transpose", "spam_csr_transpose", "spam_spgemm_dev", "spam_spmv_dev", "spam_dok_to_csr_dev",
+    "spam_dcsr_free", "spam_dcsr_slice_rows", "spam_dcsr_select_rows", "spam_dcsr_transpose", "spam_csr_transpose", "spam_spgemm_dev", "spam_spmv_dev", "spam_dok_to_csr_dev",
     "spam_rows_to_parts", "spam_rows_to_parts_cost", "spam_offset_u64", "spam_dcsr_ewise", "spam_csr_ewise",
     "spam_csr_ewise_fetch", "spam_mm_parse", "spam_mm_free",
 ]
@@ -34,7 +34,8 @@ class SpamStats(C.Structure):
     _fields_ = [("flops", C.c_uint64), ("nnz_c", C.c_uint64), ("kernel_launches", C.c_uint64),
                 ("bytes_h2d", C.c_uint64), ("bytes_d2h", C.c_uint64), ("ms_flop", C.c_float),
                 ("ms_symbolic", C.c_float), ("ms_scan", C.c_float), ("ms_numeric", C.c_float),
-                ("ms_total", C.c_float), ("sym_bin_rows", C.c_uint32 * 16), ("num_bin_rows", C.c_uint32 * 16)]
+                ("ms_total", C.c_float), ("sym_bin_rows", C.c_uint32 * 16), ("num_bin_rows", C.c_uint32 * 16),
+                ("fallbacks", C.c_uint32 * 8)]
 
 
 TINY_BIN, HEAVY_BIN, MERGE_BIN = 0, 9, 10   # indices into sym_bin_rows / num_bin_rows; 1..8 = hash bins
@@ -88,6 +89,7 @@ def load():
     L.spam_dcsr_download.argtypes = [vp, vp, vp, vp, vp]
     L.spam_dcsr_free.argtypes = [vp, vp]
     L.spam_dcsr_slice_rows.argtypes = [vp, vp, u64, u64, C.POINTER(vp)]
+    L.spam_dcsr_select_rows.argtypes = [vp, vp, vp, u64, C.POINTER(vp)]
     L.spam_dcsr_ewise.argtypes = [vp, i32, vp, vp, C.POINTER(vp)]
     L.spam_csr_ewise.argtypes = [vp, i32, i32, u64, u64, vp, vp, vp, vp, vp, vp, vp, C.POINTER(u64)]
     L.spam_csr_ewise_fetch.argtypes = [vp, vp, vp]

@@ -8,8 +8,8 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libspam_cuda.so")
-SOURCES = ["api.cu", "spgemm.cu", "scan.cu", "convert.cu", "spmv.cu", "dok.cu", "ewise.cu", "mm.cu"]
-HEADERS = [os.path.join(CSRC, f) for f in ("common.cuh", "merge.cuh", "rowhash.cuh")] + [
+SOURCES = sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))   # every .cu of csrc/, like rust/spam_cuda/build.rs
+HEADERS = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith(".cuh")] + [
     os.path.join(os.path.dirname(HERE), "include", "spam_cuda.h")]
 
 
@@ -32,7 +32,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not is_stale():
         return SO
     cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-           "-Xcompiler", "-fPIC", "-shared", "-o", SO] + [os.path.join(CSRC, s) for s in SOURCES]
+           "-Xcompiler", "-fPIC", "-shared", "-o", SO] + [os.path.join(CSRC, s) for s in SOURCES] + ["-lpthread", "-ldl"]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     subprocess.check_call(cmd)

@@ -65,7 +65,7 @@ class Handle:
         return {"flops": s.flops, "nnz_c": s.nnz_c, "kernel_launches": s.kernel_launches, "bytes_h2d": s.bytes_h2d,
                 "bytes_d2h": s.bytes_d2h, "ms_flop": s.ms_flop, "ms_symbolic": s.ms_symbolic, "ms_scan": s.ms_scan,
                 "ms_numeric": s.ms_numeric, "ms_total": s.ms_total, "sym_bin_rows": list(s.sym_bin_rows),
-                "num_bin_rows": list(s.num_bin_rows)}
+                "num_bin_rows": list(s.num_bin_rows), "fallbacks": list(s.fallbacks)}
 
 
 def _phase_totals(self, reset: bool = False) -> dict:
@@ -162,6 +162,14 @@ class DeviceCsr:
     def slice_rows(self, r0: int, r1: int) -> "DeviceCsr":
         out = C.c_void_p()
         check(self.handle.h, self.handle.L.spam_dcsr_slice_rows(self.handle.h, self.p, r0, r1, C.byref(out)))
+        return DeviceCsr(self.handle, out)
+
+    def select_rows(self, rows) -> "DeviceCsr":
+        """The listed rows (any order) as a new device matrix."""
+        rows = np.ascontiguousarray(rows, dtype=np.uint64)
+        out = C.c_void_p()
+        check(self.handle.h, self.handle.L.spam_dcsr_select_rows(self.handle.h, self.p, ptr(rows), rows.shape[0],
+                                                                 C.byref(out)))
         return DeviceCsr(self.handle, out)
 
     def rows_to_parts(self, rhs: "DeviceCsr", parts: int, balance: str = "flops") -> Tuple[np.ndarray, int]:

@@ -20,7 +20,7 @@ int spam_fail(spam_handle* h, int status, const char* what, cudaError_t ce) {
 int dev_alloc(spam_handle* h, void** p, size_t bytes) {
   *p = nullptr;
   if (bytes == 0) bytes = 16;
-  cudaError_t e = cudaMallocAsync(p, bytes, h->stream);
+  cudaError_t e = h->pool ? cudaMallocFromPoolAsync(p, bytes, h->pool, h->stream) : cudaMallocAsync(p, bytes, h->stream);
   if (e == cudaErrorMemoryAllocation) {
     cudaGetLastError();
     return spam_fail(h, SPAM_ENOMEM, "device allocation failed", e);
@@ -117,6 +117,29 @@ __global__ void __launch_bounds__(256) k_rebase_ptr(const u64* __restrict__ in, 
   for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = in[i] - base;
 }
 
+// rows of a matrix picked by index: lengths, then (after the scan) one warp per picked row copies it
+__global__ void __launch_bounds__(256) k_select_len(const u64* __restrict__ ptr, const u64* __restrict__ rows, u64 n,
+                                                    u64 m, u32* __restrict__ len, Counters* cnt) {
+  const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const u64 r = rows[i];
+  if (r >= m) { atomicOr(&cnt->error, 2u); len[i] = 0; return; }
+  const u64 l = ptr[r + 1] - ptr[r];
+  len[i] = l > 0xFFFFFFFFull ? 0xFFFFFFFFu : (u32)l;
+}
+template <class W>
+__global__ void __launch_bounds__(256) k_select_copy(const u64* __restrict__ ptr, const u32* __restrict__ idx,
+                                                     const W* __restrict__ val, const u64* __restrict__ rows, u64 n,
+                                                     const u64* __restrict__ optr, u32* __restrict__ oidx,
+                                                     W* __restrict__ oval) {
+  const u64 w = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= n) return;
+  const u64 r = rows[w];
+  const u64 lo = ptr[r], hi = ptr[r + 1], o = optr[w];
+  for (u64 e = lo + lane; e < hi; e += 32) { oidx[o + (e - lo)] = idx[e]; oval[o + (e - lo)] = val[e]; }
+}
+
 int set_device(spam_handle* h) {
   CK(cudaSetDevice(h->device));
   return SPAM_OK;
@@ -189,7 +212,7 @@ void finish_timing(spam_handle* h) {
 
 extern "C" {
 
-int spam_cuda_abi_version(void) { return 5; }  // 2: 16-entry bin arrays; 3: spam_rows_to_parts_cost; 4: transpose, phase totals; 5: ewise, spam_mm_parse
+int spam_cuda_abi_version(void) { return 6; }  // 2: 16-entry bin arrays; 3: spam_rows_to_parts_cost; 4: transpose, phase totals; 5: ewise, spam_mm_parse; 6: stats.fallbacks/paths, sorted = 0, spam_comm_*, pageable host path
 
 const char* spam_strerror(int s) {
   switch (s) {
@@ -219,6 +242,11 @@ int spam_cuda_create(spam_handle** out, int device) {
   if (!h) return SPAM_ENOMEM;
   h->device = device; h->timing = false; h->pending = nullptr; h->dok_pending = nullptr;
   h->scan_ws = nullptr; h->scan_ws_cap = 0;
+  h->pool = nullptr;
+  {
+    const char* e = getenv("SPAM_LANES");  // read once: 0 keeps every row bin on the main stream
+    h->use_lanes = !(e && e[0] == '0');
+  }
   h->d_cnt = nullptr; h->h_cnt = nullptr; h->own_stream = nullptr; h->stream = nullptr;
   h->stats = spam_stats{};
   for (auto& set : h->evs) for (auto& e : set) e = nullptr;
@@ -240,11 +268,17 @@ int spam_cuda_create(spam_handle** out, int device) {
   if (e == cudaSuccess) {
     h->num_sms = prop.multiProcessorCount;
     h->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
-    // keep freed blocks in the stream-ordered pool: steady-state products do no cudaMalloc
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+    // A PRIVATE stream-ordered pool that keeps its freed blocks: steady-state products do no cudaMalloc, and
+    // the process-wide default pool (shared with torch, NCCL, ...) is left alone.
+    cudaMemPoolProps pp = {};
+    pp.allocType = cudaMemAllocationTypePinned;
+    pp.handleTypes = cudaMemHandleTypeNone;
+    pp.location.type = cudaMemLocationTypeDevice;
+    pp.location.id = device;
+    e = cudaMemPoolCreate(&h->pool, &pp);
+    if (e == cudaSuccess) {
       unsigned long long thr = ~0ull;
-      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+      e = cudaMemPoolSetAttribute(h->pool, cudaMemPoolAttrReleaseThreshold, &thr);
     }
   }
   if (e != cudaSuccess) {
@@ -270,13 +304,21 @@ int spam_cuda_destroy(spam_handle* h) {
   if (h->d_cnt) cudaFree(h->d_cnt);
   if (h->h_cnt) cudaFreeHost(h->h_cnt);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  if (h->pool) cudaMemPoolDestroy(h->pool);
   delete h;
   return SPAM_OK;
 }
 
 int spam_cuda_set_stream(spam_handle* h, void* s) {
   if (!h) return SPAM_EINVAL;
-  h->stream = s ? (cudaStream_t)s : h->own_stream;
+  cudaStream_t next = s ? (cudaStream_t)s : h->own_stream;
+  if (next == h->stream) return SPAM_OK;
+  // Everything queued so far (kernels, stream-ordered frees of scratch that the pool may hand out again) happens
+  // before anything queued on the new stream.
+  CKS(set_device(h));
+  CK(cudaEventRecord(h->lane_ev[0], h->stream));
+  CK(cudaStreamWaitEvent(next, h->lane_ev[0], 0));
+  h->stream = next;
   return SPAM_OK;
 }
 
@@ -289,6 +331,14 @@ int spam_cuda_set_timing(spam_handle* h, int enabled) {
 int spam_cuda_get_stats(spam_handle* h, spam_stats* out) {
   if (!h || !out) return SPAM_EINVAL;
   finish_timing(h);
+  // the rare-path counters of the last product live in the device counter block (zeroed per product)
+  CKS(set_device(h));
+  CK(cudaMemcpyAsync(h->h_cnt, h->d_cnt, sizeof(Counters), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  h->stats.fallbacks[0] = h->h_cnt->fb_warp_bitonic;
+  h->stats.fallbacks[1] = h->h_cnt->fb_team_bitonic;
+  h->stats.fallbacks[2] = h->h_cnt->fb_heavy_bitonic;
+  h->stats.fallbacks[3] = h->h_cnt->fb_esc;
   *out = h->stats;
   return SPAM_OK;
 }
@@ -441,12 +491,12 @@ int spam_dcsr_download(spam_handle* h, const spam_dcsr* m, uint64_t* ptr, uint64
   if (!h || !m) return spam_fail(h, SPAM_EINVAL, "bad argument");
   CKS(set_device(h));
   if (ptr) CK(cudaMemcpyAsync(ptr, m->ptr, (m->rows + 1) * sizeof(u64), cudaMemcpyDeviceToHost, h->stream));
+  DevGuard g(h);
   u64* wide = nullptr;
   if (idx && m->nnz) {
-    CKS(dev_alloc_t(h, &wide, m->nnz));
+    CKS(g.alloc(&wide, m->nnz));
     CKS(widen_u32_to_u64(h, m->idx, wide, m->nnz));
     CK(cudaMemcpyAsync(idx, wide, m->nnz * sizeof(u64), cudaMemcpyDeviceToHost, h->stream));
-    CKS(dev_free(h, wide));
   }
   if (val && m->nnz) CK(cudaMemcpyAsync(val, m->val, m->nnz * dtype_size(m->dtype), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
@@ -489,6 +539,51 @@ int spam_dcsr_slice_rows(spam_handle* h, const spam_dcsr* m, uint64_t r0, uint64
     if (e != cudaSuccess) st = spam_fail(h, SPAM_ECUDA, "slice copy", e);
   }
   if (st != SPAM_OK) { free_dcsr(h, s); return st; }
+  *out = s;
+  return SPAM_OK;
+}
+
+int spam_dcsr_select_rows(spam_handle* h, const spam_dcsr* m, const uint64_t* rows, uint64_t n, spam_dcsr** out) {
+  if (!h || !m || !out || (n && !rows)) return spam_fail(h, SPAM_EINVAL, "bad argument");
+  *out = nullptr;
+  if (n >= 0xFFFFFFFFull) return spam_fail(h, SPAM_ECOLS, "more than 2^32-2 rows selected");
+  CKS(set_device(h));
+  DevGuard g(h);
+  u64* d_rows = nullptr;
+  u32* d_len = nullptr;
+  u64* optr = nullptr;
+  CKS(g.alloc(&d_rows, n));
+  CKS(g.alloc(&d_len, n));
+  CKS(g.alloc(&optr, n + 1));
+  CK(cudaMemsetAsync(h->d_cnt, 0, sizeof(Counters), h->stream));
+  if (n) {
+    CK(cudaMemcpyAsync(d_rows, rows, n * sizeof(u64), cudaMemcpyHostToDevice, h->stream));
+    k_select_len<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(m->ptr, d_rows, n, m->rows, d_len, h->d_cnt);
+    count_launch(h);
+    CK(cudaGetLastError());
+  }
+  CKS(scan_u32_to_u64(h, d_len, optr, n, &h->d_cnt->total_nnz));
+  CK(cudaMemcpyAsync(h->h_cnt, h->d_cnt, sizeof(Counters), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  if (h->h_cnt->error & 2u) return spam_fail(h, SPAM_EINDEX, "a selected row index is >= rows");
+  const u64 nnz = h->h_cnt->total_nnz;
+  u32* oidx = nullptr;
+  void* oval = nullptr;
+  CKS(g.alloc(&oidx, nnz));
+  CKS(g.alloc_bytes(&oval, nnz * dtype_size(m->dtype)));
+  if (n && nnz) {
+    const unsigned grid = (unsigned)((n * 32 + 255) / 256);
+    if (dtype_size(m->dtype) == 4)
+      k_select_copy<uint32_t><<<grid, 256, 0, h->stream>>>(m->ptr, m->idx, (const uint32_t*)m->val, d_rows, n, optr, oidx, (uint32_t*)oval);
+    else
+      k_select_copy<uint64_t><<<grid, 256, 0, h->stream>>>(m->ptr, m->idx, (const uint64_t*)m->val, d_rows, n, optr, oidx, (uint64_t*)oval);
+    count_launch(h);
+    CK(cudaGetLastError());
+  }
+  spam_dcsr* s = new spam_dcsr();
+  s->dtype = m->dtype; s->rows = n; s->cols = m->cols; s->nnz = nnz; s->owning = true; s->rows_sorted = -1; s->max_row_len = 0;
+  s->ptr = optr; s->idx = oidx; s->val = oval;
+  g.release(optr); g.release(oidx); g.release(oval);
   *out = s;
   return SPAM_OK;
 }
@@ -723,11 +818,14 @@ static int rows_to_parts_impl(spam_handle* h, const spam_dcsr* a, const spam_dcs
   if (a->cols != b->rows) return spam_fail(h, SPAM_EDIM, "A.cols != B.rows");
   CKS(set_device(h));
   const u64 m = a->rows;
+  CKS(ensure_matrix_stats(h, a));
+  if (b != a) CKS(ensure_matrix_stats(h, b));
+  DevGuard g(h);
   u32* flop = nullptr;
   u64 *ps = nullptr, *d_out = nullptr;
-  CKS(dev_alloc_t(h, &flop, m));
-  CKS(dev_alloc_t(h, &ps, m + 1));
-  CKS(dev_alloc_t(h, &d_out, (u64)parts + 1));
+  CKS(g.alloc(&flop, m));
+  CKS(g.alloc(&ps, m + 1));
+  CKS(g.alloc(&d_out, (u64)parts + 1));
   CK(cudaMemsetAsync(h->d_cnt, 0, sizeof(Counters), h->stream));
   CKS(flop_count_dev(h, a, b, flop, false, 0));
   if (by_cost && m) {
@@ -742,7 +840,6 @@ static int rows_to_parts_impl(spam_handle* h, const spam_dcsr* a, const spam_dcs
   CK(cudaMemcpyAsync(row_starts, d_out, ((u64)parts + 1) * 8, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaMemcpyAsync(h->h_cnt, h->d_cnt, sizeof(Counters), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
-  dev_free(h, flop); dev_free(h, ps); dev_free(h, d_out);
   if (h->h_cnt->error & 1u) return spam_fail(h, SPAM_EINDEX, "a column index of A is >= rows(B)");
   if (total_flops) *total_flops = h->h_cnt->total_flops;
   return SPAM_OK;

@@ -9,6 +9,7 @@
 #include <stdlib.h>
 
 #include <string>
+#include <vector>
 
 #include "../../include/spam_cuda.h"
 
@@ -79,7 +80,13 @@ struct Counters {
   u32 max_alen;   // longest A row among the rows of the merge bin (picks the head-count template)
   u32 unsorted;   // set by k_rows_sorted when some row is not strictly increasing
   u32 max_rowlen; // longest row seen by k_rows_sorted
-
+  u32 invalid;    // set by k_rows_sorted: bit0 row_ptr not monotone / out of range, bit1 a column index >= cols
+  // how often the rarely taken code paths ran during the last product (spam_stats.fallbacks, tests assert them)
+  u32 fb_warp_bitonic;   // NW = 1 rows sorted by the shared-memory bitonic network (columns too wide to pack)
+  u32 fb_team_bitonic;   // team rows whose bucket drain overflowed (compaction + block bitonic network)
+  u32 fb_heavy_bitonic;  // global-table rows whose bucket drain overflowed (global-memory bitonic network)
+  u32 fb_esc;            // rows the bucket-sort (ESC) bins handed back to the global-table kernel
+  u32 fb_list_n;         // number of row ids in the ESC fallback list
 };
 
 struct BinBase { u32 v[NBINS]; };
@@ -151,6 +158,8 @@ struct spam_dcsr {
   bool owning;
   int rows_sorted;  // cached property: -1 unknown, 0 no, 1 every row strictly increasing (IS_SORTED)
   u64 max_row_len;  // cached with rows_sorted: longest row (picks DIRECT vs FLAT product enumeration)
+  int invalid;      // cached with rows_sorted: 0 = row_ptr monotone from 0 to nnz and every column < cols
+                    // (invariants 3, 4, 5, 7 of spam_csr/src/lib.rs:47-81); bit0 row_ptr, bit1 column range
 };
 
 struct SpgemmPending;  // state between the two host phases
@@ -183,6 +192,8 @@ struct spam_handle {
   cudaEvent_t lane_ev[4];  // [0] fork, [1..3] join
   u64* scan_ws;      // look-back scan tile states + tile counter (grow-only, stream-ordered reuse)
   u64 scan_ws_cap;   // in u64 words
+  cudaMemPool_t pool;  // private stream-ordered pool: freed blocks stay with this handle, not with the process
+  bool use_lanes;      // SPAM_LANES=0 in the environment at create time keeps every bin on the main stream
 };
 
 static inline size_t dtype_size(int dt) { return (dt == SPAM_F32 || dt == SPAM_I32) ? 4 : 8; }
@@ -207,6 +218,31 @@ int dev_free(spam_handle* h, void* p);
 template <class T>
 static inline int dev_alloc_t(spam_handle* h, T** p, size_t n) { return dev_alloc(h, (void**)p, n * sizeof(T)); }
 
+// Frees every buffer it allocated when it goes out of scope, unless release()d: early error returns cannot
+// leak stream-ordered allocations.
+struct DevGuard {
+  spam_handle* h;
+  std::vector<void*> owned;
+  explicit DevGuard(spam_handle* hh) : h(hh) {}
+  DevGuard(const DevGuard&) = delete;
+  DevGuard& operator=(const DevGuard&) = delete;
+  ~DevGuard() { for (void* p : owned) dev_free(h, p); }
+  template <class T>
+  int alloc(T** p, size_t n) {
+    const int st = dev_alloc(h, (void**)p, n * sizeof(T));
+    if (st == SPAM_OK) owned.push_back((void*)*p);
+    return st;
+  }
+  int alloc_bytes(void** p, size_t bytes) {
+    const int st = dev_alloc(h, p, bytes);
+    if (st == SPAM_OK) owned.push_back(*p);
+    return st;
+  }
+  void release(void* p) {  // ownership moves to the caller
+    for (auto& q : owned) if (q == p) { q = owned.back(); owned.pop_back(); return; }
+  }
+};
+
 static inline void count_launch(spam_handle* h, u64 n = 1) { h->stats.kernel_launches += n; }
 
 // fork: the side lanes wait for everything queued on the main stream so far; join: the main stream waits
@@ -228,8 +264,7 @@ static inline cudaError_t lanes_join(spam_handle* h) {
 // global-table (heavy) kernels always run alone, after the join: overlapping them with the team kernels cost
 // 10% of the whole product on R-MAT 22 (their L2 atomics and the teams' B gathers fight over L2).
 static inline cudaStream_t lane_of(spam_handle* h, int bin) {
-  const char* e = getenv("SPAM_LANES");
-  if (e && e[0] == '0') return h->stream;
+  if (!h->use_lanes) return h->stream;
   switch (bin) {
     case 8: case 5: return h->lane[0];
     case 7: case 4: return h->lane[1];

@@ -7,7 +7,10 @@ namespace {
 
 __global__ void __launch_bounds__(256) k_narrow(const u64* __restrict__ in, u32* __restrict__ out, u64 n) {
   const u64 stride = (u64)gridDim.x * blockDim.x;
-  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = (u32)in[i];
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const u64 v = in[i];
+    out[i] = v > 0xFFFFFFFFull ? 0xFFFFFFFFu : (u32)v;  // saturate: the validation pass then reports it as >= cols
+  }
 }
 __global__ void __launch_bounds__(256) k_widen(const u32* __restrict__ in, u64* __restrict__ out, u64 n) {
   const u64 stride = (u64)gridDim.x * blockDim.x;

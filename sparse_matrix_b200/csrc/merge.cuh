@@ -19,27 +19,47 @@ namespace {
 
 constexpr u32 INF_COL = 0xFFFFFFFFu;
 
-// Are all rows strictly increasing by column?  (invariant6 with IS_SORTED, lib.rs:69-77)
+// One pass over a matrix the first time it is used (the result is cached with the matrix):
+//  * are all rows strictly increasing by column?  (invariant6 with IS_SORTED, lib.rs:69-77)
+//  * longest row
+//  * the invariants the kernels rely on for memory safety (lib.rs:47-81): row_ptr starts at 0, is monotone and
+//    ends at nnz (invariants 3, 4, 7), every column index < cols (invariant 5).  The reference panics safely
+//    on a bad matrix; here it is SPAM_EINVAL / SPAM_EINDEX instead of a device fault.
 template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK) k_rows_sorted(u64 m, const u64* __restrict__ ptr,
+__global__ void __launch_bounds__(BLOCK) k_rows_sorted(u64 m, u64 nnz, u64 cols, const u64* __restrict__ ptr,
                                                        const u32* __restrict__ idx, Counters* cnt) {
   const int lane = threadIdx.x & 31;
   const u64 row = (u64)blockIdx.x * BLOCK + threadIdx.x;
-  const bool valid = row < m;
+  bool valid = row < m;
   u64 lo = 0, hi = 0;
-  if (valid) { lo = ptr[row]; hi = ptr[row + 1]; }
+  u32 inval = 0;
+  if (valid) {
+    lo = ptr[row]; hi = ptr[row + 1];
+    if (lo > hi || hi > nnz || (row == 0 && lo != 0) || (row + 1 == m && hi != nnz)) { inval |= 1u; valid = false; lo = hi = 0; }
+  }
   bool bad = false;
   if (valid && hi - lo <= 32) {
-    for (u64 e = lo + 1; e < hi; ++e) bad |= idx[e - 1] >= idx[e];
+    u32 prev = 0;
+    for (u64 e = lo; e < hi; ++e) {
+      const u32 c = idx[e];
+      if (c >= cols) inval |= 2u;
+      if (e > lo) bad |= prev >= c;
+      prev = c;
+    }
   }
   unsigned longmask = __ballot_sync(0xffffffffu, valid && hi - lo > 32);
   while (longmask) {
     const int src = __ffs(longmask) - 1;
     longmask &= longmask - 1;
     const u64 l = __shfl_sync(0xffffffffu, lo, src), hh = __shfl_sync(0xffffffffu, hi, src);
-    for (u64 e = l + 1 + lane; e < hh; e += 32) bad |= idx[e - 1] >= idx[e];
+    for (u64 e = l + lane; e < hh; e += 32) {
+      const u32 c = idx[e];
+      if (c >= cols) inval |= 2u;
+      if (e > l) bad |= idx[e - 1] >= c;
+    }
   }
   if (bad) atomicOr(&cnt->unsorted, 1u);
+  if (inval) atomicOr(&cnt->invalid, inval);
   u64 len = hi - lo;
   u32 l32 = len > 0xFFFFFFFFull ? 0xFFFFFFFFu : (u32)len;
 #pragma unroll

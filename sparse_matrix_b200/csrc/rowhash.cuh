@@ -331,104 +331,6 @@ __device__ __forceinline__ void warp_bitonic_sort(u32 kbase, u32 vbase, u32 n2, 
 }
 
 // ------------------------------------------------------------------------------------------------
-// finishing the order-preserving buckets of the team drain (entries already sit in C, bucket by bucket)
-// ------------------------------------------------------------------------------------------------
-constexpr u32 SMALL_BUCKET_MAX = 8;    // up to here: insertion sort by one thread
-constexpr u32 BIG_BUCKET_MAX = 256;    // up to here: rank sort by one warp; beyond: whole-row bitonic fallback
-constexpr int BIG_QUEUE = 128;         // long buckets queued per row (overflow falls back to insertion sort)
-
-// A short bucket (2..8 entries) sorted by one thread IN REGISTERS: all loads issued at once, an odd-even
-// transposition network with static indices, stores back.  The first version insertion-sorted in global
-// memory: a chain of dependent L2 loads that was 38% of the team kernel's instructions and a third of its
-// stall samples on R-MAT (profiles/r01_rmat20_v2_finebins.txt).
-template <class V, int N>
-__device__ __forceinline__ void sort_bucket_regs(u32* __restrict__ c_col, V* __restrict__ c_val, u64 base, u32 n) {
-  u32 k[N];
-  V v[N];
-#pragma unroll
-  for (int i = 0; i < N; ++i) {
-    k[i] = 0xFFFFFFFFu; v[i] = V();
-    if ((u32)i < n) { k[i] = c_col[base + i]; v[i] = c_val[base + i]; }
-  }
-#pragma unroll
-  for (int round = 0; round < N; ++round) {
-#pragma unroll
-    for (int i = round & 1; i + 1 < N; i += 2) {
-      if (k[i] > k[i + 1]) {
-        const u32 tk = k[i]; k[i] = k[i + 1]; k[i + 1] = tk;
-        const V tv = v[i]; v[i] = v[i + 1]; v[i + 1] = tv;
-      }
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < N; ++i)
-    if ((u32)i < n) { c_col[base + i] = k[i]; c_val[base + i] = v[i]; }
-}
-
-template <class V>
-__device__ __forceinline__ void sort_small_bucket(u32* __restrict__ c_col, V* __restrict__ c_val, u64 c0, u32 lo_b, u32 hi_b) {
-  const u32 n = hi_b - lo_b;
-  if (n < 2) return;
-  if (n == 2) {
-    const u32 k0 = c_col[c0 + lo_b], k1 = c_col[c0 + lo_b + 1];
-    if (k0 > k1) {
-      const V v0 = c_val[c0 + lo_b], v1 = c_val[c0 + lo_b + 1];
-      c_col[c0 + lo_b] = k1; c_col[c0 + lo_b + 1] = k0;
-      c_val[c0 + lo_b] = v1; c_val[c0 + lo_b + 1] = v0;
-    }
-  } else if (n <= 4) {
-    sort_bucket_regs<V, 4>(c_col, c_val, c0 + lo_b, n);
-  } else {
-    sort_bucket_regs<V, 8>(c_col, c_val, c0 + lo_b, n);
-  }
-}
-
-template <class V>
-__device__ __forceinline__ void insertion_sort_bucket(u32* __restrict__ c_col, V* __restrict__ c_val, u64 c0, u32 lo_b,
-                                                      u32 hi_b) {
-  for (u32 i = lo_b + 1; i < hi_b; ++i) {
-    const u32 k = c_col[c0 + i];
-    const V v = c_val[c0 + i];
-    u32 j = i;
-    while (j > lo_b && c_col[c0 + j - 1] > k) { c_col[c0 + j] = c_col[c0 + j - 1]; c_val[c0 + j] = c_val[c0 + j - 1]; --j; }
-    c_col[c0 + j] = k;
-    c_val[c0 + j] = v;
-  }
-}
-
-// n <= BIG_BUCKET_MAX distinct keys at c_col[base..base+n): each lane holds up to 8, counts for each how
-// many keys of the bucket are smaller (keys broadcast by shuffle), then stores it at its rank.
-template <class V>
-__device__ __forceinline__ void rank_sort_bucket_warp(u32* __restrict__ c_col, V* __restrict__ c_val, u64 base, u32 n,
-                                                      int lane) {
-  constexpr int R = BIG_BUCKET_MAX / 32;
-  u32 k[R], rank[R];
-  V v[R];
-  const int rounds = (int)((n + 31) / 32);
-#pragma unroll
-  for (int r = 0; r < R; ++r) {
-    const u32 i = lane + 32 * r;
-    k[r] = 0xFFFFFFFFu; rank[r] = 0; v[r] = V();
-    if (i < n) { k[r] = c_col[base + i]; v[r] = c_val[base + i]; }
-  }
-#pragma unroll
-  for (int rr = 0; rr < R; ++rr) {
-    if (rr < rounds) {
-      for (int src = 0; src < 32; ++src) {
-        const u32 ko = __shfl_sync(FULL, k[rr], src);
-#pragma unroll
-        for (int r = 0; r < R; ++r) rank[r] += (ko < k[r]) ? 1u : 0u;  // padding keys are never smaller
-      }
-    }
-  }
-  __syncwarp();
-#pragma unroll
-  for (int r = 0; r < R; ++r) {
-    if (lane + 32 * r < n) { c_col[base + rank[r]] = k[r]; c_val[base + rank[r]] = v[r]; }
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
 // NUMERIC (mul_hash.rs:105-201)
 // ------------------------------------------------------------------------------------------------
 // NW = 1, DIRECT: the lanes of a batch hold distinct columns -> distinct slots: plain read-modify-write
@@ -480,7 +382,7 @@ __global__ void __launch_bounds__(NW == 1 ? 32 * ROWS_PER_BLOCK_W1 : 32 * NW)
 k_num_row(u32 n, const u32* __restrict__ perm, const u64* __restrict__ a_ptr, const u32* __restrict__ a_col,
           const V* __restrict__ a_val, const u64* __restrict__ b_ptr, const u32* __restrict__ b_col,
           const V* __restrict__ b_val, const u64* __restrict__ c_ptr, u32* __restrict__ c_col, V* __restrict__ c_val,
-          int pack_ok) {
+          int pack_ok, Counters* cnt_dev) {
   static_assert(!DIRECT || NW == 1, "DIRECT enumeration is a single-warp mode");
   constexpr int RPB = NW == 1 ? ROWS_PER_BLOCK_W1 : 1;
   constexpr int TT = 32 * NW;  // threads in the row's team
@@ -612,6 +514,7 @@ k_num_row(u32 n, const u32* __restrict__ perm, const u64* __restrict__ a_ptr, co
       else if (CAP >= 512 && n2 <= 256) warp_sort_store<V, (CAP >= 512 ? 8 : 1)>(kbase, vbase, z, idxbits, lane, c_col, c_val, c0);
       else if (CAP >= 1024) warp_sort_store<V, (CAP >= 1024 ? 16 : 1)>(kbase, vbase, z, idxbits, lane, c_col, c_val, c0);
     } else {
+      if (lane == 0) atomicAdd(&cnt_dev->fb_warp_bitonic, 1u);
       for (u32 s = z + lane; s < n2; s += 32) sts32(kbase + 4u * s, EMPTY_KEY);
       __syncwarp();
       warp_bitonic_sort<V>(kbase, vbase, n2, lane);
@@ -690,7 +593,7 @@ k_num_row(u32 n, const u32* __restrict__ perm, const u64* __restrict__ a_ptr, co
     }
   } else {
     // pathological column distribution: compact in shared memory and run the bitonic network
-    if (threadIdx.x == 0) s_kmax = 0;  // reused as the compaction cursor
+    if (threadIdx.x == 0) { s_kmax = 0; atomicAdd(&cnt_dev->fb_team_bitonic, 1u); }  // s_kmax reused as the compaction cursor
     __syncthreads();
     for (u32 base = 0; base < cap; base += TT) {
       const u32 s = base + rt;

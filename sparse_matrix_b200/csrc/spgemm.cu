@@ -418,7 +418,7 @@ __global__ void __launch_bounds__(T) k_num_heavy(u32 n, const u32* __restrict__ 
                                                  const V* __restrict__ b_val, const u64* __restrict__ c_ptr,
                                                  u32* __restrict__ c_col, V* __restrict__ c_val, u32* key_tables,
                                                  V* val_tables, u64 table_stride, u32* cnt_tables, u32* ord_tables,
-                                                 u32 b_cols, u32* work) {
+                                                 u32 b_cols, u32* work, Counters* cnt_dev) {
   constexpr int ITEMS = 4;
   constexpr u32 HEAVY_RANK_MAX = 2048;  // longest bucket ranked by counting; beyond: bitonic fallback
   __shared__ u32 s_item, s_maxcnt;
@@ -563,6 +563,7 @@ __global__ void __launch_bounds__(T) k_num_heavy(u32 n, const u32* __restrict__ 
     }
     // fallback: in-place chunked compaction: chunk c is read into registers, barrier, then written at
     // the running output offset, which never passes the start of the next unread chunk.
+    if (tid == 0) atomicAdd(&cnt_dev->fb_heavy_bitonic, 1u);
     u32 run = 0;
     for (u64 cbase = 0; cbase < cap; cbase += (u64)T * ITEMS) {
       u32 rk[ITEMS];
@@ -601,6 +602,10 @@ __global__ void __launch_bounds__(T) k_num_heavy(u32 n, const u32* __restrict__ 
 // One B row per warp batch (DIRECT) pays off when B rows are about a warp long and not skewed (stencils);
 // otherwise the products are flattened over the lanes (FLAT).  Uses the per-matrix cached stats.
 bool direct_enumeration(const spam_dcsr* b) {
+  // DIRECT updates values with a plain read-modify-write per batch, which needs distinct columns inside a B
+  // row: known only when the rows are strictly increasing (a duplicate column in an unsorted row is folded
+  // correctly by the FLAT path's match-any)
+  if (b->rows_sorted != 1) return false;
   const double mean = b->rows ? (double)b->nnz / (double)b->rows : 0.0;
   return mean >= 12.0 && (double)b->max_row_len <= 3.0 * mean + 8.0;
 }
@@ -671,17 +676,23 @@ namespace {
 // Cached per matrix: are all rows strictly increasing by column?  One pass over col_idx the first
 // time a matrix is used as a right-hand side (device matrices are immutable through this API).
 int ensure_rows_sorted(spam_handle* h, const spam_dcsr* b) {
-  if (b->rows_sorted >= 0) return SPAM_OK;
   spam_dcsr* mb = const_cast<spam_dcsr*>(b);
-  if (b->rows == 0 || b->nnz == 0) { mb->rows_sorted = 1; mb->max_row_len = 0; return SPAM_OK; }
-  CK(cudaMemsetAsync(&h->d_cnt->unsorted, 0, 2 * sizeof(u32), h->stream));  // unsorted, max_rowlen
-  k_rows_sorted<256><<<(unsigned)((b->rows + 255) / 256), 256, 0, h->stream>>>(b->rows, b->ptr, b->idx, h->d_cnt);
-  count_launch(h);
-  CK(cudaGetLastError());
-  CK(cudaMemcpyAsync(&h->h_cnt->unsorted, &h->d_cnt->unsorted, 2 * sizeof(u32), cudaMemcpyDeviceToHost, h->stream));
-  CK(cudaStreamSynchronize(h->stream));
-  mb->rows_sorted = h->h_cnt->unsorted ? 0 : 1;
-  mb->max_row_len = h->h_cnt->max_rowlen;
+  if (b->rows_sorted < 0) {
+    if (b->rows == 0) { mb->rows_sorted = 1; mb->max_row_len = 0; mb->invalid = b->nnz ? 1 : 0; }
+    else {
+      CK(cudaMemsetAsync(&h->d_cnt->unsorted, 0, 3 * sizeof(u32), h->stream));  // unsorted, max_rowlen, invalid
+      k_rows_sorted<256><<<(unsigned)((b->rows + 255) / 256), 256, 0, h->stream>>>(b->rows, b->nnz, b->cols, b->ptr, b->idx, h->d_cnt);
+      count_launch(h);
+      CK(cudaGetLastError());
+      CK(cudaMemcpyAsync(&h->h_cnt->unsorted, &h->d_cnt->unsorted, 3 * sizeof(u32), cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaStreamSynchronize(h->stream));
+      mb->rows_sorted = h->h_cnt->unsorted ? 0 : 1;
+      mb->max_row_len = h->h_cnt->max_rowlen;
+      mb->invalid = (int)h->h_cnt->invalid;
+    }
+  }
+  if (b->invalid & 1) return spam_fail(h, SPAM_EINVAL, "row_ptr is not a monotone sequence from 0 to nnz (invariants 3, 4, 7)");
+  if (b->invalid & 2) return spam_fail(h, SPAM_EINDEX, "a column index is >= cols (invariant 5)");
   return SPAM_OK;
 }
 
@@ -720,7 +731,8 @@ int spgemm_symbolic_dev(spam_handle* h, const spam_dcsr* a, const spam_dcsr* b, 
     return spam_fail(h, SPAM_ECOLS, "dimension >= 2^32-1 (u32::MAX is the empty-slot sentinel)");
 
   h->stats = spam_stats{};
-  CKS(ensure_rows_sorted(h, b));
+  CKS(ensure_rows_sorted(h, b));  // one cached pass per matrix: sortedness, longest row, CSR invariants
+  if (a != b) CKS(ensure_rows_sorted(h, a));
   const int merge_ok = (b->rows_sorted == 1 && b->nnz < 0xFFFFFFFFull) ? 1 : 0;
   SpgemmPending* p = new SpgemmPending();
   p->a = a; p->b = b; p->d_flop = nullptr; p->d_row_nnz = nullptr; p->d_cptr = nullptr; p->nnz = 0; p->max_nnz = 0;
@@ -740,7 +752,6 @@ int spgemm_symbolic_dev(spam_handle* h, const spam_dcsr* a, const spam_dcsr* b, 
     // B sorted: flop count and the merge-bin symbolic pass in ONE kernel, then a speculative scan —
     // when every row is in the merge bin (stencils) that scan is final and the product needs a
     // single host sync before the numeric pass.
-    if (a != b) FAIL_FREE(ensure_rows_sorted(h, a));  // only for A's longest row (cached with the matrix)
     const u64 amax = a->max_row_len;
     const u32 kk = amax <= 4 ? 4 : amax <= 6 ? 6 : 8;
     p->max_alen = kk;
@@ -903,7 +914,13 @@ int numeric_typed(spam_handle* h, SpgemmPending* p, spam_dcsr* c) {
   const spam_dcsr* b = p->b;
   const u64 m = a->rows;
   Bins nb;
+  // the symbolic phase's memset zeroed these, but another product may have run on this handle between the two
+  // host phases (spam_spgemm_symbolic ... spam_spgemm_dev ... spam_spgemm_numeric)
+  CK(cudaMemsetAsync(h->d_cnt->num_cursor, 0, sizeof(u32) * NBINS, h->stream));
+  CK(cudaMemsetAsync(&h->d_cnt->work_b, 0, sizeof(u32), h->stream));
+  DevGuard g(h);
   CKS(build_perm(h, m, p->num_counts, true, a->ptr, p->d_row_nnz, p->d_flop, p->merge_ok, &nb));
+  if (nb.perm) g.owned.push_back(nb.perm);
   const u64* ap = a->ptr; const u32* ac = a->idx; const V* av = (const V*)a->val;
   const u64* bp = b->ptr; const u32* bc = b->idx; const V* bv = (const V*)b->val;
   const u64* cp = c->ptr; u32* cc = c->idx; V* cv = (V*)c->val;
@@ -916,7 +933,7 @@ int numeric_typed(spam_handle* h, SpgemmPending* p, spam_dcsr* c) {
     /* NW = 1 sorts (column << log2(CAP/2)) | index packed in 32 bits when the columns are narrow enough */ \
     const int pack_ok = b->cols < (1ull << (32 - (31 - __builtin_clz((unsigned)(CAP) / 2)))) ? 1 : 0;   \
     k_num_row<V, NW, CAP, DIRECT><<<grid, NW == 1 ? 32 * ROWS_PER_BLOCK_W1 : 32 * NW, smem, lane_of(h, BIN)>>>( \
-        nb.count[BIN], seg(BIN), ap, ac, av, bp, bc, bv, cp, cc, cv, pack_ok);                           \
+        nb.count[BIN], seg(BIN), ap, ac, av, bp, bc, bv, cp, cc, cv, pack_ok, h->d_cnt);                 \
     count_launch(h);                                                                                     \
   }
   // The bins touch disjoint rows of C.  The team bins (largest first) go to the side lanes so that the tail of
@@ -934,10 +951,10 @@ int numeric_typed(spam_handle* h, SpgemmPending* p, spam_dcsr* c) {
     const u64 budget = 16ull << 30;
     // per block: keys + values (stride each), bucket counters (stride/2), bucket-ordered keys + slots (stride)
     while (heavy_nblk > 1 && heavy_nblk * heavy_stride * (2 * sizeof(u32) + sizeof(V) + 2) > budget) heavy_nblk /= 2;
-    CKS(dev_alloc_t(h, &hk, heavy_nblk * heavy_stride));
-    CKS(dev_alloc_t(h, &hv, heavy_nblk * heavy_stride));
-    CKS(dev_alloc_t(h, &hc, heavy_nblk * (heavy_stride / 2 + 4)));
-    CKS(dev_alloc_t(h, &ho, heavy_nblk * heavy_stride));
+    CKS(g.alloc(&hk, heavy_nblk * heavy_stride));
+    CKS(g.alloc(&hv, heavy_nblk * heavy_stride));
+    CKS(g.alloc(&hc, heavy_nblk * (heavy_stride / 2 + 4)));
+    CKS(g.alloc(&ho, heavy_nblk * heavy_stride));
   }
   if (side) CK(lanes_fork(h));
   // numeric hash bin b: z <= 32 << b, table 64 << b (key, value) slots.  Team sizes: these kernels are
@@ -986,16 +1003,11 @@ int numeric_typed(spam_handle* h, SpgemmPending* p, spam_dcsr* c) {
   if (nb.count[HEAVY_BIN]) {
     k_num_heavy<V, 1024><<<(unsigned)heavy_nblk, 1024, 0, h->stream>>>(nb.count[HEAVY_BIN], seg(HEAVY_BIN), ap, ac, av, bp, bc, bv,
                                                                                   cp, cc, cv, hk, hv, heavy_stride, hc, ho,
-                                                                                  (u32)b->cols, &h->d_cnt->work_b);
+                                                                                  (u32)b->cols, &h->d_cnt->work_b, h->d_cnt);
     count_launch(h);
     CK(cudaGetLastError());
   }
-  if (ho) CKS(dev_free(h, ho));
-  if (hc) CKS(dev_free(h, hc));
-  if (hk) CKS(dev_free(h, hk));
-  if (hv) CKS(dev_free(h, hv));
-  if (nb.perm) CKS(dev_free(h, nb.perm));
-  return SPAM_OK;
+  return SPAM_OK;  // the guard frees the tables and the permutation (stream-ordered: after the kernels above)
 }
 
 }  // namespace

@@ -269,13 +269,83 @@ def test_config3_stencil27_reduced(oracle, handle):
 
 
 def test_config4_rmat_reduced(oracle, handle):
-    r = G.rmat(15, 16)
+    r = G.rmat(16, 16)
     handle.set_timing(True)
     c = gpu_mul(r, r, handle)
     st = handle.stats()
     handle.set_timing(False)
     check_against_oracle(oracle, r, r, c)
-    assert st["sym_bin_rows"][HEAVY] > 0 or st["sym_bin_rows"][8] > 0 or st["sym_bin_rows"][7] > 0   # power-law rows reach the big bins
+    assert st["sym_bin_rows"][HEAVY] > 0, st["sym_bin_rows"]      # power-law rows reach the global-table bin
+    assert sum(st["num_bin_rows"][11:16]) + st["num_bin_rows"][HEAVY] > 0, st["num_bin_rows"]
+
+
+# ---------------------------------------------------------------------------------------------
+# the rarely taken code paths: each is forced by a hand-built shape and asserted through spam_stats.fallbacks
+# ---------------------------------------------------------------------------------------------
+def _csr_from_rows(rows_cols, ncols, rng, dtype=np.float64):
+    off = np.zeros(len(rows_cols) + 1, np.uint64)
+    off[1:] = np.cumsum([len(c) for c in rows_cols])
+    idx = np.concatenate([np.asarray(c, np.uint64) for c in rows_cols]) if rows_cols else np.empty(0, np.uint64)
+    if np.dtype(dtype).kind == "f":
+        val = rng.uniform(-1, 1, size=len(idx)).astype(dtype)
+        val[val == 0] = 0.5
+    else:
+        val = rng.integers(1, 50, size=len(idx)).astype(dtype)
+    return len(rows_cols), ncols, off, idx, val
+
+
+@pytest.mark.parametrize("sorted_b", [False, True])
+def test_fallback_wide_columns_warp_bitonic(oracle, handle, sorted_b):
+    """The fuzz target's shape space (fuzz/fuzz_targets/mul_hash.rs:15-19: n up to 2^31): with cols(B) = 2^31 - 2 a
+    column no longer packs with its index into 32 bits, so the one-warp bins sort with the shared-memory bitonic
+    network (rowhash.cuh warp_bitonic_sort)."""
+    rng = np.random.default_rng(2024)
+    n = 2**31 - 2
+    inner = 200
+    brows = [np.unique(rng.integers(0, n, size=int(k))) for k in rng.integers(0, 25, size=inner)]
+    brows[7] = np.array([0, 1, n - 2, n - 1])                  # both ends of the column range
+    if not sorted_b:
+        brows = [rng.permutation(c) for c in brows]
+    b = _csr_from_rows(brows, n, rng)
+    a = random_csr(rng, 300, inner, rng.integers(0, 22, size=300), sorted_rows=False)
+    c = gpu_mul(a, b, handle)
+    st = handle.stats()
+    check_against_oracle(oracle, a, b, c)
+    assert sum(st["num_bin_rows"][1:4]) > 0 and st["fallbacks"][0] > 0, (st["num_bin_rows"], st["fallbacks"])
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.int64])
+def test_fallback_team_bucket_overflow(oracle, handle, dtype):
+    """A team-bin row whose columns are 600 consecutive ids plus one far away: the order-preserving buckets over the
+    row's column range put all 600 into one bucket (> 512), so the drain compacts in shared memory and runs the
+    block-wide bitonic network (rowhash.cuh, NW > 1 fallback).  Three copies of every product keep the row on
+    the hash path (it compresses 3x)."""
+    rng = np.random.default_rng(7)
+    far = 2**30
+    base = [np.arange(0, 300), np.arange(300, 600), np.array([far])]
+    b = _csr_from_rows(base * 3 + [np.arange(5, 9)], far + 1, rng, dtype)
+    a = _csr_from_rows([np.arange(9), np.array([9]), np.arange(3)], 10, rng, dtype)
+    c = gpu_mul(a, b, handle)
+    st = handle.stats()
+    check_against_oracle(oracle, a, b, c)
+    assert st["num_bin_rows"][5] >= 1 and st["fallbacks"][1] >= 1, (st["num_bin_rows"], st["fallbacks"])
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.int32])
+def test_fallback_heavy_bucket_overflow(oracle, handle, dtype):
+    """A global-table row (nnz > 8192) with 3000 consecutive columns in one drain bucket (> 2048): in-place
+    compaction and the global-memory bitonic network of k_num_heavy.  Every column is produced three times."""
+    rng = np.random.default_rng(8)
+    ncols = 2**30
+    spread = np.unique(rng.integers(1 << 20, ncols, size=6500))
+    cols = np.concatenate([np.arange(70000, 73000), spread])     # 3000 consecutive ids: one 65536-wide bucket
+    chunks = np.array_split(cols, 40)
+    b = _csr_from_rows(chunks * 3, ncols, rng, dtype)
+    a = _csr_from_rows([np.arange(120), np.arange(40)], 120, rng, dtype)
+    c = gpu_mul(a, b, handle)
+    st = handle.stats()
+    check_against_oracle(oracle, a, b, c)
+    assert len(cols) > 8192 and st["num_bin_rows"][HEAVY] >= 1 and st["fallbacks"][2] >= 1, (st["num_bin_rows"], st["fallbacks"])
 
 
 def test_config5_rectangular_i64_and_dok(oracle, handle):

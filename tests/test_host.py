@@ -29,7 +29,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(L, name), f"{name} declared in include/spam_cuda.h but not exported"
     assert sorted(_lib.EXPORTS) == declared, "python binding list and header disagree"
-    assert S.load().spam_cuda_abi_version() == 5
+    assert S.load().spam_cuda_abi_version() == 6
 
 
 def test_strerror_covers_every_status():
