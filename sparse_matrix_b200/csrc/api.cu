@@ -246,6 +246,8 @@ int spam_cuda_create(spam_handle** out, int device) {
   {
     const char* e = getenv("SPAM_LANES");  // read once: 0 keeps every row bin on the main stream
     h->use_lanes = !(e && e[0] == '0');
+    e = getenv("SPAM_ESC");
+    h->use_esc = !(e && e[0] == '0');
   }
   h->d_cnt = nullptr; h->h_cnt = nullptr; h->own_stream = nullptr; h->stream = nullptr;
   h->stats = spam_stats{};

@@ -22,7 +22,7 @@ constexpr u32 EMPTY_KEY = 0xFFFFFFFFu;  // linprobe/src/set.rs:45
 constexpr u32 HASH_SCAL = 107u;         // linprobe/src/lib.rs:13
 constexpr u32 MIN_TABLE = 16u;          // linprobe/src/lib.rs:14
 
-constexpr int NBINS = 12;
+constexpr int NBINS = 16;
 
 // ---- row bins ---------------------------------------------------------------------------
 // One hash bin per power of two, so a row's shared-memory table is at most 2x what linprobe's rule
@@ -34,7 +34,13 @@ constexpr int NBINS = 12;
 //                   one warp per row while the table is <= 12 KB, then teams of 4 .. 32 warps (k_*_row)
 //   9        heavy  above: global-memory table, persistent 1024-thread blocks (k_*_heavy)
 //   10       merge  B sorted, len(A row) <= MERGE_K, f <= 128: k-way merge of sorted runs (merge.cuh)
-constexpr int NHASH = 8, HEAVY_BIN = 9, MERGE_BIN = 10;
+//   11..15   esc    numeric only: rows that do not compress (z > 256 and 2 z >= f) are bucket-sorted instead of
+//                   hashed (esc.cuh): f <= 1024 / 2048 / 4096 / 8192 one block per row, 15 = longer rows in
+//                   column ranges
+constexpr int NHASH = 8, HEAVY_BIN = 9, MERGE_BIN = 10, ESC_BIN0 = 11, ESC_HEAVY_BIN = 15;
+constexpr u32 ESC_ZMIN = 256;
+// `mode` bits of the binning functions: which optional bins the product may use
+constexpr int MODE_MERGE = 1, MODE_ESC = 2;
 constexpr u32 SYM_TINY_MAX = 32, NUM_TINY_MAX = 16, NUM_TINY_FLOP_MAX = 128;
 constexpr u32 SYM_HASH_FMAX = 64u << NHASH, NUM_HASH_ZMAX = 32u << NHASH;
 constexpr u32 MERGE_K = 8, MERGE_FLOP_MAX = 128;
@@ -55,9 +61,16 @@ __host__ __device__ __forceinline__ int sym_bin_of(u32 f, u32 alen = 0xFFFFFFFFu
   const int b = ceil_log2_u32(f) - 6;  // smallest b with f <= 64 << b
   return b < 1 ? 1 : b;
 }
-__host__ __device__ __forceinline__ int num_bin_of(u32 z, u32 f, u32 alen = 0xFFFFFFFFu, bool merge_ok = false) {
-  if (merge_ok && alen <= MERGE_K && f <= MERGE_FLOP_MAX) return MERGE_BIN;
+__host__ __device__ __forceinline__ int num_bin_of(u32 z, u32 f, u32 alen = 0xFFFFFFFFu, int mode = 0) {
+  if ((mode & MODE_MERGE) && alen <= MERGE_K && f <= MERGE_FLOP_MAX) return MERGE_BIN;
   if (z <= NUM_TINY_MAX && f <= NUM_TINY_FLOP_MAX) return 0;
+  if ((mode & MODE_ESC) && z > ESC_ZMIN && 2ull * z >= f && f != 0xFFFFFFFFu) {  // f saturates at u32::MAX
+    if (f <= 1024) return ESC_BIN0;
+    if (f <= 2048) return ESC_BIN0 + 1;
+    if (f <= 4096) return ESC_BIN0 + 2;
+    if (f <= 8192) return ESC_BIN0 + 3;
+    return ESC_HEAVY_BIN;
+  }
   if (z > NUM_HASH_ZMAX) return HEAVY_BIN;
   const int b = ceil_log2_u32(z < 1 ? 1 : z) - 5;  // smallest b with z <= 32 << b
   return b < 1 ? 1 : b;
@@ -76,7 +89,7 @@ struct Counters {
   u32 error;      // bit0: column index of A >= rows(B); bit1: triplet index out of range
   u32 work_a;     // dynamic work counters for the persistent heavy-row kernels
   u32 work_b;
-  u32 scan_tile;  // dynamic tile id for the look-back scan
+  u32 work_c;     // row queue of the global-table kernel when it runs the bucket-sort bins' fallback list
   u32 max_alen;   // longest A row among the rows of the merge bin (picks the head-count template)
   u32 unsorted;   // set by k_rows_sorted when some row is not strictly increasing
   u32 max_rowlen; // longest row seen by k_rows_sorted
@@ -194,6 +207,7 @@ struct spam_handle {
   u64 scan_ws_cap;   // in u64 words
   cudaMemPool_t pool;  // private stream-ordered pool: freed blocks stay with this handle, not with the process
   bool use_lanes;      // SPAM_LANES=0 in the environment at create time keeps every bin on the main stream
+  bool use_esc;        // SPAM_ESC=0 at create time: hash bins only (A/B measurements of the bucket-sort bins)
 };
 
 static inline size_t dtype_size(int dt) { return (dt == SPAM_F32 || dt == SPAM_I32) ? 4 : 8; }
@@ -266,9 +280,9 @@ static inline cudaError_t lanes_join(spam_handle* h) {
 static inline cudaStream_t lane_of(spam_handle* h, int bin) {
   if (!h->use_lanes) return h->stream;
   switch (bin) {
-    case 8: case 5: return h->lane[0];
-    case 7: case 4: return h->lane[1];
-    case 6: return h->lane[2];
+    case 8: case 5: case 14: case 11: return h->lane[0];
+    case 7: case 4: case 13: return h->lane[1];
+    case 6: case 12: case 15: return h->lane[2];
     default: return h->stream;
   }
 }
@@ -287,7 +301,7 @@ int spgemm_numeric_dev(spam_handle* h, SpgemmPending* p, spam_dcsr** c);
 void spgemm_pending_free(spam_handle* h, SpgemmPending* p);
 u64 spgemm_pending_nnz(const SpgemmPending* p);
 const u64* spgemm_pending_cptr(const SpgemmPending* p);
-int flop_count_dev(spam_handle* h, const spam_dcsr* a, const spam_dcsr* b, u32* d_flop, bool do_bins, int merge_ok);
+int flop_count_dev(spam_handle* h, const spam_dcsr* a, const spam_dcsr* b, u32* d_flop, bool do_bins, int mode);
 // cached per-matrix properties (rows sorted? longest row), one pass over col_idx on first use
 int ensure_matrix_stats(spam_handle* h, const spam_dcsr* m);
 // spmv.cu

@@ -6,12 +6,26 @@
 // LAST write of the stream unless that write is zero.  BTreeMap iteration order is (row, col)
 // lexicographic (spam_dok/src/lib.rs:234-242); empty rows get repeated offsets (lib.rs:321,325).
 //
-//   1. key = row << cbits | col (only the bits the shape needs), payload = stream position
-//   2. hand-written LSD radix sort, 8 bits per pass, stable => equal keys stay in stream order
-//   3. keep entry i iff it ends its key run and its value is non-zero; count kept entries per row
-//   4. look-back scans (scan.cu) give output positions and row_ptr; scatter col_idx / val
+// Two paths, chosen after a histogram of the stream by row (one small host sync):
 //
-// All integer work, HBM-bound: each pass streams keys+payload (12 B) in and out once.
+//  COUNTING PATH (no row holds more than SEG_MAX = 32 triplets — C5: 8 per row): CSR is a counting sort by row,
+//    1. k_dok_hist     raw count per row (L2 atomics), index validation
+//    2. look-back scan (scan.cu) -> start of every row's segment
+//    3. k_dok_scatter  (col, stream position, value) into the row's segment, order inside it arbitrary
+//    4. k_dok_seg      one thread per row: an entry survives iff no entry of the segment has the same column and a
+//                      later stream position, and its value is non-zero; survivors as a 32-bit mask + their count
+//    5. look-back scan -> row_ptr, nnz            [host sync: the caller allocates exactly nnz]
+//    6. k_dok_emit     one thread per row: every survivor ranks itself by column among the survivors
+//   The stream is read twice (16 B + 16 B + value), the segments written once and read twice: about 1.7x the
+//   algorithmic bytes, against 5.5x for six radix passes.
+//
+//  RADIX PATH (some row is longer): the general stable sort,
+//    1. key = row << cbits | col (only the bits the shape needs), payload = stream position
+//    2. hand-written LSD radix sort, 8 bits per pass, stable => equal keys stay in stream order
+//    3. keep entry i iff it ends its key run and its value is non-zero; count kept entries per row
+//    4. look-back scans give output positions and row_ptr; scatter col_idx / val
+//
+// All integer work, HBM/L2-bound.
 #include "common.cuh"
 
 namespace {
@@ -136,6 +150,147 @@ __global__ void __launch_bounds__(256) k_emit(u64 n, int cbits, const u64* __res
   }
 }
 
+// ---- counting path ----------------------------------------------------------------------------------
+constexpr u32 SEG_MAX = 32;  // longest row / column segment the counting paths sort with one thread
+
+__global__ void __launch_bounds__(256) k_dok_hist(u64 n, u64 rows, u64 cols, const u64* __restrict__ r,
+                                                  const u64* __restrict__ c, u32* __restrict__ raw_cnt, Counters* cnt) {
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  bool bad = false;
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const u64 ri = r[i], ci = c[i];
+    if (ri < rows && ci < cols) atomicAdd(&raw_cnt[ri], 1u); else bad = true;  // IndexError (spam_dok lib.rs:168-170)
+  }
+  if (bad) atomicOr(&cnt->error, 2u);
+}
+
+// max of a u32 array into cnt->max_flop (zeroed by the caller)
+__global__ void __launch_bounds__(256) k_max_u32(const u32* __restrict__ a, u64 n, Counters* cnt) {
+  u32 mx = 0;
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) mx = max(mx, a[i]);
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+  if ((threadIdx.x & 31) == 0 && mx) atomicMax(&cnt->max_flop, mx);
+}
+
+template <class V>
+__global__ void __launch_bounds__(256) k_dok_scatter(u64 n, const u64* __restrict__ r, const u64* __restrict__ c,
+                                                     const V* __restrict__ v, const u64* __restrict__ seg_ptr,
+                                                     u32* __restrict__ raw_cnt, uint2* __restrict__ ent,
+                                                     V* __restrict__ ev) {
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const u64 ri = r[i];
+    const u64 pos = seg_ptr[ri] + (atomicSub(&raw_cnt[ri], 1u) - 1u);  // afterwards raw_cnt is all zero again
+    ent[pos] = make_uint2((u32)c[i], (u32)i);
+    ev[pos] = v[i];
+  }
+}
+
+// One thread per row.  DokMatrix::set_element semantics over the row's triplets (spam_dok lib.rs:167-176): per
+// column the LAST write of the stream decides; a zero deletes (num_traits::Zero::is_zero: -0.0 is zero, NaN is not).
+template <class V>
+__global__ void __launch_bounds__(128) k_dok_seg(u64 rows, const u64* __restrict__ seg_ptr, const uint2* __restrict__ ent,
+                                                 const V* __restrict__ ev, u32* __restrict__ row_cnt,
+                                                 u32* __restrict__ kept) {
+  const u64 row = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= rows) return;
+  const u64 lo = seg_ptr[row];
+  const u32 len = (u32)(seg_ptr[row + 1] - lo);  // <= SEG_MAX (checked on the host before this path is taken)
+  u32 mask = 0;
+  for (u32 a = 0; a < len; ++a) {
+    const uint2 ea = ent[lo + a];
+    bool last = true;
+    for (u32 b = 0; b < len; ++b) {
+      const uint2 eb = ent[lo + b];
+      last = last && !(eb.x == ea.x && eb.y > ea.y);
+    }
+    if (last && !(ev[lo + a] == (V)0)) mask |= 1u << a;
+  }
+  row_cnt[row] = __popc(mask);
+  kept[row] = mask;
+}
+
+template <class V>
+__global__ void __launch_bounds__(128) k_dok_emit(u64 rows, const u64* __restrict__ seg_ptr, const uint2* __restrict__ ent,
+                                                  const V* __restrict__ ev, const u32* __restrict__ kept,
+                                                  const u64* __restrict__ c_ptr, u32* __restrict__ c_idx,
+                                                  V* __restrict__ c_val) {
+  const u64 row = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= rows) return;
+  const u32 mask = kept[row];
+  if (!mask) return;
+  const u64 lo = seg_ptr[row], o = c_ptr[row];
+  for (u32 ma = mask; ma; ma &= ma - 1) {
+    const u32 a = __ffs(ma) - 1;
+    const u32 ca = ent[lo + a].x;
+    u32 rank = 0;
+    for (u32 mb = mask; mb; mb &= mb - 1) rank += ent[lo + (__ffs(mb) - 1)].x < ca ? 1u : 0u;
+    c_idx[o + rank] = ca;
+    c_val[o + rank] = ev[lo + a];
+  }
+}
+
+// ---- transpose, counting path: histogram by column, scan, scatter (row, value) into the column's segment, then
+// one thread per column puts its segment in increasing row order (rows are distinct inside a column) ----
+__global__ void __launch_bounds__(256) k_tr_hist(u64 nnz, u64 cols, const u32* __restrict__ idx, u32* __restrict__ col_cnt,
+                                                 Counters* cnt) {
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  bool bad = false;
+  for (u64 e = (u64)blockIdx.x * blockDim.x + threadIdx.x; e < nnz; e += stride) {
+    const u32 c = idx[e];
+    if (c < cols) atomicAdd(&col_cnt[c], 1u); else bad = true;
+  }
+  if (bad) atomicOr(&cnt->error, 2u);
+}
+
+template <class W>
+__global__ void __launch_bounds__(256) k_tr_scatter(u64 m, const u64* __restrict__ ptr, const u32* __restrict__ idx,
+                                                    const W* __restrict__ val, const u64* __restrict__ t_ptr,
+                                                    u32* __restrict__ col_cnt, u32* __restrict__ t_idx,
+                                                    W* __restrict__ t_val) {
+  const int lane = threadIdx.x & 31;
+  const u64 row = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = row < m;
+  u64 lo = 0, hi = 0;
+  if (valid) { lo = ptr[row]; hi = ptr[row + 1]; }
+  if (valid && hi - lo <= 32) {
+    for (u64 e = lo; e < hi; ++e) {
+      const u32 c = idx[e];
+      const u64 pos = t_ptr[c] + (atomicSub(&col_cnt[c], 1u) - 1u);
+      t_idx[pos] = (u32)row; t_val[pos] = val[e];
+    }
+  }
+  unsigned longmask = __ballot_sync(0xffffffffu, valid && hi - lo > 32);  // long rows: the whole warp helps
+  while (longmask) {
+    const int src = __ffs(longmask) - 1;
+    longmask &= longmask - 1;
+    const u64 l = __shfl_sync(0xffffffffu, lo, src), hh = __shfl_sync(0xffffffffu, hi, src);
+    const u32 rr = (u32)__shfl_sync(0xffffffffu, row, src);
+    for (u64 e = l + lane; e < hh; e += 32) {
+      const u32 c = idx[e];
+      const u64 pos = t_ptr[c] + (atomicSub(&col_cnt[c], 1u) - 1u);
+      t_idx[pos] = rr; t_val[pos] = val[e];
+    }
+  }
+}
+
+template <class W>
+__global__ void __launch_bounds__(128) k_tr_segsort(u64 cols, const u64* __restrict__ t_ptr, u32* __restrict__ t_idx,
+                                                    W* __restrict__ t_val) {
+  const u64 col = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= cols) return;
+  const u64 lo = t_ptr[col], hi = t_ptr[col + 1];  // hi - lo <= SEG_MAX
+  for (u64 i = lo + 1; i < hi; ++i) {
+    const u32 k = t_idx[i];
+    const W v = t_val[i];
+    u64 j = i;
+    while (j > lo && t_idx[j - 1] > k) { t_idx[j] = t_idx[j - 1]; t_val[j] = t_val[j - 1]; --j; }
+    if (j != i) { t_idx[j] = k; t_val[j] = v; }
+  }
+}
+
 int bits_for(u64 x) {  // bits needed to represent values in [0, x)
   int b = 0;
   while (b < 63 && (1ull << b) < x) ++b;
@@ -169,16 +324,18 @@ int radix_sort_pairs(spam_handle* h, u64 n, int keybits, u64*& k0, u32*& p0, u64
   return SPAM_OK;
 }
 
+// the general path: stable LSD radix sort of (row, col) keys, last write of every key run wins
 template <class V>
-int dok_typed(spam_handle* h, u64 rows, u64 cols, u64 n, const u64* d_r, const u64* d_c, const V* d_v, spam_dcsr* out) {
+int dok_radix(spam_handle* h, u64 rows, u64 cols, u64 n, const u64* d_r, const u64* d_c, const V* d_v, spam_dcsr* out) {
   const int cbits = bits_for(cols), rbits = bits_for(rows);
-  // one workspace allocation, carved up (allocator calls were a visible part of this ~1.5 ms routine)
+  // one workspace allocation, carved up (allocator calls were a visible part of this routine)
   const u64 nblocks = (n + RS_TILE - 1) / RS_TILE;
   auto al = [](u64 bytes) { return (bytes + 255) & ~255ull; };
   const u64 sz_k = al(n * 8), sz_pos = al((n + 1) * 8), sz_p = al(n * 4), sz_rc = al(rows * 4),
             sz_hist = al((u64)RADIX * nblocks * 4), sz_offs = al(((u64)RADIX * nblocks + 1) * 8);
+  DevGuard g(h);
   char* ws = nullptr;
-  CKS(dev_alloc(h, (void**)&ws, 2 * sz_k + sz_pos + 3 * sz_p + sz_rc + sz_hist + sz_offs));
+  CKS(g.alloc(&ws, 2 * sz_k + sz_pos + 3 * sz_p + sz_rc + sz_hist + sz_offs));
   char* cur = ws;
   u64* k0 = (u64*)cur; cur += sz_k;
   u64* k1 = (u64*)cur; cur += sz_k;
@@ -189,7 +346,6 @@ int dok_typed(spam_handle* h, u64 rows, u64 cols, u64 n, const u64* d_r, const u
   u32* flags = (u32*)cur; cur += sz_p;
   u32* row_cnt = (u32*)cur; cur += sz_rc;
   u32* hist = (u32*)cur;
-  CKS(dev_alloc_t(h, &out->ptr, rows + 1));
   CK(cudaMemsetAsync(h->d_cnt, 0, sizeof(Counters), h->stream));
   CK(cudaMemsetAsync(row_cnt, 0, rows * sizeof(u32), h->stream));
   if (n) {
@@ -205,21 +361,66 @@ int dok_typed(spam_handle* h, u64 rows, u64 cols, u64 n, const u64* d_r, const u
   CKS(scan_u32_to_u64(h, row_cnt, out->ptr, rows, nullptr));
   CK(cudaMemcpyAsync(h->h_cnt, h->d_cnt, sizeof(Counters), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
-  int st = SPAM_OK;
-  if (h->h_cnt->error & 2u) st = spam_fail(h, SPAM_EINDEX, "triplet index out of range");
-  if (st == SPAM_OK) {
-    out->nnz = h->h_cnt->total_nnz;
-    st = dev_alloc_t(h, &out->idx, out->nnz);
-    if (st == SPAM_OK) st = dev_alloc(h, &out->val, out->nnz * sizeof(V));
-    if (st == SPAM_OK && n) {
-      k_emit<V><<<grid_for(h, n), 256, 0, h->stream>>>(n, cbits, k0, p0, d_v, flags, pos, out->idx, (V*)out->val);
-      count_launch(h);
-      cudaError_t e = cudaGetLastError();
-      if (e != cudaSuccess) st = spam_fail(h, SPAM_ECUDA, "k_emit", e);
-    }
+  if (h->h_cnt->error & 2u) return spam_fail(h, SPAM_EINDEX, "triplet index out of range");
+  out->nnz = h->h_cnt->total_nnz;
+  CKS(dev_alloc_t(h, &out->idx, out->nnz));   // owned by `out`: the caller frees it on failure
+  CKS(dev_alloc(h, &out->val, out->nnz * sizeof(V)));
+  if (n) {
+    k_emit<V><<<grid_for(h, n), 256, 0, h->stream>>>(n, cbits, k0, p0, d_v, flags, pos, out->idx, (V*)out->val);
+    count_launch(h);
+    CK(cudaGetLastError());
   }
-  dev_free(h, ws);
-  return st;
+  return SPAM_OK;
+}
+
+template <class V>
+int dok_typed(spam_handle* h, u64 rows, u64 cols, u64 n, const u64* d_r, const u64* d_c, const V* d_v, spam_dcsr* out) {
+  CKS(dev_alloc_t(h, &out->ptr, rows + 1));
+  DevGuard g(h);
+  u32 *raw_cnt = nullptr, *kept = nullptr;
+  u64* seg_ptr = nullptr;
+  CKS(g.alloc(&raw_cnt, rows));
+  CKS(g.alloc(&seg_ptr, rows + 1));
+  CK(cudaMemsetAsync(h->d_cnt, 0, sizeof(Counters), h->stream));
+  CK(cudaMemsetAsync(raw_cnt, 0, rows * sizeof(u32), h->stream));
+  if (n) {
+    k_dok_hist<<<grid_for(h, n), 256, 0, h->stream>>>(n, rows, cols, d_r, d_c, raw_cnt, h->d_cnt);
+    k_max_u32<<<grid_for(h, rows), 256, 0, h->stream>>>(raw_cnt, rows, h->d_cnt);
+    count_launch(h, 2);
+    CK(cudaGetLastError());
+  }
+  CKS(scan_u32_to_u64(h, raw_cnt, seg_ptr, rows, nullptr));
+  CK(cudaMemcpyAsync(h->h_cnt, h->d_cnt, sizeof(Counters), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  if (h->h_cnt->error & 2u) return spam_fail(h, SPAM_EINDEX, "triplet index out of range");
+  if (h->h_cnt->max_flop > SEG_MAX) {
+    h->stats.fallbacks[4] = 2;
+    return dok_radix<V>(h, rows, cols, n, d_r, d_c, d_v, out);
+  }
+  h->stats.fallbacks[4] = 1;
+  uint2* ent = nullptr;
+  V* ev = nullptr;
+  CKS(g.alloc(&ent, n));
+  CKS(g.alloc(&ev, n));
+  CKS(g.alloc(&kept, rows));
+  const unsigned rgrid = (unsigned)((rows + 127) / 128);   // rows >= 1 (NonZeroUsize in the reference)
+  if (n) {
+    k_dok_scatter<V><<<grid_for(h, n), 256, 0, h->stream>>>(n, d_r, d_c, d_v, seg_ptr, raw_cnt, ent, ev);
+    count_launch(h);
+  }
+  k_dok_seg<V><<<rgrid, 128, 0, h->stream>>>(rows, seg_ptr, ent, ev, raw_cnt, kept);  // raw_cnt reused: survivors per row
+  count_launch(h);
+  CK(cudaGetLastError());
+  CKS(scan_u32_to_u64(h, raw_cnt, out->ptr, rows, &h->d_cnt->total_nnz));
+  CK(cudaMemcpyAsync(h->h_cnt, h->d_cnt, sizeof(Counters), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  out->nnz = h->h_cnt->total_nnz;
+  CKS(dev_alloc_t(h, &out->idx, out->nnz));
+  CKS(dev_alloc(h, &out->val, out->nnz * sizeof(V)));
+  k_dok_emit<V><<<rgrid, 128, 0, h->stream>>>(rows, seg_ptr, ent, ev, kept, out->ptr, out->idx, (V*)out->val);
+  count_launch(h);
+  CK(cudaGetLastError());
+  return SPAM_OK;
 }
 
 // ---- CSR transpose ------------------------------------------------------------
@@ -275,11 +476,11 @@ __global__ void __launch_bounds__(256) k_transpose_emit(u64 n, const u32* __rest
 
 }  // namespace
 
-int transpose_dev(spam_handle* h, const spam_dcsr* a, spam_dcsr** out) {
+static int transpose_radix(spam_handle* h, const spam_dcsr* a, spam_dcsr** out) {
   *out = nullptr;
   const u64 m = a->rows, n = a->nnz, tc = a->cols;
   if (n >= 0xFFFFFFFFull) return spam_fail(h, SPAM_EOVERFLOW, "more than 2^32-1 entries");
-  h->stats = spam_stats{};
+  h->stats.fallbacks[4] = 2;
   spam_dcsr* t = new spam_dcsr();
   t->dtype = a->dtype; t->rows = a->cols; t->cols = a->rows; t->nnz = n; t->owning = true;
   t->rows_sorted = -1; t->max_row_len = 0;  // sorted by construction; the cached stats (longest row) are taken lazily
@@ -333,6 +534,60 @@ int transpose_dev(spam_handle* h, const spam_dcsr* a, spam_dcsr** out) {
   if (e != cudaSuccess) return fail(spam_fail(h, SPAM_ECUDA, "transpose sync", e));
   if (h->h_cnt->error & 2u) return fail(spam_fail(h, SPAM_EINDEX, "a column index is >= cols"));
   dev_free(h, ws);
+  *out = t;
+  return SPAM_OK;
+}
+
+int transpose_dev(spam_handle* h, const spam_dcsr* a, spam_dcsr** out) {
+  *out = nullptr;
+  const u64 m = a->rows, n = a->nnz, tc = a->cols;
+  if (n >= 0xFFFFFFFFull) return spam_fail(h, SPAM_EOVERFLOW, "more than 2^32-1 entries");
+  if (m >= 0xFFFFFFFFull || tc >= 0xFFFFFFFFull) return spam_fail(h, SPAM_ECOLS, "dimension >= 2^32-1");
+  h->stats = spam_stats{};
+  if (m == 0 || tc == 0) return transpose_radix(h, a, out);
+  // Counting path: histogram by column -> scan -> scatter -> per-column order by row.  Taken when no column holds
+  // more than SEG_MAX entries (one thread sorts a column); otherwise the stable radix sort above.
+  const size_t es = dtype_size(a->dtype);
+  DevGuard g(h);
+  u32 *col_cnt = nullptr, *t_idx = nullptr;
+  u64* t_ptr = nullptr;
+  void* t_val = nullptr;
+  CKS(g.alloc(&col_cnt, tc));
+  CKS(g.alloc(&t_ptr, tc + 1));
+  CK(cudaMemsetAsync(h->d_cnt, 0, sizeof(Counters), h->stream));
+  CK(cudaMemsetAsync(col_cnt, 0, tc * sizeof(u32), h->stream));
+  if (n) {
+    k_tr_hist<<<grid_for(h, n), 256, 0, h->stream>>>(n, tc, a->idx, col_cnt, h->d_cnt);
+    count_launch(h);
+  }
+  k_max_u32<<<grid_for(h, tc), 256, 0, h->stream>>>(col_cnt, tc, h->d_cnt);
+  count_launch(h);
+  CK(cudaGetLastError());
+  CKS(scan_u32_to_u64(h, col_cnt, t_ptr, tc, nullptr));
+  CK(cudaMemcpyAsync(h->h_cnt, h->d_cnt, sizeof(Counters), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  if (h->h_cnt->error & 2u) return spam_fail(h, SPAM_EINDEX, "a column index is >= cols");
+  if (h->h_cnt->max_flop > SEG_MAX) return transpose_radix(h, a, out);
+  h->stats.fallbacks[4] = 1;
+  CKS(g.alloc(&t_idx, n));
+  CKS(g.alloc_bytes(&t_val, n * es));
+  if (n) {
+    const unsigned rgrid = (unsigned)((m + 255) / 256), cgrid = (unsigned)((tc + 127) / 128);
+    if (es == 4) {
+      k_tr_scatter<uint32_t><<<rgrid, 256, 0, h->stream>>>(m, a->ptr, a->idx, (const uint32_t*)a->val, t_ptr, col_cnt, t_idx, (uint32_t*)t_val);
+      k_tr_segsort<uint32_t><<<cgrid, 128, 0, h->stream>>>(tc, t_ptr, t_idx, (uint32_t*)t_val);
+    } else {
+      k_tr_scatter<uint64_t><<<rgrid, 256, 0, h->stream>>>(m, a->ptr, a->idx, (const uint64_t*)a->val, t_ptr, col_cnt, t_idx, (uint64_t*)t_val);
+      k_tr_segsort<uint64_t><<<cgrid, 128, 0, h->stream>>>(tc, t_ptr, t_idx, (uint64_t*)t_val);
+    }
+    count_launch(h, 2);
+    CK(cudaGetLastError());
+  }
+  spam_dcsr* t = new spam_dcsr();
+  t->dtype = a->dtype; t->rows = a->cols; t->cols = a->rows; t->nnz = n; t->owning = true;
+  t->rows_sorted = -1; t->max_row_len = 0;  // sorted by construction; the cached stats (longest row) are taken lazily
+  t->ptr = t_ptr; t->idx = t_idx; t->val = t_val;
+  g.release(t_ptr); g.release(t_idx); g.release(t_val);
   *out = t;
   return SPAM_OK;
 }

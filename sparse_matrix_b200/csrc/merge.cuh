@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(BLOCK) k_sym_merge(u32 n, const u32* __restric
       }
     }
     row_nnz[row] = z;  // mul_hash.rs:95
-    atomicAdd(&s_hist[num_bin_of(z, flop[row], k, true)], 1u);
+    atomicAdd(&s_hist[num_bin_of(z, flop[row], k, MODE_MERGE)], 1u);
   }
   __syncthreads();
   if (tid < NBINS && s_hist[tid]) atomicAdd(&cnt->num_bins[tid], s_hist[tid]);

@@ -20,6 +20,7 @@
 #include "common.cuh"
 #include "merge.cuh"
 #include "rowhash.cuh"
+#include "esc.cuh"
 
 namespace {
 
@@ -77,7 +78,8 @@ template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK) k_flop_count(u64 m, u64 b_rows, const u64* __restrict__ a_ptr,
                                                       const u32* __restrict__ a_col, const u64* __restrict__ b_ptr,
                                                       u32* __restrict__ flop_out, Counters* cnt, int do_bins,
-                                                      int merge_ok) {
+                                                      int mode) {
+  const bool merge_ok = (mode & MODE_MERGE) != 0;
   __shared__ u32 s_hist[NBINS];
   __shared__ ull s_total;
   __shared__ u32 s_max, s_maxalen;
@@ -118,7 +120,7 @@ __global__ void __launch_bounds__(BLOCK) k_flop_count(u64 m, u64 b_rows, const u
     flop_out[row] = fs;
     if (do_bins) {
       const u32 alen = len > 0xFFFFFFFFull ? 0xFFFFFFFFu : (u32)len;
-      const int bin = sym_bin_of(fs, alen, merge_ok != 0);
+      const int bin = sym_bin_of(fs, alen, merge_ok);
       atomicAdd(&s_hist[bin], 1u);
       if (merge_ok && alen <= MERGE_K) atomicMax(&s_maxalen, alen);  // bound for both merge bins
       if (bin != MERGE_BIN) atomicMax(&s_max, fs);
@@ -142,7 +144,7 @@ __global__ void __launch_bounds__(BLOCK) k_flop_count(u64 m, u64 b_rows, const u
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK) k_num_bin_count(u64 m, const u64* __restrict__ a_ptr,
                                                          const u32* __restrict__ row_nnz,
-                                                         const u32* __restrict__ flop, Counters* cnt, int merge_ok) {
+                                                         const u32* __restrict__ flop, Counters* cnt, int mode) {
   __shared__ u32 s_hist[NBINS];
   __shared__ u32 s_max;
   const int tid = threadIdx.x;
@@ -155,8 +157,12 @@ __global__ void __launch_bounds__(BLOCK) k_num_bin_count(u64 m, const u64* __res
     const u64 len = a_ptr[row + 1] - a_ptr[row];
     const u32 alen = len > 0xFFFFFFFFull ? 0xFFFFFFFFu : (u32)len;
     // rows of the symbolic merge bin were already histogrammed by k_sym_merge
-    if (sym_bin_of(f, alen, merge_ok != 0) != MERGE_BIN) atomicAdd(&s_hist[num_bin_of(z, f, alen, merge_ok != 0)], 1u);
-    if (z > NUM_HASH_ZMAX) atomicMax(&s_max, z);
+    if (sym_bin_of(f, alen, (mode & MODE_MERGE) != 0) != MERGE_BIN) {
+      const int bin = num_bin_of(z, f, alen, mode);
+      atomicAdd(&s_hist[bin], 1u);
+      // longest row that can reach the global-table kernel (its own bin, or handed back by a bucket-sort bin)
+      if (bin == HEAVY_BIN || bin >= ESC_BIN0) atomicMax(&s_max, z);
+    }
   }
   __syncthreads();
   if (tid < NBINS && s_hist[tid]) atomicAdd(&cnt->num_bins[tid], s_hist[tid]);
@@ -169,7 +175,7 @@ template <int BLOCK, bool NUMERIC>
 __global__ void __launch_bounds__(BLOCK) k_bin_scatter(u64 m, const u64* __restrict__ a_ptr,
                                                        const u32* __restrict__ row_nnz,
                                                        const u32* __restrict__ flop, BinBase base, u32* cursors,
-                                                       u32* __restrict__ perm, int merge_ok) {
+                                                       u32* __restrict__ perm, int mode) {
   __shared__ u32 s_cnt[NBINS];
   __shared__ u32 s_base[NBINS];
   const int tid = threadIdx.x;
@@ -181,7 +187,7 @@ __global__ void __launch_bounds__(BLOCK) k_bin_scatter(u64 m, const u64* __restr
   if (row < m) {
     const u64 len = a_ptr[row + 1] - a_ptr[row];
     const u32 alen = len > 0xFFFFFFFFull ? 0xFFFFFFFFu : (u32)len;
-    b = NUMERIC ? num_bin_of(row_nnz[row], flop[row], alen, merge_ok != 0) : sym_bin_of(flop[row], alen, merge_ok != 0);
+    b = NUMERIC ? num_bin_of(row_nnz[row], flop[row], alen, mode) : sym_bin_of(flop[row], alen, (mode & MODE_MERGE) != 0);
     r = atomicAdd(&s_cnt[b], 1u);
   }
   __syncthreads();
@@ -418,7 +424,9 @@ __global__ void __launch_bounds__(T) k_num_heavy(u32 n, const u32* __restrict__ 
                                                  const V* __restrict__ b_val, const u64* __restrict__ c_ptr,
                                                  u32* __restrict__ c_col, V* __restrict__ c_val, u32* key_tables,
                                                  V* val_tables, u64 table_stride, u32* cnt_tables, u32* ord_tables,
-                                                 u32 b_cols, u32* work, Counters* cnt_dev) {
+                                                 u32 b_cols, u32* work, Counters* cnt_dev, const u32* n_dev) {
+  // n_dev != nullptr: the row list was filled on the device (rows handed back by the bucket-sort bins)
+  if (n_dev) n = *n_dev;
   constexpr int ITEMS = 4;
   constexpr u32 HEAVY_RANK_MAX = 2048;  // longest bucket ranked by counting; beyond: bitonic fallback
   __shared__ u32 s_item, s_maxcnt;
@@ -440,7 +448,7 @@ __global__ void __launch_bounds__(T) k_num_heavy(u32 n, const u32* __restrict__ 
     const u32 z = (u32)(c_ptr[row + 1] - c0);
     if (z == 0) continue;
     const u64 cap = 2ull * npow2_u64(z), mask = cap - 1; const int hshift = 64 - (63 - __clzll((long long)cap));
-    const u32 NB = npow2_u32(z);
+    const u32 NB = max(npow2_u32(z), 4u * T);  // every thread scans a multiple of four counters below
     for (u64 s = tid; s < cap; s += T) { __stcg(&keys[s], EMPTY_KEY); __stcg(&vals[s], Num<V>::zero()); }
     for (u32 b = tid; b <= NB; b += T) __stcg(&cnt[b], 0u);
     if (tid == 0) s_maxcnt = 0;
@@ -492,7 +500,7 @@ __global__ void __launch_bounds__(T) k_num_heavy(u32 n, const u32* __restrict__ 
         for (int i = 0; i < U; ++i) if (kk[i] != EMPTY_KEY) atomicAdd(&cnt[kk[i] >> bshift], 1u);
       }
       __syncthreads();
-      // NB = npow2(z) >= 16384 here (z > 8192): each thread scans a multiple of four consecutive counters
+      // NB >= 4096: each thread scans a multiple of four consecutive counters
       const u32 chunk = NB / T;
       const u32 b0 = tid * chunk, b1 = b0 + chunk;
       u32 sum = 0, mx = 0;
@@ -624,6 +632,12 @@ int set_smem(spam_handle* h, K kernel, size_t bytes) {
   return SPAM_OK;
 }
 
+static inline u32 n_esc_rows(const u32* count) {
+  u32 n = 0;
+  for (int bin = ESC_BIN0; bin <= ESC_HEAVY_BIN; ++bin) n += count[bin];
+  return n;
+}
+
 struct Bins {
   u32 count[NBINS];
   u32 base[NBINS];
@@ -631,7 +645,7 @@ struct Bins {
 };
 
 int build_perm(spam_handle* h, u64 m, const u32* counts, bool numeric, const u64* d_aptr, const u32* d_row_nnz,
-               const u32* d_flop, int merge_ok, Bins* out) {
+               const u32* d_flop, int mode, Bins* out) {
   u32 acc = 0;
   bool identity = false;
   for (int b = 0; b < NBINS; ++b) {
@@ -648,9 +662,9 @@ int build_perm(spam_handle* h, u64 m, const u32* counts, bool numeric, const u64
   u32* cursors = numeric ? h->d_cnt->num_cursor : h->d_cnt->sym_cursor;
   const unsigned grid = (unsigned)((m + 255) / 256);
   if (numeric)
-    k_bin_scatter<256, true><<<grid, 256, 0, h->stream>>>(m, d_aptr, d_row_nnz, d_flop, bb, cursors, out->perm, merge_ok);
+    k_bin_scatter<256, true><<<grid, 256, 0, h->stream>>>(m, d_aptr, d_row_nnz, d_flop, bb, cursors, out->perm, mode);
   else
-    k_bin_scatter<256, false><<<grid, 256, 0, h->stream>>>(m, d_aptr, d_row_nnz, d_flop, bb, cursors, out->perm, merge_ok);
+    k_bin_scatter<256, false><<<grid, 256, 0, h->stream>>>(m, d_aptr, d_row_nnz, d_flop, bb, cursors, out->perm, mode);
   count_launch(h);
   CK(cudaGetLastError());
   return SPAM_OK;
@@ -669,6 +683,7 @@ struct SpgemmPending {
   u32 max_nnz;
   u32 max_alen;   // longest A row in the merge bins
   int merge_ok;   // B's rows are sorted and nnz(B) < 2^32: the merge bin is in use
+  int mode;       // MODE_MERGE | MODE_ESC: the optional bins this product uses
 };
 
 namespace {
@@ -711,11 +726,11 @@ void spgemm_pending_free(spam_handle* h, SpgemmPending* p) {
 
 int ensure_matrix_stats(spam_handle* h, const spam_dcsr* m) { return ensure_rows_sorted(h, m); }
 
-int flop_count_dev(spam_handle* h, const spam_dcsr* a, const spam_dcsr* b, u32* d_flop, bool do_bins, int merge_ok) {
+int flop_count_dev(spam_handle* h, const spam_dcsr* a, const spam_dcsr* b, u32* d_flop, bool do_bins, int mode) {
   const u64 m = a->rows;
   if (m == 0) return SPAM_OK;
   k_flop_count<256><<<(unsigned)((m + 255) / 256), 256, 0, h->stream>>>(m, b->rows, a->ptr, a->idx, b->ptr, d_flop,
-                                                                         h->d_cnt, do_bins ? 1 : 0, merge_ok);
+                                                                         h->d_cnt, do_bins ? 1 : 0, mode);
   count_launch(h);
   CK(cudaGetLastError());
   return SPAM_OK;
@@ -736,7 +751,8 @@ int spgemm_symbolic_dev(spam_handle* h, const spam_dcsr* a, const spam_dcsr* b, 
   const int merge_ok = (b->rows_sorted == 1 && b->nnz < 0xFFFFFFFFull) ? 1 : 0;
   SpgemmPending* p = new SpgemmPending();
   p->a = a; p->b = b; p->d_flop = nullptr; p->d_row_nnz = nullptr; p->d_cptr = nullptr; p->nnz = 0; p->max_nnz = 0;
-  p->max_alen = 0; p->merge_ok = merge_ok;
+  const int mode = (merge_ok ? MODE_MERGE : 0) | (h->use_esc ? MODE_ESC : 0);
+  p->max_alen = 0; p->merge_ok = merge_ok; p->mode = mode;
   *out = p;
 #define FAIL_FREE(expr) do { int _s = (expr); if (_s != SPAM_OK) { spgemm_pending_free(h, p); *out = nullptr; return _s; } } while (0)
 #define CK_FREE(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { spgemm_pending_free(h, p); *out = nullptr; return spam_fail(h, SPAM_ECUDA, #call, _e); } } while (0)
@@ -768,7 +784,7 @@ int spgemm_symbolic_dev(spam_handle* h, const spam_dcsr* a, const spam_dcsr* b, 
     FAIL_FREE(scan_u32_to_u64(h, p->d_row_nnz, p->d_cptr, m, &h->d_cnt->total_nnz));
     fused = true;
   } else {
-    FAIL_FREE(flop_count_dev(h, a, b, p->d_flop, true, merge_ok));
+    FAIL_FREE(flop_count_dev(h, a, b, p->d_flop, true, mode));
     if (h->timing) CK_FREE(cudaEventRecord(h->ev[1], h->stream));
   }
   CK_FREE(cudaMemcpyAsync(h->h_cnt, h->d_cnt, sizeof(Counters), cudaMemcpyDeviceToHost, h->stream));
@@ -793,7 +809,7 @@ int spgemm_symbolic_dev(spam_handle* h, const spam_dcsr* a, const spam_dcsr* b, 
 
   // ---- symbolic per bin ----
   Bins sb;
-  FAIL_FREE(build_perm(h, m, c1.sym_bins, false, a->ptr, nullptr, p->d_flop, merge_ok, &sb));
+  FAIL_FREE(build_perm(h, m, c1.sym_bins, false, a->ptr, nullptr, p->d_flop, mode, &sb));
   if (!fused) p->max_alen = c1.max_alen;
   u32* heavy_tab = nullptr;
   {
@@ -886,7 +902,7 @@ int spgemm_symbolic_dev(spam_handle* h, const spam_dcsr* a, const spam_dcsr* b, 
   // ---- numeric bin histogram + row_ptr scan ----
   if (m && sb.count[MERGE_BIN] != m) {  // the merge kernel histograms its own rows
     k_num_bin_count<256><<<(unsigned)((m + 255) / 256), 256, 0, h->stream>>>(m, a->ptr, p->d_row_nnz, p->d_flop, h->d_cnt,
-                                                                            merge_ok);
+                                                                            mode);
     count_launch(h);
     CK_FREE(cudaGetLastError());
   }
@@ -917,9 +933,10 @@ int numeric_typed(spam_handle* h, SpgemmPending* p, spam_dcsr* c) {
   // the symbolic phase's memset zeroed these, but another product may have run on this handle between the two
   // host phases (spam_spgemm_symbolic ... spam_spgemm_dev ... spam_spgemm_numeric)
   CK(cudaMemsetAsync(h->d_cnt->num_cursor, 0, sizeof(u32) * NBINS, h->stream));
-  CK(cudaMemsetAsync(&h->d_cnt->work_b, 0, sizeof(u32), h->stream));
+  CK(cudaMemsetAsync(&h->d_cnt->work_a, 0, 3 * sizeof(u32), h->stream));  // work_a, work_b, work_c: row queues
+  CK(cudaMemsetAsync(&h->d_cnt->fb_esc, 0, 2 * sizeof(u32), h->stream));   // fb_esc, fb_list_n
   DevGuard g(h);
-  CKS(build_perm(h, m, p->num_counts, true, a->ptr, p->d_row_nnz, p->d_flop, p->merge_ok, &nb));
+  CKS(build_perm(h, m, p->num_counts, true, a->ptr, p->d_row_nnz, p->d_flop, p->mode, &nb));
   if (nb.perm) g.owned.push_back(nb.perm);
   const u64* ap = a->ptr; const u32* ac = a->idx; const V* av = (const V*)a->val;
   const u64* bp = b->ptr; const u32* bc = b->idx; const V* bv = (const V*)b->val;
@@ -938,16 +955,21 @@ int numeric_typed(spam_handle* h, SpgemmPending* p, spam_dcsr* c) {
   }
   // The bins touch disjoint rows of C.  The team bins (largest first) go to the side lanes so that the tail of
   // one (a few blocks still on their last rows) overlaps the next; the heavy bin runs alone at the end.
-  bool side = false;
+  bool side = n_esc_rows(nb.count) != 0;
   for (int bin = 4; bin <= NHASH; ++bin) side = side || nb.count[bin] != 0;
   u32 *hk = nullptr, *hc = nullptr, *ho = nullptr;
   V* hv = nullptr;
   u64 heavy_nblk = 0, heavy_stride = 0;
-  if (nb.count[HEAVY_BIN]) {
+  u32 n_esc = 0;  // rows in the bucket-sort bins: any of them may be handed back to the global-table kernel
+  for (int bin = ESC_BIN0; bin <= ESC_HEAVY_BIN; ++bin) n_esc += nb.count[bin];
+  u32* fb_list = nullptr;
+  if (n_esc) CKS(g.alloc(&fb_list, n_esc));
+  if (nb.count[HEAVY_BIN] || n_esc) {
     u32 zmax = p->max_nnz;
     heavy_stride = 2ull * npow2_u64(zmax);
+    if (heavy_stride < 8192) heavy_stride = 8192;  // k_num_heavy's bucket counters: at least 4096 + 4
     heavy_nblk = (u64)h->num_sms * 2;
-    if (heavy_nblk > nb.count[HEAVY_BIN]) heavy_nblk = nb.count[HEAVY_BIN];
+    if (heavy_nblk > (u64)nb.count[HEAVY_BIN] + n_esc) heavy_nblk = (u64)nb.count[HEAVY_BIN] + n_esc;
     const u64 budget = 16ull << 30;
     // per block: keys + values (stride each), bucket counters (stride/2), bucket-ordered keys + slots (stride)
     while (heavy_nblk > 1 && heavy_nblk * heavy_stride * (2 * sizeof(u32) + sizeof(V) + 2) > budget) heavy_nblk /= 2;
@@ -957,6 +979,31 @@ int numeric_typed(spam_handle* h, SpgemmPending* p, spam_dcsr* c) {
     CKS(g.alloc(&ho, heavy_nblk * heavy_stride));
   }
   if (side) CK(lanes_fork(h));
+  // bucket-sort bins (esc.cuh): rows that do not compress.  The column-range kernel for the longest rows goes
+  // first: its persistent blocks take a whole SM each and its rows are the longest-running items of the product.
+  if (nb.count[ESC_HEAVY_BIN]) {
+    constexpr size_t smem = num_esc_heavy_smem<V>();
+    CKS(set_smem(h, k_num_esc_heavy<V>, smem));
+    unsigned grid = (unsigned)h->num_sms;
+    if (grid > nb.count[ESC_HEAVY_BIN]) grid = nb.count[ESC_HEAVY_BIN];
+    k_num_esc_heavy<V><<<grid, ESCH_T, smem, lane_of(h, ESC_HEAVY_BIN)>>>(nb.count[ESC_HEAVY_BIN], seg(ESC_HEAVY_BIN), ap, ac, av, bp, bc,
+                                                                        bv, cp, cc, cv, (u32)b->cols, &h->d_cnt->work_a,
+                                                                        h->d_cnt, fb_list);
+    count_launch(h);
+  }
+#define LAUNCH_ESC(BIN, NW)                                                                              \
+  if (nb.count[BIN]) {                                                                                   \
+    constexpr size_t smem = num_esc_smem<V, NW>();                                                       \
+    CKS(set_smem(h, k_num_esc<V, NW>, smem));                                                            \
+    k_num_esc<V, NW><<<nb.count[BIN], 32 * NW, smem, lane_of(h, BIN)>>>(nb.count[BIN], seg(BIN), ap, ac, av, bp, bc, bv, \
+                                                                       cp, cc, cv, h->d_cnt, fb_list);   \
+    count_launch(h);                                                                                     \
+  }
+  LAUNCH_ESC(ESC_BIN0 + 3, 32)
+  LAUNCH_ESC(ESC_BIN0 + 2, 16)
+  LAUNCH_ESC(ESC_BIN0 + 1, 8)
+  LAUNCH_ESC(ESC_BIN0, 4)
+#undef LAUNCH_ESC
   // numeric hash bin b: z <= 32 << b, table 64 << b (key, value) slots.  Team sizes: these kernels are
   // latency-bound (dependent shared-memory and shuffle chains), so the big-table bins get many warps per row
   LAUNCH_NUM_ROW(8, 32, 16384, false)
@@ -1003,7 +1050,15 @@ int numeric_typed(spam_handle* h, SpgemmPending* p, spam_dcsr* c) {
   if (nb.count[HEAVY_BIN]) {
     k_num_heavy<V, 1024><<<(unsigned)heavy_nblk, 1024, 0, h->stream>>>(nb.count[HEAVY_BIN], seg(HEAVY_BIN), ap, ac, av, bp, bc, bv,
                                                                                   cp, cc, cv, hk, hv, heavy_stride, hc, ho,
-                                                                                  (u32)b->cols, &h->d_cnt->work_b, h->d_cnt);
+                                                                                  (u32)b->cols, &h->d_cnt->work_b, h->d_cnt, nullptr);
+    count_launch(h);
+    CK(cudaGetLastError());
+  }
+  if (n_esc) {
+    // rows the bucket-sort bins handed back (crowded buckets): usually none, then the blocks exit at once
+    k_num_heavy<V, 1024><<<(unsigned)heavy_nblk, 1024, 0, h->stream>>>(0u, fb_list, ap, ac, av, bp, bc, bv, cp, cc, cv, hk, hv,
+                                                                                  heavy_stride, hc, ho, (u32)b->cols,
+                                                                                  &h->d_cnt->work_c, h->d_cnt, &h->d_cnt->fb_list_n);
     count_launch(h);
     CK(cudaGetLastError());
   }

@@ -99,22 +99,42 @@ def test_random_products(oracle, handle, dtype, shape):
 
 @pytest.mark.parametrize("dtype", [np.float64, np.int64])
 def test_every_bin_is_exercised(oracle, handle, dtype):
-    """Rows whose flop / nnz land in each symbolic and numeric bin, heavy (global-table) bins included."""
+    """Rows whose flop / nnz land in each symbolic and numeric bin.  Rows that do not compress (every product a new
+    column) take the bucket-sort bins 11..15; rows where every column is produced three times take the hash bins
+    1..8 and the global-table bin 9."""
     rng = np.random.default_rng(99)
     inner, n = 3000, 60000
-    # A row i has `deg[i]` entries; B rows have 40 entries => flop = 40*deg, nnz close to it
+    # (1) A row i has `deg[i]` entries; B rows have 40 entries => flop = 40*deg, nnz close to it
     deg = np.array([0, 1, 2, 5, 8, 20, 40, 90, 150, 300, 420, 700, 1000, 1500, 2500] + [3] * 40 + [60] * 20)
     a = random_csr(rng, len(deg), inner, deg, dtype=dtype, sorted_rows=False)
     b = random_csr(rng, inner, n, 40, dtype=dtype, sorted_rows=False)
     handle.set_timing(True)
     c = gpu_mul(a, b, handle)
     st = handle.stats()
-    handle.set_timing(False)
-    # bins 0 (tiny), 1..8 (one hash bin per power of two), 9 (heavy, global-memory table)
     assert all(x > 0 for x in st["sym_bin_rows"][:10]), st["sym_bin_rows"]
-    assert all(x > 0 for x in st["num_bin_rows"][:10]), st["num_bin_rows"]
+    assert all(x > 0 for x in st["num_bin_rows"][:4]) and all(x > 0 for x in st["num_bin_rows"][11:16]), st["num_bin_rows"]
     off, idx, val = check_against_oracle(oracle, a, b, c)
     assert st["nnz_c"] == len(idx) and st["flops"] == G.spgemm_counts(a, b)[0] and st["kernel_launches"] >= 10
+    assert st["fallbacks"][3] == 0          # uniform columns: no crowded bucket
+    # (2) the same B three times over (rows k, k + inner, k + 2 inner hold the same columns) and A rows that
+    # reference all three copies: every column is produced three times, so the rows compress and are hashed
+    deg3 = np.array([0, 1, 2, 4, 7, 12, 25, 50, 100, 200, 400, 2500] + [3] * 40 + [60] * 20)
+    a1 = random_csr(rng, len(deg3), inner, deg3, dtype=dtype, sorted_rows=False)
+    lens = np.diff(a1[2]).astype(np.int64)
+    idx3 = np.concatenate([np.concatenate([a1[3][int(lo):int(hi)] + np.uint64(k * inner) for k in range(3)])
+                           for lo, hi in zip(a1[2][:-1], a1[2][1:])]) if len(a1[3]) else a1[3]
+    off3 = np.zeros(len(deg3) + 1, np.uint64)
+    off3[1:] = np.cumsum(3 * lens)
+    v3 = rng.integers(1, 9, size=len(idx3)).astype(dtype)
+    a3 = (len(deg3), 3 * inner, off3, idx3, v3)
+    b3 = (3 * inner, n, np.concatenate([b[2][:-1] + np.uint64(k * len(b[3])) for k in range(3)] + [[np.uint64(3 * len(b[3]))]]),
+          np.tile(b[3], 3), rng.permutation(np.tile(b[4], 3)))
+    c3 = gpu_mul(a3, b3, handle)
+    st = handle.stats()
+    handle.set_timing(False)
+    assert all(x > 0 for x in st["sym_bin_rows"][:10]), st["sym_bin_rows"]
+    assert all(x > 0 for x in st["num_bin_rows"][:10]), st["num_bin_rows"]
+    check_against_oracle(oracle, a3, b3, c3)
     # many duplicates: few distinct columns but a large flop count (numeric bin chosen by nnz, not flop)
     b2 = random_csr(rng, inner, 24, 20, dtype=dtype, sorted_rows=False)
     c2 = gpu_mul(a, b2, handle)
@@ -402,6 +422,51 @@ def test_dok_to_csr(oracle, handle, dtype):
     d.set_element((2, 2), 5)
     m = S.CsrMatrix.from_dok(d, handle=handle)
     assert m.offsets.tolist() == [0, 1, 1, 2, 2] and m.indices.tolist() == [0, 2] and m.to_dok().entries == d.entries
+
+
+def test_dok_and_transpose_take_both_paths(oracle, handle):
+    """DOK -> CSR and transpose pick the counting path when no row (column) holds more than 32 entries and the stable
+    radix sort otherwise (spam_stats.fallbacks[4] = 1 / 2); both are bit-exact, including a stream that rewrites one
+    key many times (last write wins, a final zero deletes)."""
+    rng = np.random.default_rng(77)
+    rows, cols = 5000, 9000
+    # short rows with rewrites and deletions: counting path
+    a = random_csr(rng, rows, cols, rng.integers(0, 13, size=rows), dtype=np.int64)
+    tr, tc, tv = G.triplets_with_rewrites(a, seed=9, dup_frac=0.3, zero_frac=0.1)
+    got = S.CsrMatrix.from_triplets(rows, cols, tr, tc, tv, handle=handle)
+    assert handle.stats()["fallbacks"][4] == 1
+    off, idx, val = oracle.dok_to_csr(rows, cols, tr, tc, tv)
+    assert np.array_equal(got.offsets, off) and np.array_equal(got.indices, idx) and np.array_equal(got.vals, val)
+    # exactly 32 triplets in one row, all on two keys: still the counting path
+    tr2 = np.concatenate([tr, np.full(32, rows - 1)]); tc2 = np.concatenate([tc, np.tile([5, 6], 16)])
+    keep = tr2 != rows - 1
+    keep[-32:] = True
+    tr2, tc2 = tr2[keep], tc2[keep]
+    tv2 = np.concatenate([tv[keep[:len(tv)]], np.arange(1, 33)])
+    tv2[-1] = 0                                       # the last write of key (rows-1, 6) is a zero: deleted
+    got = S.CsrMatrix.from_triplets(rows, cols, tr2, tc2, tv2, handle=handle)
+    assert handle.stats()["fallbacks"][4] == 1
+    off, idx, val = oracle.dok_to_csr(rows, cols, tr2, tc2, tv2)
+    assert np.array_equal(got.offsets, off) and np.array_equal(got.indices, idx) and np.array_equal(got.vals, val)
+    assert got.get_element((rows - 1, 5)) == 31 and got.get_element((rows - 1, 6)) is None
+    # one more triplet in that row (33): radix path, same answer as the oracle
+    tr3, tc3, tv3 = np.append(tr2, rows - 1), np.append(tc2, 7), np.append(tv2, 9)
+    got = S.CsrMatrix.from_triplets(rows, cols, tr3, tc3, tv3, handle=handle)
+    assert handle.stats()["fallbacks"][4] == 2
+    off, idx, val = oracle.dok_to_csr(rows, cols, tr3, tc3, tv3)
+    assert np.array_equal(got.offsets, off) and np.array_equal(got.indices, idx) and np.array_equal(got.vals, val)
+    # transpose: columns of at most 32 entries -> counting path; a dense column -> radix path
+    A = as_csr_matrix(a)
+    t = A.transpose(handle=handle)
+    longest = int(np.bincount(a[3].astype(np.int64), minlength=cols).max())
+    assert longest <= 32 and handle.stats()["fallbacks"][4] == 1
+    want = oracle.transpose(a)
+    assert np.array_equal(t.offsets, want[0]) and np.array_equal(t.indices, want[1]) and np.array_equal(t.vals, want[2])
+    dense = random_csr(rng, 400, 50, np.full(400, 20), dtype=np.float64, sorted_rows=False)   # 160 per column
+    t = as_csr_matrix(dense, is_sorted=False).transpose(handle=handle)
+    assert handle.stats()["fallbacks"][4] == 2
+    want = oracle.transpose(dense)
+    assert np.array_equal(t.offsets, want[0]) and np.array_equal(t.indices, want[1]) and np.array_equal(t.vals, want[2])
 
 
 def test_rows_to_parts_and_row_slices(oracle, handle):
