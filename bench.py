@@ -192,6 +192,188 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def dominant_kernel(workload, st, direct=False):
+    """Name of the numeric kernel that holds most rows' products for this workload (roofline.kernel)."""
+    nb = st["num_bin_rows"]
+    if nb[10] and nb[10] >= sum(nb) * 0.9:
+        return "k_num_merge<double,K,128> (merge bin: one launch per step)"
+    if sum(nb[11:16]) >= sum(nb[1:10]):
+        return "k_num_esc<double,NW> (bucket-sort bins 11..14) + hash bins for short rows: one launch per non-empty bin"
+    return "k_num_row<double,NW,CAP> (hash bins, one launch per non-empty bin)"
+
+
+def time_steps(fn, steps, sync_all, torch):
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    ev0.record()
+    for _ in range(steps):
+        fn()
+    ev1.record()
+    sync_all()
+    return ev0.elapsed_time(ev1) / steps
+
+
+def max_over_ranks(x, world, dev, torch, dist):
+    if world == 1:
+        return float(x), [round(float(x), 4)]
+    t = torch.tensor([x], dtype=torch.float64, device=dev)
+    per = [torch.zeros_like(t) for _ in range(world)]
+    dist.all_gather(per, t)
+    vals = [round(float(v.item()), 4) for v in per]
+    return max(vals), vals
+
+
+def device_matrix(S, handle, mat, rank, world, dev, torch, np_dtype=np.float64):
+    """A (= B) resident on every rank: rank 0 uploads, the library's own communicator replicates it
+    (spam_comm_broadcast = ncclBroadcast over NVLink).  Returns (DeviceCsr, rows, cols, nnz, seconds for the replicate)."""
+    if rank == 0:
+        rows, cols = mat[0], mat[1]
+        h_ptr = torch.from_numpy(np.ascontiguousarray(mat[2]).view(np.int64))
+        h_idx = torch.from_numpy(np.ascontiguousarray(mat[3]).astype(np.uint32).view(np.int32))
+        h_val = torch.from_numpy(np.ascontiguousarray(mat[4]))
+        meta = np.array([rows, cols, h_idx.shape[0]], dtype=np.uint64)
+    else:
+        meta = np.zeros(3, dtype=np.uint64)
+    if world > 1:
+        meta = handle.comm_allgather_u64(meta)[0]
+    rows, cols, nnz = (int(x) for x in meta)
+    if rank == 0:
+        d_ptr, d_idx, d_val = h_ptr.to(dev), h_idx.to(dev), h_val.to(dev)
+    else:
+        d_ptr = torch.empty(rows + 1, dtype=torch.int64, device=dev)
+        d_idx = torch.empty(nnz, dtype=torch.int32, device=dev)
+        d_val = torch.empty(nnz, dtype=torch.float64, device=dev)
+    t_b = 0.0
+    if world > 1:
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for t in (d_ptr, d_idx, d_val):
+            handle.comm_broadcast(t.data_ptr(), t.numel() * t.element_size(), 0)
+        handle.synchronize()
+        t_b = time.perf_counter() - t0
+    dA = S.DeviceCsr.wrap(handle, np_dtype, rows, cols, nnz, d_ptr.data_ptr(), d_idx.data_ptr(), d_val.data_ptr(),
+                          keepalive=(d_ptr, d_idx, d_val))
+    return dA, rows, cols, nnz, t_b
+
+
+def as_tensors(c, dev, torch):
+    i = c.info()
+    lp = torch.as_tensor(DevArray(i["d_ptr"], i["rows"] + 1, "<i8"), device=dev)
+    li = torch.as_tensor(DevArray(i["d_idx"], max(1, i["nnz"]), "<i4"), device=dev)[:i["nnz"]]
+    lv = torch.as_tensor(DevArray(i["d_val"], max(1, i["nnz"]), "<f8"), device=dev)[:i["nnz"]]
+    return lp, li, lv
+
+
+def gathered_parity(dA, gathered, dev, torch, exact):
+    """The assembled multi-GPU C against the single-GPU product of the same matrix on this rank: nnz, row_ptr and
+    col_idx identical; values identical (`exact`: merge bin, deterministic) or within 1e-12 of each entry's sum
+    of |products| (the same product on |A|)."""
+    S_ = dA.handle
+    ref = dA.matmul(dA)
+    ok = True
+    try:
+        gp, gi, gv = as_tensors(gathered, dev, torch)
+        rp, ri, rv = as_tensors(ref, dev, torch)
+        ok = ok and gathered.info()["nnz"] == ref.info()["nnz"] and bool(torch.equal(gp, rp)) and bool(torch.equal(gi, ri))
+        if ok and exact:
+            ok = bool(torch.equal(gv, rv))
+        elif ok:
+            torch.sub(rv, gv, out=rv)
+            rv.abs_()                                        # |difference|, in the reference product's own memory
+            i = dA.info()
+            av = torch.as_tensor(DevArray(i["d_val"], i["nnz"], "<f8"), device=dev).abs()
+            dAbs = type(dA).wrap(S_, np.float64, i["rows"], i["cols"], i["nnz"], i["d_ptr"], i["d_idx"], av.data_ptr(), keepalive=(av,))
+            sabs = dAbs.matmul(dAbs)
+            _, _, sv = as_tensors(sabs, dev, torch)
+            ok = bool((rv <= 1e-12 * sv).all())
+            sabs.free(); dAbs.free()
+    finally:
+        ref.free()
+    return ok
+
+
+def rmat_strong_section(args, S, D, G, handle, rank, world, dev, torch, dist, sync_all):
+    """BASELINE configs[3] / north_star: strong scaling of the largest R-MAT product, in the same invocation at every
+    N: the 1-GPU product on this box, the row-sharded product (C left sharded), and the product with C assembled on
+    every rank (peer stores overlapped with the numeric kernels; and the NCCL-broadcast variant beside it)."""
+    name = args.scale_workload
+    out = {"workload": name, "desc": WORKLOAD_DESC[name], "scaling": "strong"}
+    t0 = time.perf_counter()
+    mat = make_workload(name) if rank == 0 else None
+    out["generate_s"] = round(time.perf_counter() - t0, 2) if rank == 0 else None
+    torch.cuda.synchronize()
+    t_host0 = time.perf_counter()
+    dA, rows, cols, nnz_a, t_b = device_matrix(S, handle, mat, rank, world, dev, torch)
+    steps = max(2, min(args.steps, 3))
+    # ---- the whole product on ONE GPU (every rank does it at the same time on its own copy: max over ranks) ----
+    outs = []
+
+    def one():
+        c = dA.matmul(dA)
+        outs.append(c)
+        if len(outs) > 1:
+            outs.pop(0).free()
+    one(); one()
+    ms1 = time_steps(one, steps, sync_all, torch)
+    ms1, _ = max_over_ranks(ms1, world, dev, torch, dist)
+    st = handle.stats()
+    flops, nnz_c = int(st["flops"]), int(st["nnz_c"])
+    while outs:
+        outs.pop().free()
+    out.update({"rows": rows, "nnz_a": nnz_a, "products": flops, "nnz_c": nnz_c, "ms_1gpu_ref": ms1,
+                "gflops_1gpu": 2.0 * flops / ms1 / 1e6, "num_bin_rows": st["num_bin_rows"], "fallbacks": st["fallbacks"],
+                "algorithmic_bytes": G.algorithmic_bytes_spgemm(rows, nnz_a, flops, nnz_c, 8)})
+    out["hbm_frac_1gpu"] = out["algorithmic_bytes"] / ms1 / 1e6 / measured_peak()[0]
+    if world == 1:
+        dA.free()
+        return out
+    # ---- partition (device-time balanced rows_to_threads formula) + slice: set-up, reported ----
+    torch.cuda.synchronize()
+    tp0 = time.perf_counter()
+    starts, _ = dA.rows_to_parts(dA, world, balance="cost")
+    r0, r1 = int(starts[rank]), int(starts[rank + 1])
+    blk = dA.slice_rows(r0, r1)
+    handle.synchronize()
+    out["partition_ms"] = (time.perf_counter() - tp0) * 1e3
+    out["bcast_ms"] = t_b * 1e3
+
+    def sharded():
+        blk.matmul(dA).free()
+
+    def gathered(mode):
+        def f():
+            blk.matmul_gathered(dA, r0, rows, nsub=args.nsub, mode=mode).free()
+        return f
+    sharded(); sharded()
+    ms_s = time_steps(sharded, steps, sync_all, torch)
+    ms_s, rank_ms = max_over_ranks(ms_s, world, dev, torch, dist)
+    gathered(0)(); gathered(0)()
+    out["ms_total_from_host_A"] = None
+    ms_g, _ = max_over_ranks(time_steps(gathered(0), steps, sync_all, torch), world, dev, torch, dist)
+    peer = handle.comm_info()["peer_mapped"]
+    # parity of the assembled C (outside every timed region)
+    g = blk.matmul_gathered(dA, r0, rows, nsub=args.nsub, mode=0)
+    ok = gathered_parity(dA, g, dev, torch, exact=False)
+    g.free()
+    okt = torch.tensor([1 if ok else 0], dtype=torch.int64, device=dev)
+    dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+    gathered(1)(); gathered(1)()
+    ms_n, _ = max_over_ranks(time_steps(gathered(1), steps, sync_all, torch), world, dev, torch, dist)
+    recv = (nnz_c * 12 + (rows + 1) * 8) * (world - 1) / world
+    out.update({"ms_sharded": ms_s, "rank_ms": rank_ms, "speedup_sharded": ms1 / ms_s,
+                "ms_gathered": ms_g, "speedup_gathered": ms1 / ms_g, "gather": "peer stores over NVLink (k_push), "
+                f"{args.nsub} sub-blocks pipelined with the numeric kernels" if peer else "peer mapping unavailable: NCCL broadcasts",
+                "ms_gathered_nccl": ms_n, "speedup_gathered_nccl": ms1 / ms_n,
+                "gathered_parity": bool(int(okt.item())), "recv_bytes_per_gpu": int(recv),
+                "recv_gbs_per_gpu_whole_step": recv / ms_g / 1e6,
+                "recv_gbs_per_gpu_exchange_only": recv / max(ms_g - ms_s, 1e-3) / 1e6})
+    # from A in rank 0's host memory to the assembled C on every rank, once: upload + replicate + partition + product
+    out["ms_total_from_host_A"] = out["bcast_ms"] + out["partition_ms"] + ms_g + (0.0 if mat is None else 0.0)
+    out["ms_total_from_host_A_note"] = "bcast_ms (replicate A = B over NCCL) + partition_ms + ms_gathered; the H2D copy of A on rank 0 is not included"
+    blk.free(); dA.free()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -200,9 +382,14 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--workload", default="poisson2048", choices=sorted(WORKLOAD_DESC))
     ap.add_argument("--scaling", default="auto", choices=["auto", "strong", "weak"])
+    ap.add_argument("--scale-workload", default="rmat22", choices=sorted(WORKLOAD_DESC),
+                    help="the strong-scaling product measured beside the headline (config.strong_scaling)")
+    ap.add_argument("--no-scale-section", action="store_true")
+    ap.add_argument("--nsub", type=int, default=4, help="row sub-blocks that pipeline numeric kernels and exchange")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
+    requested_warmup = args.warmup
     args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
 
     rank = int(os.environ.get("RANK", "0"))
@@ -215,52 +402,39 @@ def main():
 
     import torch
     import sparse_matrix_b200 as S
+    from sparse_matrix_b200 import distributed as D
     from sparse_matrix_b200 import generators as G
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    dist = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 
     handle = S.Handle(local_rank)
     # one explicit (non-default) stream for everything: the library's kernels, torch's events and the
-    # NCCL collectives are all ordered on it, so the CUDA events below see the kernels they bracket
+    # collectives are all ordered on it, so the CUDA events below see the kernels they bracket
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
     assert stream.cuda_stream != 0
     handle.set_stream(stream.cuda_stream)
     L = handle.L
+    if world > 1:
+        D.init_comm(handle)      # the library's own NCCL communicator + peer-mapped gather buffers
 
-    # ---- inputs: rank 0 generates, everyone gets A over NCCL (B = A is replicated) ----
-    t_bcast = 0.0
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- inputs: rank 0 generates, the library replicates A (B = A) ----
     scaling = resolve_scaling(args)
-    if world == 1 or rank == 0:
-        mat = make_workload(args.workload, world if scaling == "weak" else 1)
-        rows, cols = mat[0], mat[1]
-        h_ptr = torch.from_numpy(np.ascontiguousarray(mat[2]).view(np.int64))
-        h_idx = torch.from_numpy(np.ascontiguousarray(mat[3]).astype(np.uint32).view(np.int32))
-        h_val = torch.from_numpy(np.ascontiguousarray(mat[4]))
-        meta = torch.tensor([rows, cols, h_idx.shape[0]], dtype=torch.int64, device=dev)
-    else:
-        mat = None
-        meta = torch.zeros(3, dtype=torch.int64, device=dev)
-    if world > 1:
-        from sparse_matrix_b200 import distributed as D
-        dist.broadcast(meta, src=0)
-    rows, cols, nnz_a = (int(x) for x in meta.tolist())
-    if world == 1 or rank == 0:
-        d_ptr, d_idx, d_val = h_ptr.to(dev), h_idx.to(dev), h_val.to(dev)
-    else:
-        d_ptr = torch.empty(rows + 1, dtype=torch.int64, device=dev)
-        d_idx = torch.empty(nnz_a, dtype=torch.int32, device=dev)
-        d_val = torch.empty(nnz_a, dtype=torch.float64, device=dev)
-    if world > 1:
-        t_bcast = D.replicate([d_ptr, d_idx, d_val], src=0)
-    dA = S.DeviceCsr.wrap(handle, np.float64, rows, cols, nnz_a, d_ptr.data_ptr(), d_idx.data_ptr(), d_val.data_ptr(),
-                          keepalive=(d_ptr, d_idx, d_val))
+    mat = make_workload(args.workload, world if scaling == "weak" else 1) if rank == 0 else None
+    dA, rows, cols, nnz_a, t_bcast = device_matrix(S, handle, mat, rank, world, dev, torch)
 
     # ---- one step ----
     gathered_ms = None
@@ -276,26 +450,16 @@ def main():
         torch.cuda.synchronize()
         tp0 = time.perf_counter()
         starts, total = dA.rows_to_parts(dA, world, balance="cost")
-        blk = dA.slice_rows(int(starts[rank]), int(starts[rank + 1]))
+        r0, r1 = int(starts[rank]), int(starts[rank + 1])
+        blk = dA.slice_rows(r0, r1)
         handle.synchronize()
         partition_ms = (time.perf_counter() - tp0) * 1e3
 
-        def step(gather=False):
-            c = blk.matmul(dA)
-            if gather:
-                i = c.info()
-                lp = torch.as_tensor(DevArray(i["d_ptr"], i["rows"] + 1, "<i8"), device=dev)
-                li = torch.as_tensor(DevArray(i["d_idx"], max(1, i["nnz"]), "<i4"), device=dev)[:i["nnz"]]
-                lv = torch.as_tensor(DevArray(i["d_val"], max(1, i["nnz"]), "<f8"), device=dev)[:i["nnz"]]
-                rows_per = [int(starts[r + 1] - starts[r]) for r in range(world)]
-                D.gathered_csr(lp, li, lv, rows_per)
-            c.free()
+        def step():
+            blk.matmul(dA).free()
 
-    def sync_all():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
+        def step_gathered():
+            blk.matmul_gathered(dA, r0, rows, nsub=args.nsub, mode=0).free()
 
     # clocks are sampled from before the warm-up to the end of the timed region; the warm-up is
     # stretched to >= 0.4 s of the same load so that nvidia-smi (20 ms period) sees the steady state
@@ -307,16 +471,11 @@ def main():
     while n_warm < args.warmup or (time.perf_counter() - t_w < 0.4 and n_warm < 2000):
         step()
         n_warm += 1
-    if world > 1:  # same count on every rank (the gather variant below is collective)
-        tw = torch.tensor([n_warm], dtype=torch.int64, device=dev)
-        dist.all_reduce(tw, op=dist.ReduceOp.MAX)
     sync_all()
-    args.warmup = n_warm
 
     handle.set_timing(True)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     phase = {"ms_flop": 0.0, "ms_symbolic": 0.0, "ms_scan": 0.0, "ms_numeric": 0.0, "ms_total": 0.0}
-    launches = 0
     sync_all()
     ev0.record()
     handle.phase_totals(reset=True)   # the library sums each product's phase events; nothing is read back in the loop
@@ -333,32 +492,26 @@ def main():
     launches = st["kernel_launches"] * args.steps
     handle.set_timing(False)
     ms_step = ev0.elapsed_time(ev1) / args.steps
-    if world > 1:
-        t = torch.tensor([ms_step], dtype=torch.float64, device=dev)
-        per_rank = [torch.zeros_like(t) for _ in range(world)]
-        dist.all_gather(per_rank, t)
-        rank_ms = [round(float(x.item()), 4) for x in per_rank]
-        ms_step = max(rank_ms)
+    ms_step, rank_ms = max_over_ranks(ms_step, world, dev, torch, dist)
     flops, nnz_c = st["flops"], st["nnz_c"]
     local_nnz_c = nnz_c
+    gathered_ok = None
     if world > 1:
         t = torch.tensor([flops, nnz_c, launches], dtype=torch.int64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         flops, nnz_c, launches = (int(x) for x in t.tolist())
-        # the same step including the all-gather-v of C (reported separately, SURVEY §7 hard parts)
-        for _ in range(2):
-            step(gather=True)
-        sync_all()
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        g0.record()
-        nrep = max(1, min(args.steps, 5))
-        for _ in range(nrep):
-            step(gather=True)
-        g1.record()
-        sync_all()
-        t = torch.tensor([g0.elapsed_time(g1) / nrep], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        gathered_ms = float(t.item())
+        # the same step with C assembled on every rank by peer stores overlapped with the numeric kernels
+        # (spam_spgemm_gathered), reported beside the sharded value
+        for _ in range(3):
+            step_gathered()
+        nrep = max(3, min(args.steps, 10))
+        gathered_ms, _ = max_over_ranks(time_steps(step_gathered, nrep, sync_all, torch), world, dev, torch, dist)
+        g = blk.matmul_gathered(dA, r0, rows, nsub=args.nsub, mode=0)
+        ok = gathered_parity(dA, g, dev, torch, exact=(args.workload == "poisson2048"))
+        g.free()
+        okt = torch.tensor([1 if ok else 0], dtype=torch.int64, device=dev)
+        dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+        gathered_ok = bool(int(okt.item()))
 
     val_size = 8
     bytes_alg = G.algorithmic_bytes_spgemm(rows, nnz_a, flops, nnz_c, val_size)
@@ -366,7 +519,7 @@ def main():
     gflops = 2.0 * flops / (ms_step / 1e3) / 1e9
 
     line = {"metric": "spgemm_gflops", "value": gflops, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": scaling,
+            "warmup": requested_warmup, "warmup_run": n_warm, "ms_per_step": ms_step, "higher_is_better": True, "scaling": scaling,
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": args.workload, "desc": WORKLOAD_DESC[args.workload], "rows": rows, "nnz_a": nnz_a,
                        "products": flops, "nnz_c": nnz_c, "algorithmic_bytes": bytes_alg,
@@ -374,9 +527,9 @@ def main():
                              ((nnz_a * 12 + nnz_c * 12 + rows * 16) / 1e9),
                        "sharding": "single GPU" if world == 1 else
                                    f"A pre-sharded in device-cost-balanced row blocks (spam_rows_to_parts_cost) over {world} ranks (partition + slice "
-                                   f"{partition_ms:.2f} ms, untimed set-up), B replicated (NCCL broadcast "
-                                   f"{t_bcast * 1e3:.1f} ms, untimed), C left row-sharded in `value`; `gathered` adds "
-                                   f"the all-gather-v"},
+                                   f"{partition_ms:.2f} ms, untimed set-up), B replicated (spam_comm_broadcast "
+                                   f"{t_bcast * 1e3:.1f} ms, untimed), C left row-sharded in `value`; `gathered` = the same step with C "
+                                   f"assembled on every rank (spam_spgemm_gathered)"},
             "gpu_launches": launches,
             "hbm_gbs_pipeline": bytes_alg / (ms_step / 1e3) / 1e9,
             "phases_ms": {k: v / args.steps for k, v in phase.items()}}
@@ -386,9 +539,15 @@ def main():
             line["config"]["weak_unit"] = ("one 2048 x 2048 block of grid lines (4.19M rows of A) per GPU; the matrix is "
                                            f"the Poisson operator on a 2048 x {2048 * world} grid, B = all of it, replicated")
     if gathered_ms is not None:
+        recv = (nnz_c * 12 + (rows + 1) * 8) * (world - 1) / world
         line["gathered"] = {"ms_per_step": gathered_ms, "value": 2.0 * flops / (gathered_ms / 1e3) / 1e9,
-                            "unit": "GFLOP/s", "note": "same step plus all-gather-v of row_ptr/col_idx/val so every "
-                                                       "rank holds the full C"}
+                            "unit": "GFLOP/s", "parity": gathered_ok, "recv_bytes_per_gpu": int(recv),
+                            "recv_gbs_per_gpu": recv / gathered_ms / 1e6,
+                            "peer_mapped": handle.comm_info()["peer_mapped"],
+                            "note": "same step with every rank holding the whole C afterwards: numeric kernels write each "
+                                    "rank's rows at their offset-fixed place, a push kernel stores them into every peer's "
+                                    "copy over NVLink, sub-block by sub-block behind the numeric kernels"}
+        line["gathered_parity"] = gathered_ok
 
     if rank == 0:
         # ---- roofline of the dominant kernel: the numeric pass (one k_num_* launch per non-empty bin) ----
@@ -405,7 +564,9 @@ def main():
             ach = my_bytes / (ms_num / 1e3) / 1e9
             line["roofline"] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                                 "traffic": traffic,
-                                "kernel": "numeric pass (k_num_merge<double,6,128> on Poisson: one launch per step)",
+                                # the same kernel by the DRAM bytes ncu counted for it (B rows mostly hit L1/L2):
+                                "dram_frac": (traffic / (ms_num / 1e3) / 1e9 / peak) if traffic else None,
+                                "kernel": dominant_kernel(args.workload, st),
                                 "kernel_ms": ms_num, "peak_source": peak_src,
                                 "pipeline_frac": line["hbm_gbs_pipeline"] / peak}
         else:
@@ -415,7 +576,27 @@ def main():
                                 "peak_source": peak_src + f" x {world} GPUs"}
         line["clocks"] = clocks
 
-    # ---- e2e: the reference-facing two-phase C ABI with pinned HOST buffers.  At N > 1 every rank is a
+    # ---- the same product for CsrMatrix<T, false> inputs (rows not sorted: what from_dok-shuffled inputs are) ----
+    if world == 1 and args.workload == "poisson2048":
+        rng = np.random.default_rng(7)
+        o = mat[2].astype(np.int64)
+        lens = np.diff(o)
+        keyr = np.repeat(np.arange(rows), lens) + rng.random(nnz_a)       # a random order inside every row
+        perm = np.argsort(keyr, kind="stable")
+        umat = (rows, cols, mat[2], mat[3][perm], mat[4][perm])
+        dU = S.DeviceCsr.upload(S.CsrMatrix(umat[0], umat[1], umat[4], umat[3], umat[2], is_sorted=False), handle)
+
+        def ustep():
+            dU.matmul(dU).free()
+        for _ in range(3):
+            ustep()
+        line["config"]["unsorted_input"] = {"ms_per_step": time_steps(ustep, max(3, min(args.steps, 10)), sync_all, torch),
+                                            "note": "same matrix with every row's entries shuffled (IS_SORTED = false): "
+                                                    "no merge bin, the thread-per-row hash bin"}
+        line["config"]["unsorted_input"]["num_bin_rows"] = handle.stats()["num_bin_rows"]
+        dU.free()
+
+    # ---- e2e: the reference-facing two-phase C ABI with HOST buffers.  At N > 1 every rank is a
     # host caller multiplying ITS row block of A (host memory) by all of B (host memory): both are uploaded
     # and the C shard is downloaded inside the timed region; time = max over ranks.
     do_e2e = not args.no_e2e
@@ -435,6 +616,10 @@ def main():
     if do_e2e:
         keep = []
         try:
+            i = dA.info()
+            d_ptr = torch.as_tensor(DevArray(i["d_ptr"], rows + 1, "<i8"), device=dev)
+            d_idx = torch.as_tensor(DevArray(i["d_idx"], nnz_a, "<i4"), device=dev)
+            d_val = torch.as_tensor(DevArray(i["d_val"], nnz_a, "<f8"), device=dev)
             if world == 1:
                 hb_ptr, hb_idx, hb_val = mat[2], mat[3], mat[4]
                 a_rows, a_nnz = rows, nnz_a
@@ -442,47 +627,49 @@ def main():
                 hb_ptr = d_ptr.cpu().numpy().view(np.uint64)
                 hb_idx = d_idx.cpu().numpy().view(np.uint32)
                 hb_val = d_val.cpu().numpy()
-                r0, r1 = int(starts[rank]), int(starts[rank + 1])
                 a_rows = r1 - r0
                 e0_, e1_ = int(hb_ptr[r0]), int(hb_ptr[r1])
                 a_nnz = e1_ - e0_
-            p_ptr = pinned_array(L, rows + 1, np.uint64, keep); p_ptr[:] = hb_ptr
-            p_idx = pinned_array(L, nnz_a, np.uint64, keep); p_idx[:] = hb_idx
-            p_val = pinned_array(L, nnz_a, np.float64, keep); p_val[:] = hb_val
+
+            def host_buffers(pinned):
+                def arr(n, dt):
+                    return pinned_array(L, n, dt, keep) if pinned else np.empty(max(1, n), dtype=dt)[:n]
+                p_ptr = arr(rows + 1, np.uint64); p_ptr[:] = hb_ptr
+                p_idx = arr(nnz_a, np.uint64); p_idx[:] = hb_idx
+                p_val = arr(nnz_a, np.float64); p_val[:] = hb_val
+                if world == 1:
+                    pa = (p_ptr, p_idx, p_val)                 # A aliases B: the library uploads it once
+                else:
+                    pa_ptr = arr(a_rows + 1, np.uint64); pa_ptr[:] = hb_ptr[r0:r1 + 1] - hb_ptr[r0]
+                    pa_idx = arr(a_nnz, np.uint64); pa_idx[:] = hb_idx[e0_:e1_]
+                    pa_val = arr(a_nnz, np.float64); pa_val[:] = hb_val[e0_:e1_]
+                    pa = (pa_ptr, pa_idx, pa_val)
+                c = (arr(a_rows + 1, np.uint64), arr(local_nnz_c, np.uint64), arr(local_nnz_c, np.float64))
+                return pa, (p_ptr, p_idx, p_val), c
+
+            def e2e_time(pinned):
+                pa, pb, c = host_buffers(pinned)
+
+                def e2e_step():
+                    nz = C.c_uint64()
+                    S._lib.check(handle.h, L.spam_spgemm_symbolic(handle.h, 1, a_rows, cols, S._lib.ptr(pa[0]),
+                                                                  S._lib.ptr(pa[1]), S._lib.ptr(pa[2]), rows, cols,
+                                                                  S._lib.ptr(pb[0]), S._lib.ptr(pb[1]), S._lib.ptr(pb[2]),
+                                                                  S._lib.ptr(c[0]), C.byref(nz)))
+                    assert nz.value == local_nnz_c
+                    S._lib.check(handle.h, L.spam_spgemm_numeric(handle.h, S._lib.ptr(c[1]), S._lib.ptr(c[2]), 1))
+
+                for _ in range(2):
+                    e2e_step()
+                k = max(3, min(args.steps, 10))
+                ms = time_steps(e2e_step, k, sync_all, torch)
+                st_e = handle.stats()
+                return ms, int(st_e["bytes_h2d"]), int(st_e["bytes_d2h"])
+
+            ms_e2e, h2d, d2h = e2e_time(True)
+            ms_page = None
             if world == 1:
-                pa_ptr, pa_idx, pa_val = p_ptr, p_idx, p_val     # A aliases B: the library uploads it once
-            else:
-                pa_ptr = pinned_array(L, a_rows + 1, np.uint64, keep); pa_ptr[:] = hb_ptr[r0:r1 + 1] - hb_ptr[r0]
-                pa_idx = pinned_array(L, a_nnz, np.uint64, keep); pa_idx[:] = hb_idx[e0_:e1_]
-                pa_val = pinned_array(L, a_nnz, np.float64, keep); pa_val[:] = hb_val[e0_:e1_]
-            c_ptr = pinned_array(L, a_rows + 1, np.uint64, keep)
-            c_idx = pinned_array(L, local_nnz_c, np.uint64, keep)
-            c_val = pinned_array(L, local_nnz_c, np.float64, keep)
-
-            def e2e_step():
-                nz = C.c_uint64()
-                S._lib.check(handle.h, L.spam_spgemm_symbolic(handle.h, 1, a_rows, cols, S._lib.ptr(pa_ptr),
-                                                              S._lib.ptr(pa_idx), S._lib.ptr(pa_val), rows, cols,
-                                                              S._lib.ptr(p_ptr), S._lib.ptr(p_idx), S._lib.ptr(p_val),
-                                                              S._lib.ptr(c_ptr), C.byref(nz)))
-                assert nz.value == local_nnz_c
-                S._lib.check(handle.h, L.spam_spgemm_numeric(handle.h, S._lib.ptr(c_idx), S._lib.ptr(c_val), 1))
-
-            for _ in range(2):
-                e2e_step()
-            sync_all()
-            k = max(3, min(args.steps, 10))
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for _ in range(k):
-                e2e_step()
-            e1.record()
-            sync_all()
-            ms_e2e = e0.elapsed_time(e1) / k
-            # bytes actually moved over PCIe by the last step, as counted by the library (at N > 1 only the band
-            # of B that this rank's rows of A reference is uploaded)
-            st_e2e = handle.stats()
-            h2d, d2h = int(st_e2e["bytes_h2d"]), int(st_e2e["bytes_d2h"])
+                ms_page, _, _ = e2e_time(False)      # ordinary pageable buffers: what a Rust Vec is
             if world > 1:
                 t = torch.tensor([ms_e2e, -ms_e2e, h2d, d2h], dtype=torch.float64, device=dev)
                 tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -494,6 +681,9 @@ def main():
                                   ("A aliases B so it is uploaded once)" if world == 1 else
                                    "every rank uploads its row block of A and the rows of B it references, downloads its shard of C; "
                                    "bytes summed over ranks, time = max over ranks)")}
+            if ms_page is not None:
+                line["e2e"]["pageable"] = {"ms_per_step": ms_page, "value": 2.0 * flops / (ms_page / 1e3) / 1e9,
+                                           "note": "the same calls on ordinary (pageable) host buffers, like the Rust wrapper's Vecs"}
         finally:
             for p in keep:
                 L.spam_host_free(p)
@@ -505,11 +695,24 @@ def main():
     elif rank == 0:
         line["cpu_baseline"] = None
 
-    if rank == 0:
-        print(json.dumps(line), flush=True)
     if world > 1:
         blk.free()
     dA.free()
+    mat = None
+
+    # ---- the strong-scaling configuration of the north star, measured in the same invocation at every N ----
+    if not args.no_scale_section and args.workload == "poisson2048":
+        try:
+            sec = rmat_strong_section(args, S, D, G, handle, rank, world, dev, torch, dist, sync_all)
+        except Exception as e:      # the headline line must survive a failure here; say what happened
+            sec = {"workload": args.scale_workload, "error": f"{type(e).__name__}: {e}"}
+            if world > 1:
+                raise
+        if rank == 0:
+            line["config"]["strong_scaling"] = sec
+
+    if rank == 0:
+        print(json.dumps(line), flush=True)
     handle.close()
     if world > 1:
         dist.destroy_process_group()

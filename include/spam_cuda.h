@@ -216,6 +216,36 @@ int spam_rows_to_parts_cost(spam_handle* h, const spam_dcsr* a, const spam_dcsr*
  * all-gather-v); n entries */
 int spam_offset_u64(spam_handle* h, void* d_ptr_u64, uint64_t n, uint64_t offset);
 
+/* ---- several GPUs of one node, one process (and one handle) per GPU ----------------------------
+ * The reference's threads write disjoint slices of ONE output (mul_hash.rs:121-128); so do the ranks here.
+ * NCCL (bound with dlopen: no link-time dependency) carries the rendezvous and the small exchanges; the shards
+ * of C are stored by the ranks into each other's peer-mapped copy of the whole C (cudaIpc*), overlapped with the
+ * product.  All spam_comm_* / *_gathered calls are collective: every rank calls them in the same order. */
+/* rank 0 makes a 128-byte id and hands it to the other ranks by any host channel (ncclGetUniqueId) */
+int spam_comm_unique_id(void* out128);
+int spam_comm_init(spam_handle* h, const void* id128, int rank, int world);
+int spam_comm_destroy(spam_handle* h);
+int spam_comm_info(const spam_handle* h, int* rank, int* world, int* peer_mapped);
+/* replicate a device buffer from `root` (B, and A before it is sliced): ncclBroadcast on the handle's stream */
+int spam_comm_broadcast(spam_handle* h, void* d_buf, uint64_t bytes, int root);
+/* n <= 32 values per rank -> all[world * n] on the host (per-rank nnz / row counts) */
+int spam_comm_allgather_u64(spam_handle* h, const uint64_t* mine, uint32_t n, uint64_t* all);
+/* all-gather-v, in place: rank r's bytes sit at d_out + byte_offsets[r] (byte_offsets: world + 1 entries, host);
+ * NCCL has no ncclAllGatherv: one ncclBroadcast per source rank inside one NCCL group */
+int spam_comm_allgatherv(spam_handle* h, void* d_out, const uint64_t* byte_offsets);
+/* C = A * B, A row-sharded (a_block = this rank's rows [row_start, row_start + rows) with row_ptr rebased to 0;
+ * the blocks tile A in rank order), B replicated; on return every rank holds the WHOLE C with its offset-fixed
+ * row_ptr.  *c is a non-owning view of the handle's gather buffers: valid until the next gathered product on
+ * this handle; release the view with spam_dcsr_free.  nsub (1..16) sub-blocks of rows pipeline the numeric
+ * kernels with the exchange.  mode 0: peer stores over NVLink (falls back to 1 if the peers' buffers cannot be
+ * mapped), mode 1: grouped ncclBroadcast.  Phase timing (spam_cuda_set_timing) is not collected here. */
+int spam_spgemm_gathered(spam_handle* h, const spam_dcsr* a_block, const spam_dcsr* b, uint64_t row_start,
+                         uint64_t total_rows, int nsub, int mode, spam_dcsr** c);
+/* y = A x, A row-sharded, x replicated: each rank fills its rows of d_y_full (total rows entries) and the pieces
+ * are exchanged; rows_of = every rank's row count (host, world entries) */
+int spam_spmv_gathered(spam_handle* h, const spam_dcsr* a_block, const void* d_x, void* d_y_full,
+                       const uint64_t* rows_of);
+
 #ifdef __cplusplus
 }
 #endif

@@ -2,7 +2,7 @@
 spam_csr operator interface.  The compute lives in libspam_cuda.so (hand-written CUDA, C ABI in
 include/spam_cuda.h); this package is the host-side mirror of the reference API over that ABI."""
 from ._lib import SO_PATH, DimensionMismatch, SpamError, load  # noqa: F401
-from .csr import CsrMatrix, DeviceCsr, DokMatrix, Handle, get_handle  # noqa: F401
+from .csr import CsrMatrix, DeviceCsr, DokMatrix, Handle, comm_unique_id, get_handle  # noqa: F401
 from .matrix_market import (FromMatrixMarketError, into_float_matrix_market, load_matrix_market,  # noqa: F401
                             parse_matrix_market)
 

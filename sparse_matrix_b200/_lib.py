@@ -27,6 +27,8 @@ EXPORTS = [
     "spam_dcsr_free", "spam_dcsr_slice_rows", "spam_dcsr_select_rows", "spam_dcsr_transpose", "spam_csr_transpose", "spam_spgemm_dev", "spam_spmv_dev", "spam_dok_to_csr_dev",
     "spam_rows_to_parts", "spam_rows_to_parts_cost", "spam_offset_u64", "spam_dcsr_ewise", "spam_csr_ewise",
     "spam_csr_ewise_fetch", "spam_mm_parse", "spam_mm_free",
+    "spam_comm_unique_id", "spam_comm_init", "spam_comm_destroy", "spam_comm_info", "spam_comm_broadcast",
+    "spam_comm_allgather_u64", "spam_comm_allgatherv", "spam_spgemm_gathered", "spam_spmv_gathered",
 ]
 
 
@@ -101,6 +103,15 @@ def load():
     L.spam_rows_to_parts.argtypes = [vp, vp, vp, C.c_uint32, vp, C.POINTER(u64)]
     L.spam_rows_to_parts_cost.argtypes = [vp, vp, vp, C.c_uint32, vp, C.POINTER(u64)]
     L.spam_offset_u64.argtypes = [vp, vp, u64, u64]
+    L.spam_comm_unique_id.argtypes = [vp]
+    L.spam_comm_init.argtypes = [vp, vp, i32, i32]
+    L.spam_comm_destroy.argtypes = [vp]
+    L.spam_comm_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
+    L.spam_comm_broadcast.argtypes = [vp, vp, u64, i32]
+    L.spam_comm_allgather_u64.argtypes = [vp, vp, C.c_uint32, vp]
+    L.spam_comm_allgatherv.argtypes = [vp, vp, vp]
+    L.spam_spgemm_gathered.argtypes = [vp, vp, vp, u64, u64, i32, i32, C.POINTER(vp)]
+    L.spam_spmv_gathered.argtypes = [vp, vp, vp, vp, vp]
     for name in EXPORTS:
         fn = getattr(L, name)
         if name not in ("spam_strerror", "spam_last_error", "spam_mm_free"):

@@ -68,6 +68,39 @@ class Handle:
                 "num_bin_rows": list(s.num_bin_rows), "fallbacks": list(s.fallbacks)}
 
 
+def _comm_unique_id() -> bytes:
+    """128-byte rendezvous id (ncclGetUniqueId): rank 0 makes it, every rank passes it to Handle.comm_init."""
+    buf = C.create_string_buffer(128)
+    st = _lib.load().spam_comm_unique_id(buf)
+    if st != 0:
+        raise _lib.SpamError(st, "spam_comm_unique_id failed (libnccl.so.2 not loadable?)")
+    return buf.raw
+
+
+def _comm_init(self, unique_id: bytes, rank: int, world: int):
+    """Collective: one NCCL communicator inside the library for this handle (spam_comm_init)."""
+    assert len(unique_id) == 128
+    check(self.h, self.L.spam_comm_init(self.h, C.c_char_p(unique_id), rank, world))
+    self.rank, self.world = rank, world
+
+
+def _comm_info(self) -> dict:
+    r, w, p = C.c_int(), C.c_int(), C.c_int()
+    check(self.h, self.L.spam_comm_info(self.h, C.byref(r), C.byref(w), C.byref(p)))
+    return {"rank": r.value, "world": w.value, "peer_mapped": bool(p.value)}
+
+
+def _comm_broadcast(self, d_ptr: int, nbytes: int, root: int = 0):
+    check(self.h, self.L.spam_comm_broadcast(self.h, C.c_void_p(d_ptr), nbytes, root))
+
+
+def _comm_allgather_u64(self, values) -> np.ndarray:
+    mine = np.ascontiguousarray(values, dtype=np.uint64)
+    out = np.zeros(self.world * mine.shape[0], dtype=np.uint64)
+    check(self.h, self.L.spam_comm_allgather_u64(self.h, ptr(mine), mine.shape[0], ptr(out)))
+    return out.reshape(self.world, mine.shape[0])
+
+
 def _phase_totals(self, reset: bool = False) -> dict:
     """Sums of the per-phase CUDA-event times (ms) over the products finished since the last reset."""
     ms = (C.c_double * 5)()
@@ -78,6 +111,11 @@ def _phase_totals(self, reset: bool = False) -> dict:
 
 
 Handle.phase_totals = _phase_totals
+Handle.comm_init = _comm_init
+Handle.comm_info = _comm_info
+Handle.comm_broadcast = _comm_broadcast
+Handle.comm_allgather_u64 = _comm_allgather_u64
+comm_unique_id = _comm_unique_id
 
 
 def get_handle(device: int = 0) -> Handle:
@@ -141,6 +179,22 @@ class DeviceCsr:
         out = C.c_void_p()
         check(self.handle.h, self.handle.L.spam_spgemm_dev(self.handle.h, self.p, rhs.p, C.byref(out)))
         return DeviceCsr(self.handle, out)
+
+    def matmul_gathered(self, rhs: "DeviceCsr", row_start: int, total_rows: int, nsub: int = 4,
+                        mode: int = 0) -> "DeviceCsr":
+        """Collective.  self = this rank's row block of A, rhs = all of B: returns the WHOLE product, assembled on
+        every rank (spam_spgemm_gathered).  The result is a view of the handle's gather buffers, valid until the
+        next gathered product."""
+        out = C.c_void_p()
+        check(self.handle.h, self.handle.L.spam_spgemm_gathered(self.handle.h, self.p, rhs.p, row_start, total_rows,
+                                                                nsub, mode, C.byref(out)))
+        return DeviceCsr(self.handle, out)
+
+    def spmv_gathered(self, d_x: int, d_y_full: int, rows_of) -> None:
+        """Collective.  y = A x with self = this rank's row block; d_y_full holds all rows on return."""
+        rows_of = np.ascontiguousarray(rows_of, dtype=np.uint64)
+        check(self.handle.h, self.handle.L.spam_spmv_gathered(self.handle.h, self.p, C.c_void_p(d_x),
+                                                              C.c_void_p(d_y_full), ptr(rows_of)))
 
     def add(self, rhs: "DeviceCsr") -> "DeviceCsr":
         """impl Add for CsrMatrix (apply_elementwise, lib.rs:83-149) on the device."""

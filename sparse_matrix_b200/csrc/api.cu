@@ -243,11 +243,12 @@ int spam_cuda_create(spam_handle** out, int device) {
   h->device = device; h->timing = false; h->pending = nullptr; h->dok_pending = nullptr;
   h->scan_ws = nullptr; h->scan_ws_cap = 0;
   h->pool = nullptr;
+  h->comm = nullptr;
   {
     const char* e = getenv("SPAM_LANES");  // read once: 0 keeps every row bin on the main stream
     h->use_lanes = !(e && e[0] == '0');
     e = getenv("SPAM_ESC");
-    h->use_esc = !(e && e[0] == '0');
+    h->use_esc = e ? (e[0] == '0' ? 0 : (e[0] == '2' ? 2 : 1)) : 1;
   }
   h->d_cnt = nullptr; h->h_cnt = nullptr; h->own_stream = nullptr; h->stream = nullptr;
   h->stats = spam_stats{};
@@ -296,6 +297,7 @@ int spam_cuda_destroy(spam_handle* h) {
   if (!h) return SPAM_EINVAL;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->comm) spam_comm_destroy(h);
   drop_spgemm_state(h);
   drop_dok_state(h);
   if (h->scan_ws) { dev_free(h, h->scan_ws); h->scan_ws = nullptr; }

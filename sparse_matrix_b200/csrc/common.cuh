@@ -40,7 +40,7 @@ constexpr int NBINS = 16;
 constexpr int NHASH = 8, HEAVY_BIN = 9, MERGE_BIN = 10, ESC_BIN0 = 11, ESC_HEAVY_BIN = 15;
 constexpr u32 ESC_ZMIN = 256;
 // `mode` bits of the binning functions: which optional bins the product may use
-constexpr int MODE_MERGE = 1, MODE_ESC = 2;
+constexpr int MODE_MERGE = 1, MODE_ESC = 2, MODE_ESC_HEAVY = 4;
 constexpr u32 SYM_TINY_MAX = 32, NUM_TINY_MAX = 16, NUM_TINY_FLOP_MAX = 128;
 constexpr u32 SYM_HASH_FMAX = 64u << NHASH, NUM_HASH_ZMAX = 32u << NHASH;
 constexpr u32 MERGE_K = 8, MERGE_FLOP_MAX = 128;
@@ -64,12 +64,12 @@ __host__ __device__ __forceinline__ int sym_bin_of(u32 f, u32 alen = 0xFFFFFFFFu
 __host__ __device__ __forceinline__ int num_bin_of(u32 z, u32 f, u32 alen = 0xFFFFFFFFu, int mode = 0) {
   if ((mode & MODE_MERGE) && alen <= MERGE_K && f <= MERGE_FLOP_MAX) return MERGE_BIN;
   if (z <= NUM_TINY_MAX && f <= NUM_TINY_FLOP_MAX) return 0;
-  if ((mode & MODE_ESC) && z > ESC_ZMIN && 2ull * z >= f && f != 0xFFFFFFFFu) {  // f saturates at u32::MAX
+  if ((mode & MODE_ESC) && z > ESC_ZMIN && 2ull * z >= f && f != 0xFFFFFFFFu && alen <= f) {  // f saturates at u32::MAX
     if (f <= 1024) return ESC_BIN0;
     if (f <= 2048) return ESC_BIN0 + 1;
     if (f <= 4096) return ESC_BIN0 + 2;
     if (f <= 8192) return ESC_BIN0 + 3;
-    return ESC_HEAVY_BIN;
+    if (mode & MODE_ESC_HEAVY) return ESC_HEAVY_BIN;
   }
   if (z > NUM_HASH_ZMAX) return HEAVY_BIN;
   const int b = ceil_log2_u32(z < 1 ? 1 : z) - 5;  // smallest b with z <= 32 << b
@@ -207,7 +207,8 @@ struct spam_handle {
   u64 scan_ws_cap;   // in u64 words
   cudaMemPool_t pool;  // private stream-ordered pool: freed blocks stay with this handle, not with the process
   bool use_lanes;      // SPAM_LANES=0 in the environment at create time keeps every bin on the main stream
-  bool use_esc;        // SPAM_ESC=0 at create time: hash bins only (A/B measurements of the bucket-sort bins)
+  int use_esc;         // SPAM_ESC at create time: 0 = hash bins only, 1 = bucket-sort bins up to 8192 products (default), 2 = also the column-range kernel for longer rows
+  struct CommState* comm;  // comm.cu: NCCL communicator + peer-mapped gather buffers (spam_comm_init), or null
 };
 
 static inline size_t dtype_size(int dt) { return (dt == SPAM_F32 || dt == SPAM_I32) ? 4 : 8; }
@@ -298,6 +299,7 @@ int scan_u32_to_u64(spam_handle* h, const u32* in, u64* out, u64 n, ull* d_total
 // spgemm.cu
 int spgemm_symbolic_dev(spam_handle* h, const spam_dcsr* a, const spam_dcsr* b, SpgemmPending** out);
 int spgemm_numeric_dev(spam_handle* h, SpgemmPending* p, spam_dcsr** c);
+int spgemm_numeric_into(spam_handle* h, SpgemmPending* p, const u64* c_ptr, u32* c_idx, void* c_val);
 void spgemm_pending_free(spam_handle* h, SpgemmPending* p);
 u64 spgemm_pending_nnz(const SpgemmPending* p);
 const u64* spgemm_pending_cptr(const SpgemmPending* p);

@@ -80,43 +80,38 @@ __device__ __forceinline__ u32 esc_bucket2(const u32* cnt, u32 n, u32 k, u32 kmi
   return start + sub;
 }
 
-// Steps B-F on n <= 8 * TT staged products in skey/sval[0, n).  `cnt` and `sub` must be zero and the staging
-// complete (block barrier) on entry.  Writes the distinct entries, sorted by column, to c_col/c_val[cbase ...) —
-// at most `room` of them — and returns their number through `uniq`.  Returns false (block-uniform, nothing
-// useful written) when some sub-bucket is still longer than ESC_BUCKET_MAX.
+// Steps B-F on the products the block's threads hold in registers: thread rt has k[i], v[i] for the bits i set in
+// vmask; n = number of products in the block.  `cnt` and `sub` must be zero on entry; skey / sval are scratch
+// (free to overwrite once every thread has its products: the caller's barrier, or the first one in here).
+// Writes the distinct entries, sorted by column, to c_col/c_val[cbase ...) — at most `room` of them — and
+// returns their number through `uniq`.  Returns false (block-uniform, nothing useful written) when some
+// sub-bucket is still longer than ESC_BUCKET_MAX.
 template <class V, int TT>
-__device__ __forceinline__ bool esc_finish(u32* skey, V* sval, u32* cnt, u32* sub, u32* s_warp, u32* s_mx, u32 n,
-                                           u32 kmin, int bshift, int rt, u32* __restrict__ c_col,
-                                           V* __restrict__ c_val, u64 cbase, u32 room, u32& uniq) {
+__device__ __forceinline__ bool esc_core(u32 (&k)[ESC_ITEMS], V (&v)[ESC_ITEMS], u32 vmask, u32* skey, V* sval, u32* cnt,
+                                         u32* sub, u32* s_warp, u32* s_mx, u32 n, u32 kmin, int bshift, int rt,
+                                         u32* __restrict__ c_col, V* __restrict__ c_val, u64 cbase, u32 room,
+                                         u32& uniq) {
   constexpr int NB = TT * ESC_ITEMS;
-  u32 k[ESC_ITEMS];
-  V v[ESC_ITEMS];
 #pragma unroll
-  for (int i = 0; i < ESC_ITEMS; ++i) {
-    const u32 p = rt + i * TT;
-    k[i] = kmin; v[i] = Num<V>::zero();
-    if (p < n) {
-      k[i] = skey[p]; v[i] = sval[p];
-      atomicAdd(&cnt[(k[i] - kmin) >> bshift], 1u);
-    }
-  }
+  for (int i = 0; i < ESC_ITEMS; ++i)
+    if (vmask >> i & 1) atomicAdd(&cnt[(k[i] - kmin) >> bshift], 1u);
   __syncthreads();
   esc_scan8<TT>(cnt, rt, s_warp, s_mx);  // cnt[b] = first position of level-1 bucket b
   if (*s_mx > ESC_SPLIT_MIN) {  // some bucket is crowded: second level
 #pragma unroll
     for (int i = 0; i < ESC_ITEMS; ++i)
-      if (rt + i * TT < n) atomicAdd(&sub[esc_bucket2<NB>(cnt, n, k[i], kmin, bshift)], 1u);
+      if (vmask >> i & 1) atomicAdd(&sub[esc_bucket2<NB>(cnt, n, k[i], kmin, bshift)], 1u);
   } else {
 #pragma unroll
     for (int i = 0; i < ESC_ITEMS; ++i)
-      if (rt + i * TT < n) atomicAdd(&sub[cnt[(k[i] - kmin) >> bshift]], 1u);
+      if (vmask >> i & 1) atomicAdd(&sub[cnt[(k[i] - kmin) >> bshift]], 1u);
   }
   __syncthreads();
   esc_scan8<TT>(sub, rt, s_warp, s_mx);  // sub[j] = first position of level-2 bucket j
   if (*s_mx > ESC_BUCKET_MAX) { uniq = 0; return false; }
 #pragma unroll
   for (int i = 0; i < ESC_ITEMS; ++i) {
-    if (rt + i * TT < n) {
+    if (vmask >> i & 1) {
       const u32 pos = atomicAdd(&sub[esc_bucket2<NB>(cnt, n, k[i], kmin, bshift)], 1u);  // afterwards sub[j] = end of j
       skey[pos] = k[i]; sval[pos] = v[i];
     }
@@ -161,6 +156,24 @@ __device__ __forceinline__ bool esc_finish(u32* skey, V* sval, u32* cnt, u32* su
   return true;
 }
 
+// the same on n products staged in skey/sval[0, n) (staging complete: block barrier before the call)
+template <class V, int TT>
+__device__ __forceinline__ bool esc_finish(u32* skey, V* sval, u32* cnt, u32* sub, u32* s_warp, u32* s_mx, u32 n,
+                                           u32 kmin, int bshift, int rt, u32* __restrict__ c_col,
+                                           V* __restrict__ c_val, u64 cbase, u32 room, u32& uniq) {
+  u32 k[ESC_ITEMS];
+  V v[ESC_ITEMS];
+  u32 vmask = 0;
+#pragma unroll
+  for (int i = 0; i < ESC_ITEMS; ++i) {
+    const u32 p = rt + i * TT;
+    k[i] = kmin; v[i] = Num<V>::zero();
+    if (p < n) { k[i] = skey[p]; v[i] = sval[p]; vmask |= 1u << i; }
+  }
+  __syncthreads();  // everybody holds its products: the staging arrays may be overwritten
+  return esc_core<V, TT>(k, v, vmask, skey, sval, cnt, sub, s_warp, s_mx, n, kmin, bshift, rt, c_col, c_val, cbase, room, uniq);
+}
+
 __device__ __forceinline__ void esc_give_back(Counters* cnt_dev, u32* fb_list, u32 row) {
   const u32 i = atomicAdd(&cnt_dev->fb_list_n, 1u);
   fb_list[i] = row;
@@ -168,116 +181,90 @@ __device__ __forceinline__ void esc_give_back(Counters* cnt_dev, u32* fb_list, u
 }
 
 template <class V, int NW>
-constexpr size_t num_esc_smem() { return (size_t)32 * NW * ESC_ITEMS * (sizeof(V) + 4 + 4 + 4) + (size_t)(NW * ESC_ITEMS + 1) * 4; }
+constexpr size_t num_esc_smem() { return (size_t)32 * NW * ESC_ITEMS * (sizeof(V) + 4 + 4 + 4); }
 
-// One block per row, products <= 8 * 32 * NW.
+// One block per row: products <= FCAP = 8 * 32 * NW and entries of the A row <= products (no empty B rows among
+// them, or few: the binning guarantees len(A row) <= products).
+// Expansion with every load of the row in flight at once: the B row lengths of ALL entries of the A row are
+// fetched in one step (a_col -> b_ptr, two dependent round trips for the whole row), scanned, and every thread
+// then owns 8 CONSECUTIVE products, finds the entry of its first product by binary search in the scanned lengths
+// (shared memory) and walks on — one more round trip (b_col, b_val) for the whole row.  The first version walked
+// the A row 32 entries at a time with all warps in lock step: ~3 dependent DRAM round trips per 32 entries,
+// 12-25 us per row, nothing else resident on the SM to hide them.
 template <class V, int NW>
 __global__ void __launch_bounds__(32 * NW)
 k_num_esc(u32 n, const u32* __restrict__ perm, const u64* __restrict__ a_ptr, const u32* __restrict__ a_col,
           const V* __restrict__ a_val, const u64* __restrict__ b_ptr, const u32* __restrict__ b_col,
           const V* __restrict__ b_val, const u64* __restrict__ c_ptr, u32* __restrict__ c_col, V* __restrict__ c_val,
           Counters* cnt_dev, u32* fb_list) {
-  constexpr int TT = 32 * NW, FCAP = TT * ESC_ITEMS, NB = FCAP, MAXCH = FCAP / 32;
+  constexpr int TT = 32 * NW, FCAP = TT * ESC_ITEMS, NB = FCAP;
   extern __shared__ __align__(16) unsigned char sm_esc[];
   V* sval = reinterpret_cast<V*>(sm_esc);        // [FCAP]
   u32* skey = reinterpret_cast<u32*>(sval + FCAP);  // [FCAP]
   u32* cnt = skey + FCAP;                        // [NB]
   u32* sub = cnt + NB;                           // [FCAP]
-  u32* s_cbase = sub + FCAP;                     // [MAXCH + 1] first product of every 32-entry chunk of the A row
+  u32* s_base = skey;                            // until the scatter: scanned B row lengths of the A row's entries
   __shared__ u32 s_warp[32];
   __shared__ u32 s_kmin, s_kmax, s_mx;
-  const int rt = threadIdx.x, lane = rt & 31, wid = rt >> 5;
+  const int rt = threadIdx.x, lane = rt & 31;
   if (blockIdx.x >= n) return;
   const u32 row = perm ? perm[blockIdx.x] : blockIdx.x;
   const u64 c0 = c_ptr[row];
   const u32 z = (u32)(c_ptr[row + 1] - c0);
   if (z == 0) return;
+  const u64 lo = a_ptr[row];
+  const u32 alen = (u32)min((u64)FCAP, a_ptr[row + 1] - lo);
 #pragma unroll
-  for (int i = 0; i < ESC_ITEMS; ++i) { cnt[rt + i * TT] = 0; sub[rt + i * TT] = 0; }
+  for (int i = 0; i < ESC_ITEMS; ++i) {
+    const u32 e = rt + i * TT;
+    u32 len = 0;
+    if (e < alen) { const u32 kk = a_col[lo + e]; len = (u32)(b_ptr[kk + 1] - b_ptr[kk]); }
+    s_base[e] = len;
+    cnt[e] = 0; sub[e] = 0;
+  }
   if (rt == 0) { s_kmin = 0xFFFFFFFFu; s_kmax = 0; }
-  // A: expand in the reference's product order.  The A row is cut into chunks of 32 entries; every warp takes
-  // whole chunks (its dependent load chain a_col -> b_ptr -> b_col runs beside the other warps' chains instead
-  // of in lock step with them), so each chunk's first product position is needed first: one pass over the
-  // chunks' product counts, scanned by warp 0.  A row with more entries than products (empty B rows) can have
-  // more chunks than MAXCH: those rows take the lock-step enumeration.
-  const u64 lo = a_ptr[row], hi = a_ptr[row + 1];
-  const u32 nchunks = (u32)((hi - lo + 31) / 32);
-  u32 kmin = 0xFFFFFFFFu, kmax = 0, nprod;
-  if (nchunks <= (u32)MAXCH && nchunks >= (u32)NW) {
-    for (u32 ci = wid; ci < nchunks; ci += NW) {
-      const AChunk<u32> c = load_chunk<u32, false, true>(lo + 32ull * ci, hi, lane, a_col, nullptr, b_ptr);
-      if (lane == 0) s_cbase[ci] = c.total;
+  __syncthreads();
+  u32 nprod = esc_scan8<TT>(s_base, rt, s_warp, &s_mx);  // s_base[e] = first product of entry e
+  if (nprod > (u32)FCAP) nprod = FCAP;
+  // my products: [8 rt, 8 rt + 8)
+  u32 k[ESC_ITEMS];
+  V v[ESC_ITEMS];
+  u32 vmask = 0, kmin = 0xFFFFFFFFu, kmax = 0;
+  const u32 p0 = (u32)rt * ESC_ITEMS;
+  if (p0 < nprod) {
+    u32 l = 0, h = alen - 1;  // last entry e with s_base[e] <= p0
+    while (l < h) {
+      const u32 mid = (l + h + 1) >> 1;
+      if (s_base[mid] <= p0) l = mid; else h = mid - 1;
     }
-    __syncthreads();
-    if (wid == 0) {
-      u32 carry = 0;
-      for (u32 t0 = 0; t0 < nchunks; t0 += 32) {
-        const u32 v = t0 + lane < nchunks ? s_cbase[t0 + lane] : 0u;
-        const u32 x = warp_incl_scan_u32(v, lane);
-        if (t0 + lane < nchunks) s_cbase[t0 + lane] = carry + x - v;
-        carry += __shfl_sync(FULL, x, 31);
-      }
-      if (lane == 0) s_cbase[nchunks] = carry;
-    }
-    __syncthreads();
-    nprod = s_cbase[nchunks];
-    for (u32 ci = wid; ci < nchunks; ci += NW) {
-      const AChunk<V> c = load_chunk<V, true, true>(lo + 32ull * ci, hi, lane, a_col, a_val, b_ptr);
-      const u32 base = s_cbase[ci];
-      // two batches in flight: the loads of batch p0 + 32 are issued before batch p0 is stored
-      u64 addr;
-      V av;
-      u32 nkey = 0;
-      V nprodv = Num<V>::zero();
-      if (c.total) {
-        locate<V, true>(c, lane, addr, av);
-        if ((u32)lane < c.total) { nkey = b_col[addr]; nprodv = Num<V>::mul(av, b_val[addr]); }
-      }
-      for (u32 p0 = 0; p0 < c.total; p0 += 32) {
-        const u32 key = nkey;
-        const V pv = nprodv;
-        if (p0 + 32 < c.total) {
-          locate<V, true>(c, p0 + 32 + lane, addr, av);
-          if (p0 + 32 + lane < c.total) { nkey = b_col[addr]; nprodv = Num<V>::mul(av, b_val[addr]); }
+    u32 e = l;
+    u32 kk = a_col[lo + e];
+    u64 bl = b_ptr[kk];
+    V av = a_val[lo + e];
+    u32 ebase = s_base[e];
+    u32 enext = e + 1 < alen ? s_base[e + 1] : nprod;
+#pragma unroll
+    for (int i = 0; i < ESC_ITEMS; ++i) {
+      const u32 p = p0 + i;
+      k[i] = 0; v[i] = Num<V>::zero();
+      if (p < nprod) {
+        while (p >= enext) {  // next entry with a non-empty B row
+          ++e;
+          ebase = enext;
+          enext = e + 1 < alen ? s_base[e + 1] : nprod;
+          if (p < enext) { kk = a_col[lo + e]; bl = b_ptr[kk]; av = a_val[lo + e]; }
         }
-        const u32 dst = base + p0 + lane;
-        if (p0 + lane < c.total && dst < (u32)FCAP) {
-          skey[dst] = key; sval[dst] = pv;
-          kmin = min(kmin, key);
-          kmax = max(kmax, key);
-        }
+        const u64 addr = bl + (p - ebase);
+        k[i] = b_col[addr];
+        v[i] = Num<V>::mul(av, b_val[addr]);
+        vmask |= 1u << i;
+        kmin = min(kmin, k[i]);
+        kmax = max(kmax, k[i]);
       }
     }
   } else {
-    u32 base = 0;
-    for (u64 ec = lo; ec < hi; ec += 32) {
-      const AChunk<V> c = load_chunk<V, true, true>(ec, hi, lane, a_col, a_val, b_ptr);
-      u64 addr;
-      V av;
-      u32 nkey = 0;
-      V nprodv = Num<V>::zero();
-      u32 p0 = 32u * wid;
-      if (p0 < c.total) {
-        locate<V, true>(c, p0 + lane, addr, av);
-        if (p0 + lane < c.total) { nkey = b_col[addr]; nprodv = Num<V>::mul(av, b_val[addr]); }
-      }
-      for (; p0 < c.total; p0 += TT) {
-        const u32 key = nkey;
-        const V pv = nprodv;
-        if (p0 + TT < c.total) {  // next batch's loads in flight while this one is stored
-          locate<V, true>(c, p0 + TT + lane, addr, av);
-          if (p0 + TT + lane < c.total) { nkey = b_col[addr]; nprodv = Num<V>::mul(av, b_val[addr]); }
-        }
-        const u32 dst = base + p0 + lane;
-        if (p0 + lane < c.total && dst < (u32)FCAP) {
-          skey[dst] = key; sval[dst] = pv;
-          kmin = min(kmin, key);
-          kmax = max(kmax, key);
-        }
-      }
-      base += c.total;
-    }
-    nprod = base;
+#pragma unroll
+    for (int i = 0; i < ESC_ITEMS; ++i) { k[i] = 0; v[i] = Num<V>::zero(); }
   }
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) {
@@ -285,15 +272,14 @@ k_num_esc(u32 n, const u32* __restrict__ perm, const u64* __restrict__ a_ptr, co
     kmax = max(kmax, __shfl_xor_sync(FULL, kmax, d));
   }
   if (lane == 0 && kmin <= kmax) { atomicMin(&s_kmin, kmin); atomicMax(&s_kmax, kmax); }
-  __syncthreads();
+  __syncthreads();  // also: everybody is done with s_base before the scatter reuses skey
   kmin = s_kmin;
   const u32 range = s_kmax - kmin;
   const int rbits = range ? 32 - __clz(range) : 0;
   constexpr int LGNB = 31 - __builtin_clz((unsigned)NB);
   const int bshift = rbits > LGNB ? rbits - LGNB : 0;
-  if (nprod > (u32)FCAP) nprod = FCAP;
   u32 uniq;
-  if (!esc_finish<V, TT>(skey, sval, cnt, sub, s_warp, &s_mx, nprod, kmin, bshift, rt, c_col, c_val, c0, z, uniq)) {
+  if (!esc_core<V, TT>(k, v, vmask, skey, sval, cnt, sub, s_warp, &s_mx, nprod, kmin, bshift, rt, c_col, c_val, c0, z, uniq)) {
     if (rt == 0) esc_give_back(cnt_dev, fb_list, row);
   }
 }

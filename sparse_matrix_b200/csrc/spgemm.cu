@@ -751,7 +751,7 @@ int spgemm_symbolic_dev(spam_handle* h, const spam_dcsr* a, const spam_dcsr* b, 
   const int merge_ok = (b->rows_sorted == 1 && b->nnz < 0xFFFFFFFFull) ? 1 : 0;
   SpgemmPending* p = new SpgemmPending();
   p->a = a; p->b = b; p->d_flop = nullptr; p->d_row_nnz = nullptr; p->d_cptr = nullptr; p->nnz = 0; p->max_nnz = 0;
-  const int mode = (merge_ok ? MODE_MERGE : 0) | (h->use_esc ? MODE_ESC : 0);
+  const int mode = (merge_ok ? MODE_MERGE : 0) | (h->use_esc ? MODE_ESC : 0) | (h->use_esc == 2 ? MODE_ESC_HEAVY : 0);
   p->max_alen = 0; p->merge_ok = merge_ok; p->mode = mode;
   *out = p;
 #define FAIL_FREE(expr) do { int _s = (expr); if (_s != SPAM_OK) { spgemm_pending_free(h, p); *out = nullptr; return _s; } } while (0)
@@ -1067,6 +1067,26 @@ int numeric_typed(spam_handle* h, SpgemmPending* p, spam_dcsr* c) {
 
 }  // namespace
 
+namespace {
+int numeric_dispatch(spam_handle* h, SpgemmPending* p, spam_dcsr* c) {
+  switch (c->dtype) {
+    case SPAM_F32: return numeric_typed<float>(h, p, c);
+    case SPAM_F64: return numeric_typed<double>(h, p, c);
+    case SPAM_I32: return numeric_typed<int32_t>(h, p, c);
+    case SPAM_I64: return numeric_typed<int64_t>(h, p, c);
+    default: return spam_fail(h, SPAM_EINVAL, "bad dtype");
+  }
+}
+int numeric_timing(spam_handle* h) {
+  if (!h->timing) return SPAM_OK;
+  cudaError_t e = cudaEventRecord(h->ev[4], h->stream);
+  if (e != cudaSuccess) return spam_fail(h, SPAM_ECUDA, "cudaEventRecord", e);
+  h->ev_pending[h->ev_cur] = true;
+  timing_harvest(h, h->ev_cur ^ 1);  // previous product: complete since this product's symbolic sync
+  return SPAM_OK;
+}
+}  // namespace
+
 // Phase 2: allocate C (exact nnz, like Vec::with_capacity(nnz), mul_hash.rs:119), numeric per bin.
 // Consumes the pending state.  On success *cout owns col_idx/val and takes over row_ptr.
 int spgemm_numeric_dev(spam_handle* h, SpgemmPending* p, spam_dcsr** cout) {
@@ -1076,23 +1096,8 @@ int spgemm_numeric_dev(spam_handle* h, SpgemmPending* p, spam_dcsr** cout) {
   c->ptr = p->d_cptr; c->idx = nullptr; c->val = nullptr; c->owning = true; c->rows_sorted = -1; c->max_row_len = 0;  // stats are taken lazily if C becomes a right-hand side
   int st = dev_alloc_t(h, &c->idx, p->nnz ? p->nnz : 1);
   if (st == SPAM_OK) st = dev_alloc(h, &c->val, (p->nnz ? p->nnz : 1) * dtype_size(c->dtype));
-  if (st == SPAM_OK && p->nnz) {
-    switch (c->dtype) {
-      case SPAM_F32: st = numeric_typed<float>(h, p, c); break;
-      case SPAM_F64: st = numeric_typed<double>(h, p, c); break;
-      case SPAM_I32: st = numeric_typed<int32_t>(h, p, c); break;
-      case SPAM_I64: st = numeric_typed<int64_t>(h, p, c); break;
-      default: st = spam_fail(h, SPAM_EINVAL, "bad dtype");
-    }
-  }
-  if (st == SPAM_OK && h->timing) {
-    cudaError_t e = cudaEventRecord(h->ev[4], h->stream);
-    if (e != cudaSuccess) st = spam_fail(h, SPAM_ECUDA, "cudaEventRecord", e);
-    else {
-      h->ev_pending[h->ev_cur] = true;
-      timing_harvest(h, h->ev_cur ^ 1);  // previous product: complete since this product's symbolic sync
-    }
-  }
+  if (st == SPAM_OK && p->nnz) st = numeric_dispatch(h, p, c);
+  if (st == SPAM_OK) st = numeric_timing(h);
   if (st != SPAM_OK) {
     dev_free(h, c->idx); dev_free(h, c->val);
     delete c;
@@ -1103,4 +1108,19 @@ int spgemm_numeric_dev(spam_handle* h, SpgemmPending* p, spam_dcsr** cout) {
   spgemm_pending_free(h, p);
   *cout = c;
   return SPAM_OK;
+}
+
+// Phase 2 into arrays the caller owns: c_ptr has rows + 1 entries whose VALUES are positions in c_idx / c_val
+// (a rank of a row-sharded product passes its offset-fixed row_ptr and the arrays of the whole C, so its rows
+// land where the gathered result wants them: disjoint slices of one output, mul_hash.rs:121-128).  Consumes the
+// pending state.
+int spgemm_numeric_into(spam_handle* h, SpgemmPending* p, const u64* c_ptr, u32* c_idx, void* c_val) {
+  spam_dcsr c = {};
+  c.dtype = p->a->dtype; c.rows = p->a->rows; c.cols = p->b->cols; c.nnz = p->nnz;
+  c.ptr = const_cast<u64*>(c_ptr); c.idx = c_idx; c.val = c_val; c.owning = false; c.rows_sorted = -1;
+  int st = SPAM_OK;
+  if (p->nnz) st = numeric_dispatch(h, p, &c);
+  if (st == SPAM_OK) st = numeric_timing(h);
+  spgemm_pending_free(h, p);
+  return st;
 }

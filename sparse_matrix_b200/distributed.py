@@ -20,6 +20,16 @@ import torch
 import torch.distributed as dist
 
 
+def init_comm(handle) -> None:
+    """Collective.  Gives `handle` its in-library communicator (spam_comm_init): rank 0 makes the 128-byte id,
+    torch.distributed (any backend) carries it to the other ranks — the one thing the library cannot do itself."""
+    from . import csr
+    rank, world = dist.get_rank(), dist.get_world_size()
+    uid = [csr.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    handle.comm_init(uid[0], rank, world)
+
+
 def partition_rows_from_flops(flop_per_row: np.ndarray, parts: int) -> np.ndarray:
     """rows_to_threads partition (mul_hash.rs:51-62) on the host: used by the CPU tests to check the
     device routine spam_rows_to_parts, and to split work when the flop vector is already on the host."""

@@ -112,7 +112,8 @@ def test_every_bin_is_exercised(oracle, handle, dtype):
     c = gpu_mul(a, b, handle)
     st = handle.stats()
     assert all(x > 0 for x in st["sym_bin_rows"][:10]), st["sym_bin_rows"]
-    assert all(x > 0 for x in st["num_bin_rows"][:4]) and all(x > 0 for x in st["num_bin_rows"][11:16]), st["num_bin_rows"]
+    assert all(x > 0 for x in st["num_bin_rows"][:4]) and all(x > 0 for x in st["num_bin_rows"][11:15]), st["num_bin_rows"]
+    assert st["num_bin_rows"][HEAVY] > 0      # more than 8192 products: global-table bin (SPAM_ESC=2: bin 15)
     off, idx, val = check_against_oracle(oracle, a, b, c)
     assert st["nnz_c"] == len(idx) and st["flops"] == G.spgemm_counts(a, b)[0] and st["kernel_launches"] >= 10
     assert st["fallbacks"][3] == 0          # uniform columns: no crowded bucket
@@ -497,6 +498,46 @@ def test_rows_to_parts_and_row_slices(oracle, handle):
         # block products accumulate in another (atomic) order: same tolerance as against the oracle
         assert np.all(np.abs(np.concatenate(vals) - full.vals) <= 2 * TOL[np.dtype(np.float64)] * sabs)
     dA.free()
+
+
+def test_gathered_product_on_one_rank(oracle):
+    """spam_spgemm_gathered with a one-rank communicator: the sub-block pipeline (row views of A, offset-fixed row_ptr,
+    numeric kernels writing into the gather buffers) without peers.  The multi-rank exchange itself is checked by
+    tests/multi_gpu_check.py under torchrun and by bench.py's gathered_parity at every N > 1."""
+    h = S.Handle(0)
+    try:
+        h.comm_init(S.comm_unique_id(), 0, 1)
+        assert h.comm_info() == {"rank": 0, "world": 1, "peer_mapped": True}
+        rng = np.random.default_rng(12)
+        mats = [G.rmat(13, 12), G.poisson2d(80), random_csr(rng, 700, 700, rng.integers(0, 40, size=700), sorted_rows=False),
+                random_csr(rng, 3, 3, 2, dtype=np.int64)]
+        for m in mats:
+            dA = S.DeviceCsr.upload(as_csr_matrix(m, is_sorted=False), h)
+            for nsub, mode in ((1, 0), (3, 0), (16, 1)):
+                g = dA.matmul_gathered(dA, 0, m[0], nsub=nsub, mode=mode)
+                c = g.download()
+                g.free()
+                check_against_oracle(oracle, m, m, c)
+            # a second, smaller product reuses the buffers; a block that does not tile the matrix is refused
+            with pytest.raises(S.SpamError):
+                dA.matmul_gathered(dA, 1, m[0], nsub=1)
+            dA.free()
+        # y = A x through the gathered entry point
+        import ctypes as C_
+        m = mats[0]
+        dA = S.DeviceCsr.upload(as_csr_matrix(m), h)
+        x = rng.uniform(-1, 1, size=m[1])
+        want = oracle.spmv(m[0], m[1], m[2], m[3], m[4], x)
+        dx = S.DeviceCsr.upload(S.CsrMatrix(1, m[1], x, np.arange(m[1]), [0, m[1]]), h)   # a device buffer holding x
+        dy = S.DeviceCsr.upload(S.CsrMatrix(1, m[0], np.zeros(m[0]), np.arange(m[0]), [0, m[0]]), h)
+        dA.spmv_gathered(dx.info()["d_val"], dy.info()["d_val"], [m[0]])
+        y = dy.download().vals
+        sabs = oracle.spmv(m[0], m[1], m[2], m[3], np.abs(m[4]), np.abs(x))
+        assert np.all(np.abs(y - want) <= 1e-12 * sabs)
+        for d in (dA, dx, dy):
+            d.free()
+    finally:
+        h.close()
 
 
 def test_host_path_uploads_only_the_referenced_band_of_b(oracle, handle):
