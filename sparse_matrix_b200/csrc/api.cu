@@ -147,6 +147,7 @@ int set_device(spam_handle* h) {
 
 void free_dcsr(spam_handle* h, spam_dcsr* m) {
   if (!m) return;
+  if (m->sorted_copy) { free_dcsr(h, m->sorted_copy); m->sorted_copy = nullptr; }
   if (m->owning) {
     dev_free(h, m->ptr);
     dev_free(h, m->idx);
@@ -172,6 +173,9 @@ void drop_dok_state(spam_handle* h) {
   h->dok_pending = nullptr;
 }
 
+}  // namespace
+void free_dcsr_tree(spam_handle* h, spam_dcsr* m) { free_dcsr(h, m); }
+namespace {
 int valid_dtype(int dt) { return dt == SPAM_F32 || dt == SPAM_F64 || dt == SPAM_I32 || dt == SPAM_I64; }
 
 }  // namespace
@@ -247,8 +251,10 @@ int spam_cuda_create(spam_handle** out, int device) {
   {
     const char* e = getenv("SPAM_LANES");  // read once: 0 keeps every row bin on the main stream
     h->use_lanes = !(e && e[0] == '0');
+    e = getenv("SPAM_SORT_B");
+    h->sort_b = !(e && e[0] == '0');
     e = getenv("SPAM_ESC");
-    h->use_esc = e ? (e[0] == '0' ? 0 : (e[0] == '2' ? 2 : 1)) : 1;
+    h->use_esc = e ? (e[0] == '2' ? 2 : (e[0] == '1' ? 1 : 0)) : 0;
   }
   h->d_cnt = nullptr; h->h_cnt = nullptr; h->own_stream = nullptr; h->stream = nullptr;
   h->stats = spam_stats{};

@@ -173,6 +173,8 @@ struct spam_dcsr {
   u64 max_row_len;  // cached with rows_sorted: longest row (picks DIRECT vs FLAT product enumeration)
   int invalid;      // cached with rows_sorted: 0 = row_ptr monotone from 0 to nnz and every column < cols
                     // (invariants 3, 4, 5, 7 of spam_csr/src/lib.rs:47-81); bit0 row_ptr, bit1 column range
+  spam_dcsr* sorted_copy;  // rows_sorted == 0: the same matrix with every row in column order, made on first need
+                           // (sorted_rows_of) and owned by this object
 };
 
 struct SpgemmPending;  // state between the two host phases
@@ -207,7 +209,9 @@ struct spam_handle {
   u64 scan_ws_cap;   // in u64 words
   cudaMemPool_t pool;  // private stream-ordered pool: freed blocks stay with this handle, not with the process
   bool use_lanes;      // SPAM_LANES=0 in the environment at create time keeps every bin on the main stream
-  int use_esc;         // SPAM_ESC at create time: 0 = hash bins only, 1 = bucket-sort bins up to 8192 products (default), 2 = also the column-range kernel for longer rows
+  int use_esc;         // SPAM_ESC at create time: 0 = hash bins only (default: measured faster on B200), 1 = bucket-sort
+                       // bins for non-compressing rows up to 8192 products, 2 = also the column-range kernel for longer rows
+  bool sort_b;         // SPAM_SORT_B=0 at create time: never multiply by a sorted copy of an unsorted B (tests of the hash bins)
   struct CommState* comm;  // comm.cu: NCCL communicator + peer-mapped gather buffers (spam_comm_init), or null
 };
 
@@ -295,7 +299,7 @@ void finish_timing(spam_handle* h);                 // wait for the current set,
 
 // ---- entry points implemented across the .cu files ---------------------------------------------
 // scan.cu : exclusive scan of u32 counts into u64 offsets (out has n+1 entries), decoupled look-back
-int scan_u32_to_u64(spam_handle* h, const u32* in, u64* out, u64 n, ull* d_total);
+int scan_u32_to_u64(spam_handle* h, const u32* in, u64* out, u64 n, ull* d_total, u32* d_max = nullptr);
 // spgemm.cu
 int spgemm_symbolic_dev(spam_handle* h, const spam_dcsr* a, const spam_dcsr* b, SpgemmPending** out);
 int spgemm_numeric_dev(spam_handle* h, SpgemmPending* p, spam_dcsr** c);
@@ -312,6 +316,9 @@ int spmv_dev(spam_handle* h, const spam_dcsr* a, const void* d_x, void* d_y);
 int dok_to_csr_dev(spam_handle* h, int dtype, u64 rows, u64 cols, u64 n, const u64* d_r, const u64* d_c,
                    const void* d_v, spam_dcsr** out);
 int transpose_dev(spam_handle* h, const spam_dcsr* a, spam_dcsr** out);
+// m itself when its rows are sorted by column, else a cached copy with sorted rows (two stable transposes)
+int sorted_rows_of(spam_handle* h, const spam_dcsr* m, const spam_dcsr** view);
+void free_dcsr_tree(spam_handle* h, spam_dcsr* m);
 // ewise.cu : C = A + B (op 0) / A - B (op 1)
 int ewise_dev(spam_handle* h, int op, const spam_dcsr* a, const spam_dcsr* b, spam_dcsr** out);
 // convert.cu : index width conversion at the host boundary

@@ -153,51 +153,97 @@ __global__ void __launch_bounds__(256) k_emit(u64 n, int cbits, const u64* __res
 // ---- counting path ----------------------------------------------------------------------------------
 constexpr u32 SEG_MAX = 32;  // longest row / column segment the counting paths sort with one thread
 
+// rank of every triplet inside its row = the row counter's value when the triplet arrived (an atomic WITH return):
+// the scatter pass then needs no atomics.  Ranks saturate at 255: a row that long takes the radix path anyway.
 __global__ void __launch_bounds__(256) k_dok_hist(u64 n, u64 rows, u64 cols, const u64* __restrict__ r,
-                                                  const u64* __restrict__ c, u32* __restrict__ raw_cnt, Counters* cnt) {
+                                                  const u64* __restrict__ c, u32* __restrict__ raw_cnt,
+                                                  unsigned char* __restrict__ rank8, Counters* cnt) {
+  constexpr int U = 4;  // independent atomics in flight per thread
   const u64 stride = (u64)gridDim.x * blockDim.x;
   bool bad = false;
-  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const u64 ri = r[i], ci = c[i];
-    if (ri < rows && ci < cols) atomicAdd(&raw_cnt[ri], 1u); else bad = true;  // IndexError (spam_dok lib.rs:168-170)
+  for (u64 i0 = (u64)blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += U * stride) {
+    u64 ri[U];
+    bool ok[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const u64 i = i0 + u * stride;
+      ri[u] = 0; ok[u] = false;
+      if (i < n) {
+        ri[u] = r[i];
+        ok[u] = ri[u] < rows && c[i] < cols;
+        bad = bad || !ok[u];  // IndexError (spam_dok lib.rs:168-170)
+      }
+    }
+    u32 rk[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) rk[u] = ok[u] ? atomicAdd(&raw_cnt[ri[u]], 1u) : 0u;
+#pragma unroll
+    for (int u = 0; u < U; ++u) if (ok[u]) rank8[i0 + u * stride] = (unsigned char)(rk[u] > 255u ? 255u : rk[u]);
   }
   if (bad) atomicOr(&cnt->error, 2u);
 }
 
-// max of a u32 array into cnt->max_flop (zeroed by the caller)
-__global__ void __launch_bounds__(256) k_max_u32(const u32* __restrict__ a, u64 n, Counters* cnt) {
-  u32 mx = 0;
-  const u64 stride = (u64)gridDim.x * blockDim.x;
-  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) mx = max(mx, a[i]);
-#pragma unroll
-  for (int d = 16; d > 0; d >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
-  if ((threadIdx.x & 31) == 0 && mx) atomicMax(&cnt->max_flop, mx);
-}
-
 template <class V>
 __global__ void __launch_bounds__(256) k_dok_scatter(u64 n, const u64* __restrict__ r, const u64* __restrict__ c,
-                                                     const V* __restrict__ v, const u64* __restrict__ seg_ptr,
-                                                     u32* __restrict__ raw_cnt, uint2* __restrict__ ent,
+                                                     const V* __restrict__ v, const unsigned char* __restrict__ rank8,
+                                                     const u64* __restrict__ seg_ptr, uint2* __restrict__ ent,
                                                      V* __restrict__ ev) {
   const u64 stride = (u64)gridDim.x * blockDim.x;
   for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const u64 ri = r[i];
-    const u64 pos = seg_ptr[ri] + (atomicSub(&raw_cnt[ri], 1u) - 1u);  // afterwards raw_cnt is all zero again
+    const u64 pos = seg_ptr[r[i]] + rank8[i];
     ent[pos] = make_uint2((u32)c[i], (u32)i);
     ev[pos] = v[i];
   }
 }
 
+constexpr int SEG_REGS = 16;  // segments up to this length are held in registers (C5: 8-9 triplets per row)
+
 // One thread per row.  DokMatrix::set_element semantics over the row's triplets (spam_dok lib.rs:167-176): per
 // column the LAST write of the stream decides; a zero deletes (num_traits::Zero::is_zero: -0.0 is zero, NaN is not).
+// Output: the row's surviving entries, sorted by column, compacted to the FRONT of its own segment (in place), and
+// their count.  Short segments are loaded once into registers (every load instruction of a warp touches 32
+// different sectors: the nested loops of the first version re-read the segment len times and were bound by the
+// load/store unit).
 template <class V>
-__global__ void __launch_bounds__(128) k_dok_seg(u64 rows, const u64* __restrict__ seg_ptr, const uint2* __restrict__ ent,
-                                                 const V* __restrict__ ev, u32* __restrict__ row_cnt,
-                                                 u32* __restrict__ kept) {
+__global__ void __launch_bounds__(128) k_dok_seg(u64 rows, const u64* __restrict__ seg_ptr, uint2* __restrict__ ent,
+                                                 V* __restrict__ ev, u32* __restrict__ row_cnt) {
   const u64 row = (u64)blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= rows) return;
   const u64 lo = seg_ptr[row];
   const u32 len = (u32)(seg_ptr[row + 1] - lo);  // <= SEG_MAX (checked on the host before this path is taken)
+  if (len == 0) { row_cnt[row] = 0; return; }
+  if (len <= (u32)SEG_REGS) {
+    uint2 e[SEG_REGS];
+    V val[SEG_REGS];
+#pragma unroll
+    for (int a = 0; a < SEG_REGS; ++a) {
+      e[a] = make_uint2(0xFFFFFFFFu, 0u); val[a] = V();
+      if ((u32)a < len) { e[a] = ent[lo + a]; val[a] = ev[lo + a]; }
+    }
+    u32 mask = 0;
+#pragma unroll
+    for (int a = 0; a < SEG_REGS; ++a) {
+      bool last = (u32)a < len;
+#pragma unroll
+      for (int b = 0; b < SEG_REGS; ++b) last = last && !((u32)b < len && e[b].x == e[a].x && e[b].y > e[a].y);
+      if (last && !(val[a] == (V)0)) mask |= 1u << a;
+    }
+    // every survivor's rank by column among the survivors, then store it at the front of the segment
+    u32 rank[SEG_REGS];
+#pragma unroll
+    for (int a = 0; a < SEG_REGS; ++a) {
+      u32 rk = 0;
+#pragma unroll
+      for (int b = 0; b < SEG_REGS; ++b) rk += ((mask >> b) & 1u) && e[b].x < e[a].x ? 1u : 0u;
+      rank[a] = rk;
+    }
+#pragma unroll
+    for (int a = 0; a < SEG_REGS; ++a)
+      if ((mask >> a) & 1u) { ent[lo + rank[a]] = e[a]; ev[lo + rank[a]] = val[a]; }
+    row_cnt[row] = __popc(mask);
+    return;
+  }
+  // 17..32 triplets: the same with the segment re-read from L1
   u32 mask = 0;
   for (u32 a = 0; a < len; ++a) {
     const uint2 ea = ent[lo + a];
@@ -208,47 +254,69 @@ __global__ void __launch_bounds__(128) k_dok_seg(u64 rows, const u64* __restrict
     }
     if (last && !(ev[lo + a] == (V)0)) mask |= 1u << a;
   }
-  row_cnt[row] = __popc(mask);
-  kept[row] = mask;
+  // selection sort of the survivors into the front of the segment: position t takes the t-th smallest survivor
+  // still at or after t (swap, so nothing is lost)
+  const u32 nk = __popc(mask);
+  u32 t = 0;
+  for (u32 a = 0; a < len; ++a) {  // compact survivors to the front (stable)
+    if ((mask >> a) & 1u) {
+      if (a != t) { ent[lo + t] = ent[lo + a]; ev[lo + t] = ev[lo + a]; }
+      ++t;
+    }
+  }
+  for (u32 i = 1; i < nk; ++i) {  // insertion sort by column
+    const uint2 ke = ent[lo + i];
+    const V kv = ev[lo + i];
+    u32 j = i;
+    while (j > 0 && ent[lo + j - 1].x > ke.x) { ent[lo + j] = ent[lo + j - 1]; ev[lo + j] = ev[lo + j - 1]; --j; }
+    ent[lo + j] = ke; ev[lo + j] = kv;
+  }
+  row_cnt[row] = nk;
 }
 
+// copy every row's survivors (front of its segment, already in column order) to their place in C
 template <class V>
 __global__ void __launch_bounds__(128) k_dok_emit(u64 rows, const u64* __restrict__ seg_ptr, const uint2* __restrict__ ent,
-                                                  const V* __restrict__ ev, const u32* __restrict__ kept,
-                                                  const u64* __restrict__ c_ptr, u32* __restrict__ c_idx,
-                                                  V* __restrict__ c_val) {
+                                                  const V* __restrict__ ev, const u64* __restrict__ c_ptr,
+                                                  u32* __restrict__ c_idx, V* __restrict__ c_val) {
   const u64 row = (u64)blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= rows) return;
-  const u32 mask = kept[row];
-  if (!mask) return;
-  const u64 lo = seg_ptr[row], o = c_ptr[row];
-  for (u32 ma = mask; ma; ma &= ma - 1) {
-    const u32 a = __ffs(ma) - 1;
-    const u32 ca = ent[lo + a].x;
-    u32 rank = 0;
-    for (u32 mb = mask; mb; mb &= mb - 1) rank += ent[lo + (__ffs(mb) - 1)].x < ca ? 1u : 0u;
-    c_idx[o + rank] = ca;
-    c_val[o + rank] = ev[lo + a];
-  }
+  const u64 o = c_ptr[row];
+  const u32 nk = (u32)(c_ptr[row + 1] - o);
+  const u64 lo = seg_ptr[row];
+  for (u32 a = 0; a < nk; ++a) { c_idx[o + a] = ent[lo + a].x; c_val[o + a] = ev[lo + a]; }
 }
 
-// ---- transpose, counting path: histogram by column, scan, scatter (row, value) into the column's segment, then
-// one thread per column puts its segment in increasing row order (rows are distinct inside a column) ----
+// ---- transpose, counting path: histogram by column (each entry keeps its arrival rank), scan, scatter (row, value)
+// into the column's segment, then one thread per column puts its segment in increasing row order (rows are
+// distinct inside a column) ----
 __global__ void __launch_bounds__(256) k_tr_hist(u64 nnz, u64 cols, const u32* __restrict__ idx, u32* __restrict__ col_cnt,
-                                                 Counters* cnt) {
+                                                 unsigned char* __restrict__ rank8, Counters* cnt) {
+  constexpr int U = 4;
   const u64 stride = (u64)gridDim.x * blockDim.x;
   bool bad = false;
-  for (u64 e = (u64)blockIdx.x * blockDim.x + threadIdx.x; e < nnz; e += stride) {
-    const u32 c = idx[e];
-    if (c < cols) atomicAdd(&col_cnt[c], 1u); else bad = true;
+  for (u64 e0 = (u64)blockIdx.x * blockDim.x + threadIdx.x; e0 < nnz; e0 += U * stride) {
+    u32 c[U];
+    bool ok[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const u64 e = e0 + u * stride;
+      c[u] = 0; ok[u] = false;
+      if (e < nnz) { c[u] = idx[e]; ok[u] = c[u] < cols; bad = bad || !ok[u]; }
+    }
+    u32 rk[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) rk[u] = ok[u] ? atomicAdd(&col_cnt[c[u]], 1u) : 0u;
+#pragma unroll
+    for (int u = 0; u < U; ++u) if (ok[u]) rank8[e0 + u * stride] = (unsigned char)(rk[u] > 255u ? 255u : rk[u]);
   }
   if (bad) atomicOr(&cnt->error, 2u);
 }
 
 template <class W>
 __global__ void __launch_bounds__(256) k_tr_scatter(u64 m, const u64* __restrict__ ptr, const u32* __restrict__ idx,
-                                                    const W* __restrict__ val, const u64* __restrict__ t_ptr,
-                                                    u32* __restrict__ col_cnt, u32* __restrict__ t_idx,
+                                                    const W* __restrict__ val, const unsigned char* __restrict__ rank8,
+                                                    const u64* __restrict__ t_ptr, u32* __restrict__ t_idx,
                                                     W* __restrict__ t_val) {
   const int lane = threadIdx.x & 31;
   const u64 row = (u64)blockIdx.x * blockDim.x + threadIdx.x;
@@ -257,8 +325,7 @@ __global__ void __launch_bounds__(256) k_tr_scatter(u64 m, const u64* __restrict
   if (valid) { lo = ptr[row]; hi = ptr[row + 1]; }
   if (valid && hi - lo <= 32) {
     for (u64 e = lo; e < hi; ++e) {
-      const u32 c = idx[e];
-      const u64 pos = t_ptr[c] + (atomicSub(&col_cnt[c], 1u) - 1u);
+      const u64 pos = t_ptr[idx[e]] + rank8[e];
       t_idx[pos] = (u32)row; t_val[pos] = val[e];
     }
   }
@@ -269,8 +336,7 @@ __global__ void __launch_bounds__(256) k_tr_scatter(u64 m, const u64* __restrict
     const u64 l = __shfl_sync(0xffffffffu, lo, src), hh = __shfl_sync(0xffffffffu, hi, src);
     const u32 rr = (u32)__shfl_sync(0xffffffffu, row, src);
     for (u64 e = l + lane; e < hh; e += 32) {
-      const u32 c = idx[e];
-      const u64 pos = t_ptr[c] + (atomicSub(&col_cnt[c], 1u) - 1u);
+      const u64 pos = t_ptr[idx[e]] + rank8[e];
       t_idx[pos] = rr; t_val[pos] = val[e];
     }
   }
@@ -282,6 +348,29 @@ __global__ void __launch_bounds__(128) k_tr_segsort(u64 cols, const u64* __restr
   const u64 col = (u64)blockIdx.x * blockDim.x + threadIdx.x;
   if (col >= cols) return;
   const u64 lo = t_ptr[col], hi = t_ptr[col + 1];  // hi - lo <= SEG_MAX
+  const u32 len = (u32)(hi - lo);
+  if (len < 2) return;
+  if (len <= (u32)SEG_REGS) {  // in registers: rank every entry by row (rows are distinct), store at its rank
+    u32 k[SEG_REGS];
+    W v[SEG_REGS];
+#pragma unroll
+    for (int a = 0; a < SEG_REGS; ++a) {
+      k[a] = 0xFFFFFFFFu; v[a] = W();
+      if ((u32)a < len) { k[a] = t_idx[lo + a]; v[a] = t_val[lo + a]; }
+    }
+    bool sorted = true;
+#pragma unroll
+    for (int a = 1; a < SEG_REGS; ++a) sorted = sorted && k[a - 1] <= k[a];  // padding is u32::MAX
+    if (sorted) return;
+#pragma unroll
+    for (int a = 0; a < SEG_REGS; ++a) {
+      u32 rk = 0;
+#pragma unroll
+      for (int b = 0; b < SEG_REGS; ++b) rk += (k[b] < k[a] || (k[b] == k[a] && b < a)) ? 1u : 0u;  // stable
+      if ((u32)a < len) { t_idx[lo + rk] = k[a]; t_val[lo + rk] = v[a]; }
+    }
+    return;
+  }
   for (u64 i = lo + 1; i < hi; ++i) {
     const u32 k = t_idx[i];
     const W v = t_val[i];
@@ -377,19 +466,20 @@ template <class V>
 int dok_typed(spam_handle* h, u64 rows, u64 cols, u64 n, const u64* d_r, const u64* d_c, const V* d_v, spam_dcsr* out) {
   CKS(dev_alloc_t(h, &out->ptr, rows + 1));
   DevGuard g(h);
-  u32 *raw_cnt = nullptr, *kept = nullptr;
+  u32* raw_cnt = nullptr;
+  unsigned char* rank8 = nullptr;
   u64* seg_ptr = nullptr;
   CKS(g.alloc(&raw_cnt, rows));
   CKS(g.alloc(&seg_ptr, rows + 1));
+  CKS(g.alloc(&rank8, n ? n : 1));
   CK(cudaMemsetAsync(h->d_cnt, 0, sizeof(Counters), h->stream));
   CK(cudaMemsetAsync(raw_cnt, 0, rows * sizeof(u32), h->stream));
   if (n) {
-    k_dok_hist<<<grid_for(h, n), 256, 0, h->stream>>>(n, rows, cols, d_r, d_c, raw_cnt, h->d_cnt);
-    k_max_u32<<<grid_for(h, rows), 256, 0, h->stream>>>(raw_cnt, rows, h->d_cnt);
-    count_launch(h, 2);
+    k_dok_hist<<<grid_for(h, (n + 3) / 4), 256, 0, h->stream>>>(n, rows, cols, d_r, d_c, raw_cnt, rank8, h->d_cnt);
+    count_launch(h);
     CK(cudaGetLastError());
   }
-  CKS(scan_u32_to_u64(h, raw_cnt, seg_ptr, rows, nullptr));
+  CKS(scan_u32_to_u64(h, raw_cnt, seg_ptr, rows, nullptr, &h->d_cnt->max_flop));  // also: the longest row
   CK(cudaMemcpyAsync(h->h_cnt, h->d_cnt, sizeof(Counters), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   if (h->h_cnt->error & 2u) return spam_fail(h, SPAM_EINDEX, "triplet index out of range");
@@ -400,15 +490,14 @@ int dok_typed(spam_handle* h, u64 rows, u64 cols, u64 n, const u64* d_r, const u
   h->stats.fallbacks[4] = 1;
   uint2* ent = nullptr;
   V* ev = nullptr;
-  CKS(g.alloc(&ent, n));
-  CKS(g.alloc(&ev, n));
-  CKS(g.alloc(&kept, rows));
+  CKS(g.alloc(&ent, n ? n : 1));
+  CKS(g.alloc(&ev, n ? n : 1));
   const unsigned rgrid = (unsigned)((rows + 127) / 128);   // rows >= 1 (NonZeroUsize in the reference)
   if (n) {
-    k_dok_scatter<V><<<grid_for(h, n), 256, 0, h->stream>>>(n, d_r, d_c, d_v, seg_ptr, raw_cnt, ent, ev);
+    k_dok_scatter<V><<<grid_for(h, n), 256, 0, h->stream>>>(n, d_r, d_c, d_v, rank8, seg_ptr, ent, ev);
     count_launch(h);
   }
-  k_dok_seg<V><<<rgrid, 128, 0, h->stream>>>(rows, seg_ptr, ent, ev, raw_cnt, kept);  // raw_cnt reused: survivors per row
+  k_dok_seg<V><<<rgrid, 128, 0, h->stream>>>(rows, seg_ptr, ent, ev, raw_cnt);  // raw_cnt reused: survivors per row
   count_launch(h);
   CK(cudaGetLastError());
   CKS(scan_u32_to_u64(h, raw_cnt, out->ptr, rows, &h->d_cnt->total_nnz));
@@ -417,7 +506,7 @@ int dok_typed(spam_handle* h, u64 rows, u64 cols, u64 n, const u64* d_r, const u
   out->nnz = h->h_cnt->total_nnz;
   CKS(dev_alloc_t(h, &out->idx, out->nnz));
   CKS(dev_alloc(h, &out->val, out->nnz * sizeof(V)));
-  k_dok_emit<V><<<rgrid, 128, 0, h->stream>>>(rows, seg_ptr, ent, ev, kept, out->ptr, out->idx, (V*)out->val);
+  k_dok_emit<V><<<rgrid, 128, 0, h->stream>>>(rows, seg_ptr, ent, ev, out->ptr, out->idx, (V*)out->val);
   count_launch(h);
   CK(cudaGetLastError());
   return SPAM_OK;
@@ -552,18 +641,18 @@ int transpose_dev(spam_handle* h, const spam_dcsr* a, spam_dcsr** out) {
   u32 *col_cnt = nullptr, *t_idx = nullptr;
   u64* t_ptr = nullptr;
   void* t_val = nullptr;
+  unsigned char* rank8 = nullptr;
   CKS(g.alloc(&col_cnt, tc));
   CKS(g.alloc(&t_ptr, tc + 1));
+  CKS(g.alloc(&rank8, n ? n : 1));
   CK(cudaMemsetAsync(h->d_cnt, 0, sizeof(Counters), h->stream));
   CK(cudaMemsetAsync(col_cnt, 0, tc * sizeof(u32), h->stream));
   if (n) {
-    k_tr_hist<<<grid_for(h, n), 256, 0, h->stream>>>(n, tc, a->idx, col_cnt, h->d_cnt);
+    k_tr_hist<<<grid_for(h, (n + 3) / 4), 256, 0, h->stream>>>(n, tc, a->idx, col_cnt, rank8, h->d_cnt);
     count_launch(h);
+    CK(cudaGetLastError());
   }
-  k_max_u32<<<grid_for(h, tc), 256, 0, h->stream>>>(col_cnt, tc, h->d_cnt);
-  count_launch(h);
-  CK(cudaGetLastError());
-  CKS(scan_u32_to_u64(h, col_cnt, t_ptr, tc, nullptr));
+  CKS(scan_u32_to_u64(h, col_cnt, t_ptr, tc, nullptr, &h->d_cnt->max_flop));  // also: the longest column
   CK(cudaMemcpyAsync(h->h_cnt, h->d_cnt, sizeof(Counters), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   if (h->h_cnt->error & 2u) return spam_fail(h, SPAM_EINDEX, "a column index is >= cols");
@@ -574,10 +663,10 @@ int transpose_dev(spam_handle* h, const spam_dcsr* a, spam_dcsr** out) {
   if (n) {
     const unsigned rgrid = (unsigned)((m + 255) / 256), cgrid = (unsigned)((tc + 127) / 128);
     if (es == 4) {
-      k_tr_scatter<uint32_t><<<rgrid, 256, 0, h->stream>>>(m, a->ptr, a->idx, (const uint32_t*)a->val, t_ptr, col_cnt, t_idx, (uint32_t*)t_val);
+      k_tr_scatter<uint32_t><<<rgrid, 256, 0, h->stream>>>(m, a->ptr, a->idx, (const uint32_t*)a->val, rank8, t_ptr, t_idx, (uint32_t*)t_val);
       k_tr_segsort<uint32_t><<<cgrid, 128, 0, h->stream>>>(tc, t_ptr, t_idx, (uint32_t*)t_val);
     } else {
-      k_tr_scatter<uint64_t><<<rgrid, 256, 0, h->stream>>>(m, a->ptr, a->idx, (const uint64_t*)a->val, t_ptr, col_cnt, t_idx, (uint64_t*)t_val);
+      k_tr_scatter<uint64_t><<<rgrid, 256, 0, h->stream>>>(m, a->ptr, a->idx, (const uint64_t*)a->val, rank8, t_ptr, t_idx, (uint64_t*)t_val);
       k_tr_segsort<uint64_t><<<cgrid, 128, 0, h->stream>>>(tc, t_ptr, t_idx, (uint64_t*)t_val);
     }
     count_launch(h, 2);
@@ -589,6 +678,30 @@ int transpose_dev(spam_handle* h, const spam_dcsr* a, spam_dcsr** out) {
   t->ptr = t_ptr; t->idx = t_idx; t->val = t_val;
   g.release(t_ptr); g.release(t_idx); g.release(t_val);
   *out = t;
+  return SPAM_OK;
+}
+
+// Rows in column order: a stable sort of the entries by column, twice (A -> A^T -> A), each a counting or radix
+// sort above.  Cached with the matrix: device matrices are immutable through this API.
+int sorted_rows_of(spam_handle* h, const spam_dcsr* m, const spam_dcsr** view) {
+  *view = m;
+  CKS(ensure_matrix_stats(h, m));
+  if (m->rows_sorted == 1) return SPAM_OK;
+  if (!m->sorted_copy) {
+    const spam_stats keep = h->stats;
+    spam_dcsr* t = nullptr;
+    CKS(transpose_dev(h, m, &t));
+    spam_dcsr* tt = nullptr;
+    const int st = transpose_dev(h, t, &tt);
+    free_dcsr_tree(h, t);
+    h->stats = keep;
+    if (st != SPAM_OK) return st;
+    tt->rows_sorted = 1;
+    tt->max_row_len = m->max_row_len;
+    tt->invalid = 0;
+    const_cast<spam_dcsr*>(m)->sorted_copy = tt;
+  }
+  *view = m->sorted_copy;
   return SPAM_OK;
 }
 

@@ -94,23 +94,6 @@ void free_owned(spam_handle* h, spam_dcsr* m) {
   delete m;
 }
 
-// rows sorted by column: the matrix itself, or a sorted copy made by two transposes (*tmp owns it)
-int sorted_view(spam_handle* h, const spam_dcsr* m, const spam_dcsr** view, spam_dcsr** tmp) {
-  *tmp = nullptr;
-  *view = m;
-  CKS(ensure_matrix_stats(h, m));
-  if (m->rows_sorted == 1) return SPAM_OK;
-  spam_dcsr* t = nullptr;
-  CKS(transpose_dev(h, m, &t));
-  spam_dcsr* tt = nullptr;
-  const int st = transpose_dev(h, t, &tt);
-  free_owned(h, t);
-  if (st != SPAM_OK) return st;
-  *tmp = tt;
-  *view = tt;
-  return SPAM_OK;
-}
-
 }  // namespace
 
 int ewise_dev(spam_handle* h, int op, const spam_dcsr* a_in, const spam_dcsr* b_in, spam_dcsr** out) {
@@ -119,11 +102,11 @@ int ewise_dev(spam_handle* h, int op, const spam_dcsr* a_in, const spam_dcsr* b_
   // lib.rs:87-91: assert_eq!((self.rows, self.cols), (rhs.rows, rhs.cols))
   if (a_in->rows != b_in->rows || a_in->cols != b_in->cols) return spam_fail(h, SPAM_EDIM, "matrices must have identical dimensions");
   if (a_in->dtype != b_in->dtype) return spam_fail(h, SPAM_EDTYPE, "operand dtypes differ");
+  // rows that are not sorted by column: the cached sorted copy of the operand (two stable transposes, dok.cu)
   const spam_dcsr *a = nullptr, *b = nullptr;
-  spam_dcsr *ta = nullptr, *tb = nullptr;
-  int st = sorted_view(h, a_in, &a, &ta);
-  if (st == SPAM_OK) st = (b_in == a_in) ? (b = a, SPAM_OK) : sorted_view(h, b_in, &b, &tb);
-  if (st != SPAM_OK) { free_owned(h, ta); free_owned(h, tb); return st; }
+  int st = sorted_rows_of(h, a_in, &a);
+  if (st == SPAM_OK) st = (b_in == a_in) ? (b = a, SPAM_OK) : sorted_rows_of(h, b_in, &b);
+  if (st != SPAM_OK) return st;
   h->stats = spam_stats{};
   const u64 m = a->rows;
   spam_dcsr* c = new spam_dcsr();
@@ -132,7 +115,7 @@ int ewise_dev(spam_handle* h, int op, const spam_dcsr* a_in, const spam_dcsr* b_
   u32* row_nnz = nullptr;
   auto fail = [&](int s) {
     dev_free(h, row_nnz);
-    free_owned(h, c); free_owned(h, ta); free_owned(h, tb);
+    free_owned(h, c);
     return s;
   };
   st = dev_alloc_t(h, &row_nnz, m);
@@ -163,7 +146,6 @@ int ewise_dev(spam_handle* h, int op, const spam_dcsr* a_in, const spam_dcsr* b_
   }
   if (st != SPAM_OK) return fail(st);
   dev_free(h, row_nnz);
-  free_owned(h, ta); free_owned(h, tb);
   h->stats.nnz_c = c->nnz;
   *out = c;
   return SPAM_OK;

@@ -26,7 +26,8 @@ __device__ __forceinline__ u64 warp_incl_scan_u64(u64 x, int lane) {
 }
 
 __global__ void __launch_bounds__(SCAN_T) k_scan_lookback(const u32* __restrict__ in, u64* __restrict__ out, u64 n,
-                                                          volatile u64* state, u32* tile_counter, ull* total_out) {
+                                                          volatile u64* state, u32* tile_counter, ull* total_out,
+                                                          u32* max_out) {
   __shared__ u32 s_tile;
   __shared__ u64 s_warp[SCAN_T / 32];
   __shared__ u64 s_prefix;
@@ -48,6 +49,14 @@ __global__ void __launch_bounds__(SCAN_T) k_scan_lookback(const u32* __restrict_
   u64 tsum = 0;
 #pragma unroll
   for (int i = 0; i < SCAN_ITEMS; ++i) tsum += v[i];
+  if (max_out) {  // largest input value, for callers that pick a code path by it (dok.cu)
+    u32 mx = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) mx = max(mx, v[i]);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+    if (lane == 0 && mx) atomicMax(max_out, mx);
+  }
 
   const u64 incl = warp_incl_scan_u64(tsum, lane);
   if (lane == 31) s_warp[wid] = incl;
@@ -112,7 +121,7 @@ __global__ void __launch_bounds__(SCAN_T) k_scan_lookback(const u32* __restrict_
 
 }  // namespace
 
-int scan_u32_to_u64(spam_handle* h, const u32* in, u64* out, u64 n, ull* d_total) {
+int scan_u32_to_u64(spam_handle* h, const u32* in, u64* out, u64 n, ull* d_total, u32* d_max) {
   if (n == 0) {
     CK(cudaMemsetAsync(out, 0, sizeof(u64), h->stream));
     if (d_total) CK(cudaMemsetAsync(d_total, 0, sizeof(ull), h->stream));
@@ -133,7 +142,7 @@ int scan_u32_to_u64(spam_handle* h, const u32* in, u64* out, u64 n, ull* d_total
   u64* state = h->scan_ws;
   CK(cudaMemsetAsync(state, 0, (tiles + 1) * sizeof(u64), h->stream));
   u32* tile_counter = reinterpret_cast<u32*>(state + tiles);
-  k_scan_lookback<<<(unsigned)tiles, SCAN_T, 0, h->stream>>>(in, out, n, state, tile_counter, d_total);
+  k_scan_lookback<<<(unsigned)tiles, SCAN_T, 0, h->stream>>>(in, out, n, state, tile_counter, d_total, d_max);
   count_launch(h);
   CK(cudaGetLastError());
   return SPAM_OK;

@@ -27,3 +27,33 @@ def handle():
     import sparse_matrix_b200 as S
     h = S.get_handle(0)
     yield h
+
+
+@pytest.fixture(scope="session")
+def handle_nosort():
+    """A handle created with SPAM_SORT_B=0: an unsorted right-hand side is multiplied as it is (thread-per-row and
+    warp hash bins) instead of through its cached sorted copy — the tests that pin those bins use it."""
+    import sparse_matrix_b200 as S
+    os.environ["SPAM_SORT_B"] = "0"
+    try:
+        h = S.Handle(0)
+    finally:
+        del os.environ["SPAM_SORT_B"]
+    yield h
+    h.close()
+
+
+@pytest.fixture(scope="session")
+def handle_esc():
+    """SPAM_ESC=2 (and SPAM_SORT_B=0): rows that do not compress take the bucket-sort bins 11..15 (esc.cuh), which are
+    off by default because the hash bins measured faster on B200."""
+    import sparse_matrix_b200 as S
+    os.environ["SPAM_SORT_B"] = "0"
+    os.environ["SPAM_ESC"] = "2"
+    try:
+        h = S.Handle(0)
+    finally:
+        del os.environ["SPAM_SORT_B"]
+        del os.environ["SPAM_ESC"]
+    yield h
+    h.close()

@@ -98,10 +98,11 @@ def test_random_products(oracle, handle, dtype, shape):
 
 
 @pytest.mark.parametrize("dtype", [np.float64, np.int64])
-def test_every_bin_is_exercised(oracle, handle, dtype):
-    """Rows whose flop / nnz land in each symbolic and numeric bin.  Rows that do not compress (every product a new
-    column) take the bucket-sort bins 11..15; rows where every column is produced three times take the hash bins
-    1..8 and the global-table bin 9."""
+def test_every_bin_is_exercised(oracle, handle_nosort, handle_esc, dtype):
+    """Rows whose flop / nnz land in each symbolic and numeric bin: hash bins 1..8 and the global-table bin 9 by
+    default; with SPAM_ESC=2 the rows that do not compress (every product a new column) take the bucket-sort bins
+    11..15 instead."""
+    handle = handle_nosort
     rng = np.random.default_rng(99)
     inner, n = 3000, 60000
     # (1) A row i has `deg[i]` entries; B rows have 40 entries => flop = 40*deg, nnz close to it
@@ -112,11 +113,14 @@ def test_every_bin_is_exercised(oracle, handle, dtype):
     c = gpu_mul(a, b, handle)
     st = handle.stats()
     assert all(x > 0 for x in st["sym_bin_rows"][:10]), st["sym_bin_rows"]
-    assert all(x > 0 for x in st["num_bin_rows"][:4]) and all(x > 0 for x in st["num_bin_rows"][11:15]), st["num_bin_rows"]
-    assert st["num_bin_rows"][HEAVY] > 0      # more than 8192 products: global-table bin (SPAM_ESC=2: bin 15)
+    assert all(x > 0 for x in st["num_bin_rows"][:10]) and sum(st["num_bin_rows"][11:16]) == 0, st["num_bin_rows"]
     off, idx, val = check_against_oracle(oracle, a, b, c)
     assert st["nnz_c"] == len(idx) and st["flops"] == G.spgemm_counts(a, b)[0] and st["kernel_launches"] >= 10
+    c = gpu_mul(a, b, handle_esc)
+    st = handle_esc.stats()
+    assert all(x > 0 for x in st["num_bin_rows"][:4]) and all(x > 0 for x in st["num_bin_rows"][11:16]), st["num_bin_rows"]
     assert st["fallbacks"][3] == 0          # uniform columns: no crowded bucket
+    check_against_oracle(oracle, a, b, c)
     # (2) the same B three times over (rows k, k + inner, k + 2 inner hold the same columns) and A rows that
     # reference all three copies: every column is produced three times, so the rows compress and are hashed
     deg3 = np.array([0, 1, 2, 4, 7, 12, 25, 50, 100, 200, 400, 2500] + [3] * 40 + [60] * 20)
@@ -142,7 +146,7 @@ def test_every_bin_is_exercised(oracle, handle, dtype):
     check_against_oracle(oracle, a, b2, c2)
 
 
-def test_tiny_rows_are_bit_identical_for_floats(oracle, handle):
+def test_tiny_rows_are_bit_identical_for_floats(oracle, handle, handle_nosort):
     """The thread-per-row path visits products in the reference's order with unfused mul/add, so the
     f64 sums must equal the oracle's bit for bit, not just within tolerance."""
     for dtype in (np.float64, np.float32):
@@ -162,10 +166,16 @@ def test_tiny_rows_are_bit_identical_for_floats(oracle, handle):
             idx[lo:hi] = idx[lo:hi][perm]
             val[lo:hi] = val[lo:hi][perm]
         q = (p[0], p[1], off, idx, val)
-        c = gpu_mul(q, q, handle)
-        st = handle.stats()
+        c = gpu_mul(q, q, handle_nosort)
+        st = handle_nosort.stats()
         handle.set_timing(False)
         assert st["sym_bin_rows"][0] == p[0] and st["num_bin_rows"][0] == p[0]
+        check_against_oracle(oracle, q, q, c, exact_values=True)
+        # default handle: the unsorted right-hand side is replaced by its cached sorted copy, so the merge bin runs —
+        # and the sums are still the reference's bit for bit (one product per entry of A's row, in A's order)
+        c = gpu_mul(q, q, handle)
+        st = handle.stats()
+        assert st["num_bin_rows"][MERGE] == p[0]
         check_against_oracle(oracle, q, q, c, exact_values=True)
 
 
@@ -289,13 +299,18 @@ def test_config3_stencil27_reduced(oracle, handle):
     assert len(idx) == (5 * 40 - 6) ** 3
 
 
-def test_config4_rmat_reduced(oracle, handle):
+def test_config4_rmat_reduced(oracle, handle, handle_esc):
     r = G.rmat(16, 16)
     handle.set_timing(True)
     c = gpu_mul(r, r, handle)
     st = handle.stats()
     handle.set_timing(False)
     check_against_oracle(oracle, r, r, c)
+    # the bucket-sort bins on power-law columns (crowded level-1 buckets are split a second time)
+    c = gpu_mul(r, r, handle_esc)
+    se = handle_esc.stats()
+    check_against_oracle(oracle, r, r, c)
+    assert sum(se["num_bin_rows"][11:16]) > 0 and se["num_bin_rows"][15] > 0, se["num_bin_rows"]
     assert st["sym_bin_rows"][HEAVY] > 0, st["sym_bin_rows"]      # power-law rows reach the global-table bin
     assert sum(st["num_bin_rows"][11:16]) + st["num_bin_rows"][HEAVY] > 0, st["num_bin_rows"]
 
