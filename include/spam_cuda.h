@@ -19,8 +19,9 @@
  *   - Host-side indices are uint64_t (Rust usize on 64-bit; CsrMatrix fields
  *     spam_csr/src/lib.rs:25-32: vals, indices, offsets).  On the device col_idx is u32
  *     (the reference truncates keys to u32, mul_hash.rs:92,157), row_ptr u64.
- *   - Output rows are always emitted sorted by column (valid for both IS_SORTED
- *     variants: invariant6, lib.rs:69-77).  Cancellation zeros are kept (mul_hash.rs:88-96).
+ *   - Output rows are sorted by column unless the caller asks for the reference's unsorted order
+ *     (`sorted = 0`); sorted rows are valid for both IS_SORTED variants (invariant6, lib.rs:69-77).
+ *     Cancellation zeros are kept (mul_hash.rs:88-96).
  *   - Integer dtypes wrap (two's complement), floats: products mul-then-add, no FMA.
  *   - Every function returns a spam_status; nothing unwinds across the boundary.  The
  *     reference panics where we return an error (mul_hash.rs:47-48, lib.rs:270).
@@ -112,8 +113,12 @@ int spam_spgemm_symbolic(spam_handle* h, int dtype, uint64_t a_rows, uint64_t a_
                          const uint64_t* a_idx, const void* a_val, uint64_t b_rows, uint64_t b_cols,
                          const uint64_t* b_ptr, const uint64_t* b_idx, const void* b_val, uint64_t* c_ptr,
                          uint64_t* c_nnz);
-/* Phase 2: numeric pass + per-row column sort; fills caller-owned c_idx[c_nnz], c_val[c_nnz].
- * `sorted` must be 1 (rows sorted by column; see header note). Releases the pending product. */
+/* Phase 2: numeric pass; fills caller-owned c_idx[c_nnz], c_val[c_nnz].  Releases the pending product.
+ * sorted = 1: rows sorted by column — mul_hash::<_, true> (mul_hash.rs:164-175), and a valid CsrMatrix<T, false>
+ *             as well (invariant6 only asks for distinct columns).
+ * sorted = 0: the rows in the reference's B2 = false order, column for column: the slot order of linprobe's map
+ *             (mul_hash.rs:176-186, map.rs:59-63) under the reference's insertion order.  Same entries and values
+ *             as sorted = 1, permuted inside each row by one more pass (slotorder.cu). */
 int spam_spgemm_numeric(spam_handle* h, uint64_t* c_idx, void* c_val, int sorted);
 
 /* y = A x with dense x (a_cols) and y (a_rows); empty rows give 0. */
@@ -192,6 +197,8 @@ int spam_csr_ewise_fetch(spam_handle* h, uint64_t* c_idx, void* c_val);
 
 /* C = A * B, all on the device; *c is a new owning matrix (stream-ordered allocation). */
 int spam_spgemm_dev(spam_handle* h, const spam_dcsr* a, const spam_dcsr* b, spam_dcsr** c);
+/* the same with the B2 const generic as an argument: sorted = 0 gives the reference's unsorted (slot) order */
+int spam_spgemm_dev_b2(spam_handle* h, const spam_dcsr* a, const spam_dcsr* b, int sorted, spam_dcsr** c);
 int spam_spmv_dev(spam_handle* h, const spam_dcsr* a, const void* d_x, void* d_y);
 /* device triplets (u64 rows, u64 cols, T vals) -> device CSR */
 int spam_dok_to_csr_dev(spam_handle* h, int dtype, uint64_t rows, uint64_t cols, uint64_t n_triplets,

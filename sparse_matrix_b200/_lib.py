@@ -24,7 +24,7 @@ EXPORTS = [
     "spam_cuda_synchronize", "spam_cuda_get_phase_totals", "spam_strerror", "spam_last_error", "spam_cuda_abi_version", "spam_host_alloc",
     "spam_host_free", "spam_spgemm_symbolic", "spam_spgemm_numeric", "spam_spmv", "spam_dok_to_csr",
     "spam_dok_to_csr_fetch", "spam_csr_upload", "spam_dcsr_wrap", "spam_dcsr_info", "spam_dcsr_download",
-    "spam_dcsr_free", "spam_dcsr_slice_rows", "spam_dcsr_select_rows", "spam_dcsr_transpose", "spam_csr_transpose", "spam_spgemm_dev", "spam_spmv_dev", "spam_dok_to_csr_dev",
+    "spam_dcsr_free", "spam_dcsr_slice_rows", "spam_dcsr_select_rows", "spam_dcsr_transpose", "spam_csr_transpose", "spam_spgemm_dev", "spam_spgemm_dev_b2", "spam_spmv_dev", "spam_dok_to_csr_dev",
     "spam_rows_to_parts", "spam_rows_to_parts_cost", "spam_offset_u64", "spam_dcsr_ewise", "spam_csr_ewise",
     "spam_csr_ewise_fetch", "spam_mm_parse", "spam_mm_free",
     "spam_comm_unique_id", "spam_comm_init", "spam_comm_destroy", "spam_comm_info", "spam_comm_broadcast",
@@ -98,6 +98,7 @@ def load():
     L.spam_dcsr_transpose.argtypes = [vp, vp, C.POINTER(vp)]
     L.spam_csr_transpose.argtypes = [vp, i32, u64, u64, vp, vp, vp, vp, vp, vp]
     L.spam_spgemm_dev.argtypes = [vp, vp, vp, C.POINTER(vp)]
+    L.spam_spgemm_dev_b2.argtypes = [vp, vp, vp, i32, C.POINTER(vp)]
     L.spam_spmv_dev.argtypes = [vp, vp, vp, vp]
     L.spam_dok_to_csr_dev.argtypes = [vp, i32, u64, u64, u64, vp, vp, vp, C.POINTER(vp)]
     L.spam_rows_to_parts.argtypes = [vp, vp, vp, C.c_uint32, vp, C.POINTER(u64)]

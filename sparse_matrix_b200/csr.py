@@ -175,9 +175,13 @@ class DeviceCsr:
                                                               ptr(vals)))
         return CsrMatrix(i["rows"], i["cols"], vals, indices, offsets, is_sorted=is_sorted)
 
-    def matmul(self, rhs: "DeviceCsr") -> "DeviceCsr":
+    def matmul(self, rhs: "DeviceCsr", reference_order: bool = False) -> "DeviceCsr":
+        """C = self * rhs on the device.  reference_order: rows in the reference's B2 = false (slot) order."""
         out = C.c_void_p()
-        check(self.handle.h, self.handle.L.spam_spgemm_dev(self.handle.h, self.p, rhs.p, C.byref(out)))
+        if reference_order:
+            check(self.handle.h, self.handle.L.spam_spgemm_dev_b2(self.handle.h, self.p, rhs.p, 0, C.byref(out)))
+        else:
+            check(self.handle.h, self.handle.L.spam_spgemm_dev(self.handle.h, self.p, rhs.p, C.byref(out)))
         return DeviceCsr(self.handle, out)
 
     def matmul_gathered(self, rhs: "DeviceCsr", row_start: int, total_rows: int, nsub: int = 4,
@@ -376,10 +380,12 @@ class CsrMatrix:
         return True
 
     # ---- the hot path -----------------------------------------------------------------------
-    def mul_hash(self, rhs: "CsrMatrix", sorted_output: bool = False, handle: Optional[Handle] = None) -> "CsrMatrix":
+    def mul_hash(self, rhs: "CsrMatrix", sorted_output: bool = False, handle: Optional[Handle] = None,
+                 reference_order: bool = False) -> "CsrMatrix":
         """CsrMatrix::mul_hash::<B1, B2> (mul_hash.rs:13-36) on the GPU through the two-phase C ABI
-        (spam_spgemm_symbolic / spam_spgemm_numeric).  `sorted_output` is B2; the device always emits
-        rows sorted by column, which satisfies both variants."""
+        (spam_spgemm_symbolic / spam_spgemm_numeric).  `sorted_output` is B2.  By default the rows come back
+        sorted by column, which satisfies both variants; with B2 = false and `reference_order` they
+        come back in the reference's own order (the slot order of its hash map), column for column."""
         if self.vals.dtype != rhs.vals.dtype:
             raise TypeError("operand element types differ")
         handle = handle or get_handle()
@@ -394,7 +400,7 @@ class CsrMatrix:
                                         ptr(self.vals if same else rhs.vals), ptr(c_ptr), C.byref(nnz)))
         c_idx = np.empty(nnz.value, dtype=np.uint64)   # Vec::with_capacity(nnz), mul_hash.rs:119
         c_val = np.empty(nnz.value, dtype=self.vals.dtype)
-        check(h, L.spam_spgemm_numeric(h, ptr(c_idx), ptr(c_val), 1))
+        check(h, L.spam_spgemm_numeric(h, ptr(c_idx), ptr(c_val), 0 if (reference_order and not sorted_output) else 1))
         return CsrMatrix(self.rows_, rhs.cols_, c_val, c_idx, c_ptr, is_sorted=sorted_output)
 
     def __mul__(self, rhs: "CsrMatrix") -> "CsrMatrix":  # impl Mul for &CsrMatrix, lib.rs:292-297

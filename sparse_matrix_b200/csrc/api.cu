@@ -638,6 +638,16 @@ int spam_spgemm_dev(spam_handle* h, const spam_dcsr* a, const spam_dcsr* b, spam
   return SPAM_OK;
 }
 
+int spam_spgemm_dev_b2(spam_handle* h, const spam_dcsr* a, const spam_dcsr* b, int sorted, spam_dcsr** c) {
+  if (!h || !a || !b || !c) return spam_fail(h, SPAM_EINVAL, "null argument");
+  *c = nullptr;
+  CKS(set_device(h));
+  SpgemmPending* p = nullptr;
+  CKS(spgemm_symbolic_dev(h, a, b, &p));
+  CKS(spgemm_numeric_dev(h, p, c, sorted ? 1 : 0));
+  return SPAM_OK;
+}
+
 int spam_spgemm_symbolic(spam_handle* h, int dtype, uint64_t a_rows, uint64_t a_cols, const uint64_t* a_ptr,
                          const uint64_t* a_idx, const void* a_val, uint64_t b_rows, uint64_t b_cols,
                          const uint64_t* b_ptr, const uint64_t* b_idx, const void* b_val, uint64_t* c_ptr,
@@ -685,14 +695,13 @@ int spam_spgemm_numeric(spam_handle* h, uint64_t* c_idx, void* c_val, int sorted
   if (!h) return SPAM_EINVAL;
   SpgemmHostState* s = static_cast<SpgemmHostState*>(h->pending);
   if (!s || !s->pend) return spam_fail(h, SPAM_ESTATE, "spam_spgemm_numeric without spam_spgemm_symbolic");
-  if (sorted != 1) return spam_fail(h, SPAM_EINVAL, "only sorted output (B2=true) is produced on the device");
   const u64 nnz = spgemm_pending_nnz(s->pend);
   if (nnz && (!c_idx || !c_val)) return spam_fail(h, SPAM_EINVAL, "null output buffer");
   CKS(set_device(h));
   spam_dcsr* c = nullptr;
   SpgemmPending* p = s->pend;
   s->pend = nullptr;  // consumed by numeric whatever the outcome
-  int st = spgemm_numeric_dev(h, p, &c);
+  int st = spgemm_numeric_dev(h, p, &c, sorted ? 1 : 0);
   if (st == SPAM_OK) st = spam_dcsr_download(h, c, nullptr, c_idx, c_val);
   if (st == SPAM_OK) finish_timing(h);
   free_dcsr(h, c);

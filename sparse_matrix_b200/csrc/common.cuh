@@ -302,7 +302,9 @@ void finish_timing(spam_handle* h);                 // wait for the current set,
 int scan_u32_to_u64(spam_handle* h, const u32* in, u64* out, u64 n, ull* d_total, u32* d_max = nullptr);
 // spgemm.cu
 int spgemm_symbolic_dev(spam_handle* h, const spam_dcsr* a, const spam_dcsr* b, SpgemmPending** out);
-int spgemm_numeric_dev(spam_handle* h, SpgemmPending* p, spam_dcsr** c);
+int spgemm_numeric_dev(spam_handle* h, SpgemmPending* p, spam_dcsr** c, int sorted = 1);
+// slotorder.cu : rows of a sorted product permuted into the reference's B2 = false (linear-probe slot) order
+int slot_order_dev(spam_handle* h, const spam_dcsr* a, const spam_dcsr* b_original, spam_dcsr* c);
 int spgemm_numeric_into(spam_handle* h, SpgemmPending* p, const u64* c_ptr, u32* c_idx, void* c_val);
 void spgemm_pending_free(spam_handle* h, SpgemmPending* p);
 u64 spgemm_pending_nnz(const SpgemmPending* p);

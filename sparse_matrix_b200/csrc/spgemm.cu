@@ -674,7 +674,8 @@ int build_perm(spam_handle* h, u64 m, const u32* counts, bool numeric, const u64
 
 struct SpgemmPending {
   const spam_dcsr* a;
-  const spam_dcsr* b;
+  const spam_dcsr* b;        // the right-hand side the kernels read (a cached sorted copy when B's rows are unsorted)
+  const spam_dcsr* b_orig;   // the caller's right-hand side: its row order defines the B2 = false output order
   u32* d_flop;
   u32* d_row_nnz;
   u64* d_cptr;
@@ -752,6 +753,7 @@ int spgemm_symbolic_dev(spam_handle* h, const spam_dcsr* a, const spam_dcsr* b, 
   // entry of C sums one product per entry of A's row, in A's order, whatever the order inside B's rows, so the
   // result is the same bit for bit — and the merge bin and the DIRECT enumeration apply (Poisson with shuffled
   // rows: 3.1 ms through the thread-per-row hash bin, 0.6 ms like this).
+  const spam_dcsr* b_orig = b;
   if (b->rows_sorted == 0 && b->nnz < 0xFFFFFFFFull && h->sort_b) {
     const spam_dcsr* sb = nullptr;
     CKS(sorted_rows_of(h, b, &sb));
@@ -760,7 +762,7 @@ int spgemm_symbolic_dev(spam_handle* h, const spam_dcsr* a, const spam_dcsr* b, 
   }
   const int merge_ok = (b->rows_sorted == 1 && b->nnz < 0xFFFFFFFFull) ? 1 : 0;
   SpgemmPending* p = new SpgemmPending();
-  p->a = a; p->b = b; p->d_flop = nullptr; p->d_row_nnz = nullptr; p->d_cptr = nullptr; p->nnz = 0; p->max_nnz = 0;
+  p->a = a; p->b = b; p->b_orig = b_orig; p->d_flop = nullptr; p->d_row_nnz = nullptr; p->d_cptr = nullptr; p->nnz = 0; p->max_nnz = 0;
   const int mode = (merge_ok ? MODE_MERGE : 0) | (h->use_esc ? MODE_ESC : 0) | (h->use_esc == 2 ? MODE_ESC_HEAVY : 0);
   p->max_alen = 0; p->merge_ok = merge_ok; p->mode = mode;
   *out = p;
@@ -1099,7 +1101,7 @@ int numeric_timing(spam_handle* h) {
 
 // Phase 2: allocate C (exact nnz, like Vec::with_capacity(nnz), mul_hash.rs:119), numeric per bin.
 // Consumes the pending state.  On success *cout owns col_idx/val and takes over row_ptr.
-int spgemm_numeric_dev(spam_handle* h, SpgemmPending* p, spam_dcsr** cout) {
+int spgemm_numeric_dev(spam_handle* h, SpgemmPending* p, spam_dcsr** cout, int sorted) {
   *cout = nullptr;
   spam_dcsr* c = new spam_dcsr();
   c->dtype = p->a->dtype; c->rows = p->a->rows; c->cols = p->b->cols; c->nnz = p->nnz;
@@ -1107,6 +1109,7 @@ int spgemm_numeric_dev(spam_handle* h, SpgemmPending* p, spam_dcsr** cout) {
   int st = dev_alloc_t(h, &c->idx, p->nnz ? p->nnz : 1);
   if (st == SPAM_OK) st = dev_alloc(h, &c->val, (p->nnz ? p->nnz : 1) * dtype_size(c->dtype));
   if (st == SPAM_OK && p->nnz) st = numeric_dispatch(h, p, c);
+  if (st == SPAM_OK && !sorted) st = slot_order_dev(h, p->a, p->b_orig, c);  // B2 = false: the reference's slot order
   if (st == SPAM_OK) st = numeric_timing(h);
   if (st != SPAM_OK) {
     dev_free(h, c->idx); dev_free(h, c->val);

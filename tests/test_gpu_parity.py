@@ -515,6 +515,66 @@ def test_rows_to_parts_and_row_slices(oracle, handle):
     dA.free()
 
 
+def _check_unsorted(oracle, a, b, c, exact=False):
+    off, idx, val = oracle.mul_hash(a, b, False)          # B2 = false: the reference's slot order
+    assert np.array_equal(c.offsets, off), "row_ptr differs"
+    assert np.array_equal(c.indices, idx), "col_idx (slot order) differs"
+    dt = np.dtype(val.dtype)
+    if dt.kind != "f" or exact:
+        assert np.array_equal(c.vals, val)
+    else:
+        sabs = oracle.mul_hash(a[:4] + (np.abs(a[4]),), b[:4] + (np.abs(b[4]),), False)[2]
+        assert np.all(np.abs(c.vals.astype(np.float64) - val.astype(np.float64)) <= TOL[dt] * sabs.astype(np.float64))
+
+
+@pytest.mark.parametrize("dtype", ALL_DTYPES)
+def test_unsorted_output_in_reference_slot_order(oracle, handle, dtype):
+    """B2 = false (what `&a * &b` and the reference's bench return, mul_hash.rs:176-186): col_idx must come back in
+    the slot order of linprobe's map under the reference's insertion order, bit for bit — rows short enough for the
+    thread-per-row replay (<= 32 columns), block-per-row priority insertion (<= 4096) and the global-scratch kernel."""
+    g = GOLD["map_slot_order"]
+    a = (1, 4, g["a"]["offsets"], g["a"]["indices"], np.array(g["a"]["vals"], dtype=dtype))
+    b = (4, 4, g["b"]["offsets"], g["b"]["indices"], np.array(g["b"]["vals"], dtype=dtype))
+    c = as_csr_matrix(a, False).mul_hash(as_csr_matrix(b, False), sorted_output=False, handle=handle, reference_order=True)
+    assert c.indices.tolist() == g["unsorted"]["indices"]
+    rng = np.random.default_rng(2718)
+    # many short rows with colliding columns (multiples of the table size), unsorted inputs
+    a = random_csr(rng, 400, 300, rng.integers(0, 7, size=400), dtype=dtype, sorted_rows=False)
+    b = random_csr(rng, 300, 4096, rng.integers(0, 9, size=300), dtype=dtype, sorted_rows=False)
+    b[3][:] = (b[3] // 16) * 16 % 4096 + (b[3] % 2)          # columns cluster on few hash slots
+    b = _dedupe_rows(b)
+    c = as_csr_matrix(a, False).mul_hash(as_csr_matrix(b, False), sorted_output=False, handle=handle, reference_order=True)
+    _check_unsorted(oracle, a, b, c)
+    # medium and long rows: up to ~20 000 columns in a row, compressing and not
+    deg = np.array([0, 3, 12, 40, 90, 200, 520, 130, 7] + [25] * 30)
+    a = random_csr(rng, len(deg), 600, deg, dtype=dtype, sorted_rows=False)
+    b = random_csr(rng, 600, 30000, 40, dtype=dtype, sorted_rows=False)
+    A, B = as_csr_matrix(a, False), as_csr_matrix(b, False)
+    c = A.mul_hash(B, sorted_output=False, handle=handle, reference_order=True)
+    _check_unsorted(oracle, a, b, c)
+    assert max(np.diff(c.offsets.astype(np.int64))) > 4096
+    assert c.invariants()
+    # sorted inputs (merge bin) and the device-resident entry point
+    p = G.poisson2d(40, dtype=dtype) if np.dtype(dtype).kind == "f" else None
+    if p is not None:
+        dA = S.DeviceCsr.upload(as_csr_matrix(p), handle)
+        dC = dA.matmul(dA, reference_order=True)
+        _check_unsorted(oracle, p, p, dC.download(is_sorted=False), exact=True)
+        dC.free(); dA.free()
+
+
+def _dedupe_rows(m):
+    rows, cols, off, idx, val = m
+    noff, nidx, nval = [0], [], []
+    for r in range(rows):
+        lo, hi = int(off[r]), int(off[r + 1])
+        _, first = np.unique(idx[lo:hi], return_index=True)
+        first = np.sort(first)                        # keep the original (unsorted) order of the survivors
+        nidx.append(idx[lo:hi][first]); nval.append(val[lo:hi][first])
+        noff.append(noff[-1] + len(first))
+    return rows, cols, np.array(noff, np.uint64), np.concatenate(nidx), np.concatenate(nval)
+
+
 def test_gathered_product_on_one_rank(oracle):
     """spam_spgemm_gathered with a one-rank communicator: the sub-block pipeline (row views of A, offset-fixed row_ptr,
     numeric kernels writing into the gather buffers) without peers.  The multi-rank exchange itself is checked by
