@@ -48,6 +48,7 @@ def lib():
         L.oracle_hash.restype = C.c_uint64
         L.oracle_hash.argtypes = [C.c_uint32]
         L.oracle_hashset_run.restype = C.c_uint64
+        L.oracle_hashset_run2.restype = C.c_uint64
         L.oracle_free.argtypes = [C.c_void_p]
         L.oracle_hardware_threads.restype = C.c_uint
         _lib = L
@@ -248,6 +249,18 @@ def hashset_run(keys, cap_hint=0, slots_cap=4096):
     n = L.oracle_hashset_run(_ptr(keys), C.c_uint64(len(keys)), C.c_uint64(cap_hint), C.byref(ub), _ptr(slots),
                              C.c_uint64(slots_cap))
     return n, ub.value, slots[: min(slots_cap, ub.value)].copy()
+
+
+def hashset_run2(keys, initial_capacity, shrink_cap=0, slots_cap=4096):
+    """HashSet::with_capacity(initial_capacity), optional shrink_to(shrink_cap), then the inserts.
+    Returns (len, upper_bound, allocated slots, slots[:upper_bound])."""
+    L = lib()
+    keys = np.ascontiguousarray(keys, dtype=np.uint32)
+    ub, alloc = C.c_uint64(), C.c_uint64()
+    slots = np.zeros(slots_cap, dtype=np.uint32)
+    n = L.oracle_hashset_run2(_ptr(keys), C.c_uint64(len(keys)), C.c_uint64(initial_capacity), C.c_uint64(shrink_cap),
+                              C.byref(ub), C.byref(alloc), _ptr(slots), C.c_uint64(slots_cap))
+    return n, ub.value, alloc.value, slots[: min(slots_cap, ub.value)].copy()
 
 
 def hardware_threads() -> int:

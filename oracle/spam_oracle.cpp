@@ -607,6 +607,19 @@ uint64_t oracle_hashset_run(const uint32_t* keys, uint64_t n, uint64_t cap_hint,
   return hs.len();
 }
 
+// a set that was allocated for `initial_capacity` keys (HashSet::with_capacity, set.rs:27-29) and then told
+// shrink_to(shrink_cap) (0: not called), as the symbolic pass does with a set that grew on an earlier row
+uint64_t oracle_hashset_run2(const uint32_t* keys, uint64_t n, uint64_t initial_capacity, uint64_t shrink_cap,
+                             uint64_t* upper_bound_out, uint64_t* allocated_out, uint32_t* slots_out, uint64_t slots_cap) {
+  HashSet hs(initial_capacity);
+  if (shrink_cap) hs.shrink_to(shrink_cap);
+  for (u64 i = 0; i < n; ++i) hs.insert(keys[i]);
+  *upper_bound_out = hs.upper_bound;
+  *allocated_out = hs.slots.size();
+  for (u64 i = 0; i < std::min<u64>(slots_cap, hs.upper_bound); ++i) slots_out[i] = hs.slots[i];
+  return hs.len();
+}
+
 void oracle_free(void* p) { std::free(p); }
 unsigned oracle_hardware_threads(void) { return std::max(1u, std::thread::hardware_concurrency()); }
 

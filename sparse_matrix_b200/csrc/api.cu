@@ -248,6 +248,7 @@ int spam_cuda_create(spam_handle** out, int device) {
   h->scan_ws = nullptr; h->scan_ws_cap = 0;
   h->pool = nullptr;
   h->comm = nullptr;
+  h->stage = nullptr;
   {
     const char* e = getenv("SPAM_LANES");  // read once: 0 keeps every row bin on the main stream
     h->use_lanes = !(e && e[0] == '0');
@@ -304,6 +305,7 @@ int spam_cuda_destroy(spam_handle* h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->comm) spam_comm_destroy(h);
+  host_stage_free(h);
   drop_spgemm_state(h);
   drop_dok_state(h);
   if (h->scan_ws) { dev_free(h, h->scan_ws); h->scan_ws = nullptr; }
@@ -401,14 +403,10 @@ int spam_csr_upload(spam_handle* h, int dtype, uint64_t rows, uint64_t cols, uin
   if (st == SPAM_OK) st = dev_alloc_t(h, &m->idx, nnz);
   if (st == SPAM_OK) st = dev_alloc(h, &m->val, nnz * dtype_size(dtype));
   if (st == SPAM_OK) st = dev_alloc_t(h, &tmp, nnz);
-  cudaError_t e = cudaSuccess;
-  if (st == SPAM_OK) {
-    e = cudaMemcpyAsync(m->ptr, ptr, (rows + 1) * sizeof(u64), cudaMemcpyHostToDevice, h->stream);
-    if (e == cudaSuccess && nnz) e = cudaMemcpyAsync(tmp, idx, nnz * sizeof(u64), cudaMemcpyHostToDevice, h->stream);
-    if (e == cudaSuccess && nnz) e = cudaMemcpyAsync(m->val, val, nnz * dtype_size(dtype), cudaMemcpyHostToDevice, h->stream);
-    if (e != cudaSuccess) st = spam_fail(h, SPAM_ECUDA, "cudaMemcpyAsync H2D", e);
-  }
-  if (st == SPAM_OK) st = narrow_u64_to_u32(h, tmp, m->idx, nnz);
+  if (st == SPAM_OK) st = host_to_dev(h, m->ptr, ptr, (rows + 1) * sizeof(u64));
+  if (st == SPAM_OK && nnz) st = host_to_dev(h, tmp, idx, nnz * sizeof(u64));
+  if (st == SPAM_OK) st = narrow_u64_to_u32(h, tmp, m->idx, nnz);   // runs while the values are still on the bus
+  if (st == SPAM_OK && nnz) st = host_to_dev(h, m->val, val, nnz * dtype_size(dtype));
   dev_free(h, tmp);
   if (st != SPAM_OK) { free_dcsr(h, m); return st; }
   h->stats.bytes_h2d += (rows + 1) * 8 + nnz * (8 + dtype_size(dtype));
@@ -500,15 +498,15 @@ int spam_dcsr_info(const spam_dcsr* m, int* dtype, uint64_t* rows, uint64_t* col
 int spam_dcsr_download(spam_handle* h, const spam_dcsr* m, uint64_t* ptr, uint64_t* idx, void* val) {
   if (!h || !m) return spam_fail(h, SPAM_EINVAL, "bad argument");
   CKS(set_device(h));
-  if (ptr) CK(cudaMemcpyAsync(ptr, m->ptr, (m->rows + 1) * sizeof(u64), cudaMemcpyDeviceToHost, h->stream));
   DevGuard g(h);
   u64* wide = nullptr;
   if (idx && m->nnz) {
     CKS(g.alloc(&wide, m->nnz));
     CKS(widen_u32_to_u64(h, m->idx, wide, m->nnz));
-    CK(cudaMemcpyAsync(idx, wide, m->nnz * sizeof(u64), cudaMemcpyDeviceToHost, h->stream));
   }
-  if (val && m->nnz) CK(cudaMemcpyAsync(val, m->val, m->nnz * dtype_size(m->dtype), cudaMemcpyDeviceToHost, h->stream));
+  if (ptr) CKS(dev_to_host(h, ptr, m->ptr, (m->rows + 1) * sizeof(u64)));
+  if (val && m->nnz) CKS(dev_to_host(h, val, m->val, m->nnz * dtype_size(m->dtype)));
+  if (idx && m->nnz) CKS(dev_to_host(h, idx, wide, m->nnz * sizeof(u64)));
   CK(cudaStreamSynchronize(h->stream));
   h->stats.bytes_d2h += (ptr ? (m->rows + 1) * 8 : 0) + (idx ? m->nnz * 8 : 0) + (val ? m->nnz * dtype_size(m->dtype) : 0);
   return SPAM_OK;
@@ -683,9 +681,9 @@ int spam_spgemm_symbolic(spam_handle* h, int dtype, uint64_t a_rows, uint64_t a_
   if (st == SPAM_OK) st = spgemm_symbolic_dev(h, s->a, s->b, &s->pend);  // resets stats
   if (st != SPAM_OK) { drop_spgemm_state(h); return st; }
   h->stats.bytes_h2d = h2d;
-  cudaError_t e = cudaMemcpyAsync(c_ptr, spgemm_pending_cptr(s->pend), (a_rows + 1) * sizeof(u64), cudaMemcpyDeviceToHost, h->stream);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-  if (e != cudaSuccess) { drop_spgemm_state(h); return spam_fail(h, SPAM_ECUDA, "D2H row_ptr", e); }
+  st = dev_to_host(h, c_ptr, spgemm_pending_cptr(s->pend), (a_rows + 1) * sizeof(u64));
+  cudaError_t e = st == SPAM_OK ? cudaStreamSynchronize(h->stream) : cudaSuccess;
+  if (st != SPAM_OK || e != cudaSuccess) { drop_spgemm_state(h); return st != SPAM_OK ? st : spam_fail(h, SPAM_ECUDA, "D2H row_ptr", e); }
   h->stats.bytes_d2h += (a_rows + 1) * 8;
   *c_nnz = spgemm_pending_nnz(s->pend);
   return SPAM_OK;

@@ -177,6 +177,12 @@ struct spam_dcsr {
                            // (sorted_rows_of) and owned by this object
 };
 
+struct HostStage {  // hostio.cu: ring of pinned slots for copies from / to pageable caller memory
+  unsigned char* buf;
+  cudaEvent_t ev[4];
+  int nthreads;
+};
+
 struct SpgemmPending;  // state between the two host phases
 struct DokPending;
 
@@ -212,6 +218,7 @@ struct spam_handle {
   int use_esc;         // SPAM_ESC at create time: 0 = hash bins only (default: measured faster on B200), 1 = bucket-sort
                        // bins for non-compressing rows up to 8192 products, 2 = also the column-range kernel for longer rows
   bool sort_b;         // SPAM_SORT_B=0 at create time: never multiply by a sorted copy of an unsorted B (tests of the hash bins)
+  HostStage* stage;    // created on the first copy that involves a pageable host buffer
   struct CommState* comm;  // comm.cu: NCCL communicator + peer-mapped gather buffers (spam_comm_init), or null
 };
 
@@ -323,6 +330,10 @@ int sorted_rows_of(spam_handle* h, const spam_dcsr* m, const spam_dcsr** view);
 void free_dcsr_tree(spam_handle* h, spam_dcsr* m);
 // ewise.cu : C = A + B (op 0) / A - B (op 1)
 int ewise_dev(spam_handle* h, int op, const spam_dcsr* a, const spam_dcsr* b, spam_dcsr** out);
+// hostio.cu : host <-> device copies; pageable host memory goes through the handle's pinned staging ring
+int host_to_dev(spam_handle* h, void* d_dst, const void* h_src, size_t bytes);
+int dev_to_host(spam_handle* h, void* h_dst, const void* d_src, size_t bytes);
+void host_stage_free(spam_handle* h);
 // convert.cu : index width conversion at the host boundary
 int narrow_u64_to_u32(spam_handle* h, const u64* in, u32* out, u64 n);
 int widen_u32_to_u64(spam_handle* h, const u32* in, u64* out, u64 n);

@@ -39,6 +39,17 @@ def test_golden_kats_on_gpu(handle):
     c = gpu_mul(a, b, handle)
     assert c.offsets.tolist() == g["sorted"]["offsets"] and c.indices.tolist() == g["sorted"]["indices"]
     assert c.vals.tolist() == g["sorted"]["vals"]
+    # hand-derived slot orders: one map re-sized per row, and a collision chain with wrap-around and accumulation
+    for name in ("map_reuse_shrink", "map_collision_chain"):
+        g = GOLD[name]
+        a = (g["a"]["rows"], g["a"]["cols"], g["a"]["offsets"], g["a"]["indices"], np.array(g["a"]["vals"]))
+        b = ((65, 65, np.arange(66), np.arange(65), np.ones(65)) if g["b"] == "identity 65" else
+             (g["b"]["rows"], g["b"]["cols"], g["b"]["offsets"], g["b"]["indices"], np.array(g["b"]["vals"])))
+        c = gpu_mul(a, b, handle)
+        assert c.indices.tolist() == g["sorted"]["indices"] and c.vals.tolist() == g["sorted"]["vals"]
+        c = as_csr_matrix(a, False).mul_hash(as_csr_matrix(b, False), sorted_output=False, handle=handle, reference_order=True)
+        assert c.offsets.tolist() == g["unsorted"]["offsets"] and c.indices.tolist() == g["unsorted"]["indices"], name
+        assert c.vals.tolist() == g["unsorted"]["vals"]
     g = GOLD["unfused_cancellation"]
     av = np.array([float.fromhex(x) for x in g["a"]["vals_hex"]])
     bv = np.array([float.fromhex(x) for x in g["b"]["vals_hex"]])

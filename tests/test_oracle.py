@@ -59,6 +59,42 @@ def test_map_slot_order_kat(oracle):
         assert val.tolist() == g[key]["vals"]
 
 
+@pytest.mark.parametrize("name", ["map_reuse_shrink", "map_collision_chain"])
+def test_map_reuse_and_collision_chain_kats(oracle, name):
+    """One map serves every row of a thread block and is re-sized per row (map.rs:49-58); entry() probes with
+    wrap-around and accumulates on a hit (map.rs:66-93): hand-derived slot orders and sums."""
+    g = GOLD[name]
+    a = (g["a"]["rows"], g["a"]["cols"], g["a"]["offsets"], g["a"]["indices"], np.array(g["a"]["vals"]))
+    if g["b"] == "identity 65":
+        b = (65, 65, np.arange(66), np.arange(65), np.ones(65))
+    else:
+        b = (g["b"]["rows"], g["b"]["cols"], g["b"]["offsets"], g["b"]["indices"], np.array(g["b"]["vals"]))
+    for tnum in (1, 2, 0):            # the answer does not depend on how rows are split over threads
+        for mode, key in ((False, "unsorted"), (True, "sorted")):
+            off, idx, val = oracle.mul_hash(a, b, mode, tnum)
+            assert off.tolist() == g[key]["offsets"]
+            assert idx.tolist() == g[key]["indices"], (name, key, tnum)
+            assert val.tolist() == g[key]["vals"]
+
+
+def test_set_grow_after_shrink_kat(oracle):
+    g = GOLD["set_grow_after_shrink"]
+    n, ub, alloc, slots = oracle.hashset_run2(g["keys"], g["initial_capacity"], g["shrink_to"])
+    assert (n, ub, alloc) == (g["len"], g["upper_bound"], 128)          # no re-allocation: 128 slots from with_capacity(40)
+    occ = {str(i): int(k) for i, k in enumerate(slots) if k != 0xFFFFFFFF}
+    assert occ == g["occupied"]
+    n, ub, slots = oracle.hashset_run(g["keys"])                         # HashSet::new(): grow() re-allocates 16 -> 32
+    assert (n, ub) == (g["len"], g["upper_bound"])
+    assert {str(i): int(k) for i, k in enumerate(slots) if k != 0xFFFFFFFF} == g["occupied"]
+
+
+def test_rows_to_threads_ties_kat(oracle):
+    g = GOLD["rows_to_threads_ties"]
+    for tnum, want in g["rows_offset"].items():
+        flop, ro = oracle.rows_to_threads(g["a"]["rows"], g["a"]["offsets"], g["a"]["indices"], g["b_offsets"], int(tnum))
+        assert flop.tolist() == g["flops"] and ro.tolist() == want, (tnum, ro.tolist())
+
+
 def test_unfused_cancellation_kat(oracle):
     g = GOLD["unfused_cancellation"]
     av = np.array([float.fromhex(x) for x in g["a"]["vals_hex"]])
