@@ -340,19 +340,20 @@ def rmat_strong_section(args, S, D, G, handle, rank, world, dev, torch, dist, sy
     def sharded():
         blk.matmul(dA).free()
 
-    def gathered(mode):
+    def gathered(mode, nsub=None):
         def f():
-            blk.matmul_gathered(dA, r0, rows, nsub=args.nsub, mode=mode).free()
+            blk.matmul_gathered(dA, r0, rows, nsub=nsub or args.nsub, mode=mode).free()
         return f
     sharded(); sharded()
     ms_s = time_steps(sharded, steps, sync_all, torch)
     ms_s, rank_ms = max_over_ranks(ms_s, world, dev, torch, dist)
-    gathered(0)(); gathered(0)()
+    gm = args.gather_mode
+    gathered(gm)(); gathered(gm)()
     out["ms_total_from_host_A"] = None
-    ms_g, _ = max_over_ranks(time_steps(gathered(0), steps, sync_all, torch), world, dev, torch, dist)
+    ms_g, _ = max_over_ranks(time_steps(gathered(gm), steps, sync_all, torch), world, dev, torch, dist)
     peer = handle.comm_info()["peer_mapped"]
     # parity of the assembled C (outside every timed region)
-    g = blk.matmul_gathered(dA, r0, rows, nsub=args.nsub, mode=0)
+    g = blk.matmul_gathered(dA, r0, rows, nsub=args.nsub, mode=gm)
     ok = gathered_parity(dA, g, dev, torch, exact=False)
     g.free()
     okt = torch.tensor([1 if ok else 0], dtype=torch.int64, device=dev)
@@ -360,9 +361,18 @@ def rmat_strong_section(args, S, D, G, handle, rank, world, dev, torch, dist, sy
     gathered(1)(); gathered(1)()
     ms_n, _ = max_over_ranks(time_steps(gathered(1), steps, sync_all, torch), world, dev, torch, dist)
     recv = (nnz_c * 12 + (rows + 1) * 8) * (world - 1) / world
+    if args.gather_sweep:       # how the exchange is done and how finely it is pipelined (builder runs only)
+        sweep = {}
+        for mode in (0, 2):
+            for nsub in (1, 4, 8, 16):
+                f = gathered(mode, nsub)
+                f(); f()
+                t, _ = max_over_ranks(time_steps(f, steps, sync_all, torch), world, dev, torch, dist)
+                sweep[f"mode{mode}_nsub{nsub}"] = round(t, 3)
+        out["gather_sweep_ms"] = sweep
     out.update({"ms_sharded": ms_s, "rank_ms": rank_ms, "speedup_sharded": ms1 / ms_s,
-                "ms_gathered": ms_g, "speedup_gathered": ms1 / ms_g, "gather": "peer stores over NVLink (k_push), "
-                f"{args.nsub} sub-blocks pipelined with the numeric kernels" if peer else "peer mapping unavailable: NCCL broadcasts",
+                "ms_gathered": ms_g, "speedup_gathered": ms1 / ms_g, "gather": (("peer stores over NVLink (k_push), " if gm == 0 else "peer-to-peer copies by the copy engines, ")
+                           + f"{args.nsub} sub-blocks pipelined with the numeric kernels") if peer else "peer mapping unavailable: NCCL broadcasts",
                 "ms_gathered_nccl": ms_n, "speedup_gathered_nccl": ms1 / ms_n,
                 "gathered_parity": bool(int(okt.item())), "recv_bytes_per_gpu": int(recv),
                 "recv_gbs_per_gpu_whole_step": recv / ms_g / 1e6,
@@ -386,6 +396,8 @@ def main():
                     help="the strong-scaling product measured beside the headline (config.strong_scaling)")
     ap.add_argument("--no-scale-section", action="store_true")
     ap.add_argument("--nsub", type=int, default=4, help="row sub-blocks that pipeline numeric kernels and exchange")
+    ap.add_argument("--gather-mode", type=int, default=0, choices=[0, 2], help="0: push kernel (peer stores), 2: copy engines")
+    ap.add_argument("--gather-sweep", action="store_true", help="time every gather mode x sub-block count (strong-scaling section)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -459,7 +471,7 @@ def main():
             blk.matmul(dA).free()
 
         def step_gathered():
-            blk.matmul_gathered(dA, r0, rows, nsub=args.nsub, mode=0).free()
+            blk.matmul_gathered(dA, r0, rows, nsub=args.nsub, mode=args.gather_mode).free()
 
     # clocks are sampled from before the warm-up to the end of the timed region; the warm-up is
     # stretched to >= 0.4 s of the same load so that nvidia-smi (20 ms period) sees the steady state
@@ -506,7 +518,7 @@ def main():
             step_gathered()
         nrep = max(3, min(args.steps, 10))
         gathered_ms, _ = max_over_ranks(time_steps(step_gathered, nrep, sync_all, torch), world, dev, torch, dist)
-        g = blk.matmul_gathered(dA, r0, rows, nsub=args.nsub, mode=0)
+        g = blk.matmul_gathered(dA, r0, rows, nsub=args.nsub, mode=args.gather_mode)
         ok = gathered_parity(dA, g, dev, torch, exact=(args.workload == "poisson2048"))
         g.free()
         okt = torch.tensor([1 if ok else 0], dtype=torch.int64, device=dev)

@@ -122,8 +122,16 @@ __global__ void __launch_bounds__(512) k_push(const unsigned char* __restrict__ 
   }
 }
 
-int push_range(spam_handle* h, CommState* c, int which, u64 off_bytes, u64 bytes) {
+int push_range(spam_handle* h, CommState* c, int which, u64 off_bytes, u64 bytes, bool dma) {
   if (!bytes) return SPAM_OK;
+  if (dma) {  // copy engines instead of SMs: one peer-to-peer copy per destination
+    for (int r = 1; r < c->world; ++r) {
+      const int dst = (c->rank + r) % c->world;  // every rank starts with a different peer
+      CK(cudaMemcpyAsync((unsigned char*)c->buf[which].peer[dst] + off_bytes, (const unsigned char*)c->buf[which].local + off_bytes,
+                         bytes, cudaMemcpyDeviceToDevice, c->push));
+    }
+    return SPAM_OK;
+  }
   PeerDst d;
   d.n = 0;
   for (int r = 0; r < c->world; ++r)
@@ -327,7 +335,8 @@ int spam_comm_allgatherv(spam_handle* h, void* d_out, const uint64_t* byte_offse
 // [row_start, row_start + a_block.rows) of A (row_ptr rebased to 0); b: all of B, replicated.  *c is a NON-owning
 // view of the handle's gather buffers (valid until the next gathered product or spam_comm_destroy; release the
 // view itself with spam_dcsr_free).  nsub >= 1 sub-blocks pipeline the product with the exchange; mode 0 = peer
-// stores (falls back to 1 when the peers' buffers could not be mapped), 1 = grouped ncclBroadcast.
+// stores by a kernel (falls back to 1 when the peers' buffers could not be mapped), 1 = grouped ncclBroadcast,
+// 2 = peer-to-peer copies by the copy engines (cudaMemcpyAsync on the mapped buffers) instead of the push kernel.
 // ms4 (optional, host): {symbolic + counts exchange, numeric (last sub-block done), whole call, 0}.
 int spam_spgemm_gathered(spam_handle* h, const spam_dcsr* a_block, const spam_dcsr* b, uint64_t row_start,
                          uint64_t total_rows, int nsub, int mode, spam_dcsr** cout) {
@@ -387,7 +396,8 @@ int spam_spgemm_gathered(spam_handle* h, const spam_dcsr* a_block, const spam_dc
     }
   }
   if (rows_sum != total_rows || rows_before != row_start) { drop(); return spam_fail(h, SPAM_EINVAL, "the ranks' row blocks do not tile the matrix in rank order"); }
-  const bool want_peers = mode == 0;
+  const bool want_peers = mode == 0 || mode == 2;
+  const bool dma = mode == 2;
   int st = ensure_buf(h, c, 0, (total_rows + 1) * 8, want_peers);
   if (st == SPAM_OK) st = ensure_buf(h, c, 1, (total_nnz ? total_nnz : 1) * 4, want_peers);
   if (st == SPAM_OK) st = ensure_buf(h, c, 2, (total_nnz ? total_nnz : 1) * es, want_peers);
@@ -415,9 +425,9 @@ int spam_spgemm_gathered(spam_handle* h, const spam_dcsr* a_block, const spam_dc
       CK(cudaStreamWaitEvent(c->push, c->ev_ready, 0));
       // entries r0 .. r0+nr-1 of row_ptr (+ the closing entry on the very last sub-block): entry r0+nr belongs
       // to the next sub-block / rank, which writes the same value
-      st = push_range(h, c, 0, r0 * 8, (nr + (last ? 1 : 0)) * 8);
-      if (st == SPAM_OK) st = push_range(h, c, 1, off * 4, sub_nnz[s] * 4);
-      if (st == SPAM_OK) st = push_range(h, c, 2, off * es, sub_nnz[s] * es);
+      st = push_range(h, c, 0, r0 * 8, (nr + (last ? 1 : 0)) * 8, dma);
+      if (st == SPAM_OK) st = push_range(h, c, 1, off * 4, sub_nnz[s] * 4, dma);
+      if (st == SPAM_OK) st = push_range(h, c, 2, off * es, sub_nnz[s] * es, dma);
       if (st != SPAM_OK) { drop(); return st; }
     }
     off += sub_nnz[s];

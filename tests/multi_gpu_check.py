@@ -54,7 +54,7 @@ def main():
         starts, _ = dAfull.rows_to_parts(dB, world)
         r0, r1 = int(starts[rank]), int(starts[rank + 1])
         blk = dAfull.slice_rows(r0, r1)
-        for nsub, mode in ((1, 0), (4, 0), (3, 1), (2, 0)):
+        for nsub, mode in ((1, 0), (4, 0), (3, 1), (2, 2), (5, 2)):
             g = blk.matmul_gathered(dB, r0, m[0], nsub=nsub, mode=mode)
             c = g.download()
             g.free()
