@@ -604,7 +604,8 @@ def main():
             ustep()
         line["config"]["unsorted_input"] = {"ms_per_step": time_steps(ustep, max(3, min(args.steps, 10)), sync_all, torch),
                                             "note": "same matrix with every row's entries shuffled (IS_SORTED = false): "
-                                                    "no merge bin, the thread-per-row hash bin"}
+                                                    "multiplied by the cached copy of B with sorted rows (merge bin; r1 took the "
+                                                    "thread-per-row hash bin: 3.1 ms)"}
         line["config"]["unsorted_input"]["num_bin_rows"] = handle.stats()["num_bin_rows"]
         dU.free()
 

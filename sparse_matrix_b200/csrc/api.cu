@@ -254,8 +254,6 @@ int spam_cuda_create(spam_handle** out, int device) {
     h->use_lanes = !(e && e[0] == '0');
     e = getenv("SPAM_SORT_B");
     h->sort_b = !(e && e[0] == '0');
-    e = getenv("SPAM_MERGE_OCC");
-    h->merge_occ = e ? atoi(e) : 0;
     e = getenv("SPAM_ESC");
     h->use_esc = e ? (e[0] == '2' ? 2 : (e[0] == '1' ? 1 : 0)) : 0;
   }

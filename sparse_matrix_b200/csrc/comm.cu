@@ -84,7 +84,7 @@ struct CommState {
   unsigned char* h_x;      // pinned mirror
   cudaStream_t push;       // high-priority stream of the push kernels
   cudaEvent_t ev_ready, ev_pushed;
-  float last_ms[4];
+  int push_blocks;         // SPAM_PUSH_BLOCKS at init: grid of the push kernel (0: two blocks per SM)
 };
 
 namespace {
@@ -138,7 +138,8 @@ int push_range(spam_handle* h, CommState* c, int which, u64 off_bytes, u64 bytes
     if (r != c->rank) d.p[d.n++] = (unsigned char*)c->buf[which].peer[r] + off_bytes;
   if (!d.n) return SPAM_OK;
   u64 blocks = (bytes / 16 + 511) / 512;
-  const u64 cap = (u64)h->num_sms * 2;
+  // few blocks are enough to fill NVLink and leave the SMs to the numeric kernels that run beside the push
+  const u64 cap = c->push_blocks ? (u64)c->push_blocks : (u64)h->num_sms * 2;
   if (blocks > cap) blocks = cap;
   if (blocks == 0) blocks = 1;
   k_push<<<(unsigned)blocks, 512, 0, c->push>>>((const unsigned char*)c->buf[which].local + off_bytes, d, bytes);
@@ -248,6 +249,7 @@ int spam_comm_init(spam_handle* h, const void* id128, int rank, int world) {
   CommState* c = new CommState();
   memset(c, 0, sizeof(*c));
   c->rank = rank; c->world = world; c->peer_ok = true;
+  { const char* e = getenv("SPAM_PUSH_BLOCKS"); c->push_blocks = e ? atoi(e) : 0; }
   ncclUniqueId id;
   memcpy(&id, id128, 128);
   ncclResult_t r = g_nccl.CommInitRank(&c->comm, world, id, rank);

@@ -218,7 +218,6 @@ struct spam_handle {
   int use_esc;         // SPAM_ESC at create time: 0 = hash bins only (default: measured faster on B200), 1 = bucket-sort
                        // bins for non-compressing rows up to 8192 products, 2 = also the column-range kernel for longer rows
   bool sort_b;         // SPAM_SORT_B=0 at create time: never multiply by a sorted copy of an unsorted B (tests of the hash bins)
-  int merge_occ;       // SPAM_MERGE_OCC at create time: 12 = k_num_merge compiled for 12 blocks per SM
   HostStage* stage;    // created on the first copy that involves a pageable host buffer
   struct CommState* comm;  // comm.cu: NCCL communicator + peer-mapped gather buffers (spam_comm_init), or null
 };

@@ -183,17 +183,30 @@ __global__ void __launch_bounds__(256) k_dok_hist(u64 n, u64 rows, u64 cols, con
   if (bad) atomicOr(&cnt->error, 2u);
 }
 
+// one 16-byte record per triplet: (column, stream position, value bits) — a single store in the scatter, a single
+// load per entry afterwards (scattered 8-byte stores cost a whole 32-byte sector each at the L2: the scatter is
+// bound by sector transactions, not bytes)
+template <class V>
+__device__ __forceinline__ uint4 dok_pack(u32 col, u32 pos, V v) {
+  unsigned long long bits = 0;
+  memcpy(&bits, &v, sizeof(V));
+  return make_uint4(col, pos, (u32)bits, (u32)(bits >> 32));
+}
+template <class V>
+__device__ __forceinline__ V dok_val(const uint4& e) {
+  const unsigned long long bits = (unsigned long long)e.z | ((unsigned long long)e.w << 32);
+  V v;
+  memcpy(&v, &bits, sizeof(V));
+  return v;
+}
+
 template <class V>
 __global__ void __launch_bounds__(256) k_dok_scatter(u64 n, const u64* __restrict__ r, const u64* __restrict__ c,
                                                      const V* __restrict__ v, const unsigned char* __restrict__ rank8,
-                                                     const u64* __restrict__ seg_ptr, uint2* __restrict__ ent,
-                                                     V* __restrict__ ev) {
+                                                     const u64* __restrict__ seg_ptr, uint4* __restrict__ ent) {
   const u64 stride = (u64)gridDim.x * blockDim.x;
-  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const u64 pos = seg_ptr[r[i]] + rank8[i];
-    ent[pos] = make_uint2((u32)c[i], (u32)i);
-    ev[pos] = v[i];
-  }
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    ent[seg_ptr[r[i]] + rank8[i]] = dok_pack<V>((u32)c[i], (u32)i, v[i]);
 }
 
 constexpr int SEG_REGS = 16;  // segments up to this length are held in registers (C5: 8-9 triplets per row)
@@ -205,20 +218,19 @@ constexpr int SEG_REGS = 16;  // segments up to this length are held in register
 // different sectors: the nested loops of the first version re-read the segment len times and were bound by the
 // load/store unit).
 template <class V>
-__global__ void __launch_bounds__(128) k_dok_seg(u64 rows, const u64* __restrict__ seg_ptr, uint2* __restrict__ ent,
-                                                 V* __restrict__ ev, u32* __restrict__ row_cnt) {
+__global__ void __launch_bounds__(128) k_dok_seg(u64 rows, const u64* __restrict__ seg_ptr, uint4* __restrict__ ent,
+                                                 u32* __restrict__ row_cnt) {
   const u64 row = (u64)blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= rows) return;
   const u64 lo = seg_ptr[row];
   const u32 len = (u32)(seg_ptr[row + 1] - lo);  // <= SEG_MAX (checked on the host before this path is taken)
   if (len == 0) { row_cnt[row] = 0; return; }
   if (len <= (u32)SEG_REGS) {
-    uint2 e[SEG_REGS];
-    V val[SEG_REGS];
+    uint4 e[SEG_REGS];
 #pragma unroll
     for (int a = 0; a < SEG_REGS; ++a) {
-      e[a] = make_uint2(0xFFFFFFFFu, 0u); val[a] = V();
-      if ((u32)a < len) { e[a] = ent[lo + a]; val[a] = ev[lo + a]; }
+      e[a] = make_uint4(0xFFFFFFFFu, 0u, 0u, 0u);
+      if ((u32)a < len) e[a] = ent[lo + a];
     }
     u32 mask = 0;
 #pragma unroll
@@ -226,65 +238,62 @@ __global__ void __launch_bounds__(128) k_dok_seg(u64 rows, const u64* __restrict
       bool last = (u32)a < len;
 #pragma unroll
       for (int b = 0; b < SEG_REGS; ++b) last = last && !((u32)b < len && e[b].x == e[a].x && e[b].y > e[a].y);
-      if (last && !(val[a] == (V)0)) mask |= 1u << a;
+      if (last && !(dok_val<V>(e[a]) == (V)0)) mask |= 1u << a;
     }
     // every survivor's rank by column among the survivors, then store it at the front of the segment
-    u32 rank[SEG_REGS];
 #pragma unroll
     for (int a = 0; a < SEG_REGS; ++a) {
       u32 rk = 0;
 #pragma unroll
       for (int b = 0; b < SEG_REGS; ++b) rk += ((mask >> b) & 1u) && e[b].x < e[a].x ? 1u : 0u;
-      rank[a] = rk;
+      if ((mask >> a) & 1u) ent[lo + rk] = e[a];
     }
-#pragma unroll
-    for (int a = 0; a < SEG_REGS; ++a)
-      if ((mask >> a) & 1u) { ent[lo + rank[a]] = e[a]; ev[lo + rank[a]] = val[a]; }
     row_cnt[row] = __popc(mask);
     return;
   }
   // 17..32 triplets: the same with the segment re-read from L1
   u32 mask = 0;
   for (u32 a = 0; a < len; ++a) {
-    const uint2 ea = ent[lo + a];
+    const uint4 ea = ent[lo + a];
     bool last = true;
     for (u32 b = 0; b < len; ++b) {
-      const uint2 eb = ent[lo + b];
+      const uint4 eb = ent[lo + b];
       last = last && !(eb.x == ea.x && eb.y > ea.y);
     }
-    if (last && !(ev[lo + a] == (V)0)) mask |= 1u << a;
+    if (last && !(dok_val<V>(ea) == (V)0)) mask |= 1u << a;
   }
-  // selection sort of the survivors into the front of the segment: position t takes the t-th smallest survivor
-  // still at or after t (swap, so nothing is lost)
   const u32 nk = __popc(mask);
   u32 t = 0;
   for (u32 a = 0; a < len; ++a) {  // compact survivors to the front (stable)
     if ((mask >> a) & 1u) {
-      if (a != t) { ent[lo + t] = ent[lo + a]; ev[lo + t] = ev[lo + a]; }
+      if (a != t) ent[lo + t] = ent[lo + a];
       ++t;
     }
   }
   for (u32 i = 1; i < nk; ++i) {  // insertion sort by column
-    const uint2 ke = ent[lo + i];
-    const V kv = ev[lo + i];
+    const uint4 ke = ent[lo + i];
     u32 j = i;
-    while (j > 0 && ent[lo + j - 1].x > ke.x) { ent[lo + j] = ent[lo + j - 1]; ev[lo + j] = ev[lo + j - 1]; --j; }
-    ent[lo + j] = ke; ev[lo + j] = kv;
+    while (j > 0 && ent[lo + j - 1].x > ke.x) { ent[lo + j] = ent[lo + j - 1]; --j; }
+    ent[lo + j] = ke;
   }
   row_cnt[row] = nk;
 }
 
 // copy every row's survivors (front of its segment, already in column order) to their place in C
 template <class V>
-__global__ void __launch_bounds__(128) k_dok_emit(u64 rows, const u64* __restrict__ seg_ptr, const uint2* __restrict__ ent,
-                                                  const V* __restrict__ ev, const u64* __restrict__ c_ptr,
-                                                  u32* __restrict__ c_idx, V* __restrict__ c_val) {
+__global__ void __launch_bounds__(128) k_dok_emit(u64 rows, const u64* __restrict__ seg_ptr, const uint4* __restrict__ ent,
+                                                  const u64* __restrict__ c_ptr, u32* __restrict__ c_idx,
+                                                  V* __restrict__ c_val) {
   const u64 row = (u64)blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= rows) return;
   const u64 o = c_ptr[row];
   const u32 nk = (u32)(c_ptr[row + 1] - o);
   const u64 lo = seg_ptr[row];
-  for (u32 a = 0; a < nk; ++a) { c_idx[o + a] = ent[lo + a].x; c_val[o + a] = ev[lo + a]; }
+  for (u32 a = 0; a < nk; ++a) {
+    const uint4 e = ent[lo + a];
+    c_idx[o + a] = e.x;
+    c_val[o + a] = dok_val<V>(e);
+  }
 }
 
 // ---- transpose, counting path: histogram by column (each entry keeps its arrival rank), scan, scatter (row, value)
@@ -488,16 +497,14 @@ int dok_typed(spam_handle* h, u64 rows, u64 cols, u64 n, const u64* d_r, const u
     return dok_radix<V>(h, rows, cols, n, d_r, d_c, d_v, out);
   }
   h->stats.fallbacks[4] = 1;
-  uint2* ent = nullptr;
-  V* ev = nullptr;
+  uint4* ent = nullptr;
   CKS(g.alloc(&ent, n ? n : 1));
-  CKS(g.alloc(&ev, n ? n : 1));
   const unsigned rgrid = (unsigned)((rows + 127) / 128);   // rows >= 1 (NonZeroUsize in the reference)
   if (n) {
-    k_dok_scatter<V><<<grid_for(h, n), 256, 0, h->stream>>>(n, d_r, d_c, d_v, rank8, seg_ptr, ent, ev);
+    k_dok_scatter<V><<<grid_for(h, n), 256, 0, h->stream>>>(n, d_r, d_c, d_v, rank8, seg_ptr, ent);
     count_launch(h);
   }
-  k_dok_seg<V><<<rgrid, 128, 0, h->stream>>>(rows, seg_ptr, ent, ev, raw_cnt);  // raw_cnt reused: survivors per row
+  k_dok_seg<V><<<rgrid, 128, 0, h->stream>>>(rows, seg_ptr, ent, raw_cnt);  // raw_cnt reused: survivors per row
   count_launch(h);
   CK(cudaGetLastError());
   CKS(scan_u32_to_u64(h, raw_cnt, out->ptr, rows, &h->d_cnt->total_nnz));
@@ -506,7 +513,7 @@ int dok_typed(spam_handle* h, u64 rows, u64 cols, u64 n, const u64* d_r, const u
   out->nnz = h->h_cnt->total_nnz;
   CKS(dev_alloc_t(h, &out->idx, out->nnz));
   CKS(dev_alloc(h, &out->val, out->nnz * sizeof(V)));
-  k_dok_emit<V><<<rgrid, 128, 0, h->stream>>>(rows, seg_ptr, ent, ev, out->ptr, out->idx, (V*)out->val);
+  k_dok_emit<V><<<rgrid, 128, 0, h->stream>>>(rows, seg_ptr, ent, out->ptr, out->idx, (V*)out->val);
   count_launch(h);
   CK(cudaGetLastError());
   return SPAM_OK;

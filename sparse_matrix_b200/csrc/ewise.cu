@@ -43,30 +43,45 @@ __device__ __forceinline__ V apply(V x, V y) {
   return Num<V>::sub(x, y);
 }
 
+constexpr int EW_STAGE = 3072;  // output entries a block stages in shared memory (128 rows x 24)
+
+// One thread per row walks the two sorted rows.  The rows of a block are consecutive, so their output is one
+// contiguous span of C: the threads write it into shared memory and the block then stores it with full sectors
+// (thread-per-row stores straight to C are row-length strided: 32 sectors per store instruction, 0.18 of the copy
+// peak in r1).  A block whose span does not fit (long rows) stores directly.
 template <class V, int OP, bool KEEP_LEFT, int BLOCK>
 __global__ void __launch_bounds__(BLOCK) k_ewise_fill(u64 m, const u64* __restrict__ ap, const u32* __restrict__ ac,
                                                       const V* __restrict__ av, const u64* __restrict__ bp,
                                                       const u32* __restrict__ bc, const V* __restrict__ bv,
                                                       const u64* __restrict__ cp, u32* __restrict__ cc,
                                                       V* __restrict__ cv) {
-  const u64 row = (u64)blockIdx.x * BLOCK + threadIdx.x;
-  if (row >= m) return;
-  u64 i = ap[row], j = bp[row], o = cp[row];
-  const u64 ie = ap[row + 1], je = bp[row + 1];
-  const V zero = Num<V>::zero();
-  while (i < ie && j < je) {
-    const u32 ca = ac[i], cb = bc[j];
-    if (ca == cb) {
-      cc[o] = ca; cv[o] = apply<V, OP>(av[i], bv[j]); ++i; ++j;
-    } else if (ca < cb) {
-      cc[o] = ca; cv[o] = KEEP_LEFT ? av[i] : apply<V, OP>(av[i], zero); ++i;
-    } else {
-      cc[o] = cb; cv[o] = apply<V, OP>(zero, bv[j]); ++j;
+  __shared__ u32 sk[EW_STAGE];
+  __shared__ V sv[EW_STAGE];
+  const u64 row0 = (u64)blockIdx.x * BLOCK;
+  const u64 row = row0 + threadIdx.x;
+  const u64 rend = row0 + BLOCK < m ? row0 + BLOCK : m;
+  const u64 base = cp[row0], span = cp[rend] - base;
+  const bool staged = span <= (u64)EW_STAGE;  // block-uniform
+  if (row < m) {
+    u64 i = ap[row], j = bp[row], o = cp[row];
+    const u64 ie = ap[row + 1], je = bp[row + 1];
+    const V zero = Num<V>::zero();
+    auto put = [&](u32 c, V v) {
+      if (staged) { sk[o - base] = c; sv[o - base] = v; } else { cc[o] = c; cv[o] = v; }
+      ++o;
+    };
+    while (i < ie && j < je) {
+      const u32 ca = ac[i], cb = bc[j];
+      if (ca == cb) { put(ca, apply<V, OP>(av[i], bv[j])); ++i; ++j; }
+      else if (ca < cb) { put(ca, KEEP_LEFT ? av[i] : apply<V, OP>(av[i], zero)); ++i; }
+      else { put(cb, apply<V, OP>(zero, bv[j])); ++j; }
     }
-    ++o;
+    for (; i < ie; ++i) put(ac[i], KEEP_LEFT ? av[i] : apply<V, OP>(av[i], zero));
+    for (; j < je; ++j) put(bc[j], apply<V, OP>(zero, bv[j]));
   }
-  for (; i < ie; ++i, ++o) { cc[o] = ac[i]; cv[o] = KEEP_LEFT ? av[i] : apply<V, OP>(av[i], zero); }
-  for (; j < je; ++j, ++o) { cc[o] = bc[j]; cv[o] = apply<V, OP>(zero, bv[j]); }
+  if (!staged) return;
+  __syncthreads();
+  for (u64 q = threadIdx.x; q < span; q += BLOCK) { cc[base + q] = sk[q]; cv[base + q] = sv[q]; }
 }
 
 template <class V>

@@ -1042,15 +1042,12 @@ int numeric_typed(spam_handle* h, SpgemmPending* p, spam_dcsr* c) {
     const u32 nm = nb.count[MERGE_BIN];
     const unsigned grid = (nm + BL - 1) / BL;
     const u32 kmax = p->max_alen;  // longest A row among all rows short enough for a merge bin
-    // SPAM_MERGE_OCC=12: the same kernel compiled for 12 resident blocks per SM (40 registers, a few spilled
-    // bytes) instead of what the compiler picks (54 registers for K = 6: 9 blocks)
-#define LAUNCH_MERGE(KK)                                                                                        \
-    if (h->merge_occ == 12) k_num_merge<V, KK, BL, 12><<<grid, BL, smem, h->stream>>>(nm, seg(MERGE_BIN), ap, ac, av, bp, bc, bv, cp, cc, cv); \
-    else k_num_merge<V, KK, BL, 1><<<grid, BL, smem, h->stream>>>(nm, seg(MERGE_BIN), ap, ac, av, bp, bc, bv, cp, cc, cv);
-    if (kmax <= 4) { LAUNCH_MERGE(4) }
-    else if (kmax <= 6) { LAUNCH_MERGE(6) }
-    else { LAUNCH_MERGE(8) }
-#undef LAUNCH_MERGE
+    if (kmax <= 4)
+      k_num_merge<V, 4, BL><<<grid, BL, smem, h->stream>>>(nm, seg(MERGE_BIN), ap, ac, av, bp, bc, bv, cp, cc, cv);
+    else if (kmax <= 6)
+      k_num_merge<V, 6, BL><<<grid, BL, smem, h->stream>>>(nm, seg(MERGE_BIN), ap, ac, av, bp, bc, bv, cp, cc, cv);
+    else
+      k_num_merge<V, 8, BL><<<grid, BL, smem, h->stream>>>(nm, seg(MERGE_BIN), ap, ac, av, bp, bc, bv, cp, cc, cv);
     count_launch(h);
   }
   if (nb.count[0]) {
