@@ -11,11 +11,13 @@ use crate::CsrMatrix;
 impl<T: DeviceScalar + num_traits::NumAssign + Send + Sync, const B: bool> CsrMatrix<T, B> {
     // requires: rhs column indices be less than u32::MAX (unchanged, mul_hash.rs:12)
     pub fn mul_hash<const B1: bool, const B2: bool>(&self, rhs: &CsrMatrix<T, B1>) -> CsrMatrix<T, B2> {
-        // The device always emits rows sorted by column: valid for B2 = true (strictly increasing) and
-        // for B2 = false (merely distinct), invariant6 lib.rs:69-77.
+        // B2 = true: rows sorted by column.  B2 = false: sorted rows are valid too (invariant6 only asks for distinct
+        // columns, lib.rs:69-77) and cost one pass less; with the crate feature `reference-order` the device
+        // permutes every row into the order the reference's own drain produces (mul_hash.rs:176-186).
         let (indices, vals, offsets) = spam_cuda::spgemm(
             self.rows.get(), self.cols.get(), &self.offsets, &self.indices, &self.vals,
             rhs.rows.get(), rhs.cols.get(), &rhs.offsets, &rhs.indices, &rhs.vals,
+            !B2 && cfg!(feature = "reference-order"),
         );
         CsrMatrix { rows: self.rows, cols: rhs.cols, indices, vals, offsets }
     }

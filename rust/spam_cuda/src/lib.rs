@@ -19,7 +19,16 @@ extern "C" {
     pub fn spam_spgemm_symbolic(h: *mut spam_handle, dtype: c_int, a_rows: u64, a_cols: u64, a_ptr: *const u64,
         a_idx: *const u64, a_val: *const c_void, b_rows: u64, b_cols: u64, b_ptr: *const u64, b_idx: *const u64,
         b_val: *const c_void, c_ptr: *mut u64, c_nnz: *mut u64) -> c_int;
+    /// sorted = 1: rows sorted by column (B2 = true, and a valid B2 = false result); sorted = 0: the reference's own
+    /// B2 = false order (slot order of linprobe's map, mul_hash.rs:176-186)
     pub fn spam_spgemm_numeric(h: *mut spam_handle, c_idx: *mut u64, c_val: *mut c_void, sorted: c_int) -> c_int;
+    /// page-locked host memory for callers that want full-rate PCIe copies (ordinary Vecs are staged by the library)
+    pub fn spam_host_alloc(p: *mut *mut c_void, bytes: u64) -> c_int;
+    pub fn spam_host_free(p: *mut c_void) -> c_int;
+    /// several GPUs of one node, one process per GPU (collective calls; see include/spam_cuda.h)
+    pub fn spam_comm_unique_id(out128: *mut c_void) -> c_int;
+    pub fn spam_comm_init(h: *mut spam_handle, id128: *const c_void, rank: c_int, world: c_int) -> c_int;
+    pub fn spam_comm_destroy(h: *mut spam_handle) -> c_int;
     pub fn spam_spmv(h: *mut spam_handle, dtype: c_int, a_rows: u64, a_cols: u64, a_ptr: *const u64, a_idx: *const u64,
         a_val: *const c_void, x: *const c_void, y: *mut c_void) -> c_int;
     pub fn spam_dok_to_csr(h: *mut spam_handle, dtype: c_int, rows: u64, cols: u64, n: u64, tri_rows: *const u64,
@@ -80,10 +89,12 @@ impl Drop for Handle { fn drop(&mut self) { unsafe { spam_cuda_destroy(self.0); 
 thread_local! { static HANDLE: RefCell<Option<Handle>> = RefCell::new(None); }
 
 /// C = A * B on the GPU.  Slices are the CsrMatrix fields (offsets, indices, vals); returns the same
-/// three vectors for C, rows sorted by column, cancellation zeros kept.
+/// three vectors for C, cancellation zeros kept; rows sorted by column, or (`reference_order`) in the order the
+/// reference's B2 = false branch emits them.  The Vecs are ordinary pageable memory: the library moves them through
+/// its own ring of pinned slots (hostio.cu).
 pub fn spgemm<T: DeviceScalar>(a_rows: usize, a_cols: usize, a_off: &[usize], a_idx: &[usize], a_val: &[T],
-                               b_rows: usize, b_cols: usize, b_off: &[usize], b_idx: &[usize], b_val: &[T])
-                               -> (Vec<usize>, Vec<T>, Vec<usize>) {
+                               b_rows: usize, b_cols: usize, b_off: &[usize], b_idx: &[usize], b_val: &[T],
+                               reference_order: bool) -> (Vec<usize>, Vec<T>, Vec<usize>) {
     const _: () = assert!(std::mem::size_of::<usize>() == 8);
     HANDLE.with(|cell| {
         let mut slot = cell.borrow_mut();
@@ -96,7 +107,9 @@ pub fn spgemm<T: DeviceScalar>(a_rows: usize, a_cols: usize, a_off: &[usize], a_
             offsets.as_mut_ptr() as *mut u64, &mut nnz) });
         // Vec::with_capacity(nnz) + set_len, exactly like mul_hash.rs:119,196-199
         let (mut indices, mut vals): (Vec<usize>, Vec<T>) = (Vec::with_capacity(nnz as usize), Vec::with_capacity(nnz as usize));
-        h.check(unsafe { spam_spgemm_numeric(h.0, indices.as_mut_ptr() as *mut u64, vals.as_mut_ptr() as *mut c_void, 1) });
+        // reference_order: B2 = false with the reference's slot order; otherwise rows sorted by column (valid for both B2)
+        h.check(unsafe { spam_spgemm_numeric(h.0, indices.as_mut_ptr() as *mut u64, vals.as_mut_ptr() as *mut c_void,
+                                             if reference_order { 0 } else { 1 }) });
         unsafe { indices.set_len(nnz as usize); vals.set_len(nnz as usize); }
         (indices, vals, offsets)
     })

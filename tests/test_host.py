@@ -32,6 +32,24 @@ def test_library_builds_and_exports_every_declared_symbol():
     assert S.load().spam_cuda_abi_version() == 6
 
 
+def test_rust_binding_and_build_recipes_agree_with_the_header():
+    """rust/spam_cuda: every `extern "C"` name is declared in include/spam_cuda.h (and exported by the library), and
+    build.rs compiles every .cu of csrc/ — the r1 recipe had fallen behind build.py and would not have linked."""
+    declared = set(_header_functions())
+    rs = open(os.path.join(ROOT, "rust", "spam_cuda", "src", "lib.rs")).read()
+    ext = re.search(r'extern "C" \{(.*?)\n\}', rs, flags=re.S).group(1)
+    rust_names = set(re.findall(r"pub fn (spam_[a-z0-9_]+)\s*\(", ext))
+    assert len(rust_names) >= 15 and rust_names <= declared, rust_names - declared
+    L = ctypes.CDLL(S.SO_PATH)
+    assert all(hasattr(L, n) for n in rust_names)
+    from sparse_matrix_b200 import build
+    csrc = os.path.join(ROOT, "sparse_matrix_b200", "csrc")
+    on_disk = sorted(f for f in os.listdir(csrc) if f.endswith(".cu"))
+    assert build.SOURCES == on_disk and len(on_disk) >= 10
+    brs = open(os.path.join(ROOT, "rust", "spam_cuda", "build.rs")).read()
+    assert "read_dir" in brs and 'Some("cu")' in brs        # globs the directory instead of listing files
+
+
 def test_strerror_covers_every_status():
     L = S.load()
     seen = set()

@@ -11,6 +11,7 @@ import scipy.io
 import scipy.sparse as sp
 
 import sparse_matrix_b200 as S
+from sparse_matrix_b200 import generators as G
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 
@@ -143,3 +144,19 @@ def test_file_to_device_csr(oracle, handle, tmp_path):
     assert np.array_equal(got.offsets, off) and np.array_equal(got.indices, idx) and np.array_equal(got.vals, val)
     assert all(got.get_element((j, i)) == v for (i, j), v in list(got.iter())[:200])   # symmetric
     _ = cols
+
+
+def test_config1_written_for_the_reference_bench(tmp_path):
+    """scripts/write_c1_matrix_market.py: BASELINE configs[0] as the file the reference's bench reads from ./matrices
+    (spam_csr/src/lib.rs:419-431).  The file parses back to exactly the generated matrix (values round-trip through
+    Rust's `{}` float format)."""
+    import subprocess
+    import sys
+    out = tmp_path / "matrices" / "uniform10k.mtx"
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.check_call([sys.executable, os.path.join(root, "scripts", "write_c1_matrix_market.py"), str(out)])
+    kind, r, c, tr, tc, tv = S.parse_matrix_market(out.read_bytes())
+    m = G.uniform_random(10_000, 10_000, 10, seed=1)
+    rows_of = np.repeat(np.arange(m[0], dtype=np.uint64), np.diff(m[2]).astype(np.int64))
+    assert (kind, r, c) == ("real", 10_000, 10_000)
+    assert np.array_equal(tr, rows_of) and np.array_equal(tc, m[3]) and np.array_equal(tv, m[4])
