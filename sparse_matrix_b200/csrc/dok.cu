@@ -322,11 +322,12 @@ __global__ void __launch_bounds__(256) k_tr_hist(u64 nnz, u64 cols, const u32* _
   if (bad) atomicOr(&cnt->error, 2u);
 }
 
+// scatter: one 16-byte record (row, value bits) per entry into its column's segment of a temporary array (a single
+// store per entry: scattered stores cost one L2 sector transaction each whatever their size)
 template <class W>
 __global__ void __launch_bounds__(256) k_tr_scatter(u64 m, const u64* __restrict__ ptr, const u32* __restrict__ idx,
                                                     const W* __restrict__ val, const unsigned char* __restrict__ rank8,
-                                                    const u64* __restrict__ t_ptr, u32* __restrict__ t_idx,
-                                                    W* __restrict__ t_val) {
+                                                    const u64* __restrict__ t_ptr, uint4* __restrict__ rec) {
   const int lane = threadIdx.x & 31;
   const u64 row = (u64)blockIdx.x * blockDim.x + threadIdx.x;
   const bool valid = row < m;
@@ -334,8 +335,8 @@ __global__ void __launch_bounds__(256) k_tr_scatter(u64 m, const u64* __restrict
   if (valid) { lo = ptr[row]; hi = ptr[row + 1]; }
   if (valid && hi - lo <= 32) {
     for (u64 e = lo; e < hi; ++e) {
-      const u64 pos = t_ptr[idx[e]] + rank8[e];
-      t_idx[pos] = (u32)row; t_val[pos] = val[e];
+      const unsigned long long bits = (unsigned long long)val[e];
+      rec[t_ptr[idx[e]] + rank8[e]] = make_uint4((u32)row, 0u, (u32)bits, (u32)(bits >> 32));
     }
   }
   unsigned longmask = __ballot_sync(0xffffffffu, valid && hi - lo > 32);  // long rows: the whole warp helps
@@ -345,47 +346,44 @@ __global__ void __launch_bounds__(256) k_tr_scatter(u64 m, const u64* __restrict
     const u64 l = __shfl_sync(0xffffffffu, lo, src), hh = __shfl_sync(0xffffffffu, hi, src);
     const u32 rr = (u32)__shfl_sync(0xffffffffu, row, src);
     for (u64 e = l + lane; e < hh; e += 32) {
-      const u64 pos = t_ptr[idx[e]] + rank8[e];
-      t_idx[pos] = rr; t_val[pos] = val[e];
+      const unsigned long long bits = (unsigned long long)val[e];
+      rec[t_ptr[idx[e]] + rank8[e]] = make_uint4(rr, 0u, (u32)bits, (u32)(bits >> 32));
     }
   }
 }
 
+// one thread per column: its records in increasing row order (rows are distinct inside a column; ties — an invalid
+// matrix with a repeated column in a row — keep their arrival order) into the final arrays
 template <class W>
-__global__ void __launch_bounds__(128) k_tr_segsort(u64 cols, const u64* __restrict__ t_ptr, u32* __restrict__ t_idx,
-                                                    W* __restrict__ t_val) {
+__global__ void __launch_bounds__(128) k_tr_segsort(u64 cols, const u64* __restrict__ t_ptr, const uint4* __restrict__ rec,
+                                                    u32* __restrict__ t_idx, W* __restrict__ t_val) {
   const u64 col = (u64)blockIdx.x * blockDim.x + threadIdx.x;
   if (col >= cols) return;
   const u64 lo = t_ptr[col], hi = t_ptr[col + 1];  // hi - lo <= SEG_MAX
   const u32 len = (u32)(hi - lo);
-  if (len < 2) return;
-  if (len <= (u32)SEG_REGS) {  // in registers: rank every entry by row (rows are distinct), store at its rank
-    u32 k[SEG_REGS];
-    W v[SEG_REGS];
+  if (len == 0) return;
+  auto val_of = [](const uint4& r) { return (W)((unsigned long long)r.z | ((unsigned long long)r.w << 32)); };
+  if (len <= (u32)SEG_REGS) {
+    uint4 r[SEG_REGS];
 #pragma unroll
     for (int a = 0; a < SEG_REGS; ++a) {
-      k[a] = 0xFFFFFFFFu; v[a] = W();
-      if ((u32)a < len) { k[a] = t_idx[lo + a]; v[a] = t_val[lo + a]; }
+      r[a] = make_uint4(0xFFFFFFFFu, 0u, 0u, 0u);
+      if ((u32)a < len) r[a] = rec[lo + a];
     }
-    bool sorted = true;
-#pragma unroll
-    for (int a = 1; a < SEG_REGS; ++a) sorted = sorted && k[a - 1] <= k[a];  // padding is u32::MAX
-    if (sorted) return;
 #pragma unroll
     for (int a = 0; a < SEG_REGS; ++a) {
       u32 rk = 0;
 #pragma unroll
-      for (int b = 0; b < SEG_REGS; ++b) rk += (k[b] < k[a] || (k[b] == k[a] && b < a)) ? 1u : 0u;  // stable
-      if ((u32)a < len) { t_idx[lo + rk] = k[a]; t_val[lo + rk] = v[a]; }
+      for (int b = 0; b < SEG_REGS; ++b) rk += (r[b].x < r[a].x || (r[b].x == r[a].x && b < a)) ? 1u : 0u;  // stable
+      if ((u32)a < len) { t_idx[lo + rk] = r[a].x; t_val[lo + rk] = val_of(r[a]); }
     }
     return;
   }
-  for (u64 i = lo + 1; i < hi; ++i) {
-    const u32 k = t_idx[i];
-    const W v = t_val[i];
-    u64 j = i;
-    while (j > lo && t_idx[j - 1] > k) { t_idx[j] = t_idx[j - 1]; t_val[j] = t_val[j - 1]; --j; }
-    if (j != i) { t_idx[j] = k; t_val[j] = v; }
+  for (u32 a = 0; a < len; ++a) {  // 17..32 records: rank by re-reading the segment (L1)
+    const uint4 ra = rec[lo + a];
+    u32 rk = 0;
+    for (u32 b = 0; b < len; ++b) { const u32 rb = rec[lo + b].x; rk += (rb < ra.x || (rb == ra.x && b < a)) ? 1u : 0u; }
+    t_idx[lo + rk] = ra.x; t_val[lo + rk] = val_of(ra);
   }
 }
 
@@ -668,13 +666,15 @@ int transpose_dev(spam_handle* h, const spam_dcsr* a, spam_dcsr** out) {
   CKS(g.alloc(&t_idx, n));
   CKS(g.alloc_bytes(&t_val, n * es));
   if (n) {
+    uint4* rec = nullptr;
+    CKS(g.alloc(&rec, n));
     const unsigned rgrid = (unsigned)((m + 255) / 256), cgrid = (unsigned)((tc + 127) / 128);
     if (es == 4) {
-      k_tr_scatter<uint32_t><<<rgrid, 256, 0, h->stream>>>(m, a->ptr, a->idx, (const uint32_t*)a->val, rank8, t_ptr, t_idx, (uint32_t*)t_val);
-      k_tr_segsort<uint32_t><<<cgrid, 128, 0, h->stream>>>(tc, t_ptr, t_idx, (uint32_t*)t_val);
+      k_tr_scatter<uint32_t><<<rgrid, 256, 0, h->stream>>>(m, a->ptr, a->idx, (const uint32_t*)a->val, rank8, t_ptr, rec);
+      k_tr_segsort<uint32_t><<<cgrid, 128, 0, h->stream>>>(tc, t_ptr, rec, t_idx, (uint32_t*)t_val);
     } else {
-      k_tr_scatter<uint64_t><<<rgrid, 256, 0, h->stream>>>(m, a->ptr, a->idx, (const uint64_t*)a->val, rank8, t_ptr, t_idx, (uint64_t*)t_val);
-      k_tr_segsort<uint64_t><<<cgrid, 128, 0, h->stream>>>(tc, t_ptr, t_idx, (uint64_t*)t_val);
+      k_tr_scatter<uint64_t><<<rgrid, 256, 0, h->stream>>>(m, a->ptr, a->idx, (const uint64_t*)a->val, rank8, t_ptr, rec);
+      k_tr_segsort<uint64_t><<<cgrid, 128, 0, h->stream>>>(tc, t_ptr, rec, t_idx, (uint64_t*)t_val);
     }
     count_launch(h, 2);
     CK(cudaGetLastError());
