@@ -254,6 +254,14 @@ int spam_spgemm_gathered(spam_handle* h, const spam_dcsr* a_block, const spam_dc
 int spam_spmv_gathered(spam_handle* h, const spam_dcsr* a_block, const void* d_x, void* d_y_full,
                        const uint64_t* rows_of);
 
+/* DOK -> CSR with the triplet stream spread over the ranks (rank r holds the r-th contiguous piece, on the device):
+ * rows are range-partitioned (ceil(rows / world) per rank), the pieces are grouped by owner and exchanged with one
+ * grouped ncclSend / ncclRecv all-to-all, every rank builds its row block with the single-GPU routine.  Last write
+ * wins across ranks (the pieces arrive in stream order).  *row_start = first global row of *out_block. */
+int spam_dok_to_csr_sharded(spam_handle* h, int dtype, uint64_t rows, uint64_t cols, uint64_t n_local,
+                            const void* d_tri_rows, const void* d_tri_cols, const void* d_tri_vals,
+                            uint64_t* row_start, spam_dcsr** out_block);
+
 #ifdef __cplusplus
 }
 #endif

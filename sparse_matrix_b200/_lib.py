@@ -28,7 +28,7 @@ EXPORTS = [
     "spam_rows_to_parts", "spam_rows_to_parts_cost", "spam_offset_u64", "spam_dcsr_ewise", "spam_csr_ewise",
     "spam_csr_ewise_fetch", "spam_mm_parse", "spam_mm_free",
     "spam_comm_unique_id", "spam_comm_init", "spam_comm_destroy", "spam_comm_info", "spam_comm_broadcast",
-    "spam_comm_allgather_u64", "spam_comm_allgatherv", "spam_spgemm_gathered", "spam_spmv_gathered",
+    "spam_comm_allgather_u64", "spam_comm_allgatherv", "spam_spgemm_gathered", "spam_spmv_gathered", "spam_dok_to_csr_sharded",
 ]
 
 
@@ -113,6 +113,7 @@ def load():
     L.spam_comm_allgatherv.argtypes = [vp, vp, vp]
     L.spam_spgemm_gathered.argtypes = [vp, vp, vp, u64, u64, i32, i32, C.POINTER(vp)]
     L.spam_spmv_gathered.argtypes = [vp, vp, vp, vp, vp]
+    L.spam_dok_to_csr_sharded.argtypes = [vp, i32, u64, u64, u64, vp, vp, vp, C.POINTER(u64), C.POINTER(vp)]
     for name in EXPORTS:
         fn = getattr(L, name)
         if name not in ("spam_strerror", "spam_last_error", "spam_mm_free"):

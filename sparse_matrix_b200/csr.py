@@ -158,6 +158,17 @@ class DeviceCsr:
                                                 C.c_void_p(d_idx), C.c_void_p(d_val), C.byref(out)))
         return DeviceCsr(handle, out, keepalive)
 
+    @staticmethod
+    def from_triplets_sharded(handle: Handle, dtype, rows: int, cols: int, n_local: int, d_rows: int, d_cols: int,
+                              d_vals: int) -> Tuple["DeviceCsr", int]:
+        """Collective.  This rank's contiguous piece of the triplet stream (device pointers: u64 rows, u64 cols, T
+        vals) -> its row block of the CSR matrix (spam_dok_to_csr_sharded).  Returns (block, first global row)."""
+        out, r0 = C.c_void_p(), C.c_uint64()
+        check(handle.h, handle.L.spam_dok_to_csr_sharded(handle.h, _dtype_code(dtype), rows, cols, n_local,
+                                                         C.c_void_p(d_rows), C.c_void_p(d_cols), C.c_void_p(d_vals),
+                                                         C.byref(r0), C.byref(out)))
+        return DeviceCsr(handle, out), r0.value
+
     def info(self) -> dict:
         dt, r, c, n = C.c_int(), C.c_uint64(), C.c_uint64(), C.c_uint64()
         dp, di, dv = C.c_void_p(), C.c_void_p(), C.c_void_p()

@@ -20,6 +20,7 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <algorithm>
 #include <cstring>
 
 #include "common.cuh"
@@ -36,6 +37,8 @@ struct NcclApi {
   ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t);
   ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t);
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
   ncclResult_t (*GroupStart)();
   ncclResult_t (*GroupEnd)();
   const char* (*GetErrorString)(ncclResult_t);
@@ -58,6 +61,8 @@ int load_nccl(std::string* err) {
   BIND(AllGather, "ncclAllGather")
   BIND(Broadcast, "ncclBroadcast")
   BIND(AllReduce, "ncclAllReduce")
+  BIND(Send, "ncclSend")
+  BIND(Recv, "ncclRecv")
   BIND(GroupStart, "ncclGroupStart")
   BIND(GroupEnd, "ncclGroupEnd")
   BIND(GetErrorString, "ncclGetErrorString")
@@ -490,6 +495,89 @@ int spam_spmv_gathered(spam_handle* h, const spam_dcsr* a_block, const void* d_x
   CKS(spmv_dev(h, a_block, d_x, (unsigned char*)d_y_full + bo[c->rank]));
   if (c->world > 1) CKS(spam_comm_allgatherv(h, d_y_full, bo));
   return SPAM_OK;
+}
+
+// DOK -> CSR with the triplet stream spread over the ranks: rank r holds the r-th contiguous piece of the stream
+// (n_local triplets on the device).  The rows are range-partitioned — rank r owns rows [r * per, (r + 1) * per),
+// per = ceil(rows / world) — every rank groups its piece by owner (stable), one grouped ncclSend / ncclRecv
+// all-to-all moves the groups, and each rank builds its block with the single-GPU routine.  Received groups are
+// laid out in source-rank order, so the concatenation is the global stream order restricted to the rank's rows:
+// "last write wins" holds across ranks.  *out_block: rows of the rank's range (row indices rebased to 0);
+// *row_start: first global row of the block.
+int spam_dok_to_csr_sharded(spam_handle* h, int dtype, uint64_t rows, uint64_t cols, uint64_t n_local,
+                            const void* d_tri_rows, const void* d_tri_cols, const void* d_tri_vals,
+                            uint64_t* row_start, spam_dcsr** out_block) {
+  if (!h || !out_block || !row_start || (n_local && (!d_tri_rows || !d_tri_cols || !d_tri_vals))) return spam_fail(h, SPAM_EINVAL, "bad argument");
+  *out_block = nullptr;
+  CommState* c = h->comm;
+  if (!c) return spam_fail(h, SPAM_ESTATE, "spam_comm_init first");
+  if (rows == 0 || rows >= 0xFFFFFFFFull || cols >= 0xFFFFFFFFull) return spam_fail(h, SPAM_ECOLS, "dimension >= 2^32-1 (or zero rows)");
+  if (c->world > 32) return spam_fail(h, SPAM_EINVAL, "at most 32 ranks");
+  CK(cudaSetDevice(h->device));
+  const size_t es = dtype_size(dtype);
+  const u64 per = (rows + c->world - 1) / c->world;
+  const u64 r0 = std::min<u64>(rows, per * c->rank), r1 = std::min<u64>(rows, r0 + per);
+  DevGuard g(h);
+  u64 *s_r = nullptr, *s_c = nullptr, *q_r = nullptr, *q_c = nullptr;
+  void *s_v = nullptr, *q_v = nullptr;
+  CKS(g.alloc(&s_r, n_local ? n_local : 1));
+  CKS(g.alloc(&s_c, n_local ? n_local : 1));
+  CKS(g.alloc_bytes(&s_v, (n_local ? n_local : 1) * es));
+  u64 cnt_to[MAXR * 2] = {};
+  int st = dok_partition_dev(h, dtype, rows, cols, per, c->world, n_local, (const u64*)d_tri_rows, (const u64*)d_tri_cols,
+                             d_tri_vals, s_r, s_c, s_v, cnt_to);
+  // every rank must reach the collective below, error or not: a failed rank sends nothing and reports afterwards
+  u64 mine[MAXR + 1] = {};
+  for (int d = 0; d < c->world; ++d) mine[d] = st == SPAM_OK ? cnt_to[d] : 0;
+  mine[c->world] = st == SPAM_OK ? 0 : 1;
+  static_assert((MAXR + 1) * 8 <= 256, "counts row does not fit the staging slot");
+  CKS(small_allgather(h, c, mine, (size_t)(c->world + 1) * 8));
+  const u64* all = reinterpret_cast<const u64*>(c->h_x + MAXR * 256);
+  u64 recv_from[MAXR] = {}, total = 0, failed = 0;
+  for (int s = 0; s < c->world; ++s) {
+    recv_from[s] = all[(size_t)s * (c->world + 1) + c->rank];
+    failed |= all[(size_t)s * (c->world + 1) + c->world];
+    total += recv_from[s];
+  }
+  if (st != SPAM_OK) return st;
+  if (failed) return spam_fail(h, SPAM_EINDEX, "another rank's slice holds a triplet index out of range");
+  if (total >= 0xFFFFFFFFull) return spam_fail(h, SPAM_EOVERFLOW, "more than 2^32-1 triplets for one rank");
+  CKS(g.alloc(&q_r, total ? total : 1));
+  CKS(g.alloc(&q_c, total ? total : 1));
+  CKS(g.alloc_bytes(&q_v, (total ? total : 1) * es));
+  u64 soff[MAXR + 1] = {}, roff[MAXR + 1] = {};
+  for (int d = 0; d < c->world; ++d) { soff[d + 1] = soff[d] + cnt_to[d]; roff[d + 1] = roff[d] + recv_from[d]; }
+  NCK(g_nccl.GroupStart());
+  ncclResult_t rr = ncclSuccess;
+  for (int p = 0; p < c->world && rr == ncclSuccess; ++p) {
+    if (p == c->rank) continue;
+    if (cnt_to[p]) {
+      rr = g_nccl.Send(s_r + soff[p], cnt_to[p] * 8, ncclUint8, p, c->comm, h->stream);
+      if (rr == ncclSuccess) rr = g_nccl.Send(s_c + soff[p], cnt_to[p] * 8, ncclUint8, p, c->comm, h->stream);
+      if (rr == ncclSuccess) rr = g_nccl.Send((const char*)s_v + soff[p] * es, cnt_to[p] * es, ncclUint8, p, c->comm, h->stream);
+    }
+    if (recv_from[p] && rr == ncclSuccess) {
+      rr = g_nccl.Recv(q_r + roff[p], recv_from[p] * 8, ncclUint8, p, c->comm, h->stream);
+      if (rr == ncclSuccess) rr = g_nccl.Recv(q_c + roff[p], recv_from[p] * 8, ncclUint8, p, c->comm, h->stream);
+      if (rr == ncclSuccess) rr = g_nccl.Recv((char*)q_v + roff[p] * es, recv_from[p] * es, ncclUint8, p, c->comm, h->stream);
+    }
+  }
+  {
+    const ncclResult_t ge = g_nccl.GroupEnd();
+    if (rr != ncclSuccess || ge != ncclSuccess) return spam_fail(h, SPAM_ECUDA, g_nccl.GetErrorString(rr != ncclSuccess ? rr : ge));
+  }
+  const u64 self = cnt_to[c->rank];
+  if (self) {
+    CK(cudaMemcpyAsync(q_r + roff[c->rank], s_r + soff[c->rank], self * 8, cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaMemcpyAsync(q_c + roff[c->rank], s_c + soff[c->rank], self * 8, cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaMemcpyAsync((char*)q_v + roff[c->rank] * es, (const char*)s_v + soff[c->rank] * es, self * es, cudaMemcpyDeviceToDevice, h->stream));
+  }
+  *row_start = r0;
+  const u64 my_rows = r1 - r0;
+  if (my_rows == 0) {  // more ranks than rows: an empty 0-row block is not representable (rows are NonZero): report 1 empty row
+    return dok_to_csr_dev(h, dtype, 1, cols, 0, q_r, q_c, q_v, out_block);
+  }
+  return dok_to_csr_dev(h, dtype, my_rows, cols, total, q_r, q_c, q_v, out_block);
 }
 
 }  // extern "C"

@@ -325,6 +325,8 @@ int spmv_dev(spam_handle* h, const spam_dcsr* a, const void* d_x, void* d_y);
 int dok_to_csr_dev(spam_handle* h, int dtype, u64 rows, u64 cols, u64 n, const u64* d_r, const u64* d_c,
                    const void* d_v, spam_dcsr** out);
 int transpose_dev(spam_handle* h, const spam_dcsr* a, spam_dcsr** out);
+int dok_partition_dev(spam_handle* h, int dtype, u64 rows, u64 cols, u64 rows_per, int world, u64 n, const u64* d_r,
+                      const u64* d_c, const void* d_v, u64* o_r, u64* o_c, void* o_v, u64* counts_host);
 // m itself when its rows are sorted by column, else a cached copy with sorted rows (two stable transposes)
 int sorted_rows_of(spam_handle* h, const spam_dcsr* m, const spam_dcsr** view);
 void free_dcsr_tree(spam_handle* h, spam_dcsr* m);

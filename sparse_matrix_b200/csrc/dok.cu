@@ -688,6 +688,82 @@ int transpose_dev(spam_handle* h, const spam_dcsr* a, spam_dcsr** out) {
   return SPAM_OK;
 }
 
+// ---- multi-GPU DOK -> CSR, local half: stable partition of a slice of the triplet stream by the rank that owns the
+// row (rows_per consecutive rows per rank), rows rebased to the owner's block ----
+namespace {
+__global__ void __launch_bounds__(256) k_dest_keys(u64 n, u64 rows, u64 cols, u64 rows_per, const u64* __restrict__ r,
+                                                   const u64* __restrict__ c, u64* __restrict__ keys, u32* __restrict__ pay,
+                                                   ull* __restrict__ counts, Counters* cnt) {
+  __shared__ u32 s_cnt[32];
+  if (threadIdx.x < 32) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  bool bad = false;
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const u64 ri = r[i];
+    u64 d = 0;
+    if (ri < rows && c[i] < cols) { d = ri / rows_per; atomicAdd(&s_cnt[d & 31], 1u); } else bad = true;
+    keys[i] = d;
+    pay[i] = (u32)i;
+  }
+  if (bad) atomicOr(&cnt->error, 2u);
+  __syncthreads();
+  if (threadIdx.x < 32 && s_cnt[threadIdx.x]) atomicAdd(&counts[threadIdx.x], (ull)s_cnt[threadIdx.x]);
+}
+template <class V>
+__global__ void __launch_bounds__(256) k_dest_gather(u64 n, u64 rows_per, const u64* __restrict__ keys, const u32* __restrict__ pay,
+                                                     const u64* __restrict__ r, const u64* __restrict__ c,
+                                                     const V* __restrict__ v, u64* __restrict__ o_r, u64* __restrict__ o_c,
+                                                     V* __restrict__ o_v) {
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  for (u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
+    const u32 i = pay[j];
+    o_r[j] = r[i] - keys[j] * rows_per;
+    o_c[j] = c[i];
+    o_v[j] = v[i];
+  }
+}
+}  // namespace
+
+// counts_host[d] = triplets of this slice owned by rank d; o_r / o_c / o_v = the slice grouped by owner (stream order
+// kept inside every group: the radix pass is stable).  world <= 32.
+int dok_partition_dev(spam_handle* h, int dtype, u64 rows, u64 cols, u64 rows_per, int world, u64 n, const u64* d_r,
+                      const u64* d_c, const void* d_v, u64* o_r, u64* o_c, void* o_v, u64* counts_host) {
+  for (int d = 0; d < world; ++d) counts_host[d] = 0;
+  if (n == 0) return SPAM_OK;
+  if (n >= 0xFFFFFFFFull) return spam_fail(h, SPAM_EOVERFLOW, "more than 2^32-1 triplets in one slice");
+  const u64 nblocks = (n + RS_TILE - 1) / RS_TILE;
+  DevGuard g(h);
+  u64 *k0 = nullptr, *k1 = nullptr, *offs = nullptr;
+  u32 *p0 = nullptr, *p1 = nullptr, *hist = nullptr;
+  ull* counts = nullptr;
+  CKS(g.alloc(&k0, n)); CKS(g.alloc(&k1, n)); CKS(g.alloc(&p0, n)); CKS(g.alloc(&p1, n));
+  CKS(g.alloc(&hist, (u64)RADIX * nblocks)); CKS(g.alloc(&offs, (u64)RADIX * nblocks + 1));
+  CKS(g.alloc(&counts, 32));
+  CK(cudaMemsetAsync(h->d_cnt, 0, sizeof(Counters), h->stream));
+  CK(cudaMemsetAsync(counts, 0, 32 * sizeof(ull), h->stream));
+  k_dest_keys<<<grid_for(h, n), 256, 0, h->stream>>>(n, rows, cols, rows_per, d_r, d_c, k0, p0, counts, h->d_cnt);
+  count_launch(h);
+  CK(cudaGetLastError());
+  CKS(radix_sort_pairs(h, n, 8, k0, p0, k1, p1, hist, offs));  // one stable 8-bit pass: at most 32 owners
+  const unsigned grid = grid_for(h, n);
+  switch (dtype) {
+    case SPAM_F32: case SPAM_I32:
+      k_dest_gather<uint32_t><<<grid, 256, 0, h->stream>>>(n, rows_per, k0, p0, d_r, d_c, (const uint32_t*)d_v, o_r, o_c, (uint32_t*)o_v); break;
+    default:
+      k_dest_gather<uint64_t><<<grid, 256, 0, h->stream>>>(n, rows_per, k0, p0, d_r, d_c, (const uint64_t*)d_v, o_r, o_c, (uint64_t*)o_v); break;
+  }
+  count_launch(h);
+  CK(cudaGetLastError());
+  ull hc[32];
+  CK(cudaMemcpyAsync(hc, counts, sizeof(hc), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(h->h_cnt, h->d_cnt, sizeof(Counters), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  if (h->h_cnt->error & 2u) return spam_fail(h, SPAM_EINDEX, "triplet index out of range");
+  for (int d = 0; d < world; ++d) counts_host[d] = hc[d];
+  return SPAM_OK;
+}
+
 // Rows in column order: a stable sort of the entries by column, twice (A -> A^T -> A), each a counting or radix
 // sort above.  Cached with the matrix: device matrices are immutable through this API.
 int sorted_rows_of(spam_handle* h, const spam_dcsr* m, const spam_dcsr** view) {

@@ -81,6 +81,28 @@ def main():
         if dB is not dAfull:
             dB.free()
         dAfull.free()
+    # DOK -> CSR with the triplet stream spread over the ranks: rank r holds the r-th contiguous piece
+    for dt in (np.int64, np.float64):
+        u = G.uniform_random(20_000, 30_000, 8, seed=6, dtype=dt, int_range=1 << 12)
+        tr, tc, tv = G.triplets_with_rewrites(u, seed=5, dup_frac=0.2, zero_frac=0.05)
+        n = len(tv)
+        lo, hi = n * rank // world, n * (rank + 1) // world
+        d_r = torch.from_numpy(tr[lo:hi].view(np.int64).copy()).cuda()
+        d_c = torch.from_numpy(tc[lo:hi].view(np.int64).copy()).cuda()
+        d_v = torch.from_numpy(tv[lo:hi].copy()).cuda()
+        torch.cuda.synchronize()
+        blk, r0 = S.DeviceCsr.from_triplets_sharded(h, dt, u[0], u[1], hi - lo, d_r.data_ptr(), d_c.data_ptr(), d_v.data_ptr())
+        got = blk.download()
+        blk.free()
+        off, idx, val = O.dok_to_csr(u[0], u[1], tr, tc, tv)
+        per = -(-u[0] // world)
+        assert r0 == min(u[0], per * rank), (r0, per, rank)
+        r1 = min(u[0], r0 + per)
+        e0, e1 = int(off[r0]), int(off[r1])
+        assert got.rows() == r1 - r0
+        assert np.array_equal(got.offsets, off[r0:r1 + 1] - off[r0]) and np.array_equal(got.indices, idx[e0:e1])
+        assert np.array_equal(got.vals, val[e0:e1]), "sharded DOK -> CSR values"
+        checked += 1
     print(f"rank {rank}/{world}: {checked} gathered results match the oracle; peer_mapped={h.comm_info()['peer_mapped']}", flush=True)
     h.close()
     dist.barrier()

@@ -622,6 +622,21 @@ def test_gathered_product_on_one_rank(oracle):
         assert np.all(np.abs(y - want) <= 1e-12 * sabs)
         for d in (dA, dx, dy):
             d.free()
+        # DOK -> CSR through the sharded entry point (one rank owns every row): partition, self-copy, local build
+        u = G.uniform_random(3000, 5000, 7, seed=8, dtype=np.int64, int_range=40)
+        tr, tc, tv = G.triplets_with_rewrites(u, seed=3, dup_frac=0.2, zero_frac=0.05)
+        n = len(tv)
+
+        def dev_buf(a64):      # a device buffer with these 8-byte words (values of a 1 x n matrix)
+            return S.DeviceCsr.upload(S.CsrMatrix(1, max(1, n), a64.view(np.int64), np.arange(n), [0, n]), h)
+        br, bc, bv = dev_buf(tr), dev_buf(tc), dev_buf(tv)
+        blk, r0 = S.DeviceCsr.from_triplets_sharded(h, np.int64, u[0], u[1], n, br.info()["d_val"], bc.info()["d_val"],
+                                                    bv.info()["d_val"])
+        got = blk.download()
+        off, idx, val = oracle.dok_to_csr(u[0], u[1], tr, tc, tv)
+        assert r0 == 0 and np.array_equal(got.offsets, off) and np.array_equal(got.indices, idx) and np.array_equal(got.vals, val)
+        for d in (blk, br, bc, bv):
+            d.free()
     finally:
         h.close()
 
