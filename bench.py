@@ -371,7 +371,7 @@ def rmat_strong_section(args, S, D, G, handle, rank, world, dev, torch, dist, sy
                 sweep[f"mode{mode}_nsub{nsub}"] = round(t, 3)
         out["gather_sweep_ms"] = sweep
     out.update({"ms_sharded": ms_s, "rank_ms": rank_ms, "speedup_sharded": ms1 / ms_s,
-                "ms_gathered": ms_g, "speedup_gathered": ms1 / ms_g, "gather": (("peer stores over NVLink (k_push), " if gm == 0 else "peer-to-peer copies by the copy engines, ")
+                "ms_gathered": ms_g, "speedup_gathered": ms1 / ms_g, "gather": (("peer stores over NVLink (k_push), " if (gm == 0 or (gm < 0 and world > 2)) else "peer-to-peer copies by the copy engines, ")
                            + f"{args.nsub} sub-blocks pipelined with the numeric kernels") if peer else "peer mapping unavailable: NCCL broadcasts",
                 "ms_gathered_nccl": ms_n, "speedup_gathered_nccl": ms1 / ms_n,
                 "gathered_parity": bool(int(okt.item())), "recv_bytes_per_gpu": int(recv),
@@ -396,7 +396,8 @@ def main():
                     help="the strong-scaling product measured beside the headline (config.strong_scaling)")
     ap.add_argument("--no-scale-section", action="store_true")
     ap.add_argument("--nsub", type=int, default=4, help="row sub-blocks that pipeline numeric kernels and exchange")
-    ap.add_argument("--gather-mode", type=int, default=0, choices=[0, 2], help="0: push kernel (peer stores), 2: copy engines")
+    ap.add_argument("--gather-mode", type=int, default=-1, choices=[-1, 0, 2],
+                    help="0: push kernel (peer stores), 2: copy engines, -1: the library picks by the number of ranks")
     ap.add_argument("--gather-sweep", action="store_true", help="time every gather mode x sub-block count (strong-scaling section)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")

@@ -246,7 +246,8 @@ int spam_comm_allgatherv(spam_handle* h, void* d_out, const uint64_t* byte_offse
  * this handle; release the view with spam_dcsr_free.  nsub (1..16) sub-blocks of rows pipeline the numeric
  * kernels with the exchange.  mode 0: peer stores over NVLink by a push kernel (falls back to 1 if the peers'
  * buffers cannot be mapped), mode 1: grouped ncclBroadcast, mode 2: like 0 with the copy engines doing the
- * peer-to-peer copies.  Phase timing (spam_cuda_set_timing) is not collected here. */
+ * peer-to-peer copies, mode -1: the library picks 0 or 2 by the number of ranks.  Phase timing
+ * (spam_cuda_set_timing) is not collected here. */
 int spam_spgemm_gathered(spam_handle* h, const spam_dcsr* a_block, const spam_dcsr* b, uint64_t row_start,
                          uint64_t total_rows, int nsub, int mode, spam_dcsr** c);
 /* y = A x, A row-sharded, x replicated: each rank fills its rows of d_y_full (total rows entries) and the pieces

@@ -196,7 +196,7 @@ class DeviceCsr:
         return DeviceCsr(self.handle, out)
 
     def matmul_gathered(self, rhs: "DeviceCsr", row_start: int, total_rows: int, nsub: int = 4,
-                        mode: int = 0) -> "DeviceCsr":
+                        mode: int = -1) -> "DeviceCsr":
         """Collective.  self = this rank's row block of A, rhs = all of B: returns the WHOLE product, assembled on
         every rank (spam_spgemm_gathered).  The result is a view of the handle's gather buffers, valid until the
         next gathered product."""

@@ -89,7 +89,7 @@ struct CommState {
   unsigned char* h_x;      // pinned mirror
   cudaStream_t push;       // high-priority stream of the push kernels
   cudaEvent_t ev_ready, ev_pushed;
-  int push_blocks;         // SPAM_PUSH_BLOCKS at init: grid of the push kernel (0: four blocks of 512 threads per SM)
+  int push_blocks;         // SPAM_PUSH_BLOCKS at init: grid of the push kernel (0: two blocks of 512 threads per SM)
 };
 
 namespace {
@@ -114,17 +114,7 @@ __global__ void __launch_bounds__(512) k_push(const unsigned char* __restrict__ 
   const u64 body = (bytes - head) / 16;
   const u64 tail0 = head + body * 16;
   const uint4* s16 = reinterpret_cast<const uint4*>(src + head);
-  // two independent 16-byte loads in flight per thread, each stored to every peer
-  u64 i = tid;
-  for (; i + nth < body; i += 2 * nth) {
-    const uint4 v0 = __ldcs(s16 + i), v1 = __ldcs(s16 + i + nth);
-#pragma unroll 1
-    for (int j = 0; j < dst.n; ++j) {
-      uint4* d = reinterpret_cast<uint4*>((unsigned char*)dst.p[j] + head);
-      d[i] = v0; d[i + nth] = v1;
-    }
-  }
-  if (i < body) {
+  for (u64 i = tid; i < body; i += nth) {
     const uint4 v = __ldcs(s16 + i);
 #pragma unroll 1
     for (int j = 0; j < dst.n; ++j) reinterpret_cast<uint4*>((unsigned char*)dst.p[j] + head)[i] = v;
@@ -152,9 +142,10 @@ int push_range(spam_handle* h, CommState* c, int which, u64 off_bytes, u64 bytes
   for (int r = 0; r < c->world; ++r)
     if (r != c->rank) d.p[d.n++] = (unsigned char*)c->buf[which].peer[r] + off_bytes;
   if (!d.n) return SPAM_OK;
-  u64 blocks = (bytes / 32 + 511) / 512;
-  // measured on 8 GPUs (R-MAT 22): 32 blocks 472 GB/s received per GPU, two blocks per SM 552 GB/s — the stores want threads
-  const u64 cap = c->push_blocks ? (u64)c->push_blocks : (u64)h->num_sms * 4;
+  u64 blocks = (bytes / 16 + 511) / 512;
+  // measured (R-MAT 22): 8 GPUs: 32 blocks 472 GB/s received per GPU, two blocks per SM 552 GB/s; 2 GPUs: two blocks per SM
+  // 73 ms per step, four blocks per SM with two loads in flight 81 ms (the push then takes SMs from the product)
+  const u64 cap = c->push_blocks ? (u64)c->push_blocks : (u64)h->num_sms * 2;
   if (blocks > cap) blocks = cap;
   if (blocks == 0) blocks = 1;
   k_push<<<(unsigned)blocks, 512, 0, c->push>>>((const unsigned char*)c->buf[which].local + off_bytes, d, bytes);
@@ -413,6 +404,10 @@ int spam_spgemm_gathered(spam_handle* h, const spam_dcsr* a_block, const spam_dc
     }
   }
   if (rows_sum != total_rows || rows_before != row_start) { drop(); return spam_fail(h, SPAM_EINVAL, "the ranks' row blocks do not tile the matrix in rank order"); }
+  // mode < 0: pick by measurement — with one peer the copy engines leave every SM to the product (R-MAT 22 on 2 GPUs:
+  // 61 ms against 73 ms with the push kernel); with more peers their per-destination copies run one after another and
+  // the push kernel, which stores every 16 bytes to all peers at once, wins (8 GPUs: 61 ms against 82 ms)
+  if (mode < 0) mode = c->world <= 2 ? 2 : 0;
   const bool want_peers = mode == 0 || mode == 2;
   const bool dma = mode == 2;
   int st = ensure_buf(h, c, 0, (total_rows + 1) * 8, want_peers);
