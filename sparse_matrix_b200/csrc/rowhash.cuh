@@ -34,12 +34,10 @@ namespace {
 constexpr unsigned FULL = 0xffffffffu;
 constexpr u32 SYM_REDO = 0xFFFFFFFFu;  // row_nnz marker: the optimistic symbolic table overflowed, redo the row
 constexpr int ROWS_PER_BLOCK_W1 = 4;  // NW = 1: four independent warps (rows) per 128-thread block
-// Teams (NW > 1) walk the A row in chunks of 32 entries.  Every warp that works on a chunk pays the chunk's prologue
-// (three dependent loads, a 5-step scan) whatever its share of the chunk's products — with all NW warps on every
-// chunk a 16-warp team spent ~40% of its accumulation instructions there (a chunk of R-MAT holds ~512 products: one
-// batch per warp).  So the team is cut into groups of TEAM_WPG warps: group g takes chunks g, g + groups, ...
-constexpr int TEAM_WPG = 4;
-__host__ __device__ constexpr int team_wpg(int nw) { return nw < TEAM_WPG ? nw : TEAM_WPG; }
+// Two changes to the team / global-table kernels were tried in r2 and dropped (R-MAT 22, numeric pass 79 ms):
+//  * groups of four warps taking separate 32-entry chunks of the A row, to save the chunk prologue every warp pays:
+//    109 ms — all warps on one chunk is what keeps enough loads in flight;
+//  * loading chunk k + 1 (a_col -> b_ptr) before chunk k is processed: 87 ms (and the symbolic pass 15.4 -> 16.5 ms).
 
 __device__ __forceinline__ u32 slot_fib(u32 key, u32 shift) { return (key * 2654435769u) >> shift; }
 
@@ -174,9 +172,7 @@ k_sym_row(u32 n, const u32* __restrict__ perm, const u64* __restrict__ a_ptr, co
   if (NW == 1) __syncwarp(); else __syncthreads();
   const u64 lo = a_ptr[row], hi = a_ptr[row + 1];
   u32 cnt = 0;
-  constexpr int WPG = team_wpg(NW), NGRP = NW / WPG;  // warps per group, groups per team
-  const int gw = rw % WPG;                             // this warp inside its group
-  for (u64 ec = lo + 32ull * (rw / WPG); ec < hi; ec += 32ull * NGRP) {
+  for (u64 ec = lo; ec < hi; ec += 32) {
     if (DIRECT) {
       const AChunk<u32> c = load_chunk<u32, false, false>(ec, hi, lane, a_col, nullptr, b_ptr);
       const int na = (int)((hi - ec) < 32 ? (hi - ec) : 32);
@@ -221,7 +217,7 @@ k_sym_row(u32 n, const u32* __restrict__ perm, const u64* __restrict__ a_ptr, co
     } else {
       const AChunk<u32> c = load_chunk<u32, false, true>(ec, hi, lane, a_col, nullptr, b_ptr);
       // software pipeline: the next batch's search + load is issued before the current batch is probed
-      u32 p0 = 32 * gw;
+      u32 p0 = 32 * rw;
       u64 addr;
       u32 dummy;
       u32 nkey = 0;
@@ -234,7 +230,7 @@ k_sym_row(u32 n, const u32* __restrict__ perm, const u64* __restrict__ a_ptr, co
       while (p0 < c.total) {
         const u32 key = nkey;
         const bool active = nact;
-        p0 += 32 * WPG;
+        p0 += 32 * NW;
         if (p0 < c.total) {
           locate<u32, false>(c, p0 + lane, addr, dummy);
           nact = p0 + lane < c.total;
@@ -422,9 +418,7 @@ k_num_row(u32 n, const u32* __restrict__ perm, const u64* __restrict__ a_ptr, co
 
   const u64 lo = a_ptr[row], hi = a_ptr[row + 1];
   u32 kmin = 0xFFFFFFFFu, kmax = 0;
-  constexpr int WPG = team_wpg(NW), NGRP = NW / WPG;
-  const int gw = rw % WPG;
-  for (u64 ec = lo + 32ull * (rw / WPG); ec < hi; ec += 32ull * NGRP) {
+  for (u64 ec = lo; ec < hi; ec += 32) {
     if (DIRECT) {
       const AChunk<V> c = load_chunk<V, true, false>(ec, hi, lane, a_col, a_val, b_ptr);
       const int na = (int)((hi - ec) < 32 ? (hi - ec) : 32);
@@ -457,7 +451,7 @@ k_num_row(u32 n, const u32* __restrict__ perm, const u64* __restrict__ a_ptr, co
       }
     } else {
       const AChunk<V> c = load_chunk<V, true, true>(ec, hi, lane, a_col, a_val, b_ptr);
-      u32 p0 = 32 * gw;
+      u32 p0 = 32 * rw;
       u64 addr;
       V av;
       u32 nkey = 0;
@@ -472,7 +466,7 @@ k_num_row(u32 n, const u32* __restrict__ perm, const u64* __restrict__ a_ptr, co
         const u32 key = nkey;
         const V prod = nprod;
         const bool active = nact;
-        p0 += 32 * WPG;
+        p0 += TT;
         if (p0 < c.total) {  // next batch: search + loads in flight while this one is accumulated
           locate<V, true>(c, p0 + lane, addr, av);
           nact = p0 + lane < c.total;

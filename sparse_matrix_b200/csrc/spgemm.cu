@@ -457,10 +457,9 @@ __global__ void __launch_bounds__(T) k_num_heavy(u32 n, const u32* __restrict__ 
     // whatever the B row lengths (a sub-warp per A entry left a quarter of the kernel waiting at the
     // barrier below for the warps that drew the hub rows: profiles/r01_rmat20_v3_team_drain.txt)
     const u64 lo = a_ptr[row], hi = a_ptr[row + 1];
-    constexpr int WPG = TEAM_WPG, NGRP = T / 32 / WPG;  // groups of 4 warps take every NGRP-th chunk (rowhash.cuh)
-    for (u64 ec = lo + 32ull * (wid / WPG); ec < hi; ec += 32ull * NGRP) {
+    for (u64 ec = lo; ec < hi; ec += 32) {
       const AChunk<V> c = load_chunk<V, true, true>(ec, hi, ln, a_col, a_val, b_ptr);
-      for (u32 p0 = 32u * (wid % WPG); p0 < c.total; p0 += 32u * WPG) {
+      for (u32 p0 = 32u * wid; p0 < c.total; p0 += T) {
         u64 addr;
         V av;
         locate<V, true>(c, p0 + ln, addr, av);
