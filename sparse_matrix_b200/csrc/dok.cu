@@ -155,8 +155,7 @@ constexpr u32 SEG_MAX = 32;  // longest row / column segment the counting paths 
 
 // rank of every triplet inside its row = the row counter's value when the triplet arrived (an atomic WITH return):
 // the scatter pass then needs no atomics.  Ranks saturate at 255: a row that long takes the radix path anyway.
-__global__ void __launch_bounds__(256) k_dok_hist(u64 n, u64 rows, u64 cols, const u64* __restrict__ r,
-                                                  const u64* __restrict__ c, u32* __restrict__ raw_cnt,
+__global__ void __launch_bounds__(256) k_dok_hist(u64 n, u64 rows, const u64* __restrict__ r, u32* __restrict__ raw_cnt,
                                                   unsigned char* __restrict__ rank8, Counters* cnt) {
   constexpr int U = 4;  // independent atomics in flight per thread
   const u64 stride = (u64)gridDim.x * blockDim.x;
@@ -170,8 +169,8 @@ __global__ void __launch_bounds__(256) k_dok_hist(u64 n, u64 rows, u64 cols, con
       ri[u] = 0; ok[u] = false;
       if (i < n) {
         ri[u] = r[i];
-        ok[u] = ri[u] < rows && c[i] < cols;
-        bad = bad || !ok[u];  // IndexError (spam_dok lib.rs:168-170)
+        ok[u] = ri[u] < rows;   // the column is checked by the scatter pass, which reads it anyway
+        bad = bad || !ok[u];    // IndexError (spam_dok lib.rs:168-170)
       }
     }
     u32 rk[U];
@@ -201,12 +200,17 @@ __device__ __forceinline__ V dok_val(const uint4& e) {
 }
 
 template <class V>
-__global__ void __launch_bounds__(256) k_dok_scatter(u64 n, const u64* __restrict__ r, const u64* __restrict__ c,
+__global__ void __launch_bounds__(256) k_dok_scatter(u64 n, u64 cols, const u64* __restrict__ r, const u64* __restrict__ c,
                                                      const V* __restrict__ v, const unsigned char* __restrict__ rank8,
-                                                     const u64* __restrict__ seg_ptr, uint4* __restrict__ ent) {
+                                                     const u64* __restrict__ seg_ptr, uint4* __restrict__ ent, Counters* cnt) {
   const u64 stride = (u64)gridDim.x * blockDim.x;
-  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-    ent[seg_ptr[r[i]] + rank8[i]] = dok_pack<V>((u32)c[i], (u32)i, v[i]);
+  bool bad = false;
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const u64 ci = c[i];
+    bad = bad || ci >= cols;  // IndexError: reported after the second scan, before anything is returned
+    ent[seg_ptr[r[i]] + rank8[i]] = dok_pack<V>((u32)ci, (u32)i, v[i]);
+  }
+  if (bad) atomicOr(&cnt->error, 2u);
 }
 
 constexpr int SEG_REGS = 16;  // segments up to this length are held in registers (C5: 8-9 triplets per row)
@@ -482,7 +486,7 @@ int dok_typed(spam_handle* h, u64 rows, u64 cols, u64 n, const u64* d_r, const u
   CK(cudaMemsetAsync(h->d_cnt, 0, sizeof(Counters), h->stream));
   CK(cudaMemsetAsync(raw_cnt, 0, rows * sizeof(u32), h->stream));
   if (n) {
-    k_dok_hist<<<grid_for(h, (n + 3) / 4), 256, 0, h->stream>>>(n, rows, cols, d_r, d_c, raw_cnt, rank8, h->d_cnt);
+    k_dok_hist<<<grid_for(h, (n + 3) / 4), 256, 0, h->stream>>>(n, rows, d_r, raw_cnt, rank8, h->d_cnt);
     count_launch(h);
     CK(cudaGetLastError());
   }
@@ -499,7 +503,7 @@ int dok_typed(spam_handle* h, u64 rows, u64 cols, u64 n, const u64* d_r, const u
   CKS(g.alloc(&ent, n ? n : 1));
   const unsigned rgrid = (unsigned)((rows + 127) / 128);   // rows >= 1 (NonZeroUsize in the reference)
   if (n) {
-    k_dok_scatter<V><<<grid_for(h, n), 256, 0, h->stream>>>(n, d_r, d_c, d_v, rank8, seg_ptr, ent);
+    k_dok_scatter<V><<<grid_for(h, n), 256, 0, h->stream>>>(n, cols, d_r, d_c, d_v, rank8, seg_ptr, ent, h->d_cnt);
     count_launch(h);
   }
   k_dok_seg<V><<<rgrid, 128, 0, h->stream>>>(rows, seg_ptr, ent, raw_cnt);  // raw_cnt reused: survivors per row
@@ -508,6 +512,7 @@ int dok_typed(spam_handle* h, u64 rows, u64 cols, u64 n, const u64* d_r, const u
   CKS(scan_u32_to_u64(h, raw_cnt, out->ptr, rows, &h->d_cnt->total_nnz));
   CK(cudaMemcpyAsync(h->h_cnt, h->d_cnt, sizeof(Counters), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
+  if (h->h_cnt->error & 2u) return spam_fail(h, SPAM_EINDEX, "triplet index out of range");
   out->nnz = h->h_cnt->total_nnz;
   CKS(dev_alloc_t(h, &out->idx, out->nnz));
   CKS(dev_alloc(h, &out->val, out->nnz * sizeof(V)));
