@@ -184,7 +184,10 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": "spgemm_gflops", "value": val, "unit": "GFLOP/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": args.workload, "desc": WORKLOAD_DESC[args.workload], "rows": int(mat[0])},
+            "config": {"workload": args.workload, "desc": WORKLOAD_DESC[args.workload], "rows": int(mat[0]),
+                       "nnz_a": int(len(mat[3])), "products": int(flops), "nnz_c": int(nnz),
+                       "algorithmic_bytes": int(len(mat[3]) * 12 + (mat[0] + 1) * 16 + flops * 12 + nnz * 12),
+                       "sharding": "CPU: flop-balanced row blocks over the host threads (rows_to_threads, mul_hash.rs:38-64)"},
             "cpu_baseline": {"value": val, "unit": "GFLOP/s", "cores": O.hardware_threads(), "kind": "port",
                              "sample": "full workload A*A per step; C++ restatement of spam_csr::mul_hash "
                                        "(the Rust reference cannot be built: no cargo/rustc in the image)"},

@@ -43,81 +43,56 @@ __device__ __forceinline__ V apply(V x, V y) {
   return Num<V>::sub(x, y);
 }
 
-constexpr int EW_IN = 2304;   // entries of each operand a block stages in shared memory (128 rows x 18)
-constexpr int EW_OUT = 3072;  // output entries a block stages (128 rows x 24)
-template <class V>
-constexpr size_t ewise_smem() { return (size_t)(2 * EW_IN + EW_OUT) * (sizeof(V) + 4); }
+constexpr int EW_STAGE = 3072;  // output entries a block stages in shared memory (128 rows x 24)
 
-// One thread per row walks the two sorted rows.  The rows of a block are consecutive, so its slices of A, B and C
-// are three contiguous spans: the block loads the two input spans into shared memory with full-sector loads, the
-// threads merge out of shared memory into a staged output span, and the block stores that with full sectors.
-// (Thread-per-row loads and stores straight from / to global memory are row-length strided — 32 sectors per
-// instruction: 0.18 of the copy peak in r1, 0.30 with only the stores staged.)  A block whose spans do not fit
-// (long rows) works on global memory directly.
+// One thread per row walks the two sorted rows.  The rows of a block are consecutive, so their output is one
+// contiguous span of C: the threads write it into shared memory and the block then stores it with full sectors
+// (thread-per-row stores straight to C are row-length strided: 32 sectors per store instruction, 0.18 of the copy
+// peak in r1, 0.30 with the staged stores).  Staging the two INPUT spans the same way was tried and was slower (0.96 ms
+// against 0.87 ms on A*A + A: 90 KB of shared memory per block leave two blocks per SM).  A block whose span does not
+// fit (long rows) stores directly.
 template <class V, int OP, bool KEEP_LEFT, int BLOCK>
 __global__ void __launch_bounds__(BLOCK) k_ewise_fill(u64 m, const u64* __restrict__ ap, const u32* __restrict__ ac,
                                                       const V* __restrict__ av, const u64* __restrict__ bp,
                                                       const u32* __restrict__ bc, const V* __restrict__ bv,
                                                       const u64* __restrict__ cp, u32* __restrict__ cc,
                                                       V* __restrict__ cv) {
-  extern __shared__ __align__(16) unsigned char sm_ew[];
-  V* sva = reinterpret_cast<V*>(sm_ew);
-  V* svb = sva + EW_IN;
-  V* svo = svb + EW_IN;
-  u32* ska = reinterpret_cast<u32*>(svo + EW_OUT);
-  u32* skb = ska + EW_IN;
-  u32* sko = skb + EW_IN;
+  __shared__ u32 sk[EW_STAGE];
+  __shared__ V sv[EW_STAGE];
   const u64 row0 = (u64)blockIdx.x * BLOCK;
   const u64 row = row0 + threadIdx.x;
   const u64 rend = row0 + BLOCK < m ? row0 + BLOCK : m;
-  const u64 a0 = ap[row0], b0 = bp[row0], c0 = cp[row0];
-  const u64 na = ap[rend] - a0, nb = bp[rend] - b0, nc = cp[rend] - c0;
-  const bool staged = na <= (u64)EW_IN && nb <= (u64)EW_IN && nc <= (u64)EW_OUT;  // block-uniform
-  const V zero = Num<V>::zero();
-  if (staged) {
-    for (u64 q = threadIdx.x; q < na; q += BLOCK) { ska[q] = ac[a0 + q]; sva[q] = av[a0 + q]; }
-    for (u64 q = threadIdx.x; q < nb; q += BLOCK) { skb[q] = bc[b0 + q]; svb[q] = bv[b0 + q]; }
-    __syncthreads();
-    if (row < m) {
-      u32 i = (u32)(ap[row] - a0), j = (u32)(bp[row] - b0), o = (u32)(cp[row] - c0);
-      const u32 ie = (u32)(ap[row + 1] - a0), je = (u32)(bp[row + 1] - b0);
-      while (i < ie && j < je) {
-        const u32 ca = ska[i], cb = skb[j];
-        if (ca == cb) { sko[o] = ca; svo[o] = apply<V, OP>(sva[i], svb[j]); ++i; ++j; }
-        else if (ca < cb) { sko[o] = ca; svo[o] = KEEP_LEFT ? sva[i] : apply<V, OP>(sva[i], zero); ++i; }
-        else { sko[o] = cb; svo[o] = apply<V, OP>(zero, svb[j]); ++j; }
-        ++o;
-      }
-      for (; i < ie; ++i, ++o) { sko[o] = ska[i]; svo[o] = KEEP_LEFT ? sva[i] : apply<V, OP>(sva[i], zero); }
-      for (; j < je; ++j, ++o) { sko[o] = skb[j]; svo[o] = apply<V, OP>(zero, svb[j]); }
+  const u64 base = cp[row0], span = cp[rend] - base;
+  const bool staged = span <= (u64)EW_STAGE;  // block-uniform
+  if (row < m) {
+    u64 i = ap[row], j = bp[row], o = cp[row];
+    const u64 ie = ap[row + 1], je = bp[row + 1];
+    const V zero = Num<V>::zero();
+    auto put = [&](u32 c, V v) {
+      if (staged) { sk[o - base] = c; sv[o - base] = v; } else { cc[o] = c; cv[o] = v; }
+      ++o;
+    };
+    while (i < ie && j < je) {
+      const u32 ca = ac[i], cb = bc[j];
+      if (ca == cb) { put(ca, apply<V, OP>(av[i], bv[j])); ++i; ++j; }
+      else if (ca < cb) { put(ca, KEEP_LEFT ? av[i] : apply<V, OP>(av[i], zero)); ++i; }
+      else { put(cb, apply<V, OP>(zero, bv[j])); ++j; }
     }
-    __syncthreads();
-    for (u64 q = threadIdx.x; q < nc; q += BLOCK) { cc[c0 + q] = sko[q]; cv[c0 + q] = svo[q]; }
-    return;
+    for (; i < ie; ++i) put(ac[i], KEEP_LEFT ? av[i] : apply<V, OP>(av[i], zero));
+    for (; j < je; ++j) put(bc[j], apply<V, OP>(zero, bv[j]));
   }
-  if (row >= m) return;
-  u64 i = ap[row], j = bp[row], o = cp[row];
-  const u64 ie = ap[row + 1], je = bp[row + 1];
-  while (i < ie && j < je) {
-    const u32 ca = ac[i], cb = bc[j];
-    if (ca == cb) { cc[o] = ca; cv[o] = apply<V, OP>(av[i], bv[j]); ++i; ++j; }
-    else if (ca < cb) { cc[o] = ca; cv[o] = KEEP_LEFT ? av[i] : apply<V, OP>(av[i], zero); ++i; }
-    else { cc[o] = cb; cv[o] = apply<V, OP>(zero, bv[j]); ++j; }
-    ++o;
-  }
-  for (; i < ie; ++i, ++o) { cc[o] = ac[i]; cv[o] = KEEP_LEFT ? av[i] : apply<V, OP>(av[i], zero); }
-  for (; j < je; ++j, ++o) { cc[o] = bc[j]; cv[o] = apply<V, OP>(zero, bv[j]); }
+  if (!staged) return;
+  __syncthreads();
+  for (u64 q = threadIdx.x; q < span; q += BLOCK) { cc[base + q] = sk[q]; cv[base + q] = sv[q]; }
 }
 
 template <class V>
 int fill_typed(spam_handle* h, int op, const spam_dcsr* a, const spam_dcsr* b, spam_dcsr* c) {
   constexpr int BL = 128;
   const unsigned grid = (unsigned)((a->rows + BL - 1) / BL);
-  constexpr size_t smem = ewise_smem<V>();
 #define EW_LAUNCH(OP, KEEP)                                                                                          \
-  CK(cudaFuncSetAttribute(k_ewise_fill<V, OP, KEEP, BL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
-  k_ewise_fill<V, OP, KEEP, BL><<<grid, BL, smem, h->stream>>>(a->rows, a->ptr, a->idx, (const V*)a->val, b->ptr, b->idx, \
-                                                               (const V*)b->val, c->ptr, c->idx, (V*)c->val)
+  k_ewise_fill<V, OP, KEEP, BL><<<grid, BL, 0, h->stream>>>(a->rows, a->ptr, a->idx, (const V*)a->val, b->ptr, b->idx, \
+                                                            (const V*)b->val, c->ptr, c->idx, (V*)c->val)
   switch (op) {
     case 0: EW_LAUNCH(0, false); break;
     case 1: EW_LAUNCH(1, false); break;
