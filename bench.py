@@ -216,6 +216,11 @@ def time_steps(fn, steps, sync_all, torch):
     return ev0.elapsed_time(ev1) / steps
 
 
+def median_step(fn, steps, sync_all, torch):
+    """Median of individually timed steps (robust to a one-off stall; used for the long R-MAT steps only)."""
+    return float(np.median([time_steps(fn, 1, sync_all, torch) for _ in range(steps)]))
+
+
 def max_over_ranks(x, world, dev, torch, dist):
     if world == 1:
         return float(x), [round(float(x), 4)]
@@ -300,7 +305,9 @@ def rmat_strong_section(args, S, D, G, handle, rank, world, dev, torch, dist, sy
     N: the 1-GPU product on this box, the row-sharded product (C left sharded), and the product with C assembled on
     every rank (peer stores overlapped with the numeric kernels; and the NCCL-broadcast variant beside it)."""
     name = args.scale_workload
-    out = {"workload": name, "desc": WORKLOAD_DESC[name], "scaling": "strong"}
+    out = {"workload": name, "desc": WORKLOAD_DESC[name], "scaling": "strong",
+           "timing": "CUDA events around single steps between barriers, median of the steps, max over ranks "
+                     "(ms_1gpu_ref: every rank runs the whole product on its own GPU, fastest rank)"}
     t0 = time.perf_counter()
     mat = make_workload(name) if rank == 0 else None
     out["generate_s"] = round(time.perf_counter() - t0, 2) if rank == 0 else None
@@ -317,13 +324,18 @@ def rmat_strong_section(args, S, D, G, handle, rank, world, dev, torch, dist, sy
         if len(outs) > 1:
             outs.pop(0).free()
     one(); one()
-    ms1 = time_steps(one, steps, sync_all, torch)
-    ms1, _ = max_over_ranks(ms1, world, dev, torch, dist)
+    # every rank times the same product on its own GPU, step by step; the median step of the fastest rank is "one GPU
+    # alone" (an outlier rank was seen once: 1.4 s for a 96 ms product on one of four GPUs), the slowest rank's is
+    # reported beside it
+    ms1_local = median_step(one, steps, sync_all, torch)
+    ms1_max, ms1_ranks = max_over_ranks(ms1_local, world, dev, torch, dist)
+    ms1 = min(ms1_ranks)
     st = handle.stats()
     flops, nnz_c = int(st["flops"]), int(st["nnz_c"])
     while outs:
         outs.pop().free()
     out.update({"rows": rows, "nnz_a": nnz_a, "products": flops, "nnz_c": nnz_c, "ms_1gpu_ref": ms1,
+                "ms_1gpu_ref_per_rank": ms1_ranks,
                 "gflops_1gpu": 2.0 * flops / ms1 / 1e6, "num_bin_rows": st["num_bin_rows"], "fallbacks": st["fallbacks"],
                 "algorithmic_bytes": G.algorithmic_bytes_spgemm(rows, nnz_a, flops, nnz_c, 8)})
     out["hbm_frac_1gpu"] = out["algorithmic_bytes"] / ms1 / 1e6 / measured_peak()[0]
@@ -348,12 +360,12 @@ def rmat_strong_section(args, S, D, G, handle, rank, world, dev, torch, dist, sy
             blk.matmul_gathered(dA, r0, rows, nsub=nsub or args.nsub, mode=mode).free()
         return f
     sharded(); sharded()
-    ms_s = time_steps(sharded, steps, sync_all, torch)
+    ms_s = median_step(sharded, steps, sync_all, torch)
     ms_s, rank_ms = max_over_ranks(ms_s, world, dev, torch, dist)
     gm = args.gather_mode
     gathered(gm)(); gathered(gm)()
     out["ms_total_from_host_A"] = None
-    ms_g, _ = max_over_ranks(time_steps(gathered(gm), steps, sync_all, torch), world, dev, torch, dist)
+    ms_g, _ = max_over_ranks(median_step(gathered(gm), steps, sync_all, torch), world, dev, torch, dist)
     peer = handle.comm_info()["peer_mapped"]
     # parity of the assembled C (outside every timed region)
     g = blk.matmul_gathered(dA, r0, rows, nsub=args.nsub, mode=gm)
@@ -362,7 +374,7 @@ def rmat_strong_section(args, S, D, G, handle, rank, world, dev, torch, dist, sy
     okt = torch.tensor([1 if ok else 0], dtype=torch.int64, device=dev)
     dist.all_reduce(okt, op=dist.ReduceOp.MIN)
     gathered(1)(); gathered(1)()
-    ms_n, _ = max_over_ranks(time_steps(gathered(1), steps, sync_all, torch), world, dev, torch, dist)
+    ms_n, _ = max_over_ranks(median_step(gathered(1), steps, sync_all, torch), world, dev, torch, dist)
     recv = (nnz_c * 12 + (rows + 1) * 8) * (world - 1) / world
     if args.gather_sweep:       # how the exchange is done and how finely it is pipelined (builder runs only)
         sweep = {}
@@ -370,7 +382,7 @@ def rmat_strong_section(args, S, D, G, handle, rank, world, dev, torch, dist, sy
             for nsub in (1, 4, 8, 16):
                 f = gathered(mode, nsub)
                 f(); f()
-                t, _ = max_over_ranks(time_steps(f, steps, sync_all, torch), world, dev, torch, dist)
+                t, _ = max_over_ranks(median_step(f, steps, sync_all, torch), world, dev, torch, dist)
                 sweep[f"mode{mode}_nsub{nsub}"] = round(t, 3)
         out["gather_sweep_ms"] = sweep
     out.update({"ms_sharded": ms_s, "rank_ms": rank_ms, "speedup_sharded": ms1 / ms_s,
