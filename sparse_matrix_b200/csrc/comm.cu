@@ -90,6 +90,7 @@ struct CommState {
   cudaStream_t push;       // high-priority stream of the push kernels
   cudaEvent_t ev_ready, ev_pushed;
   int push_blocks;         // SPAM_PUSH_BLOCKS at init: grid of the push kernel (0: two blocks of 512 threads per SM)
+  int push_split;          // SPAM_PUSH_SPLIT=1 at init: every block of the push kernel serves one peer (k_push_split)
 };
 
 namespace {
@@ -127,6 +128,27 @@ __global__ void __launch_bounds__(512) k_push(const unsigned char* __restrict__ 
   }
 }
 
+// the same copy with the destinations split over the blocks: block b streams the whole slice to peer b % n (the slice
+// is read n times out of L2 / HBM, every store stream has one destination)
+__global__ void __launch_bounds__(512) k_push_split(const unsigned char* __restrict__ src, PeerDst dst, u64 bytes) {
+  const int peer = blockIdx.x % dst.n;
+  const u64 bpp = gridDim.x / dst.n;                       // blocks per peer (grid is a multiple of n)
+  const u64 tid = (u64)(blockIdx.x / dst.n) * blockDim.x + threadIdx.x, nth = bpp * blockDim.x;
+  unsigned char* d = (unsigned char*)dst.p[peer];
+  const u64 mis = (16 - ((uintptr_t)src & 15)) & 15;
+  const u64 head = mis < bytes ? mis : bytes;
+  const u64 body = (bytes - head) / 16;
+  const u64 tail0 = head + body * 16;
+  const uint4* s16 = reinterpret_cast<const uint4*>(src + head);
+  uint4* d16 = reinterpret_cast<uint4*>(d + head);
+  for (u64 i = tid; i < body; i += nth) d16[i] = s16[i];
+  const u64 nh = head / 4, nt = (bytes - tail0) / 4;
+  if (tid < nh + nt) {
+    const u64 off = tid < nh ? tid * 4 : tail0 + (tid - nh) * 4;
+    *reinterpret_cast<u32*>(d + off) = *reinterpret_cast<const u32*>(src + off);
+  }
+}
+
 int push_range(spam_handle* h, CommState* c, int which, u64 off_bytes, u64 bytes, bool dma) {
   if (!bytes) return SPAM_OK;
   if (dma) {  // copy engines instead of SMs: one peer-to-peer copy per destination
@@ -148,7 +170,13 @@ int push_range(spam_handle* h, CommState* c, int which, u64 off_bytes, u64 bytes
   const u64 cap = c->push_blocks ? (u64)c->push_blocks : (u64)h->num_sms * 2;
   if (blocks > cap) blocks = cap;
   if (blocks == 0) blocks = 1;
-  k_push<<<(unsigned)blocks, 512, 0, c->push>>>((const unsigned char*)c->buf[which].local + off_bytes, d, bytes);
+  if (c->push_split && d.n > 1) {
+    u64 bpp = (blocks + d.n - 1) / d.n;
+    if (bpp == 0) bpp = 1;
+    k_push_split<<<(unsigned)(bpp * d.n), 512, 0, c->push>>>((const unsigned char*)c->buf[which].local + off_bytes, d, bytes);
+  } else {
+    k_push<<<(unsigned)blocks, 512, 0, c->push>>>((const unsigned char*)c->buf[which].local + off_bytes, d, bytes);
+  }
   count_launch(h);
   CK(cudaGetLastError());
   return SPAM_OK;
@@ -256,6 +284,7 @@ int spam_comm_init(spam_handle* h, const void* id128, int rank, int world) {
   memset(c, 0, sizeof(*c));
   c->rank = rank; c->world = world; c->peer_ok = true;
   { const char* e = getenv("SPAM_PUSH_BLOCKS"); c->push_blocks = e ? atoi(e) : 0; }
+  { const char* e = getenv("SPAM_PUSH_SPLIT"); c->push_split = e ? atoi(e) : 0; }
   ncclUniqueId id;
   memcpy(&id, id128, 128);
   ncclResult_t r = g_nccl.CommInitRank(&c->comm, world, id, rank);
