@@ -254,6 +254,9 @@ int spam_cuda_create(spam_handle** out, int device) {
     h->use_lanes = !(e && e[0] == '0');
     e = getenv("SPAM_SORT_B");
     h->sort_b = !(e && e[0] == '0');
+    e = getenv("SPAM_L2_PERSIST");
+    h->l2_persist = e ? atoi(e) : 0;
+    h->l2_persist_max = 0; h->l2_window_max = 0;
     e = getenv("SPAM_ESC");
     h->use_esc = e ? (e[0] == '2' ? 2 : (e[0] == '1' ? 1 : 0)) : 0;
   }
@@ -278,6 +281,11 @@ int spam_cuda_create(spam_handle** out, int device) {
   if (e == cudaSuccess) {
     h->num_sms = prop.multiProcessorCount;
     h->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    if (h->l2_persist && prop.persistingL2CacheMaxSize > 0 &&
+        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)prop.persistingL2CacheMaxSize) == cudaSuccess) {
+      h->l2_persist_max = (size_t)prop.persistingL2CacheMaxSize;
+      h->l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
+    } else cudaGetLastError();
     // A PRIVATE stream-ordered pool that keeps its freed blocks: steady-state products do no cudaMalloc, and
     // the process-wide default pool (shared with torch, NCCL, ...) is left alone.
     cudaMemPoolProps pp = {};

@@ -218,6 +218,8 @@ struct spam_handle {
   int use_esc;         // SPAM_ESC at create time: 0 = hash bins only (default: measured faster on B200), 1 = bucket-sort
                        // bins for non-compressing rows up to 8192 products, 2 = also the column-range kernel for longer rows
   bool sort_b;         // SPAM_SORT_B=0 at create time: never multiply by a sorted copy of an unsorted B (tests of the hash bins)
+  int l2_persist;      // SPAM_L2_PERSIST at create time (experiment, spgemm.cu): 1 = B's col_idx, 2 = B's values persisting in L2
+  size_t l2_persist_max, l2_window_max;
   HostStage* stage;    // created on the first copy that involves a pageable host buffer
   struct CommState* comm;  // comm.cu: NCCL communicator + peer-mapped gather buffers (spam_comm_init), or null
 };

@@ -1036,6 +1036,21 @@ int numeric_typed(spam_handle* h, SpgemmPending* p, spam_dcsr* c) {
     LAUNCH_NUM_ROW(1, 1, 128, false)
   }
 #undef LAUNCH_NUM_ROW
+  // SPAM_L2_PERSIST=1|2 (experiment): keep B's col_idx (1) or values (2) persisting in L2 while the merge kernel
+  // streams A and C through it (an access-policy window on the stream; the window is removed after the launch)
+  bool l2_window = false;
+  if (nb.count[MERGE_BIN] && h->l2_persist && h->l2_persist_max) {
+    cudaStreamAttrValue av_ = {};
+    const size_t bytes = h->l2_persist == 1 ? (size_t)b->nnz * 4 : (size_t)b->nnz * sizeof(V);
+    av_.accessPolicyWindow.base_ptr = h->l2_persist == 1 ? (void*)bc : (void*)bv;
+    av_.accessPolicyWindow.num_bytes = bytes < h->l2_window_max ? bytes : h->l2_window_max;
+    const double r = (double)h->l2_persist_max / (double)av_.accessPolicyWindow.num_bytes;
+    av_.accessPolicyWindow.hitRatio = (float)(r > 1.0 ? 1.0 : r);
+    av_.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    av_.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    if (cudaStreamSetAttribute(h->stream, cudaStreamAttributeAccessPolicyWindow, &av_) == cudaSuccess) l2_window = true;
+    else cudaGetLastError();
+  }
   if (nb.count[MERGE_BIN]) {
     constexpr int BL = 128;
     constexpr size_t smem = num_merge_smem<V, BL>();
@@ -1049,6 +1064,11 @@ int numeric_typed(spam_handle* h, SpgemmPending* p, spam_dcsr* c) {
     else
       k_num_merge<V, 8, BL><<<grid, BL, smem, h->stream>>>(nm, seg(MERGE_BIN), ap, ac, av, bp, bc, bv, cp, cc, cv);
     count_launch(h);
+    if (l2_window) {
+      cudaStreamAttrValue off_ = {};
+      off_.accessPolicyWindow.num_bytes = 0;
+      cudaStreamSetAttribute(h->stream, cudaStreamAttributeAccessPolicyWindow, &off_);
+    }
   }
   if (nb.count[0]) {
     constexpr int BL = 128;

@@ -574,6 +574,35 @@ def test_unsorted_output_in_reference_slot_order(oracle, handle, dtype):
         dC.free(); dA.free()
 
 
+def test_fuzz_target_shape_space(oracle, handle):
+    """The reference's fuzz target (fuzz/fuzz_targets/mul_hash.rs:11-50): f64, l and m in [1, 256], n in [1, 2^31],
+    at most 1000 random set_element calls per matrix (spam_matrix/src/arbitrary.rs:13-19); it asserts invariants()
+    always.  Here: 60 seeded draws from that space (n log-uniform), both output orders against the oracle."""
+    rng = np.random.default_rng(20260)
+    for case in range(60):
+        l, m = int(rng.integers(1, 257)), int(rng.integers(1, 257))
+        n = int(min(2 ** 31 - 2, max(1, round(2 ** rng.uniform(0, 31)))))
+        mats = []
+        for rows, cols in ((l, m), (m, n)):
+            d = S.DokMatrix.new((rows, cols))
+            for _ in range(int(rng.integers(0, 1001))):
+                d.set_element((int(rng.integers(0, rows)), int(rng.integers(0, cols))), float(rng.normal()))
+            keys = list(d.entries)                      # insertion order: rows come out unsorted
+            order = np.argsort([k[0] for k in keys], kind="stable")
+            rr = np.array([keys[i][0] for i in order], dtype=np.int64)
+            off = np.zeros(rows + 1, np.uint64)
+            np.cumsum(np.bincount(rr, minlength=rows), out=off[1:])
+            mats.append((rows, cols, off, np.array([keys[i][1] for i in order], np.uint64),
+                         np.array([d.entries[keys[i]] for i in order], np.float64)))
+        a, b = mats
+        A, B = as_csr_matrix(a, False), as_csr_matrix(b, False)
+        c = A.mul_hash(B, sorted_output=True, handle=handle)
+        check_against_oracle(oracle, a, b, c)
+        c = A.mul_hash(B, sorted_output=False, handle=handle, reference_order=True)
+        assert c.invariants()
+        _check_unsorted(oracle, a, b, c)
+
+
 def _dedupe_rows(m):
     rows, cols, off, idx, val = m
     noff, nidx, nval = [0], [], []
