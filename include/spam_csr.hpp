@@ -121,9 +121,12 @@ class CsrMatrix {
     return true;
   }
 
-  // mul_hash::<B1, B2>: the device emits rows sorted by column, valid for either B2.
+  // mul_hash::<B1, B2>: rows come back sorted by column, valid for either B2; with B2 = false and
+  // `reference_order` they come back in the reference's own B2 = false order (the slot order of its map,
+  // mul_hash.rs:176-186), column for column.
   template <bool B2, bool B1>
-  CsrMatrix<T, B2> mul_hash(const CsrMatrix<T, B1>& rhs, Handle& h = Handle::thread_default()) const {
+  CsrMatrix<T, B2> mul_hash(const CsrMatrix<T, B1>& rhs, Handle& h = Handle::thread_default(),
+                            bool reference_order = false) const {
     CsrMatrix<T, B2> c(rows, rhs.cols);
     uint64_t nnz = 0;
     h.check(spam_spgemm_symbolic(h.get(), device_scalar<T>::dtype, rows, cols, offsets.data(), indices.data(), vals.data(),
@@ -131,7 +134,7 @@ class CsrMatrix {
                                  c.offsets.data(), &nnz));
     c.indices.resize(nnz);  // Vec::with_capacity(nnz), mul_hash.rs:119
     c.vals.resize(nnz);
-    h.check(spam_spgemm_numeric(h.get(), c.indices.data(), c.vals.data(), 1));
+    h.check(spam_spgemm_numeric(h.get(), c.indices.data(), c.vals.data(), (!B2 && reference_order) ? 0 : 1));
     return c;
   }
 

@@ -638,6 +638,27 @@ static inline u32 n_esc_rows(const u32* count) {
   return n;
 }
 
+// SPAM_L2_PERSIST (experiment): an access-policy window on the stream marks one array of B as persisting in L2 while a
+// merge kernel streams A and C through it.  Returns true when a window was set (clear it after the launch).
+static inline bool l2_window_set(spam_handle* h, const void* base, size_t bytes) {
+  if (!h->l2_persist || !h->l2_persist_max || !bytes) return false;
+  cudaStreamAttrValue v = {};
+  v.accessPolicyWindow.base_ptr = const_cast<void*>(base);
+  v.accessPolicyWindow.num_bytes = bytes < h->l2_window_max ? bytes : h->l2_window_max;
+  const double r = (double)h->l2_persist_max / (double)v.accessPolicyWindow.num_bytes;
+  v.accessPolicyWindow.hitRatio = (float)(r > 1.0 ? 1.0 : r);
+  v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+  v.accessPolicyWindow.missProp = h->l2_persist >= 10 ? cudaAccessPropertyNormal : cudaAccessPropertyStreaming;
+  if (cudaStreamSetAttribute(h->stream, cudaStreamAttributeAccessPolicyWindow, &v) == cudaSuccess) return true;
+  cudaGetLastError();
+  return false;
+}
+static inline void l2_window_clear(spam_handle* h) {
+  cudaStreamAttrValue v = {};
+  v.accessPolicyWindow.num_bytes = 0;
+  cudaStreamSetAttribute(h->stream, cudaStreamAttributeAccessPolicyWindow, &v);
+}
+
 struct Bins {
   u32 count[NBINS];
   u32 base[NBINS];
@@ -784,6 +805,7 @@ int spgemm_symbolic_dev(spam_handle* h, const spam_dcsr* a, const spam_dcsr* b, 
     const u32 kk = amax <= 4 ? 4 : amax <= 6 ? 6 : 8;
     p->max_alen = kk;
     const unsigned grid = (unsigned)((m + 127) / 128);
+    const bool l2w = l2_window_set(h, b->idx, (size_t)b->nnz * 4);
     if (kk == 4)
       k_flop_sym_merge<4, 128><<<grid, 128, 0, h->stream>>>(m, b->rows, a->ptr, a->idx, b->ptr, b->idx, p->d_flop, p->d_row_nnz, h->d_cnt);
     else if (kk == 6)
@@ -791,6 +813,7 @@ int spgemm_symbolic_dev(spam_handle* h, const spam_dcsr* a, const spam_dcsr* b, 
     else
       k_flop_sym_merge<8, 128><<<grid, 128, 0, h->stream>>>(m, b->rows, a->ptr, a->idx, b->ptr, b->idx, p->d_flop, p->d_row_nnz, h->d_cnt);
     count_launch(h);
+    if (l2w) l2_window_clear(h);
     CK_FREE(cudaGetLastError());
     if (h->timing) { CK_FREE(cudaEventRecord(h->ev[1], h->stream)); CK_FREE(cudaEventRecord(h->ev[2], h->stream)); }
     FAIL_FREE(scan_u32_to_u64(h, p->d_row_nnz, p->d_cptr, m, &h->d_cnt->total_nnz));
@@ -1036,21 +1059,9 @@ int numeric_typed(spam_handle* h, SpgemmPending* p, spam_dcsr* c) {
     LAUNCH_NUM_ROW(1, 1, 128, false)
   }
 #undef LAUNCH_NUM_ROW
-  // SPAM_L2_PERSIST=1|2 (experiment): keep B's col_idx (1) or values (2) persisting in L2 while the merge kernel
-  // streams A and C through it (an access-policy window on the stream; the window is removed after the launch)
-  bool l2_window = false;
-  if (nb.count[MERGE_BIN] && h->l2_persist && h->l2_persist_max) {
-    cudaStreamAttrValue av_ = {};
-    const size_t bytes = h->l2_persist == 1 ? (size_t)b->nnz * 4 : (size_t)b->nnz * sizeof(V);
-    av_.accessPolicyWindow.base_ptr = h->l2_persist == 1 ? (void*)bc : (void*)bv;
-    av_.accessPolicyWindow.num_bytes = bytes < h->l2_window_max ? bytes : h->l2_window_max;
-    const double r = (double)h->l2_persist_max / (double)av_.accessPolicyWindow.num_bytes;
-    av_.accessPolicyWindow.hitRatio = (float)(r > 1.0 ? 1.0 : r);
-    av_.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-    av_.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-    if (cudaStreamSetAttribute(h->stream, cudaStreamAttributeAccessPolicyWindow, &av_) == cudaSuccess) l2_window = true;
-    else cudaGetLastError();
-  }
+  // SPAM_L2_PERSIST = 1: B's col_idx, 2: B's values persisting in L2 during the merge kernel
+  const bool l2_window = nb.count[MERGE_BIN] &&
+                         (h->l2_persist % 10 == 2 ? l2_window_set(h, bv, (size_t)b->nnz * sizeof(V)) : l2_window_set(h, bc, (size_t)b->nnz * 4));
   if (nb.count[MERGE_BIN]) {
     constexpr int BL = 128;
     constexpr size_t smem = num_merge_smem<V, BL>();
@@ -1064,11 +1075,7 @@ int numeric_typed(spam_handle* h, SpgemmPending* p, spam_dcsr* c) {
     else
       k_num_merge<V, 8, BL><<<grid, BL, smem, h->stream>>>(nm, seg(MERGE_BIN), ap, ac, av, bp, bc, bv, cp, cc, cv);
     count_launch(h);
-    if (l2_window) {
-      cudaStreamAttrValue off_ = {};
-      off_.accessPolicyWindow.num_bytes = 0;
-      cudaStreamSetAttribute(h->stream, cudaStreamAttributeAccessPolicyWindow, &off_);
-    }
+    if (l2_window) l2_window_clear(h);
   }
   if (nb.count[0]) {
     constexpr int BL = 128;

@@ -27,6 +27,13 @@ static int run(const char* name, std::mt19937_64& rng) {
     for (uint64_t r = 0; r < l; ++r)
       for (uint64_t e = cs.offsets[r]; e < cs.offsets[r + 1]; ++e) got[r * n + cs.indices[e]] = cs.vals[e];
     if (want != got || c.indices != cs.indices || c.vals != cs.vals) ++fails;
+    // B2 = false in the reference's slot order: the same entries per row, permuted
+    auto cu = a.template mul_hash<false>(b, spam::Handle::thread_default(), true);
+    if (!cu.invariants() || cu.offsets != cs.offsets) { ++fails; continue; }
+    std::vector<T> gotu(l * n, T(0));
+    for (uint64_t r = 0; r < l; ++r)
+      for (uint64_t e = cu.offsets[r]; e < cu.offsets[r + 1]; ++e) gotu[r * n + cu.indices[e]] = cu.vals[e];
+    if (gotu != got) ++fails;
     // spmv against the same dense data
     std::vector<T> x(m);
     for (auto& v : x) v = (T)((int)(rng() % 7) - 3);
@@ -85,6 +92,18 @@ int main() {
     try { (void)spam::from_matrix_market<double>("%%MatrixMarket matrix coordinate pattern general\n2 2 0\n"); }
     catch (const std::runtime_error&) { threw2 = true; }
     if (!threw2) ++fails;
+  }
+  // hand-derived known answer (tests/golden/linprobe_kat.json, map_slot_order): A = [[1,2,3,4]], B = I4 -> 16 slots,
+  // columns 0,1,2,3 land in slots 0,11,6,1: the B2 = false drain yields columns 0,3,2,1
+  {
+    spam::DokMatrix<double> da(1, 4), db(4, 4);
+    for (int j = 0; j < 4; ++j) { da.set_element(0, j, 1.0 + j); db.set_element(j, j, 1.0); }
+    auto a = spam::CsrMatrix<double, true>::from(da);
+    auto b = spam::CsrMatrix<double, true>::from(db);
+    auto c = a.template mul_hash<false>(b, spam::Handle::thread_default(), true);
+    const std::vector<uint64_t> want_idx{0, 3, 2, 1};
+    const std::vector<double> want_val{1.0, 4.0, 3.0, 2.0};
+    if (c.indices != want_idx || c.vals != want_val) { std::printf("slot-order KAT mismatch\n"); ++fails; }
   }
   std::printf(fails ? "FAILED\n" : "ALL OK\n");
   return fails ? 1 : 0;
