@@ -254,6 +254,8 @@ int spam_cuda_create(spam_handle** out, int device) {
     h->use_lanes = !(e && e[0] == '0');
     e = getenv("SPAM_SORT_B");
     h->sort_b = !(e && e[0] == '0');
+    e = getenv("SPAM_MERGE_WIN");
+    h->merge_win = e ? atoi(e) & 3 : 0;
     e = getenv("SPAM_L2_PERSIST");
     h->l2_persist = e ? atoi(e) : 0;
     h->l2_persist_max = 0; h->l2_window_max = 0;

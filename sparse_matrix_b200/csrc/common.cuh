@@ -218,6 +218,7 @@ struct spam_handle {
   int use_esc;         // SPAM_ESC at create time: 0 = hash bins only (default: measured faster on B200), 1 = bucket-sort
                        // bins for non-compressing rows up to 8192 products, 2 = also the column-range kernel for longer rows
   bool sort_b;         // SPAM_SORT_B=0 at create time: never multiply by a sorted copy of an unsorted B (tests of the hash bins)
+  int merge_win;       // SPAM_MERGE_WIN at create time: bit 0 numeric, bit 1 symbolic merge kernels stage the block's B window in shared memory with cp.async.bulk (default 0: measured slower)
   int l2_persist;      // SPAM_L2_PERSIST at create time (experiment, spgemm.cu): 1 = B's col_idx, 2 = B's values persisting in L2
   size_t l2_persist_max, l2_window_max;
   HostStage* stage;    // created on the first copy that involves a pageable host buffer

@@ -226,6 +226,251 @@ __global__ void __launch_bounds__(BLOCK) k_flop_sym_merge(u64 m, u64 b_rows, con
   }
 }
 
+// The same fused pass with the block's B window staged in shared memory (see k_num_merge_win below for the
+// scheme): only col_idx is needed here, MERGE_WCAP entries are 10 KB.
+constexpr int MERGE_WCAP = 2560;
+
+// Block-wide union of the K per-head entry ranges [s_lo[h], s_hi[h]) into at most K windows laid out back to back
+// in a staging buffer of MERGE_WCAP entries.  Called by one thread.  Windows start and end on multiples of 4
+// entries (16 bytes of col_idx, 16/32 of the values) so that they can be fetched with cp.async.bulk.  Returns the
+// number of windows, 0 if they do not fit.  s_shift[h] = (first entry of the head's window) - (offset of that
+// window in the buffer).
+template <int K>
+__device__ __forceinline__ u32 merge_window_plan(const u32* s_lo, const u32* s_hi, u32* s_shift, u32* s_wlo,
+                                                 u32* s_wn, u32* s_wbase) {
+  int ord[K];
+  int nh = 0;
+  for (int h = 0; h < K; ++h)
+    if (s_lo[h] != 0xFFFFFFFFu) {
+      int j = nh++;
+      while (j > 0 && s_lo[ord[j - 1]] > s_lo[h]) { ord[j] = ord[j - 1]; --j; }
+      ord[j] = h;
+    }
+  u32 nwin = 0, total = 0;
+  for (int j = 0; j < nh; ++j) {
+    const int h = ord[j];
+    if (s_hi[h] > 0xFFFFFFF0u) return 0;
+    const u32 lo = s_lo[h] & ~3u, hi = (s_hi[h] + 3u) & ~3u;
+    if (hi - lo > (u32)MERGE_WCAP) return 0;
+    if (nwin && lo <= s_wlo[nwin - 1] + s_wn[nwin - 1]) {
+      const u32 cur_hi = s_wlo[nwin - 1] + s_wn[nwin - 1];
+      if (hi > cur_hi) { total += hi - cur_hi; s_wn[nwin - 1] = hi - s_wlo[nwin - 1]; }
+    } else {
+      s_wlo[nwin] = lo; s_wn[nwin] = hi - lo; s_wbase[nwin] = total;
+      total += hi - lo;
+      ++nwin;
+    }
+    s_shift[h] = s_wlo[nwin - 1] - s_wbase[nwin - 1];
+    if (total > (u32)MERGE_WCAP) return 0;
+  }
+  return nwin;
+}
+
+// 1-D bulk copies global -> shared through the TMA unit (SASS UBLKCP), completion on an mbarrier.
+__device__ __forceinline__ u32 msm_addr(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(u64* bar, u32 count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(msm_addr(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(u64* bar, u32 bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(msm_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, u32 bytes, u64* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(msm_addr(dst)),
+               "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(msm_addr(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64* bar, u32 parity) {
+  u32 ok;
+  do {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok)
+                 : "r"(msm_addr(bar)), "r"(parity)
+                 : "memory");
+  } while (!ok);
+}
+
+// Fetch the planned windows of one or two parallel arrays (col_idx, values) into the staging buffers: one thread
+// issues the bulk copies, every thread copies the at most 3 entries at the very end of the arrays that a 16-byte
+// copy would overrun, all wait.
+template <class V, int BLOCK, bool WITH_VAL>
+__device__ __forceinline__ void merge_window_fetch(u32 nwin, const u32* s_wlo, const u32* s_wn, const u32* s_wbase,
+                                                   u64 b_nnz, const u32* __restrict__ b_col,
+                                                   const V* __restrict__ b_val, u32* wk, V* wv, u64* bar) {
+  const int tid = threadIdx.x;
+  const u32 nnz4 = (u32)(b_nnz & ~3ull), nnz = (u32)b_nnz;
+  constexpr u32 per = WITH_VAL ? 4u + (u32)sizeof(V) : 4u;
+  if (tid == 0) {
+    u32 bytes = 0;
+    for (u32 w = 0; w < nwin; ++w) {
+      const u32 wl = s_wlo[w], we = min(wl + s_wn[w], nnz4);
+      if (we > wl) bytes += (we - wl) * per;
+    }
+    mbar_expect_tx(bar, bytes);
+    for (u32 w = 0; w < nwin; ++w) {
+      const u32 wl = s_wlo[w], we = min(wl + s_wn[w], nnz4), wb = s_wbase[w];
+      if (we > wl) {
+        bulk_g2s(wk + wb, b_col + wl, (we - wl) * 4u, bar);
+        if (WITH_VAL) bulk_g2s(wv + wb, b_val + wl, (we - wl) * (u32)sizeof(V), bar);
+      }
+    }
+  }
+  if (nnz4 != nnz) {
+    for (u32 w = 0; w < nwin; ++w) {
+      const u32 wl = s_wlo[w], wb = s_wbase[w];
+      const u32 e1 = min(wl + s_wn[w], nnz);
+      for (u32 e = max(wl, nnz4) + tid; e < e1; e += BLOCK) {
+        wk[wb + (e - wl)] = b_col[e];
+        if (WITH_VAL) wv[wb + (e - wl)] = b_val[e];
+      }
+    }
+  }
+  mbar_wait(bar, 0);
+  __syncthreads();
+}
+
+template <int K, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_flop_sym_merge_win(u64 m, u64 b_rows, const u64* __restrict__ a_ptr,
+                                                              const u32* __restrict__ a_col,
+                                                              const u64* __restrict__ b_ptr,
+                                                              const u32* __restrict__ b_col, u64 b_nnz,
+                                                              u32* __restrict__ flop_out, u32* __restrict__ row_nnz,
+                                                              Counters* cnt) {
+  __shared__ u32 s_sym[NBINS], s_num[NBINS];
+  __shared__ ull s_total;
+  __shared__ u32 s_max;
+  __shared__ __align__(16) u32 wk[MERGE_WCAP];
+  __shared__ __align__(8) u64 s_bar;
+  __shared__ u32 s_lo[K], s_hi[K], s_shift[K], s_wlo[K], s_wn[K], s_wbase[K], s_nwin;
+  const int tid = threadIdx.x, lane = tid & 31;
+  if (tid < NBINS) { s_sym[tid] = 0; s_num[tid] = 0; }
+  if (tid == 0) { s_total = 0; s_max = 0; mbar_init(&s_bar, 1); }
+  if (tid < K) { s_lo[tid] = 0xFFFFFFFFu; s_hi[tid] = 0; }
+  __syncthreads();
+  const u64 row = (u64)blockIdx.x * BLOCK + tid;
+  const bool valid = row < m;
+  u64 lo = 0, hi = 0;
+  if (valid) { lo = a_ptr[row]; hi = a_ptr[row + 1]; }
+  const u64 len = hi - lo;
+  u64 f = 0;
+  bool bad = false, merged = false;
+  u32 pos[K], end[K], col[K];
+#pragma unroll
+  for (int h = 0; h < K; ++h) { pos[h] = 0; end[h] = 0; col[h] = INF_COL; }
+  if (valid && len <= (u64)K) {
+#pragma unroll
+    for (int h = 0; h < K; ++h) {
+      if ((u64)h < len) {
+        const u32 kk = a_col[lo + h];
+        if (kk < b_rows) { pos[h] = (u32)b_ptr[kk]; end[h] = (u32)b_ptr[kk + 1]; } else bad = true;
+      }
+      f += end[h] - pos[h];
+    }
+    merged = f <= MERGE_FLOP_MAX;
+  } else if (valid && len <= 32) {
+    for (u64 e = lo; e < hi; ++e) {
+      const u32 kk = a_col[e];
+      if (kk < b_rows) f += b_ptr[kk + 1] - b_ptr[kk]; else bad = true;
+    }
+  }
+  unsigned longmask = __ballot_sync(0xffffffffu, valid && len > 32);
+  while (longmask) {
+    const int src = __ffs(longmask) - 1;
+    longmask &= longmask - 1;
+    const u64 l = __shfl_sync(0xffffffffu, lo, src), hh = __shfl_sync(0xffffffffu, hi, src);
+    u64 part = 0;
+    for (u64 e = l + lane; e < hh; e += 32) {
+      const u32 kk = a_col[e];
+      if (kk < b_rows) part += b_ptr[kk + 1] - b_ptr[kk]; else bad = true;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+    if (lane == src) f = part;
+  }
+  // window of the rows counted here
+#pragma unroll
+  for (int h = 0; h < K; ++h) {
+    const bool has = merged && pos[h] < end[h];
+    const u32 wl = __reduce_min_sync(0xffffffffu, has ? pos[h] : 0xFFFFFFFFu);
+    const u32 wh = __reduce_max_sync(0xffffffffu, has ? end[h] : 0u);
+    if (lane == 0 && wl != 0xFFFFFFFFu) { atomicMin(&s_lo[h], wl); atomicMax(&s_hi[h], wh); }
+  }
+  __syncthreads();
+  if (tid == 0) s_nwin = merge_window_plan<K>(s_lo, s_hi, s_shift, s_wlo, s_wn, s_wbase);
+  __syncthreads();
+  const u32 nwin = s_nwin;
+  if (nwin) merge_window_fetch<u32, BLOCK, false>(nwin, s_wlo, s_wn, s_wbase, b_nnz, b_col, nullptr, wk, nullptr, &s_bar);
+  if (merged) {
+    u32 z = 0;
+    if (nwin) {
+#pragma unroll
+      for (int h = 0; h < K; ++h) {
+        const u32 sh = s_shift[h];
+        if (pos[h] < end[h]) { pos[h] -= sh; end[h] -= sh; col[h] = wk[pos[h]]; }
+      }
+      for (;;) {
+        u32 cmin = col[0];
+#pragma unroll
+        for (int h = 1; h < K; ++h) cmin = min(cmin, col[h]);
+        if (cmin == INF_COL) break;
+        ++z;
+#pragma unroll
+        for (int h = 0; h < K; ++h) {
+          if (col[h] == cmin) {
+            ++pos[h];
+            col[h] = (pos[h] < end[h]) ? wk[pos[h]] : INF_COL;
+          }
+        }
+      }
+    } else {
+#pragma unroll
+      for (int h = 0; h < K; ++h)
+        if (pos[h] < end[h]) col[h] = b_col[pos[h]];
+      for (;;) {
+        u32 cmin = col[0];
+#pragma unroll
+        for (int h = 1; h < K; ++h) cmin = min(cmin, col[h]);
+        if (cmin == INF_COL) break;
+        ++z;
+#pragma unroll
+        for (int h = 0; h < K; ++h) {
+          if (col[h] == cmin) {
+            ++pos[h];
+            col[h] = (pos[h] < end[h]) ? b_col[pos[h]] : INF_COL;
+          }
+        }
+      }
+    }
+    row_nnz[row] = z;  // mul_hash.rs:95
+    atomicAdd(&s_num[MERGE_BIN], 1u);
+  }
+  if (bad) atomicOr(&cnt->error, 1u);
+  if (valid) {
+    const u32 fs = f > 0xFFFFFFFFull ? 0xFFFFFFFFu : (u32)f;
+    flop_out[row] = fs;
+    if (merged) {
+      atomicAdd(&s_sym[MERGE_BIN], 1u);
+    } else {
+      const u32 alen = len > 0xFFFFFFFFull ? 0xFFFFFFFFu : (u32)len;
+      atomicAdd(&s_sym[sym_bin_of(fs, alen, false)], 1u);
+      atomicMax(&s_max, fs);
+    }
+  }
+  u64 t = f;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) t += __shfl_xor_sync(0xffffffffu, t, d);
+  if (lane == 0 && t) atomicAdd(&s_total, (ull)t);
+  __syncthreads();
+  if (tid < NBINS) {
+    if (s_sym[tid]) atomicAdd(&cnt->sym_bins[tid], s_sym[tid]);
+    if (s_num[tid]) atomicAdd(&cnt->num_bins[tid], s_num[tid]);
+  }
+  if (tid == 0) {
+    if (s_total) atomicAdd(&cnt->total_flops, s_total);
+    if (s_max) atomicMax(&cnt->max_flop, s_max);
+  }
+}
+
 // NUMERIC merge.  Outputs are staged CH at a time in a small [slot][thread] shared-memory tile and
 // flushed by the whole warp (8 lanes per row, 4 rows per store instruction: a row's 8 columns are one
 // full 32-byte sector, its 8 values two).  Keeping the tile small matters: shared memory is carved
@@ -328,5 +573,140 @@ __global__ void __launch_bounds__(BLOCK) k_num_merge(u32 n, const u32* __restric
 
 template <class V, int BLOCK>
 constexpr size_t num_merge_smem() { return MergeTile<V, BLOCK>::bytes; }
+
+// NUMERIC merge with the B WINDOW of the block staged in shared memory.
+//
+// In k_num_merge every step of a run head is a dependent global load (col, then val): ~50 per row for the 5-point
+// stencil, served by L1/L2 but each a 200-600 cycle round trip, and the kernel sits at 38% of the HBM rate waiting
+// for them (profiles/r02_poisson_merge_full.txt).  For banded matrices the B rows a block of consecutive A rows
+// touches are a few contiguous row ranges: head h of the block's threads walks B rows [min_h, max_h], i.e. the
+// contiguous ENTRY range [b_ptr[min_h], b_ptr[max_h + 1]) of col_idx / values.  The block computes those K entry
+// ranges (warp REDUX + shared atomics), thread 0 merges overlapping ones (heads i-1, i, i+1 of a stencil walk the
+// same rows), and when the union fits MERGE_WCAP entries one thread fetches it into shared memory with 1-D bulk copies (cp.async.bulk,
+// SASS UBLKCP, completion on an mbarrier) — B is then read from HBM/L2 once per block, and the merge loop runs on shared memory.
+// Blocks whose windows do not fit (scattered rows) take the global-memory loop of k_num_merge unchanged, so the
+// kernel is correct for every input; the products, their order and the rounding are the same in both branches.
+
+template <class V, int BLOCK>
+constexpr size_t num_merge_win_smem() { return MergeTile<V, BLOCK>::bytes + (size_t)MERGE_WCAP * (sizeof(V) + 4); }
+
+template <class V, int K, int BLOCK, bool STAGED>
+__device__ __forceinline__ void merge_rows_out(u32 (&pos)[K], u32 (&end)[K], u32 (&col)[K], V (&av)[K], u32 z, u64 c0,
+                                               const u32* __restrict__ src_col, const V* __restrict__ src_val,
+                                               V* sv, u32* sk, u32* __restrict__ c_col, V* __restrict__ c_val) {
+  using Tile = MergeTile<V, BLOCK>;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int wbase = tid & ~31, rsub = lane >> 3, q = lane & 7;
+  for (u32 t0 = 0; __any_sync(0xffffffffu, t0 < z); t0 += MERGE_CH) {
+#pragma unroll
+    for (int c = 0; c < MERGE_CH; ++c) {
+      if (t0 + c < z) {
+        u32 cmin = col[0];
+#pragma unroll
+        for (int h = 1; h < K; ++h) cmin = min(cmin, col[h]);
+        V acc = Num<V>::zero();
+        bool first = true;
+#pragma unroll
+        for (int h = 0; h < K; ++h) {  // A-row storage order
+          if (col[h] == cmin && cmin != INF_COL) {
+            const V p = Num<V>::mul(av[h], src_val[pos[h]]);
+            acc = first ? p : Num<V>::add(acc, p);  // first product stored, not added to 0
+            first = false;
+            ++pos[h];
+            col[h] = (pos[h] < end[h]) ? src_col[pos[h]] : INF_COL;
+          }
+        }
+        sk[c * Tile::STRIDE_K + tid] = cmin;
+        sv[c * Tile::STRIDE_V + tid] = acc;
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int src = it * 4 + rsub;
+      const u32 zr = __shfl_sync(0xffffffffu, z, src);
+      const u64 c0r = __shfl_sync(0xffffffffu, c0, src);
+      const u32 tt = t0 + q;
+      if (tt < zr) {
+        c_col[c0r + tt] = sk[q * Tile::STRIDE_K + wbase + src];
+        c_val[c0r + tt] = sv[q * Tile::STRIDE_V + wbase + src];
+      }
+    }
+    __syncwarp();
+  }
+}
+
+template <class V, int K, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_num_merge_win(u32 n, const u32* __restrict__ perm,
+                                                         const u64* __restrict__ a_ptr, const u32* __restrict__ a_col,
+                                                         const V* __restrict__ a_val, const u64* __restrict__ b_ptr,
+                                                         const u32* __restrict__ b_col, const V* __restrict__ b_val,
+                                                         u64 b_nnz, const u64* __restrict__ c_ptr,
+                                                         u32* __restrict__ c_col, V* __restrict__ c_val) {
+  using Tile = MergeTile<V, BLOCK>;
+  extern __shared__ __align__(16) unsigned char sm_merge[];
+  V* sv = reinterpret_cast<V*>(sm_merge);                               // [MERGE_CH][STRIDE_V]
+  u32* sk = reinterpret_cast<u32*>(sv + MERGE_CH * Tile::STRIDE_V);     // [MERGE_CH][STRIDE_K]
+  V* wv = reinterpret_cast<V*>(sm_merge + Tile::bytes);                 // [MERGE_WCAP] staged B values
+  u32* wk = reinterpret_cast<u32*>(wv + MERGE_WCAP);                    // [MERGE_WCAP] staged B columns
+  __shared__ u32 s_lo[K], s_hi[K], s_shift[K];     // per head: entry range walked by the block; global - smem offset
+  __shared__ u32 s_wlo[K], s_wn[K], s_wbase[K];    // merged windows: first entry, length, offset in wv / wk
+  __shared__ u32 s_nwin;                           // 0: not staged
+  __shared__ __align__(8) u64 s_bar;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const u32 i = blockIdx.x * BLOCK + tid;
+  if (tid < K) { s_lo[tid] = 0xFFFFFFFFu; s_hi[tid] = 0; }
+  if (tid == 0) mbar_init(&s_bar, 1);
+  u64 c0 = 0;
+  u32 z = 0, row = 0;
+  if (i < n) {
+    row = perm ? perm[i] : i;
+    c0 = c_ptr[row];
+    z = (u32)(c_ptr[row + 1] - c0);
+  }
+  u32 pos[K], end[K], col[K];
+  V av[K];
+#pragma unroll
+  for (int h = 0; h < K; ++h) { pos[h] = 0; end[h] = 0; col[h] = INF_COL; av[h] = Num<V>::zero(); }
+  if (z > 0) {
+    const u64 alo = a_ptr[row];
+    const u32 k = (u32)(a_ptr[row + 1] - alo);
+#pragma unroll
+    for (int h = 0; h < K; ++h) {
+      if (h < k) {
+        const u32 kk = a_col[alo + h];
+        av[h] = a_val[alo + h];
+        pos[h] = (u32)b_ptr[kk];
+        end[h] = (u32)b_ptr[kk + 1];
+      }
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int h = 0; h < K; ++h) {
+    const bool has = pos[h] < end[h];
+    const u32 wl = __reduce_min_sync(0xffffffffu, has ? pos[h] : 0xFFFFFFFFu);
+    const u32 wh = __reduce_max_sync(0xffffffffu, has ? end[h] : 0u);
+    if (lane == 0 && wl != 0xFFFFFFFFu) { atomicMin(&s_lo[h], wl); atomicMax(&s_hi[h], wh); }
+  }
+  __syncthreads();
+  if (tid == 0) s_nwin = merge_window_plan<K>(s_lo, s_hi, s_shift, s_wlo, s_wn, s_wbase);
+  __syncthreads();
+  const u32 nwin = s_nwin;
+  if (nwin) {
+    merge_window_fetch<V, BLOCK, true>(nwin, s_wlo, s_wn, s_wbase, b_nnz, b_col, b_val, wk, wv, &s_bar);
+#pragma unroll
+    for (int h = 0; h < K; ++h) {
+      const u32 sh = s_shift[h];
+      if (pos[h] < end[h]) { pos[h] -= sh; end[h] -= sh; col[h] = wk[pos[h]]; }
+    }
+    merge_rows_out<V, K, BLOCK, true>(pos, end, col, av, z, c0, wk, wv, sv, sk, c_col, c_val);
+  } else {
+#pragma unroll
+    for (int h = 0; h < K; ++h)
+      if (pos[h] < end[h]) col[h] = b_col[pos[h]];
+    merge_rows_out<V, K, BLOCK, false>(pos, end, col, av, z, c0, b_col, b_val, sv, sk, c_col, c_val);
+  }
+}
 
 }  // namespace

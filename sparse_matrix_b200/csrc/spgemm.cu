@@ -806,7 +806,14 @@ int spgemm_symbolic_dev(spam_handle* h, const spam_dcsr* a, const spam_dcsr* b, 
     p->max_alen = kk;
     const unsigned grid = (unsigned)((m + 127) / 128);
     const bool l2w = l2_window_set(h, b->idx, (size_t)b->nnz * 4);
-    if (kk == 4)
+    if ((h->merge_win & 2) && ((uintptr_t)b->idx & 15) == 0) {
+      if (kk == 4)
+        k_flop_sym_merge_win<4, 128><<<grid, 128, 0, h->stream>>>(m, b->rows, a->ptr, a->idx, b->ptr, b->idx, b->nnz, p->d_flop, p->d_row_nnz, h->d_cnt);
+      else if (kk == 6)
+        k_flop_sym_merge_win<6, 128><<<grid, 128, 0, h->stream>>>(m, b->rows, a->ptr, a->idx, b->ptr, b->idx, b->nnz, p->d_flop, p->d_row_nnz, h->d_cnt);
+      else
+        k_flop_sym_merge_win<8, 128><<<grid, 128, 0, h->stream>>>(m, b->rows, a->ptr, a->idx, b->ptr, b->idx, b->nnz, p->d_flop, p->d_row_nnz, h->d_cnt);
+    } else if (kk == 4)
       k_flop_sym_merge<4, 128><<<grid, 128, 0, h->stream>>>(m, b->rows, a->ptr, a->idx, b->ptr, b->idx, p->d_flop, p->d_row_nnz, h->d_cnt);
     else if (kk == 6)
       k_flop_sym_merge<6, 128><<<grid, 128, 0, h->stream>>>(m, b->rows, a->ptr, a->idx, b->ptr, b->idx, p->d_flop, p->d_row_nnz, h->d_cnt);
@@ -1068,7 +1075,19 @@ int numeric_typed(spam_handle* h, SpgemmPending* p, spam_dcsr* c) {
     const u32 nm = nb.count[MERGE_BIN];
     const unsigned grid = (nm + BL - 1) / BL;
     const u32 kmax = p->max_alen;  // longest A row among all rows short enough for a merge bin
-    if (kmax <= 4)
+    if ((h->merge_win & 1) && (((uintptr_t)bc | (uintptr_t)bv) & 15) == 0) {
+      constexpr size_t wsmem = num_merge_win_smem<V, BL>();
+      if (kmax <= 4) {
+        CKS(set_smem(h, k_num_merge_win<V, 4, BL>, wsmem));
+        k_num_merge_win<V, 4, BL><<<grid, BL, wsmem, h->stream>>>(nm, seg(MERGE_BIN), ap, ac, av, bp, bc, bv, b->nnz, cp, cc, cv);
+      } else if (kmax <= 6) {
+        CKS(set_smem(h, k_num_merge_win<V, 6, BL>, wsmem));
+        k_num_merge_win<V, 6, BL><<<grid, BL, wsmem, h->stream>>>(nm, seg(MERGE_BIN), ap, ac, av, bp, bc, bv, b->nnz, cp, cc, cv);
+      } else {
+        CKS(set_smem(h, k_num_merge_win<V, 8, BL>, wsmem));
+        k_num_merge_win<V, 8, BL><<<grid, BL, wsmem, h->stream>>>(nm, seg(MERGE_BIN), ap, ac, av, bp, bc, bv, b->nnz, cp, cc, cv);
+      }
+    } else if (kmax <= 4)
       k_num_merge<V, 4, BL><<<grid, BL, smem, h->stream>>>(nm, seg(MERGE_BIN), ap, ac, av, bp, bc, bv, cp, cc, cv);
     else if (kmax <= 6)
       k_num_merge<V, 6, BL><<<grid, BL, smem, h->stream>>>(nm, seg(MERGE_BIN), ap, ac, av, bp, bc, bv, cp, cc, cv);

@@ -57,3 +57,17 @@ def handle_esc():
         del os.environ["SPAM_ESC"]
     yield h
     h.close()
+
+
+@pytest.fixture(scope="session")
+def handle_win():
+    """SPAM_MERGE_WIN=3: the merge-bin kernels that stage the block's window of B in shared memory with cp.async.bulk
+    (k_flop_sym_merge_win / k_num_merge_win, merge.cuh) — off by default because they measured slower on B200."""
+    import sparse_matrix_b200 as S
+    os.environ["SPAM_MERGE_WIN"] = "3"
+    try:
+        h = S.Handle(0)
+    finally:
+        del os.environ["SPAM_MERGE_WIN"]
+    yield h
+    h.close()

@@ -210,6 +210,48 @@ def test_merge_bin_mixed_with_other_bins(oracle, handle):
         check_against_oracle(oracle, a, b, c)
 
 
+def test_merge_bin_window_kernels(oracle, handle_win):
+    """SPAM_MERGE_WIN=3: banded matrices (the window of B fits shared memory and is fetched by bulk copies), scattered
+    ones (it does not: the block falls back to the global-memory loop) and arrays whose length is not a multiple of 4
+    entries (the last entries cannot be part of a 16-byte copy).  Floats bit-identical, as in the default kernels."""
+    h = handle_win
+    rng = np.random.default_rng(404)
+    for n, dtype in ((96, np.float64), (61, np.float32), (50, np.int64), (33, np.int32)):
+        p = G.poisson2d(n, dtype=dtype)
+        vals = (rng.uniform(-1, 1, size=p[4].shape) if np.issubdtype(dtype, np.floating)
+                else rng.integers(-9, 10, size=p[4].shape)).astype(dtype)
+        p = p[:4] + (vals,)
+        h.set_timing(True)
+        c = gpu_mul(p, p, h)
+        st = h.stats()
+        h.set_timing(False)
+        assert st["sym_bin_rows"][MERGE] == p[0] and st["num_bin_rows"][MERGE] == p[0]
+        check_against_oracle(oracle, p, p, c, exact_values=True)
+    for trial in range(4):
+        # nnz(B) = 4q + trial: every tail length; a band of A so that the last rows of B are in some block's window
+        inner = 3000
+        bdeg = np.full(inner, 4)
+        bdeg[-1] = 12
+        b = random_csr(rng, inner, 5000, bdeg, dtype=np.float64, sorted_rows=True)
+        drop = (b[3].shape[0] - trial) % 4              # shorten the last row to the wanted remainder
+        boff = b[2].copy()
+        boff[-1] -= np.uint64(drop)
+        b = (b[0], b[1], boff, b[3][:b[3].shape[0] - drop], b[4][:b[4].shape[0] - drop])
+        assert b[3].shape[0] % 4 == trial and int(boff[-1]) > int(boff[-2])
+        rows = inner
+        off = np.arange(rows + 1, dtype=np.uint64) * 3
+        idx = np.clip(np.arange(rows)[:, None] + np.array([-1, 0, 1])[None, :], 0, inner - 1)
+        idx[0] = [0, 1, 2]
+        idx[-1] = [inner - 3, inner - 2, inner - 1]
+        a = (rows, inner, off, idx.reshape(-1).astype(np.uint64), rng.uniform(-1, 1, size=rows * 3))
+        c = gpu_mul(a, b, h)
+        check_against_oracle(oracle, a, b, c, exact_values=True)
+    # scattered rows of A: windows far larger than the staging buffer
+    b = random_csr(rng, 200000, 200000, 6, dtype=np.float64, sorted_rows=True)
+    a = random_csr(rng, 20000, 200000, rng.integers(0, 9, size=20000), dtype=np.float64, sorted_rows=True)
+    check_against_oracle(oracle, a, b, gpu_mul(a, b, h), exact_values=True)
+
+
 def test_edge_cases(oracle, handle):
     # all-empty operands
     a = S.CsrMatrix.new((5, 7))
