@@ -256,6 +256,8 @@ int spam_cuda_create(spam_handle** out, int device) {
     h->sort_b = !(e && e[0] == '0');
     e = getenv("SPAM_MERGE_WIN");
     h->merge_win = e ? atoi(e) & 3 : 0;
+    e = getenv("SPAM_MERGE_PF");
+    h->merge_pf = e ? atoi(e) & 7 : -1;
     e = getenv("SPAM_L2_PERSIST");
     h->l2_persist = e ? atoi(e) : 0;
     h->l2_persist_max = 0; h->l2_window_max = 0;
@@ -541,6 +543,7 @@ int spam_dcsr_slice_rows(spam_handle* h, const spam_dcsr* m, uint64_t r0, uint64
   const u64 nnz = ends[1] - ends[0], rows = r1 - r0;
   spam_dcsr* s = new spam_dcsr();
   s->dtype = m->dtype; s->rows = rows; s->cols = m->cols; s->nnz = nnz; s->owning = true; s->rows_sorted = m->rows_sorted; s->max_row_len = m->max_row_len;
+  s->spread_sum = m->rows ? (u64)((double)m->spread_sum * (double)rows / (double)m->rows) : 0;
   s->ptr = nullptr; s->idx = nullptr; s->val = nullptr;
   int st = dev_alloc_t(h, &s->ptr, rows + 1);
   if (st == SPAM_OK) st = dev_alloc_t(h, &s->idx, nnz);

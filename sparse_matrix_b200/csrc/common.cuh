@@ -100,6 +100,7 @@ struct Counters {
   u32 fb_heavy_bitonic;  // global-table rows whose bucket drain overflowed (global-memory bitonic network)
   u32 fb_esc;            // rows the bucket-sort (ESC) bins handed back to the global-table kernel
   u32 fb_list_n;         // number of row ids in the ESC fallback list
+  ull spread_sum;        // k_rows_sorted: sum over the rows of <= 32 entries of (largest - smallest column index)
 };
 
 struct BinBase { u32 v[NBINS]; };
@@ -173,6 +174,8 @@ struct spam_dcsr {
   u64 max_row_len;  // cached with rows_sorted: longest row (picks DIRECT vs FLAT product enumeration)
   int invalid;      // cached with rows_sorted: 0 = row_ptr monotone from 0 to nnz and every column < cols
                     // (invariants 3, 4, 5, 7 of spam_csr/src/lib.rs:47-81); bit0 row_ptr, bit1 column range
+  u64 spread_sum = 0;  // cached with rows_sorted: sum over the short rows of (largest - smallest column); as a left operand,
+                       // spread_sum / rows * mean(B row) says whether the B rows a block touches can stay in L1/L2
   spam_dcsr* sorted_copy;  // rows_sorted == 0: the same matrix with every row in column order, made on first need
                            // (sorted_rows_of) and owned by this object
 };
@@ -219,6 +222,7 @@ struct spam_handle {
                        // bins for non-compressing rows up to 8192 products, 2 = also the column-range kernel for longer rows
   bool sort_b;         // SPAM_SORT_B=0 at create time: never multiply by a sorted copy of an unsorted B (tests of the hash bins)
   int merge_win;       // SPAM_MERGE_WIN at create time: bit 0 numeric, bit 1 symbolic merge kernels stage the block's B window in shared memory with cp.async.bulk (default 0: measured slower)
+  int merge_pf;        // SPAM_MERGE_PF at create time: low two bits = PF of k_num_merge (0..2), bit 2 = one-ahead columns in k_flop_sym_merge; -1 (default): 6 when A's rows scatter over B, else 0
   int l2_persist;      // SPAM_L2_PERSIST at create time (experiment, spgemm.cu): 1 = B's col_idx, 2 = B's values persisting in L2
   size_t l2_persist_max, l2_window_max;
   HostStage* stage;    // created on the first copy that involves a pageable host buffer

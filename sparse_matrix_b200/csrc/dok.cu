@@ -786,6 +786,7 @@ int sorted_rows_of(spam_handle* h, const spam_dcsr* m, const spam_dcsr** view) {
     if (st != SPAM_OK) return st;
     tt->rows_sorted = 1;
     tt->max_row_len = m->max_row_len;
+    tt->spread_sum = m->spread_sum;
     tt->invalid = 0;
     const_cast<spam_dcsr*>(m)->sorted_copy = tt;
   }

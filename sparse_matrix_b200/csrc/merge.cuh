@@ -21,7 +21,7 @@ constexpr u32 INF_COL = 0xFFFFFFFFu;
 
 // One pass over a matrix the first time it is used (the result is cached with the matrix):
 //  * are all rows strictly increasing by column?  (invariant6 with IS_SORTED, lib.rs:69-77)
-//  * longest row
+//  * longest row; how far the entries of a short row are apart (picks the prefetching merge kernels)
 //  * the invariants the kernels rely on for memory safety (lib.rs:47-81): row_ptr starts at 0, is monotone and
 //    ends at nnz (invariants 3, 4, 7), every column index < cols (invariant 5).  The reference panics safely
 //    on a bad matrix; here it is SPAM_EINVAL / SPAM_EINDEX instead of a device fault.
@@ -38,15 +38,21 @@ __global__ void __launch_bounds__(BLOCK) k_rows_sorted(u64 m, u64 nnz, u64 cols,
     if (lo > hi || hi > nnz || (row == 0 && lo != 0) || (row + 1 == m && hi != nnz)) { inval |= 1u; valid = false; lo = hi = 0; }
   }
   bool bad = false;
+  u64 spread = 0;
   if (valid && hi - lo <= 32) {
-    u32 prev = 0;
+    u32 prev = 0, cmin = 0xFFFFFFFFu, cmax = 0;
     for (u64 e = lo; e < hi; ++e) {
       const u32 c = idx[e];
       if (c >= cols) inval |= 2u;
       if (e > lo) bad |= prev >= c;
       prev = c;
+      cmin = min(cmin, c); cmax = max(cmax, c);
     }
+    if (hi > lo) spread = cmax - cmin;
   }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) spread += __shfl_xor_sync(0xffffffffu, spread, d);
+  if (lane == 0 && spread) atomicAdd(&cnt->spread_sum, (ull)spread);
   unsigned longmask = __ballot_sync(0xffffffffu, valid && hi - lo > 32);
   while (longmask) {
     const int src = __ffs(longmask) - 1;
@@ -124,7 +130,7 @@ __global__ void __launch_bounds__(BLOCK) k_sym_merge(u32 n, const u32* __restric
 // qualify for the merge bin (len(A row) <= K <= MERGE_K, flop <= MERGE_FLOP_MAX) are counted on the
 // spot — the B row extents just loaded for the flop count are exactly the run heads the merge needs.
 // For stencil-like matrices every row qualifies and no other symbolic kernel runs.
-template <int K, int BLOCK>
+template <int K, int BLOCK, int PF = 0>
 __global__ void __launch_bounds__(BLOCK) k_flop_sym_merge(u64 m, u64 b_rows, const u64* __restrict__ a_ptr,
                                                           const u32* __restrict__ a_col,
                                                           const u64* __restrict__ b_ptr,
@@ -157,9 +163,13 @@ __global__ void __launch_bounds__(BLOCK) k_flop_sym_merge(u64 m, u64 b_rows, con
     }
     if (f <= MERGE_FLOP_MAX) {
       merged = true;
+      u32 ncol[PF ? K : 1];
 #pragma unroll
       for (int h = 0; h < K; ++h)
-        if (pos[h] < end[h]) col[h] = b_col[pos[h]];
+        if (pos[h] < end[h]) {
+          col[h] = b_col[pos[h]];
+          if (PF) ncol[h] = (pos[h] + 1 < end[h]) ? b_col[pos[h] + 1] : INF_COL;
+        }
       u32 z = 0;
       for (;;) {
         u32 cmin = col[0];
@@ -171,7 +181,12 @@ __global__ void __launch_bounds__(BLOCK) k_flop_sym_merge(u64 m, u64 b_rows, con
         for (int h = 0; h < K; ++h) {
           if (col[h] == cmin) {
             ++pos[h];
-            col[h] = (pos[h] < end[h]) ? b_col[pos[h]] : INF_COL;
+            if (PF) {
+              col[h] = ncol[h];   // INF_COL when the run is finished
+              ncol[h] = (pos[h] + 1 < end[h]) ? b_col[pos[h] + 1] : INF_COL;
+            } else {
+              col[h] = (pos[h] < end[h]) ? b_col[pos[h]] : INF_COL;
+            }
           }
         }
       }
@@ -490,7 +505,9 @@ struct MergeTile {
 
 // (Compiled for 12 resident blocks per SM — 40 registers instead of 54 for K = 6, a few spilled bytes — the kernel
 // ran 0.479 ms instead of 0.380 ms on Poisson 2048^2: occupancy is not what limits it.)
-template <class V, int K, int BLOCK>
+// PF = 1: a head's value is loaded together with its column (not when it is consumed); PF = 2: also the column
+// after the head is already in a register, so that the next comparison does not wait for a load.
+template <class V, int K, int BLOCK, int PF = 0>
 __global__ void __launch_bounds__(BLOCK) k_num_merge(u32 n, const u32* __restrict__ perm,
                                                      const u64* __restrict__ a_ptr, const u32* __restrict__ a_col,
                                                      const V* __restrict__ a_val, const u64* __restrict__ b_ptr,
@@ -511,9 +528,14 @@ __global__ void __launch_bounds__(BLOCK) k_num_merge(u32 n, const u32* __restric
     z = (u32)(c_ptr[row + 1] - c0);
   }
   u32 pos[K], end[K], col[K];
-  V av[K];
+  u32 ncol[PF >= 2 ? K : 1];
+  V av[K], bvv[PF >= 1 ? K : 1];
 #pragma unroll
   for (int h = 0; h < K; ++h) { pos[h] = 0; end[h] = 0; col[h] = INF_COL; av[h] = Num<V>::zero(); }
+#pragma unroll
+  for (int h = 0; h < (PF >= 1 ? K : 1); ++h) bvv[h] = Num<V>::zero();
+#pragma unroll
+  for (int h = 0; h < (PF >= 2 ? K : 1); ++h) ncol[h] = INF_COL;
   if (z > 0) {
     const u64 alo = a_ptr[row];
     const u32 k = (u32)(a_ptr[row + 1] - alo);
@@ -528,7 +550,11 @@ __global__ void __launch_bounds__(BLOCK) k_num_merge(u32 n, const u32* __restric
     }
 #pragma unroll
     for (int h = 0; h < K; ++h)
-      if (pos[h] < end[h]) col[h] = b_col[pos[h]];
+      if (pos[h] < end[h]) {
+        col[h] = b_col[pos[h]];
+        if (PF >= 1) bvv[h] = b_val[pos[h]];
+        if (PF >= 2) ncol[h] = (pos[h] + 1 < end[h]) ? b_col[pos[h] + 1] : INF_COL;
+      }
   }
   const int wbase = tid & ~31, rsub = lane >> 3, q = lane & 7;
   for (u32 t0 = 0; __any_sync(0xffffffffu, t0 < z); t0 += MERGE_CH) {
@@ -543,11 +569,21 @@ __global__ void __launch_bounds__(BLOCK) k_num_merge(u32 n, const u32* __restric
 #pragma unroll
         for (int h = 0; h < K; ++h) {  // A-row storage order
           if (col[h] == cmin && cmin != INF_COL) {
-            const V p = Num<V>::mul(av[h], b_val[pos[h]]);
+            const V p = Num<V>::mul(av[h], PF >= 1 ? bvv[h] : b_val[pos[h]]);
             acc = first ? p : Num<V>::add(acc, p);  // first product stored, not added to 0
             first = false;
             ++pos[h];
-            col[h] = (pos[h] < end[h]) ? b_col[pos[h]] : INF_COL;
+            if (PF >= 2) {
+              col[h] = ncol[h];
+              if (pos[h] < end[h]) {
+                bvv[h] = b_val[pos[h]];
+                ncol[h] = (pos[h] + 1 < end[h]) ? b_col[pos[h] + 1] : INF_COL;
+              }
+            } else if (PF == 1) {
+              if (pos[h] < end[h]) { col[h] = b_col[pos[h]]; bvv[h] = b_val[pos[h]]; } else col[h] = INF_COL;
+            } else {
+              col[h] = (pos[h] < end[h]) ? b_col[pos[h]] : INF_COL;
+            }
           }
         }
         sk[c * Tile::STRIDE_K + tid] = cmin;

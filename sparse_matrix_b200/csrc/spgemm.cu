@@ -710,6 +710,18 @@ struct SpgemmPending {
 
 namespace {
 
+// Which merge kernels: when the entries of A's short rows are far apart, the B rows a block walks do not stay in
+// L1/L2 and every step of a run head is a real memory round trip — the variants that keep the next column (and the
+// head's value) in registers win (C5 A*A^T: 0.97 -> 0.85 ms); for banded matrices the run heads hit L1 and the extra
+// registers only cost residency (Poisson 2048^2: 0.567 -> 0.590 ms).  Footprint estimate: mean column spread of an
+// A row x mean B row in bytes, against 8 MB.
+int merge_prefetch_mode(const spam_handle* h, const spam_dcsr* a, const spam_dcsr* b) {
+  if (h->merge_pf >= 0) return h->merge_pf;
+  if (!a->rows || !b->rows) return 0;
+  const double foot = (double)a->spread_sum / (double)a->rows * ((double)b->nnz / (double)b->rows) * 12.0;
+  return foot > 8e6 ? 6 : 0;
+}
+
 // Cached per matrix: are all rows strictly increasing by column?  One pass over col_idx the first
 // time a matrix is used as a right-hand side (device matrices are immutable through this API).
 int ensure_rows_sorted(spam_handle* h, const spam_dcsr* b) {
@@ -718,11 +730,14 @@ int ensure_rows_sorted(spam_handle* h, const spam_dcsr* b) {
     if (b->rows == 0) { mb->rows_sorted = 1; mb->max_row_len = 0; mb->invalid = b->nnz ? 1 : 0; }
     else {
       CK(cudaMemsetAsync(&h->d_cnt->unsorted, 0, 3 * sizeof(u32), h->stream));  // unsorted, max_rowlen, invalid
+      CK(cudaMemsetAsync(&h->d_cnt->spread_sum, 0, sizeof(ull), h->stream));
       k_rows_sorted<256><<<(unsigned)((b->rows + 255) / 256), 256, 0, h->stream>>>(b->rows, b->nnz, b->cols, b->ptr, b->idx, h->d_cnt);
       count_launch(h);
       CK(cudaGetLastError());
       CK(cudaMemcpyAsync(&h->h_cnt->unsorted, &h->d_cnt->unsorted, 3 * sizeof(u32), cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaMemcpyAsync(&h->h_cnt->spread_sum, &h->d_cnt->spread_sum, sizeof(ull), cudaMemcpyDeviceToHost, h->stream));
       CK(cudaStreamSynchronize(h->stream));
+      mb->spread_sum = h->h_cnt->spread_sum;
       mb->rows_sorted = h->h_cnt->unsorted ? 0 : 1;
       mb->max_row_len = h->h_cnt->max_rowlen;
       mb->invalid = (int)h->h_cnt->invalid;
@@ -813,6 +828,13 @@ int spgemm_symbolic_dev(spam_handle* h, const spam_dcsr* a, const spam_dcsr* b, 
         k_flop_sym_merge_win<6, 128><<<grid, 128, 0, h->stream>>>(m, b->rows, a->ptr, a->idx, b->ptr, b->idx, b->nnz, p->d_flop, p->d_row_nnz, h->d_cnt);
       else
         k_flop_sym_merge_win<8, 128><<<grid, 128, 0, h->stream>>>(m, b->rows, a->ptr, a->idx, b->ptr, b->idx, b->nnz, p->d_flop, p->d_row_nnz, h->d_cnt);
+    } else if (merge_prefetch_mode(h, a, b) & 4) {
+      if (kk == 4)
+        k_flop_sym_merge<4, 128, 1><<<grid, 128, 0, h->stream>>>(m, b->rows, a->ptr, a->idx, b->ptr, b->idx, p->d_flop, p->d_row_nnz, h->d_cnt);
+      else if (kk == 6)
+        k_flop_sym_merge<6, 128, 1><<<grid, 128, 0, h->stream>>>(m, b->rows, a->ptr, a->idx, b->ptr, b->idx, p->d_flop, p->d_row_nnz, h->d_cnt);
+      else
+        k_flop_sym_merge<8, 128, 1><<<grid, 128, 0, h->stream>>>(m, b->rows, a->ptr, a->idx, b->ptr, b->idx, p->d_flop, p->d_row_nnz, h->d_cnt);
     } else if (kk == 4)
       k_flop_sym_merge<4, 128><<<grid, 128, 0, h->stream>>>(m, b->rows, a->ptr, a->idx, b->ptr, b->idx, p->d_flop, p->d_row_nnz, h->d_cnt);
     else if (kk == 6)
@@ -1075,6 +1097,7 @@ int numeric_typed(spam_handle* h, SpgemmPending* p, spam_dcsr* c) {
     const u32 nm = nb.count[MERGE_BIN];
     const unsigned grid = (nm + BL - 1) / BL;
     const u32 kmax = p->max_alen;  // longest A row among all rows short enough for a merge bin
+    const int mpf = merge_prefetch_mode(h, a, b);
     if ((h->merge_win & 1) && (((uintptr_t)bc | (uintptr_t)bv) & 15) == 0) {
       constexpr size_t wsmem = num_merge_win_smem<V, BL>();
       if (kmax <= 4) {
@@ -1087,6 +1110,20 @@ int numeric_typed(spam_handle* h, SpgemmPending* p, spam_dcsr* c) {
         CKS(set_smem(h, k_num_merge_win<V, 8, BL>, wsmem));
         k_num_merge_win<V, 8, BL><<<grid, BL, wsmem, h->stream>>>(nm, seg(MERGE_BIN), ap, ac, av, bp, bc, bv, b->nnz, cp, cc, cv);
       }
+    } else if ((mpf & 3) == 1) {
+      if (kmax <= 4)
+        k_num_merge<V, 4, BL, 1><<<grid, BL, smem, h->stream>>>(nm, seg(MERGE_BIN), ap, ac, av, bp, bc, bv, cp, cc, cv);
+      else if (kmax <= 6)
+        k_num_merge<V, 6, BL, 1><<<grid, BL, smem, h->stream>>>(nm, seg(MERGE_BIN), ap, ac, av, bp, bc, bv, cp, cc, cv);
+      else
+        k_num_merge<V, 8, BL, 1><<<grid, BL, smem, h->stream>>>(nm, seg(MERGE_BIN), ap, ac, av, bp, bc, bv, cp, cc, cv);
+    } else if ((mpf & 3) == 2) {
+      if (kmax <= 4)
+        k_num_merge<V, 4, BL, 2><<<grid, BL, smem, h->stream>>>(nm, seg(MERGE_BIN), ap, ac, av, bp, bc, bv, cp, cc, cv);
+      else if (kmax <= 6)
+        k_num_merge<V, 6, BL, 2><<<grid, BL, smem, h->stream>>>(nm, seg(MERGE_BIN), ap, ac, av, bp, bc, bv, cp, cc, cv);
+      else
+        k_num_merge<V, 8, BL, 2><<<grid, BL, smem, h->stream>>>(nm, seg(MERGE_BIN), ap, ac, av, bp, bc, bv, cp, cc, cv);
     } else if (kmax <= 4)
       k_num_merge<V, 4, BL><<<grid, BL, smem, h->stream>>>(nm, seg(MERGE_BIN), ap, ac, av, bp, bc, bv, cp, cc, cv);
     else if (kmax <= 6)

@@ -252,6 +252,36 @@ def test_merge_bin_window_kernels(oracle, handle_win):
     check_against_oracle(oracle, a, b, gpu_mul(a, b, h), exact_values=True)
 
 
+@pytest.mark.parametrize("pf", [1, 6])
+def test_merge_bin_prefetch_kernels(oracle, pf):
+    """SPAM_MERGE_PF: the merge kernels that load a head's value with its column (1) and keep the next column of every
+    run in a register (2 | 4) — chosen automatically only when A's rows scatter over more of B than the caches hold,
+    which no small test matrix does.  Same products in the same order: floats bit-identical."""
+    os.environ["SPAM_MERGE_PF"] = str(pf)
+    try:
+        h = S.Handle(0)
+    finally:
+        del os.environ["SPAM_MERGE_PF"]
+    try:
+        rng = np.random.default_rng(500 + pf)
+        p = G.poisson2d(70, dtype=np.float64)
+        p = p[:4] + (rng.uniform(-1, 1, size=p[4].shape),)
+        check_against_oracle(oracle, p, p, gpu_mul(p, p, h), exact_values=True)
+        for kmax, dtype in ((4, np.float32), (6, np.int64), (8, np.float64)):
+            bdeg = rng.integers(0, 12, size=3000)
+            bdeg[rng.random(3000) < 0.2] = 0                       # empty runs among the heads
+            b = random_csr(rng, 3000, 5000, bdeg, dtype=dtype, sorted_rows=True)
+            a = random_csr(rng, 4000, 3000, rng.integers(0, kmax + 1, size=4000), dtype=dtype, sorted_rows=False)
+            h.set_timing(True)
+            c = gpu_mul(a, b, h)
+            st = h.stats()
+            h.set_timing(False)
+            assert st["num_bin_rows"][MERGE] > 0
+            check_against_oracle(oracle, a, b, c, exact_values=True)
+    finally:
+        h.close()
+
+
 def test_edge_cases(oracle, handle):
     # all-empty operands
     a = S.CsrMatrix.new((5, 7))
