@@ -13,6 +13,8 @@
 // Two passes like the product: count the union per row, look-back scan (scan.cu), fill.  One thread per row:
 // HBM-bound on stencil-like matrices (reads A and B once, writes C once); rows whose columns are not sorted
 // are first put in order by two transposes (dok.cu).
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace {
@@ -86,10 +88,118 @@ __global__ void __launch_bounds__(BLOCK) k_ewise_fill(u64 m, const u64* __restri
   for (u64 q = threadIdx.x; q < span; q += BLOCK) { cc[base + q] = sk[q]; cv[base + q] = sv[q]; }
 }
 
+// The same walk with the block's three spans in shared memory.  The rows of a block are consecutive, so what it reads
+// of A and of B are two contiguous entry ranges: one thread fetches them (columns and values: four 1-D bulk copies,
+// cp.async.bulk on an mbarrier, SASS UBLKCP) while the others wait; the per-row merge then reads shared memory only,
+// writes the output span to shared memory, and the block stores it with full sectors.  k_ewise_fill lets every thread
+// walk its own row in global memory: 32 sectors per load instruction and, with 36 KB of staging per block, an L1 too
+// small to keep them (hit rate 4 %, 5.3 GB moved from L2 for 1.0 GB of input: profiles/r02_ewise_fill.txt).
+// capA / capB / capC (multiples of 4 entries) are sized by the host from the mean row lengths; a block whose spans do
+// not fit walks global memory and stores directly.  Layout: [mbarrier][A cols][B cols][C cols][A vals][B vals][C vals].
+template <class V, int OP, bool KEEP_LEFT, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_ewise_fill_tma(u64 m, const u64* __restrict__ ap, const u32* __restrict__ ac,
+                                                          const V* __restrict__ av, u64 a_nnz,
+                                                          const u64* __restrict__ bp, const u32* __restrict__ bc,
+                                                          const V* __restrict__ bv, u64 b_nnz,
+                                                          const u64* __restrict__ cp, u32* __restrict__ cc,
+                                                          V* __restrict__ cv, u32 capA, u32 capB, u32 capC) {
+  extern __shared__ __align__(16) unsigned char sm_ew[];
+  u64* bar = reinterpret_cast<u64*>(sm_ew);
+  u32* sAk = reinterpret_cast<u32*>(sm_ew + 16);
+  u32* sBk = sAk + capA;
+  u32* sCk = sBk + capB;
+  V* sAv = reinterpret_cast<V*>(sCk + capC);
+  V* sBv = sAv + capA;
+  V* sCv = sBv + capB;
+  const int tid = threadIdx.x;
+  if (tid == 0) mbar_init(bar, 1);
+  const u64 row0 = (u64)blockIdx.x * BLOCK;
+  const u64 row = row0 + tid;
+  const u64 rend = row0 + BLOCK < m ? row0 + BLOCK : m;
+  const u64 a0 = ap[row0], a1 = ap[rend], b0 = bp[row0], b1 = bp[rend], c0 = cp[row0], c1 = cp[rend];
+  const u64 a0a = a0 & ~(u64)3, b0a = b0 & ~(u64)3;  // 16-byte aligned starts
+  const bool staged = a1 - a0a <= (u64)capA && b1 - b0a <= (u64)capB && c1 - c0 <= (u64)capC;  // block-uniform
+  const V zero = Num<V>::zero();
+  __syncthreads();
+  if (!staged) {
+    if (row < m) {
+      u64 i = ap[row], j = bp[row], o = cp[row];
+      const u64 ie = ap[row + 1], je = bp[row + 1];
+      auto put = [&](u32 c, V v) { cc[o] = c; cv[o] = v; ++o; };
+      while (i < ie && j < je) {
+        const u32 ca = ac[i], cb = bc[j];
+        if (ca == cb) { put(ca, apply<V, OP>(av[i], bv[j])); ++i; ++j; }
+        else if (ca < cb) { put(ca, KEEP_LEFT ? av[i] : apply<V, OP>(av[i], zero)); ++i; }
+        else { put(cb, apply<V, OP>(zero, bv[j])); ++j; }
+      }
+      for (; i < ie; ++i) put(ac[i], KEEP_LEFT ? av[i] : apply<V, OP>(av[i], zero));
+      for (; j < je; ++j) put(bc[j], apply<V, OP>(zero, bv[j]));
+    }
+    return;
+  }
+  const u64 a4 = a_nnz & ~(u64)3, b4 = b_nnz & ~(u64)3;  // a 16-byte copy must not run past the end of the arrays
+  if (tid == 0) {
+    const u64 ra = (a1 + 3) & ~(u64)3, rb = (b1 + 3) & ~(u64)3;
+    const u64 ea = ra < a4 ? ra : a4, eb = rb < b4 ? rb : b4;
+    const u32 la = ea > a0a ? (u32)(ea - a0a) : 0, lb = eb > b0a ? (u32)(eb - b0a) : 0;
+    mbar_expect_tx(bar, (la + lb) * (4u + (u32)sizeof(V)));
+    if (la) { bulk_g2s(sAk, ac + a0a, la * 4u, bar); bulk_g2s(sAv, av + a0a, la * (u32)sizeof(V), bar); }
+    if (lb) { bulk_g2s(sBk, bc + b0a, lb * 4u, bar); bulk_g2s(sBv, bv + b0a, lb * (u32)sizeof(V), bar); }
+  }
+  for (u64 e = (a0a > a4 ? a0a : a4) + tid; e < a1; e += BLOCK) { sAk[e - a0a] = ac[e]; sAv[e - a0a] = av[e]; }
+  for (u64 e = (b0a > b4 ? b0a : b4) + tid; e < b1; e += BLOCK) { sBk[e - b0a] = bc[e]; sBv[e - b0a] = bv[e]; }
+  u32 i = 0, ie = 0, j = 0, je = 0, o = 0;
+  if (row < m) {
+    i = (u32)(ap[row] - a0a); ie = (u32)(ap[row + 1] - a0a);
+    j = (u32)(bp[row] - b0a); je = (u32)(bp[row + 1] - b0a);
+    o = (u32)(cp[row] - c0);
+  }
+  mbar_wait(bar, 0);
+  __syncthreads();
+  {
+    auto put = [&](u32 c, V v) { sCk[o] = c; sCv[o] = v; ++o; };
+    while (i < ie && j < je) {
+      const u32 ca = sAk[i], cb = sBk[j];
+      if (ca == cb) { put(ca, apply<V, OP>(sAv[i], sBv[j])); ++i; ++j; }
+      else if (ca < cb) { put(ca, KEEP_LEFT ? sAv[i] : apply<V, OP>(sAv[i], zero)); ++i; }
+      else { put(cb, apply<V, OP>(zero, sBv[j])); ++j; }
+    }
+    for (; i < ie; ++i) put(sAk[i], KEEP_LEFT ? sAv[i] : apply<V, OP>(sAv[i], zero));
+    for (; j < je; ++j) put(sBk[j], apply<V, OP>(zero, sBv[j]));
+  }
+  __syncthreads();
+  const u32 span = (u32)(c1 - c0);
+  for (u32 q = tid; q < span; q += BLOCK) { cc[c0 + q] = sCk[q]; cv[c0 + q] = sCv[q]; }
+}
+
 template <class V>
 int fill_typed(spam_handle* h, int op, const spam_dcsr* a, const spam_dcsr* b, spam_dcsr* c) {
   constexpr int BL = 128;
   const unsigned grid = (unsigned)((a->rows + BL - 1) / BL);
+  // span capacities: a block of BL mean rows plus 1/16 and a few entries of slack
+  auto cap_of = [&](u64 nnz) { return (u32)(((u64)((double)nnz / (double)a->rows * BL * 1.0625) + 64 + 3) & ~3ull); };
+  const u32 capA = cap_of(a->nnz), capB = cap_of(b->nnz), capC = cap_of(c->nnz);
+  const size_t tsmem = 16 + (size_t)(capA + capB + capC) * (4 + sizeof(V));
+  static const bool tma_on = [] { const char* e = getenv("SPAM_EWISE_TMA"); return !(e && e[0] == '0'); }();
+  const bool aligned = (((uintptr_t)a->idx | (uintptr_t)a->val | (uintptr_t)b->idx | (uintptr_t)b->val) & 15) == 0;
+  if (tma_on && aligned && tsmem <= 72 * 1024) {
+#define EW_TMA(OP, KEEP)                                                                                              \
+  {                                                                                                                   \
+    CK(cudaFuncSetAttribute(k_ewise_fill_tma<V, OP, KEEP, BL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024)); \
+    k_ewise_fill_tma<V, OP, KEEP, BL><<<grid, BL, tsmem, h->stream>>>(a->rows, a->ptr, a->idx, (const V*)a->val,      \
+        a->nnz, b->ptr, b->idx, (const V*)b->val, b->nnz, c->ptr, c->idx, (V*)c->val, capA, capB, capC);              \
+  }
+    switch (op) {
+      case 0: EW_TMA(0, false); break;
+      case 1: EW_TMA(1, false); break;
+      case 2: EW_TMA(0, true); break;
+      default: EW_TMA(1, true); break;
+    }
+#undef EW_TMA
+    count_launch(h);
+    CK(cudaGetLastError());
+    return SPAM_OK;
+  }
 #define EW_LAUNCH(OP, KEEP)                                                                                          \
   k_ewise_fill<V, OP, KEEP, BL><<<grid, BL, 0, h->stream>>>(a->rows, a->ptr, a->idx, (const V*)a->val, b->ptr, b->idx, \
                                                             (const V*)b->val, c->ptr, c->idx, (V*)c->val)

@@ -281,30 +281,6 @@ __device__ __forceinline__ u32 merge_window_plan(const u32* s_lo, const u32* s_h
   return nwin;
 }
 
-// 1-D bulk copies global -> shared through the TMA unit (SASS UBLKCP), completion on an mbarrier.
-__device__ __forceinline__ u32 msm_addr(const void* p) { return (u32)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(u64* bar, u32 count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(msm_addr(bar)), "r"(count) : "memory");
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(u64* bar, u32 bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(msm_addr(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, u32 bytes, u64* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(msm_addr(dst)),
-               "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(msm_addr(bar))
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(u64* bar, u32 parity) {
-  u32 ok;
-  do {
-    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
-                 : "=r"(ok)
-                 : "r"(msm_addr(bar)), "r"(parity)
-                 : "memory");
-  } while (!ok);
-}
-
 // Fetch the planned windows of one or two parallel arrays (col_idx, values) into the staging buffers: one thread
 // issues the bulk copies, every thread copies the at most 3 entries at the very end of the arrays that a 16-byte
 // copy would overrun, all wait.
