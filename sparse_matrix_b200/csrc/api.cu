@@ -256,6 +256,10 @@ int spam_cuda_create(spam_handle** out, int device) {
     h->sort_b = !(e && e[0] == '0');
     e = getenv("SPAM_MERGE_WIN");
     h->merge_win = e ? atoi(e) & 3 : 0;
+    e = getenv("SPAM_EWISE_TMA");
+    h->ewise_tma = !(e && e[0] == '0');
+    e = getenv("SPAM_SPMV_TMA");
+    h->spmv_tma = e && e[0] == '1';
     e = getenv("SPAM_MERGE_PF");
     h->merge_pf = e ? atoi(e) & 7 : -1;
     e = getenv("SPAM_L2_PERSIST");

@@ -248,6 +248,8 @@ struct spam_handle {
   bool sort_b;         // SPAM_SORT_B=0 at create time: never multiply by a sorted copy of an unsorted B (tests of the hash bins)
   int merge_win;       // SPAM_MERGE_WIN at create time: bit 0 numeric, bit 1 symbolic merge kernels stage the block's B window in shared memory with cp.async.bulk (default 0: measured slower)
   int merge_pf;        // SPAM_MERGE_PF at create time: low two bits = PF of k_num_merge (0..2), bit 2 = one-ahead columns in k_flop_sym_merge; -1 (default): 6 when A's rows scatter over B, else 0
+  bool spmv_tma;       // SPAM_SPMV_TMA=1 at create time: the persistent TMA-pipelined SpMV kernel (spmv.cu) instead of k_spmv_stream
+  bool ewise_tma;      // SPAM_EWISE_TMA=0 at create time: elementwise fill without the TMA-staged spans (k_ewise_fill)
   int l2_persist;      // SPAM_L2_PERSIST at create time (experiment, spgemm.cu): 1 = B's col_idx, 2 = B's values persisting in L2
   size_t l2_persist_max, l2_window_max;
   HostStage* stage;    // created on the first copy that involves a pageable host buffer

@@ -13,8 +13,6 @@
 // Two passes like the product: count the union per row, look-back scan (scan.cu), fill.  One thread per row:
 // HBM-bound on stencil-like matrices (reads A and B once, writes C once); rows whose columns are not sorted
 // are first put in order by two transposes (dok.cu).
-#include <cstdlib>
-
 #include "common.cuh"
 
 namespace {
@@ -180,9 +178,8 @@ int fill_typed(spam_handle* h, int op, const spam_dcsr* a, const spam_dcsr* b, s
   auto cap_of = [&](u64 nnz) { return (u32)(((u64)((double)nnz / (double)a->rows * BL * 1.0625) + 64 + 3) & ~3ull); };
   const u32 capA = cap_of(a->nnz), capB = cap_of(b->nnz), capC = cap_of(c->nnz);
   const size_t tsmem = 16 + (size_t)(capA + capB + capC) * (4 + sizeof(V));
-  static const bool tma_on = [] { const char* e = getenv("SPAM_EWISE_TMA"); return !(e && e[0] == '0'); }();
   const bool aligned = (((uintptr_t)a->idx | (uintptr_t)a->val | (uintptr_t)b->idx | (uintptr_t)b->val) & 15) == 0;
-  if (tma_on && aligned && tsmem <= 72 * 1024) {
+  if (h->ewise_tma && aligned && tsmem <= 72 * 1024) {
 #define EW_TMA(OP, KEEP)                                                                                              \
   {                                                                                                                   \
     CK(cudaFuncSetAttribute(k_ewise_fill_tma<V, OP, KEEP, BL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024)); \

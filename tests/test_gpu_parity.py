@@ -502,6 +502,35 @@ def test_spmv(oracle, handle, dtype):
         S.CsrMatrix.identity(3).spmv(np.ones(4), handle=handle)
 
 
+def test_spmv_tma_kernel(oracle):
+    """SPAM_SPMV_TMA=1: the persistent kernel that fetches col_idx / values with cp.async.bulk two stages deep.  Row
+    blocks with more than one chunk of 1536 entries, empty row blocks, nnz not a multiple of 4, more row blocks than
+    resident thread blocks (> 148 * 6 * 256 rows); f64 sums bit-identical to the oracle (same order, unfused)."""
+    os.environ["SPAM_SPMV_TMA"] = "1"
+    try:
+        h = S.Handle(0)
+    finally:
+        del os.environ["SPAM_SPMV_TMA"]
+    try:
+        rng = np.random.default_rng(88)
+        cases = []
+        for dtype in ALL_DTYPES:
+            for rows, cols, deg in [(1, 1, 1), (700, 300, 3), (3000, 2500, 40), (1000, 5000, 64)]:
+                cases.append(random_csr(rng, rows, cols, rng.integers(0, deg + 1, size=rows), dtype=dtype))
+        deg = rng.integers(0, 4, size=300_000)
+        deg[1000:3000] = 0                                  # whole row blocks without entries
+        cases.append(random_csr(rng, 300_000, 4000, deg, dtype=np.float64))
+        cases.append(G.poisson2d(300, dtype=np.float64))
+        for a in cases:
+            dtype = a[4].dtype
+            x = (rng.uniform(-1, 1, size=a[1]) if dtype.kind == "f" else rng.integers(-50, 50, size=a[1])).astype(dtype)
+            y = as_csr_matrix(a, True).spmv(x, handle=h)
+            want = oracle.spmv(a[0], a[1], a[2], a[3], a[4], x)
+            assert np.array_equal(y, want), (a[0], a[1], dtype)
+    finally:
+        h.close()
+
+
 @pytest.mark.parametrize("dtype", ALL_DTYPES)
 def test_dok_to_csr(oracle, handle, dtype):
     rng = np.random.default_rng(21)
@@ -797,6 +826,44 @@ def test_transpose(oracle, handle, dtype):
     bad.indices[1] = 7
     with pytest.raises(IndexError):
         bad.transpose(handle=handle)
+
+
+@pytest.mark.parametrize("tma", ["1", "0"])
+def test_elementwise_span_paths(oracle, tma):
+    """k_ewise_fill_tma stages the spans of a block when they fit the capacities taken from the mean row lengths:
+    skewed matrices (a few blocks of long rows among short ones: those blocks walk global memory), lengths that are not
+    multiples of 4 entries, empty operands; and the same with SPAM_EWISE_TMA=0 (k_ewise_fill)."""
+    os.environ["SPAM_EWISE_TMA"] = tma
+    try:
+        h = S.Handle(0)
+    finally:
+        del os.environ["SPAM_EWISE_TMA"]
+    try:
+        rng = np.random.default_rng(97)
+        for trial in range(6):
+            rows, cols = 5000 + trial, 4000
+            da = rng.integers(0, 6, size=rows)
+            db = rng.integers(0, 4, size=rows)
+            da[1000:1300] = rng.integers(100, 400, size=300)      # spans far beyond the capacities
+            db[3000:3100] = 300
+            if trial == 4:
+                db[:] = 0                                         # B empty
+            if trial == 5:
+                da[:] = 0
+            dtype = (np.float64, np.int64, np.float32, np.int32, np.float64, np.float64)[trial]
+            a = random_csr(rng, rows, cols, da, dtype=dtype)
+            b = random_csr(rng, rows, cols, db, dtype=dtype)
+            for op in ("add", "sub"):
+                want = oracle.ewise(a, b, op, True)
+                dA, dB = S.DeviceCsr.upload(as_csr_matrix(a), h), S.DeviceCsr.upload(as_csr_matrix(b), h)
+                dC = dA.add(dB) if op == "add" else dA.sub(dB)
+                got = dC.download()
+                assert np.array_equal(got.offsets, want[0]) and np.array_equal(got.indices, want[1])
+                assert np.array_equal(got.vals.view(np.uint8), want[2].view(np.uint8))
+                for d in (dA, dB, dC):
+                    d.free()
+    finally:
+        h.close()
 
 
 @pytest.mark.parametrize("dtype", ALL_DTYPES)
