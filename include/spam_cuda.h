@@ -79,7 +79,8 @@ typedef struct spam_stats {
    * [3] rows the bucket-sort (ESC) bins handed back to the global-table kernel,
    * [4] DOK->CSR / transpose path of the last build: 1 = counting sort by row (short segments),
    *     2 = LSD radix sort (some row or column holds more than 32 entries),
-   * [5..7] reserved. */
+   * [5] 1 = the product ran as the one-pass merge kernel (every row a merge row by the cached statistics),
+   * [6..7] reserved. */
   uint32_t fallbacks[8];
 } spam_stats;
 

@@ -258,6 +258,8 @@ int spam_cuda_create(spam_handle** out, int device) {
     h->merge_win = e ? atoi(e) & 3 : 0;
     e = getenv("SPAM_EWISE_TMA");
     h->ewise_tma = !(e && e[0] == '0');
+    e = getenv("SPAM_ONEPASS");
+    h->onepass = e && e[0] == '1';
     e = getenv("SPAM_SPMV_TMA");
     h->spmv_tma = e && e[0] == '1';
     e = getenv("SPAM_MERGE_PF");
@@ -647,6 +649,8 @@ int spam_spgemm_dev(spam_handle* h, const spam_dcsr* a, const spam_dcsr* b, spam
   if (!h || !a || !b || !c) return spam_fail(h, SPAM_EINVAL, "null argument");
   *c = nullptr;
   CKS(set_device(h));
+  CKS(spgemm_onepass_dev(h, a, b, c));
+  if (*c) return SPAM_OK;
   SpgemmPending* p = nullptr;
   CKS(spgemm_symbolic_dev(h, a, b, &p));
   CKS(spgemm_numeric_dev(h, p, c));
@@ -657,6 +661,10 @@ int spam_spgemm_dev_b2(spam_handle* h, const spam_dcsr* a, const spam_dcsr* b, i
   if (!h || !a || !b || !c) return spam_fail(h, SPAM_EINVAL, "null argument");
   *c = nullptr;
   CKS(set_device(h));
+  if (sorted) {
+    CKS(spgemm_onepass_dev(h, a, b, c));
+    if (*c) return SPAM_OK;
+  }
   SpgemmPending* p = nullptr;
   CKS(spgemm_symbolic_dev(h, a, b, &p));
   CKS(spgemm_numeric_dev(h, p, c, sorted ? 1 : 0));

@@ -249,6 +249,7 @@ struct spam_handle {
   int merge_win;       // SPAM_MERGE_WIN at create time: bit 0 numeric, bit 1 symbolic merge kernels stage the block's B window in shared memory with cp.async.bulk (default 0: measured slower)
   int merge_pf;        // SPAM_MERGE_PF at create time: low two bits = PF of k_num_merge (0..2), bit 2 = one-ahead columns in k_flop_sym_merge; -1 (default): 6 when A's rows scatter over B, else 0
   bool spmv_tma;       // SPAM_SPMV_TMA=1 at create time: the persistent TMA-pipelined SpMV kernel (spmv.cu) instead of k_spmv_stream
+  bool onepass;        // SPAM_ONEPASS=1 at create time: device-resident products whose rows are all merge rows by the cached statistics run as one kernel (spgemm_onepass_dev; measured slower, off by default)
   bool ewise_tma;      // SPAM_EWISE_TMA=0 at create time: elementwise fill without the TMA-staged spans (k_ewise_fill)
   int l2_persist;      // SPAM_L2_PERSIST at create time (experiment, spgemm.cu): 1 = B's col_idx, 2 = B's values persisting in L2
   size_t l2_persist_max, l2_window_max;
@@ -340,12 +341,14 @@ void finish_timing(spam_handle* h);                 // wait for the current set,
 
 // ---- entry points implemented across the .cu files ---------------------------------------------
 // scan.cu : exclusive scan of u32 counts into u64 offsets (out has n+1 entries), decoupled look-back
+int lookback_workspace(spam_handle* h, u64 tiles, u64** state, u32** tile_counter);  // scan.cu
 int scan_u32_to_u64(spam_handle* h, const u32* in, u64* out, u64 n, ull* d_total, u32* d_max = nullptr);
 // spgemm.cu
 int spgemm_symbolic_dev(spam_handle* h, const spam_dcsr* a, const spam_dcsr* b, SpgemmPending** out);
 int spgemm_numeric_dev(spam_handle* h, SpgemmPending* p, spam_dcsr** c, int sorted = 1);
 // slotorder.cu : rows of a sorted product permuted into the reference's B2 = false (linear-probe slot) order
 int slot_order_dev(spam_handle* h, const spam_dcsr* a, const spam_dcsr* b_original, spam_dcsr* c);
+int spgemm_onepass_dev(spam_handle* h, const spam_dcsr* a, const spam_dcsr* b, spam_dcsr** cout);  // *cout null: not applicable
 int spgemm_numeric_into(spam_handle* h, SpgemmPending* p, const u64* c_ptr, u32* c_idx, void* c_val);
 void spgemm_pending_free(spam_handle* h, SpgemmPending* p);
 u64 spgemm_pending_nnz(const SpgemmPending* p);

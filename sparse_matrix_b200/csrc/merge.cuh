@@ -721,4 +721,140 @@ __global__ void __launch_bounds__(BLOCK) k_num_merge_win(u32 n, const u32* __res
   }
 }
 
+// ONE-PASS product for matrices whose every row is a merge row BY THE CACHED STATISTICS (longest row of A <= K,
+// longest row of A x longest row of B <= MERGE_FLOP_MAX), so that no flop / binning pass is needed to know it and
+// nnz(A) x longest row of B bounds nnz(C) for the allocation.  Per block of BLOCK consecutive rows:
+//   1. load the run heads, count the products (flops) and the distinct columns (the symbolic merge, mul_hash.rs:84-99),
+//   2. block-wide exclusive scan of the counts; the block's total goes into a decoupled look-back over the blocks
+//      (tiles handed out by an atomic counter, {flag,value} in one 64-bit word as in scan.cu) and comes back as the
+//      block's first position in C (the row_ptr scan, lib.rs:267-274),
+//   3. write row_ptr(C), run the numeric merge of k_num_merge from the same run heads (B's rows are now in L1).
+// Against the two-phase pipeline (k_flop_sym_merge, k_scan_lookback, host sync for nnz(C), allocation, k_num_merge)
+// this saves one pass over A, the row_nnz / flop / row_ptr round trips, the scan launch and the mid-product host
+// synchronisation; the host learns nnz(C) after the kernel.  Same products, same order: bit-identical.
+template <class V, int K, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_merge_onepass(u32 m, u64 b_rows, const u64* __restrict__ a_ptr,
+                                                         const u32* __restrict__ a_col, const V* __restrict__ a_val,
+                                                         const u64* __restrict__ b_ptr, const u32* __restrict__ b_col,
+                                                         const V* __restrict__ b_val, u64* __restrict__ c_ptr,
+                                                         u32* __restrict__ c_col, V* __restrict__ c_val,
+                                                         volatile u64* state, u32* tile_counter, Counters* cnt) {
+  using Tile = MergeTile<V, BLOCK>;
+  extern __shared__ __align__(16) unsigned char sm_merge[];
+  V* sv = reinterpret_cast<V*>(sm_merge);                               // [MERGE_CH][STRIDE_V]
+  u32* sk = reinterpret_cast<u32*>(sv + MERGE_CH * Tile::STRIDE_V);     // [MERGE_CH][STRIDE_K]
+  __shared__ u32 s_tile, s_warp[BLOCK / 32];
+  __shared__ u64 s_base;
+  constexpr u64 F_AGG = 1ull << 62, F_PFX = 2ull << 62, F_MASK = (1ull << 62) - 1;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);
+  __syncthreads();
+  const u32 tile = s_tile;
+  const u32 row = tile * BLOCK + tid;
+  u32 pos0[K], pos[K], end[K], col[K];
+  V av[K];
+#pragma unroll
+  for (int h = 0; h < K; ++h) { pos0[h] = 0; end[h] = 0; col[h] = INF_COL; av[h] = Num<V>::zero(); }
+  bool bad = false;
+  u32 f = 0;
+  if (row < m) {
+    const u64 alo = a_ptr[row];
+    const u32 k = (u32)(a_ptr[row + 1] - alo);
+#pragma unroll
+    for (int h = 0; h < K; ++h) {
+      if (h < k) {
+        const u32 kk = a_col[alo + h];
+        av[h] = a_val[alo + h];
+        if (kk < b_rows) { pos0[h] = (u32)b_ptr[kk]; end[h] = (u32)b_ptr[kk + 1]; } else bad = true;
+      }
+      f += end[h] - pos0[h];
+    }
+  }
+  if (bad) atomicOr(&cnt->error, 1u);
+  // 1. symbolic merge
+#pragma unroll
+  for (int h = 0; h < K; ++h) {
+    pos[h] = pos0[h];
+    if (pos[h] < end[h]) col[h] = b_col[pos[h]];
+  }
+  u32 z = 0;
+  for (;;) {
+    u32 cmin = col[0];
+#pragma unroll
+    for (int h = 1; h < K; ++h) cmin = min(cmin, col[h]);
+    if (cmin == INF_COL) break;
+    ++z;
+#pragma unroll
+    for (int h = 0; h < K; ++h) {
+      if (col[h] == cmin) {
+        ++pos[h];
+        col[h] = (pos[h] < end[h]) ? b_col[pos[h]] : INF_COL;
+      }
+    }
+  }
+  // 2. block scan of z, look-back for the block's first position in C
+  u32 incl = z, fsum = f;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const u32 y = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += y;
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) fsum += __shfl_xor_sync(0xffffffffu, fsum, d);
+  if (lane == 31) s_warp[wid] = incl;
+  if (lane == 0 && fsum) atomicAdd(&cnt->total_flops, (ull)fsum);
+  __syncthreads();
+  if (wid == 0) {
+    const u32 w = lane < BLOCK / 32 ? s_warp[lane] : 0;
+    u32 wi = w;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const u32 y = __shfl_up_sync(0xffffffffu, wi, d);
+      if (lane >= d) wi += y;
+    }
+    if (lane < BLOCK / 32) s_warp[lane] = wi - w;  // exclusive warp offsets
+    const u64 block_total = __shfl_sync(0xffffffffu, wi, 31);
+    if (lane == 0) state[tile] = (tile == 0 ? F_PFX : F_AGG) | block_total;
+    u64 excl = 0;
+    if (tile > 0) {
+      long long p = (long long)tile - 1;
+      for (;;) {
+        const long long idx = p - lane;
+        u64 s;
+        if (idx >= 0) {
+          do { s = state[idx]; } while ((s >> 62) == 0);
+        } else {
+          s = F_PFX;
+        }
+        const unsigned pm = __ballot_sync(0xffffffffu, (s >> 62) == 2);
+        const int firstp = pm ? (__ffs(pm) - 1) : 32;
+        u64 c = (lane <= firstp) ? (s & F_MASK) : 0;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+        excl += c;
+        if (pm) break;
+        p -= 32;
+      }
+      if (lane == 0) state[tile] = F_PFX | (excl + block_total);
+    }
+    if (lane == 0) {
+      s_base = excl;
+      if ((u64)(tile + 1) * BLOCK >= (u64)m) {  // last block: row_ptr[m] = nnz(C)
+        c_ptr[m] = excl + block_total;
+        cnt->total_nnz = excl + block_total;
+      }
+    }
+  }
+  __syncthreads();
+  const u64 c0 = s_base + s_warp[wid] + (incl - z);
+  if (row < m) c_ptr[row] = c0;
+  // 3. numeric merge from the same run heads
+#pragma unroll
+  for (int h = 0; h < K; ++h) {
+    pos[h] = pos0[h];
+    col[h] = (pos[h] < end[h]) ? b_col[pos[h]] : INF_COL;
+  }
+  merge_rows_out<V, K, BLOCK, false>(pos, end, col, av, z, c0, b_col, b_val, sv, sk, c_col, c_val);
+}
+
 }  // namespace

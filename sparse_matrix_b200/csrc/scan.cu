@@ -121,6 +121,23 @@ __global__ void __launch_bounds__(SCAN_T) k_scan_lookback(const u32* __restrict_
 
 }  // namespace
 
+// Zeroed look-back state (one 64-bit word per tile) and tile counter from the handle's grow-only buffer.
+int lookback_workspace(spam_handle* h, u64 tiles, u64** state, u32** tile_counter) {
+  if (h->scan_ws_cap < tiles + 1) {
+    if (h->scan_ws) CKS(dev_free(h, h->scan_ws));
+    h->scan_ws = nullptr;
+    h->scan_ws_cap = 0;
+    u64* ws = nullptr;
+    CKS(dev_alloc_t(h, &ws, 2 * tiles + 1));
+    h->scan_ws = ws;
+    h->scan_ws_cap = 2 * tiles + 1;
+  }
+  CK(cudaMemsetAsync(h->scan_ws, 0, (tiles + 1) * sizeof(u64), h->stream));
+  *state = h->scan_ws;
+  *tile_counter = reinterpret_cast<u32*>(h->scan_ws + tiles);
+  return SPAM_OK;
+}
+
 int scan_u32_to_u64(spam_handle* h, const u32* in, u64* out, u64 n, ull* d_total, u32* d_max) {
   if (n == 0) {
     CK(cudaMemsetAsync(out, 0, sizeof(u64), h->stream));

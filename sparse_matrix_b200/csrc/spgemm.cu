@@ -1206,6 +1206,101 @@ int spgemm_numeric_dev(spam_handle* h, SpgemmPending* p, spam_dcsr** cout, int s
   return SPAM_OK;
 }
 
+// The whole product in ONE kernel (k_merge_onepass, merge.cuh) when the cached per-matrix statistics alone prove
+// that every row is a merge row: longest row of A <= MERGE_K and longest row of A x longest row of B <=
+// MERGE_FLOP_MAX (the binning rule of the two-phase pipeline, applied to the bound instead of the count), B's rows
+// sorted.  C's arrays are allocated for the bound nnz(A) x longest row of B (stencils: about 2 x nnz(C)) — the
+// price for not knowing nnz(C) before the kernel runs; products over 8 GB of bound take the two-phase pipeline.
+// *cout stays null when the operands do not qualify (not an error).
+// Measured on B200 (Poisson 2048^2 A*A f64): the kernel takes 0.558 ms against 0.132 + 0.386 ms for the two kernels it
+// replaces — the merge work is the same (the columns are still merged twice), what it saves (a pass over A, the scan,
+// the mid-product host sync: ~0.05 ms) goes into blocks waiting for their predecessors' totals in the look-back — step
+// 0.594 ms against 0.566 ms.  Opt-in (SPAM_ONEPASS=1), kept with its parity test.
+template <class V>
+static int onepass_launch(spam_handle* h, const spam_dcsr* a, const spam_dcsr* b, spam_dcsr* c, u64* state, u32* counter) {
+  constexpr int BL = 128;
+  constexpr size_t smem = num_merge_smem<V, BL>();
+  const u32 m = (u32)a->rows;
+  const unsigned grid = (m + BL - 1) / BL;
+  const u64 amax = a->max_row_len;
+#define ONEPASS(KK)                                                                                                  \
+  k_merge_onepass<V, KK, BL><<<grid, BL, smem, h->stream>>>(m, b->rows, a->ptr, a->idx, (const V*)a->val, b->ptr, b->idx, \
+                                                            (const V*)b->val, c->ptr, c->idx, (V*)c->val, state, counter, h->d_cnt)
+  if (amax <= 4) ONEPASS(4);
+  else if (amax <= 6) ONEPASS(6);
+  else ONEPASS(8);
+#undef ONEPASS
+  count_launch(h);
+  CK(cudaGetLastError());
+  return SPAM_OK;
+}
+
+int spgemm_onepass_dev(spam_handle* h, const spam_dcsr* a, const spam_dcsr* b, spam_dcsr** cout) {
+  *cout = nullptr;
+  if (!h->onepass || a->dtype != b->dtype || a->cols != b->rows) return SPAM_OK;
+  const u64 m = a->rows;
+  if (m == 0 || m >= 0xFFFFFFFFull || b->cols >= 0xFFFFFFFFull || a->cols >= 0xFFFFFFFFull) return SPAM_OK;
+  CKS(ensure_rows_sorted(h, b));
+  if (a != b) CKS(ensure_rows_sorted(h, a));
+  if (b->rows_sorted == 0 && b->nnz < 0xFFFFFFFFull && h->sort_b) {
+    const spam_dcsr* sb = nullptr;
+    CKS(sorted_rows_of(h, b, &sb));
+    b = sb;
+  }
+  if (b->rows_sorted != 1 || b->nnz >= 0xFFFFFFFFull) return SPAM_OK;
+  const u64 amax = a->max_row_len, bmax = b->max_row_len;
+  if (amax > MERGE_K || amax * bmax > MERGE_FLOP_MAX) return SPAM_OK;
+  u64 cap = a->nnz * bmax;
+  if (cap == 0) return SPAM_OK;
+  const size_t vs = dtype_size(a->dtype);
+  if (cap * (4 + vs) > (8ull << 30)) return SPAM_OK;
+
+  h->stats = spam_stats{};
+  spam_dcsr* c = new spam_dcsr();
+  c->dtype = a->dtype; c->rows = m; c->cols = b->cols; c->nnz = 0;
+  c->ptr = nullptr; c->idx = nullptr; c->val = nullptr; c->owning = true; c->rows_sorted = -1; c->max_row_len = 0;
+  auto fail = [&](int st) {
+    dev_free(h, c->ptr); dev_free(h, c->idx); dev_free(h, c->val);
+    delete c;
+    return st;
+  };
+  int st = dev_alloc_t(h, &c->ptr, m + 1);
+  if (st == SPAM_OK) st = dev_alloc_t(h, &c->idx, cap);
+  if (st == SPAM_OK) st = dev_alloc(h, &c->val, cap * vs);
+  if (st != SPAM_OK) return fail(st);
+  cudaError_t e = cudaMemsetAsync(h->d_cnt, 0, sizeof(Counters), h->stream);
+  if (e != cudaSuccess) return fail(spam_fail(h, SPAM_ECUDA, "cudaMemsetAsync", e));
+  timing_begin_product(h);
+  if (h->timing)
+    for (int i = 0; i < 4; ++i) cudaEventRecord(h->ev[i], h->stream);  // no separate flop / symbolic / scan phases
+  u64* state = nullptr;
+  u32* counter = nullptr;
+  st = lookback_workspace(h, (m + 127) / 128, &state, &counter);
+  if (st != SPAM_OK) return fail(st);
+  switch (a->dtype) {
+    case SPAM_F32: st = onepass_launch<float>(h, a, b, c, state, counter); break;
+    case SPAM_F64: st = onepass_launch<double>(h, a, b, c, state, counter); break;
+    case SPAM_I32: st = onepass_launch<int32_t>(h, a, b, c, state, counter); break;
+    case SPAM_I64: st = onepass_launch<int64_t>(h, a, b, c, state, counter); break;
+    default: st = spam_fail(h, SPAM_EINVAL, "bad dtype");
+  }
+  if (st == SPAM_OK) st = numeric_timing(h);
+  if (st != SPAM_OK) return fail(st);
+  e = cudaMemcpyAsync(h->h_cnt, h->d_cnt, sizeof(Counters), cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  if (e != cudaSuccess) return fail(spam_fail(h, SPAM_ECUDA, "one-pass product", e));
+  const Counters cn = *h->h_cnt;
+  if (cn.error & 1u) return fail(spam_fail(h, SPAM_EINDEX, "a column index of A is >= rows(B)"));
+  c->nnz = cn.total_nnz;
+  h->stats.flops = cn.total_flops;
+  h->stats.nnz_c = c->nnz;
+  h->stats.sym_bin_rows[MERGE_BIN] = (u32)m;
+  h->stats.num_bin_rows[MERGE_BIN] = (u32)m;
+  h->stats.fallbacks[5] = 1;  // the one-pass kernel ran
+  *cout = c;
+  return SPAM_OK;
+}
+
 // Phase 2 into arrays the caller owns: c_ptr has rows + 1 entries whose VALUES are positions in c_idx / c_val
 // (a rank of a row-sharded product passes its offset-fixed row_ptr and the arrays of the whole C, so its rows
 // land where the gathered result wants them: disjoint slices of one output, mul_hash.rs:121-128).  Consumes the

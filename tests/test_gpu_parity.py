@@ -282,6 +282,48 @@ def test_merge_bin_prefetch_kernels(oracle, pf):
         h.close()
 
 
+def test_onepass_product(oracle):
+    """SPAM_ONEPASS=1: device-resident products whose rows are all merge rows by the cached statistics (longest row of A
+    <= 8, x longest row of B <= 128) run as ONE kernel: symbolic merge, look-back scan over the blocks and numeric merge
+    fused; C allocated for the bound nnz(A) x longest row of B.  Bit-identical, also for floats."""
+    os.environ["SPAM_ONEPASS"] = "1"
+    try:
+        h = S.Handle(0)
+    finally:
+        del os.environ["SPAM_ONEPASS"]
+    try:
+        rng = np.random.default_rng(610)
+        cases = []
+        for n, dtype in ((130, np.float64), (77, np.float32), (40, np.int64)):
+            p = G.poisson2d(n, dtype=dtype)
+            vals = (rng.uniform(-1, 1, size=p[4].shape) if np.dtype(dtype).kind == "f"
+                    else rng.integers(-9, 10, size=p[4].shape)).astype(dtype)
+            p = p[:4] + (vals,)
+            cases.append((p, p, True))
+        bdeg = rng.integers(0, 13, size=3000)
+        bdeg[rng.random(3000) < 0.3] = 0
+        b = random_csr(rng, 3000, 5000, bdeg, dtype=np.float64)
+        a = random_csr(rng, 70_000, 3000, rng.integers(0, 9, size=70_000), dtype=np.float64, sorted_rows=False)
+        cases.append((a, b, True))                                   # 547 blocks: several look-back windows
+        a2 = random_csr(rng, 500, 3000, rng.integers(0, 12, size=500), dtype=np.float64)
+        cases.append((a2, b, False))                                 # longest row of A > 8: two-phase pipeline
+        for a, b, one in cases:
+            dA = S.DeviceCsr.upload(as_csr_matrix(a, False), h)
+            dB = dA if b is a else S.DeviceCsr.upload(as_csr_matrix(b, False), h)
+            dC = dA.matmul(dB)
+            st = h.stats()
+            assert st["fallbacks"][5] == (1 if one else 0), st["fallbacks"]
+            if one:
+                assert st["num_bin_rows"][MERGE] == a[0]
+            check_against_oracle(oracle, a, b, dC.download(), exact_values=one)
+            dC.free()
+            if dB is not dA:
+                dB.free()
+            dA.free()
+    finally:
+        h.close()
+
+
 def test_edge_cases(oracle, handle):
     # all-empty operands
     a = S.CsrMatrix.new((5, 7))
