@@ -32,7 +32,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not is_stale():
         return SO
     cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-           "-Xcompiler", "-fPIC", "-shared", "-o", SO] + [os.path.join(CSRC, s) for s in SOURCES] + ["-lpthread", "-ldl"]
+           "-Xcompiler", "-fPIC", "-shared", "--threads", "0", "-o", SO] + [os.path.join(CSRC, s) for s in SOURCES] + ["-lpthread", "-ldl"]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     subprocess.check_call(cmd)

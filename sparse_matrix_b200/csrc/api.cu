@@ -258,6 +258,10 @@ int spam_cuda_create(spam_handle** out, int device) {
     h->merge_win = e ? atoi(e) & 3 : 0;
     e = getenv("SPAM_EWISE_TMA");
     h->ewise_tma = !(e && e[0] == '0');
+    e = getenv("SPAM_DOK_BUCKET");
+    h->dok_bucket = !(e && e[0] == '0');
+    e = getenv("SPAM_MERGE_PERSIST");
+    h->merge_persist = e ? atoi(e) : 0;
     e = getenv("SPAM_ONEPASS");
     h->onepass = e && e[0] == '1';
     e = getenv("SPAM_SPMV_TMA");

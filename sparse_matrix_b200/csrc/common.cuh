@@ -100,6 +100,7 @@ struct Counters {
   u32 fb_heavy_bitonic;  // global-table rows whose bucket drain overflowed (global-memory bitonic network)
   u32 fb_esc;            // rows the bucket-sort (ESC) bins handed back to the global-table kernel
   u32 fb_list_n;         // number of row ids in the ESC fallback list
+  u32 bk_flags;          // bucket.cuh: bit0 a bucket overflowed, bit1 a segment is too long for the all-pairs loops
   ull spread_sum;        // k_rows_sorted: sum over the rows of <= 32 entries of (largest - smallest column index)
 };
 
@@ -250,6 +251,8 @@ struct spam_handle {
   int merge_pf;        // SPAM_MERGE_PF at create time: low two bits = PF of k_num_merge (0..2), bit 2 = one-ahead columns in k_flop_sym_merge; -1 (default): 6 when A's rows scatter over B, else 0
   bool spmv_tma;       // SPAM_SPMV_TMA=1 at create time: the persistent TMA-pipelined SpMV kernel (spmv.cu) instead of k_spmv_stream
   bool onepass;        // SPAM_ONEPASS=1 at create time: device-resident products whose rows are all merge rows by the cached statistics run as one kernel (spgemm_onepass_dev; measured slower, off by default)
+  int merge_persist;   // SPAM_MERGE_PERSIST=N at create time (experiment, measured slower): k_num_merge as a persistent grid of N blocks per SM
+  bool dok_bucket;     // SPAM_DOK_BUCKET=0 at create time: DOK -> CSR and transpose without the bucket path (bucket.cuh)
   bool ewise_tma;      // SPAM_EWISE_TMA=0 at create time: elementwise fill without the TMA-staged spans (k_ewise_fill)
   int l2_persist;      // SPAM_L2_PERSIST at create time (experiment, spgemm.cu): 1 = B's col_idx, 2 = B's values persisting in L2
   size_t l2_persist_max, l2_window_max;

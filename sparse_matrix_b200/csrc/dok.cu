@@ -27,6 +27,7 @@
 //
 // All integer work, HBM/L2-bound.
 #include "common.cuh"
+#include "bucket.cuh"
 
 namespace {
 
@@ -473,9 +474,64 @@ int dok_radix(spam_handle* h, u64 rows, u64 cols, u64 n, const u64* d_r, const u
   return SPAM_OK;
 }
 
+
+// ---- bucket path (bucket.cuh): one partition pass, one build pass, one host sync ----
+template <class K>
+int bk_set_smem(spam_handle* h, K kernel, size_t bytes) {
+  if (bytes > 48 * 1024) CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return SPAM_OK;
+}
+
+// *done = false with SPAM_OK: the path does not apply (shape) or raised a flag (a bucket overflowed, a row is too
+// long) — the caller takes the counting / radix path.  The result arrays are sized for n entries (nnz <= n).
+template <class V>
+int dok_bucket(spam_handle* h, u64 rows, u64 cols, u64 n, const u64* d_r, const u64* d_c, const V* d_v, spam_dcsr* out,
+               bool* done) {
+  *done = false;
+  BkPlan pl;
+  if (!h->dok_bucket || !bk_plan(rows, cols, n, &pl)) return SPAM_OK;
+  DevGuard g(h);
+  u32 *cursor = nullptr, *idx = nullptr;
+  uint4* part = nullptr;
+  V* val = nullptr;
+  CKS(g.alloc(&cursor, (u64)pl.nb * BK_CUR_STRIDE));
+  CKS(g.alloc(&part, (u64)pl.nb * BK_CAP));
+  CKS(g.alloc(&idx, n));
+  CKS(g.alloc(&val, n));
+  u64* state = nullptr;
+  u32* ticket = nullptr;
+  CKS(lookback_workspace(h, pl.nb, &state, &ticket));
+  CK(cudaMemsetAsync(h->d_cnt, 0, sizeof(Counters), h->stream));
+  CK(cudaMemsetAsync(cursor, 0, (u64)pl.nb * BK_CUR_STRIDE * sizeof(u32), h->stream));
+  const size_t psmem = (size_t)pl.nb * 2 * sizeof(u32);
+  CKS(bk_set_smem(h, k_bk_part_dok<V>, psmem));
+  CKS(bk_set_smem(h, k_bk_build<V, true>, bk_build_smem<V>()));
+  k_bk_part_dok<V><<<(unsigned)((n + BK_PTILE - 1) / BK_PTILE), BK_PT, psmem, h->stream>>>(
+      n, rows, cols, pl.shift, pl.mbits, pl.nb, d_r, d_c, d_v, cursor, part, h->d_cnt);
+  k_bk_build<V, true><<<pl.nb, BK_BT, bk_build_smem<V>(), h->stream>>>(rows, pl.shift, pl.mbits, pl.nb, cursor, part, state,
+                                                                       ticket, out->ptr, idx, val, h->d_cnt);
+  count_launch(h, 2);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(h->h_cnt, h->d_cnt, sizeof(Counters), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  if (h->h_cnt->error & 2u) return spam_fail(h, SPAM_EINDEX, "triplet index out of range");
+  if (h->h_cnt->bk_flags) return SPAM_OK;
+  out->nnz = h->h_cnt->total_nnz;
+  out->idx = idx; out->val = val;
+  g.release(idx); g.release(val);
+  h->stats.fallbacks[4] = 3;
+  *done = true;
+  return SPAM_OK;
+}
+
 template <class V>
 int dok_typed(spam_handle* h, u64 rows, u64 cols, u64 n, const u64* d_r, const u64* d_c, const V* d_v, spam_dcsr* out) {
   CKS(dev_alloc_t(h, &out->ptr, rows + 1));
+  {
+    bool done = false;
+    CKS(dok_bucket<V>(h, rows, cols, n, d_r, d_c, d_v, out, &done));
+    if (done) return SPAM_OK;
+  }
   DevGuard g(h);
   u32* raw_cnt = nullptr;
   unsigned char* rank8 = nullptr;
@@ -637,6 +693,62 @@ static int transpose_radix(spam_handle* h, const spam_dcsr* a, spam_dcsr** out) 
   return SPAM_OK;
 }
 
+// Transpose by the bucket path: buckets of columns, records (column_local << bits(rows) | row, entry position, value).
+static int transpose_bucket(spam_handle* h, const spam_dcsr* a, spam_dcsr** out, bool* done) {
+  *done = false;
+  const u64 m = a->rows, n = a->nnz, tc = a->cols;
+  BkPlan pl;
+  if (!h->dok_bucket || !bk_plan(tc, m, n, &pl)) return SPAM_OK;
+  const size_t es = dtype_size(a->dtype);
+  DevGuard g(h);
+  u32 *cursor = nullptr, *t_idx = nullptr;
+  uint4* part = nullptr;
+  u64* t_ptr = nullptr;
+  void* t_val = nullptr;
+  CKS(g.alloc(&cursor, (u64)pl.nb * BK_CUR_STRIDE));
+  CKS(g.alloc(&part, (u64)pl.nb * BK_CAP));
+  CKS(g.alloc(&t_ptr, tc + 1));
+  CKS(g.alloc(&t_idx, n));
+  CKS(g.alloc_bytes(&t_val, n * es));
+  u64* state = nullptr;
+  u32* ticket = nullptr;
+  CKS(lookback_workspace(h, pl.nb, &state, &ticket));
+  CK(cudaMemsetAsync(h->d_cnt, 0, sizeof(Counters), h->stream));
+  CK(cudaMemsetAsync(cursor, 0, (u64)pl.nb * BK_CUR_STRIDE * sizeof(u32), h->stream));
+  const size_t psmem = ((size_t)pl.nb * 2 + BK_PTILE + BK_PTILE / 32) * sizeof(u32);
+  const unsigned pgrid = (unsigned)((n + BK_PTILE - 1) / BK_PTILE);
+  if (es == 4) {
+    CKS(bk_set_smem(h, k_bk_part_csr<uint32_t>, psmem));
+    CKS(bk_set_smem(h, k_bk_build<uint32_t, false>, bk_build_smem<uint32_t>()));
+    k_bk_part_csr<uint32_t><<<pgrid, BK_PT, psmem, h->stream>>>(m, n, tc, pl.shift, pl.mbits, pl.nb, a->ptr, a->idx,
+                                                               (const uint32_t*)a->val, cursor, part, h->d_cnt);
+    k_bk_build<uint32_t, false><<<pl.nb, BK_BT, bk_build_smem<uint32_t>(), h->stream>>>(
+        tc, pl.shift, pl.mbits, pl.nb, cursor, part, state, ticket, t_ptr, t_idx, (uint32_t*)t_val, h->d_cnt);
+  } else {
+    CKS(bk_set_smem(h, k_bk_part_csr<uint64_t>, psmem));
+    CKS(bk_set_smem(h, k_bk_build<uint64_t, false>, bk_build_smem<uint64_t>()));
+    k_bk_part_csr<uint64_t><<<pgrid, BK_PT, psmem, h->stream>>>(m, n, tc, pl.shift, pl.mbits, pl.nb, a->ptr, a->idx,
+                                                               (const uint64_t*)a->val, cursor, part, h->d_cnt);
+    k_bk_build<uint64_t, false><<<pl.nb, BK_BT, bk_build_smem<uint64_t>(), h->stream>>>(
+        tc, pl.shift, pl.mbits, pl.nb, cursor, part, state, ticket, t_ptr, t_idx, (uint64_t*)t_val, h->d_cnt);
+  }
+  count_launch(h, 2);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(h->h_cnt, h->d_cnt, sizeof(Counters), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  if (h->h_cnt->error & 2u) return spam_fail(h, SPAM_EINDEX, "a column index is >= cols");
+  if (h->h_cnt->bk_flags) return SPAM_OK;
+  spam_dcsr* t = new spam_dcsr();
+  t->dtype = a->dtype; t->rows = a->cols; t->cols = a->rows; t->nnz = n; t->owning = true;
+  t->rows_sorted = -1; t->max_row_len = 0;
+  t->ptr = t_ptr; t->idx = t_idx; t->val = t_val;
+  g.release(t_ptr); g.release(t_idx); g.release(t_val);
+  h->stats.fallbacks[4] = 3;
+  *out = t;
+  *done = true;
+  return SPAM_OK;
+}
+
 int transpose_dev(spam_handle* h, const spam_dcsr* a, spam_dcsr** out) {
   *out = nullptr;
   const u64 m = a->rows, n = a->nnz, tc = a->cols;
@@ -644,6 +756,11 @@ int transpose_dev(spam_handle* h, const spam_dcsr* a, spam_dcsr** out) {
   if (m >= 0xFFFFFFFFull || tc >= 0xFFFFFFFFull) return spam_fail(h, SPAM_ECOLS, "dimension >= 2^32-1");
   h->stats = spam_stats{};
   if (m == 0 || tc == 0) return transpose_radix(h, a, out);
+  {
+    bool done = false;
+    CKS(transpose_bucket(h, a, out, &done));
+    if (done) return SPAM_OK;
+  }
   // Counting path: histogram by column -> scan -> scatter -> per-column order by row.  Taken when no column holds
   // more than SEG_MAX entries (one thread sorts a column); otherwise the stable radix sort above.
   const size_t es = dtype_size(a->dtype);

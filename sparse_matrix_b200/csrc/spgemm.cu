@@ -1095,8 +1095,12 @@ int numeric_typed(spam_handle* h, SpgemmPending* p, spam_dcsr* c) {
     constexpr int BL = 128;
     constexpr size_t smem = num_merge_smem<V, BL>();
     const u32 nm = nb.count[MERGE_BIN];
-    const unsigned grid = (nm + BL - 1) / BL;
+    unsigned grid = (nm + BL - 1) / BL;
     const u32 kmax = p->max_alen;  // longest A row among all rows short enough for a merge bin
+    if (h->merge_persist > 0) {  // persistent grid: merge_persist blocks per SM walk the row blocks
+      const unsigned pg = (unsigned)h->num_sms * (unsigned)h->merge_persist;
+      if (pg < grid) grid = pg;
+    }
     const int mpf = merge_prefetch_mode(h, a, b);
     if ((h->merge_win & 1) && (((uintptr_t)bc | (uintptr_t)bv) & 15) == 0) {
       constexpr size_t wsmem = num_merge_win_smem<V, BL>();

@@ -44,6 +44,20 @@ def handle_nosort():
 
 
 @pytest.fixture(scope="session")
+def handle_nobucket():
+    """SPAM_DOK_BUCKET=0: DOK -> CSR and transpose by the counting / radix paths of dok.cu, which the bucket path
+    (bucket.cuh, the default) falls back to for shapes it does not take."""
+    import sparse_matrix_b200 as S
+    os.environ["SPAM_DOK_BUCKET"] = "0"
+    try:
+        h = S.Handle(0)
+    finally:
+        del os.environ["SPAM_DOK_BUCKET"]
+    yield h
+    h.close()
+
+
+@pytest.fixture(scope="session")
 def handle_esc():
     """SPAM_ESC=2 (and SPAM_SORT_B=0): rows that do not compress take the bucket-sort bins 11..15 (esc.cuh), which are
     off by default because the hash bins measured faster on B200."""

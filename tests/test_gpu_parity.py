@@ -594,8 +594,9 @@ def test_dok_to_csr(oracle, handle, dtype):
     assert m.offsets.tolist() == [0, 1, 1, 2, 2] and m.indices.tolist() == [0, 2] and m.to_dok().entries == d.entries
 
 
-def test_dok_and_transpose_take_both_paths(oracle, handle):
-    """DOK -> CSR and transpose pick the counting path when no row (column) holds more than 32 entries and the stable
+def test_dok_and_transpose_take_both_paths(oracle, handle_nobucket):
+    """Without the bucket path (SPAM_DOK_BUCKET=0; it is what the bucket path falls back to): DOK -> CSR and transpose
+    pick the counting path when no row (column) holds more than 32 entries and the stable
     radix sort otherwise (spam_stats.fallbacks[4] = 1 / 2); both are bit-exact, including a stream that rewrites one
     key many times (last write wins, a final zero deletes)."""
     rng = np.random.default_rng(77)
@@ -603,8 +604,8 @@ def test_dok_and_transpose_take_both_paths(oracle, handle):
     # short rows with rewrites and deletions: counting path
     a = random_csr(rng, rows, cols, rng.integers(0, 13, size=rows), dtype=np.int64)
     tr, tc, tv = G.triplets_with_rewrites(a, seed=9, dup_frac=0.3, zero_frac=0.1)
-    got = S.CsrMatrix.from_triplets(rows, cols, tr, tc, tv, handle=handle)
-    assert handle.stats()["fallbacks"][4] == 1
+    got = S.CsrMatrix.from_triplets(rows, cols, tr, tc, tv, handle=handle_nobucket)
+    assert handle_nobucket.stats()["fallbacks"][4] == 1
     off, idx, val = oracle.dok_to_csr(rows, cols, tr, tc, tv)
     assert np.array_equal(got.offsets, off) and np.array_equal(got.indices, idx) and np.array_equal(got.vals, val)
     # exactly 32 triplets in one row, all on two keys: still the counting path
@@ -614,29 +615,93 @@ def test_dok_and_transpose_take_both_paths(oracle, handle):
     tr2, tc2 = tr2[keep], tc2[keep]
     tv2 = np.concatenate([tv[keep[:len(tv)]], np.arange(1, 33)])
     tv2[-1] = 0                                       # the last write of key (rows-1, 6) is a zero: deleted
-    got = S.CsrMatrix.from_triplets(rows, cols, tr2, tc2, tv2, handle=handle)
-    assert handle.stats()["fallbacks"][4] == 1
+    got = S.CsrMatrix.from_triplets(rows, cols, tr2, tc2, tv2, handle=handle_nobucket)
+    assert handle_nobucket.stats()["fallbacks"][4] == 1
     off, idx, val = oracle.dok_to_csr(rows, cols, tr2, tc2, tv2)
     assert np.array_equal(got.offsets, off) and np.array_equal(got.indices, idx) and np.array_equal(got.vals, val)
     assert got.get_element((rows - 1, 5)) == 31 and got.get_element((rows - 1, 6)) is None
     # one more triplet in that row (33): radix path, same answer as the oracle
     tr3, tc3, tv3 = np.append(tr2, rows - 1), np.append(tc2, 7), np.append(tv2, 9)
-    got = S.CsrMatrix.from_triplets(rows, cols, tr3, tc3, tv3, handle=handle)
-    assert handle.stats()["fallbacks"][4] == 2
+    got = S.CsrMatrix.from_triplets(rows, cols, tr3, tc3, tv3, handle=handle_nobucket)
+    assert handle_nobucket.stats()["fallbacks"][4] == 2
     off, idx, val = oracle.dok_to_csr(rows, cols, tr3, tc3, tv3)
     assert np.array_equal(got.offsets, off) and np.array_equal(got.indices, idx) and np.array_equal(got.vals, val)
     # transpose: columns of at most 32 entries -> counting path; a dense column -> radix path
     A = as_csr_matrix(a)
-    t = A.transpose(handle=handle)
+    t = A.transpose(handle=handle_nobucket)
     longest = int(np.bincount(a[3].astype(np.int64), minlength=cols).max())
-    assert longest <= 32 and handle.stats()["fallbacks"][4] == 1
+    assert longest <= 32 and handle_nobucket.stats()["fallbacks"][4] == 1
     want = oracle.transpose(a)
     assert np.array_equal(t.offsets, want[0]) and np.array_equal(t.indices, want[1]) and np.array_equal(t.vals, want[2])
     dense = random_csr(rng, 400, 50, np.full(400, 20), dtype=np.float64, sorted_rows=False)   # 160 per column
-    t = as_csr_matrix(dense, is_sorted=False).transpose(handle=handle)
-    assert handle.stats()["fallbacks"][4] == 2
+    t = as_csr_matrix(dense, is_sorted=False).transpose(handle=handle_nobucket)
+    assert handle_nobucket.stats()["fallbacks"][4] == 2
     want = oracle.transpose(dense)
     assert np.array_equal(t.offsets, want[0]) and np.array_equal(t.indices, want[1]) and np.array_equal(t.vals, want[2])
+
+
+def test_dok_and_transpose_bucket_path(oracle, handle):
+    """The default path (bucket.cuh, spam_stats.fallbacks[4] = 3): one partition pass into buckets of consecutive rows
+    (columns), one build pass in shared memory.  Bit-exact against the oracle for every dtype, for streams with
+    rewrites and deletions, rows from empty to several hundred triplets, a row count that is not a multiple of the
+    bucket width, and wide column spaces; a row past 512 triplets or a crowded bucket hands the build to the
+    counting / radix paths (fallbacks[4] = 1 / 2) with the same answer."""
+    rng = np.random.default_rng(404)
+    shapes = [(5000, 9000, 13), (1, 70000, 300), (70001, 3, 3), (3000, (1 << 31) - 2, 9), (1 << 17, 1 << 22, 6),
+              (40000, 1 << 26, 20)]
+    for k, (rows, cols, per) in enumerate(shapes):
+        dtype = [np.int64, np.float64, np.float32, np.int32][k % 4]
+        lens = rng.integers(0, min(per, cols) + 1, size=rows)
+        a = random_csr(rng, rows, cols, lens, dtype=dtype)
+        tr, tc, tv = G.triplets_with_rewrites(a, seed=k, dup_frac=0.3, zero_frac=0.1)
+        got = S.CsrMatrix.from_triplets(rows, cols, tr, tc, tv, handle=handle)
+        assert handle.stats()["fallbacks"][4] == 3, (rows, cols, handle.stats()["fallbacks"])
+        off, idx, val = oracle.dok_to_csr(rows, cols, tr, tc, tv)
+        assert np.array_equal(got.offsets, off) and np.array_equal(got.indices, idx)
+        assert np.array_equal(got.vals.view(np.uint8), val.view(np.uint8)), (rows, cols)
+        if cols <= (1 << 22):   # the transpose keeps cols + 1 offsets
+            t = as_csr_matrix(a).transpose(handle=handle)
+            want = oracle.transpose(a)
+            assert np.array_equal(t.offsets, want[0]) and np.array_equal(t.indices, want[1])
+            assert np.array_equal(t.vals.view(np.uint8), want[2].view(np.uint8))
+    # one key rewritten 400 times (last write wins), another ending in a zero (deleted): still the bucket path
+    rows, cols = 5000, 9000
+    a = random_csr(rng, rows, cols, rng.integers(0, 13, size=rows), dtype=np.int64)
+    tr, tc, tv = G.triplets_with_rewrites(a, seed=9, dup_frac=0.3, zero_frac=0.1)
+    keep = tr != rows - 1
+    tr2 = np.concatenate([tr[keep], np.full(400, rows - 1)])
+    tc2 = np.concatenate([tc[keep], np.tile([5, 6], 200)])
+    tv2 = np.concatenate([tv[keep], np.arange(1, 401)])
+    tv2[-1] = 0
+    got = S.CsrMatrix.from_triplets(rows, cols, tr2, tc2, tv2, handle=handle)
+    assert handle.stats()["fallbacks"][4] == 3
+    off, idx, val = oracle.dok_to_csr(rows, cols, tr2, tc2, tv2)
+    assert np.array_equal(got.offsets, off) and np.array_equal(got.indices, idx) and np.array_equal(got.vals, val)
+    assert got.get_element((rows - 1, 5)) == 399 and got.get_element((rows - 1, 6)) is None
+    # 600 triplets in one row: past the all-pairs limit -> flag -> the radix path, same answer
+    tr3 = np.concatenate([tr2, np.full(200, rows - 1)]); tc3 = np.concatenate([tc2, np.arange(100, 300)])
+    tv3 = np.concatenate([tv2, np.arange(1, 201)])
+    got = S.CsrMatrix.from_triplets(rows, cols, tr3, tc3, tv3, handle=handle)
+    assert handle.stats()["fallbacks"][4] == 2
+    off, idx, val = oracle.dok_to_csr(rows, cols, tr3, tc3, tv3)
+    assert np.array_equal(got.offsets, off) and np.array_equal(got.indices, idx) and np.array_equal(got.vals, val)
+    # every triplet in the first 64 of 200000 rows: the buckets of those rows overflow -> counting path
+    rows, cols = 200000, 1000
+    tr = rng.integers(0, 64, size=300000).astype(np.uint64); tc = rng.integers(0, cols, size=300000).astype(np.uint64)
+    tv = rng.integers(1, 100, size=300000).astype(np.int64)
+    got = S.CsrMatrix.from_triplets(rows, cols, tr, tc, tv, handle=handle)
+    assert handle.stats()["fallbacks"][4] in (1, 2)
+    off, idx, val = oracle.dok_to_csr(rows, cols, tr, tc, tv)
+    assert np.array_equal(got.offsets, off) and np.array_equal(got.indices, idx) and np.array_equal(got.vals, val)
+    # a dense column block (160 entries per column) and an out-of-range column
+    dense = random_csr(rng, 400, 50, np.full(400, 20), dtype=np.float64, sorted_rows=False)
+    t = as_csr_matrix(dense, is_sorted=False).transpose(handle=handle)
+    assert handle.stats()["fallbacks"][4] == 3
+    want = oracle.transpose(dense)
+    assert np.array_equal(t.offsets, want[0]) and np.array_equal(t.indices, want[1]) and np.array_equal(t.vals, want[2])
+    with pytest.raises(Exception):
+        S.CsrMatrix.from_triplets(10, 10, np.array([1, 10], np.uint64), np.array([1, 1], np.uint64),
+                                  np.array([1, 2], np.int64), handle=handle)
 
 
 def test_rows_to_parts_and_row_slices(oracle, handle):
