@@ -46,12 +46,13 @@ def resolve_scaling(args):
     """`strong`: the named matrix, rows split over the ranks (BASELINE configs[2], [3]: "row-partitioned
     1/2/4/8 B200").  `weak`: every rank owns one unit of the named workload — for Poisson (configs[1], a
     1-GPU configuration) a 2048 x 2048 block of lines of a 2048 x (2048 N) grid, B = the whole matrix
-    replicated; per-GPU work is fixed as N grows.  `auto` = weak for poisson2048, strong otherwise."""
+    replicated; per-GPU work is fixed as N grows.  `auto` = weak for poisson2048 at every N (the N = 1 line carries the
+    same label as the N > 1 lines it is compared with), strong otherwise."""
     if args.scaling != "auto":
         if args.scaling == "weak" and args.workload != "poisson2048":
             raise SystemExit("--scaling weak is defined for poisson2048 only")
         return args.scaling
-    return "weak" if (args.workload == "poisson2048" and args.gpus > 1) else "strong"
+    return "weak" if args.workload == "poisson2048" else "strong"
 
 
 def make_workload(name, units=1):

@@ -272,7 +272,7 @@ int spam_cuda_create(spam_handle** out, int device) {
     h->l2_persist = e ? atoi(e) : 0;
     h->l2_persist_max = 0; h->l2_window_max = 0;
     e = getenv("SPAM_ESC");
-    h->use_esc = e ? (e[0] == '2' ? 2 : (e[0] == '1' ? 1 : 0)) : 0;
+    h->use_esc = e ? (e[0] == '3' ? 3 : (e[0] == '2' ? 2 : (e[0] == '1' ? 1 : 0))) : 0;
   }
   h->d_cnt = nullptr; h->h_cnt = nullptr; h->own_stream = nullptr; h->stream = nullptr;
   h->stats = spam_stats{};

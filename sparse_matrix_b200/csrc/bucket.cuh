@@ -66,6 +66,8 @@ __device__ __forceinline__ V bk_val(const uint4& e) {
   return v;
 }
 
+__device__ __forceinline__ void bk_prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 constexpr int BK_CUR_STRIDE = 8;  // one bucket cursor per 32-byte sector: a warp's 32 atomics spread over 8 lines
 
 // Second half of both partition kernels.  br[it] = bucket << 16 | rank inside (block, bucket), or ~0 for an entry that
@@ -124,6 +126,10 @@ __global__ void __launch_bounds__(BK_PT, 2) k_bk_part_dok(u64 n, u64 rows, u64 c
   __syncthreads();
   const u64 t0 = (u64)blockIdx.x * BK_PTILE;
   const u64 rmask = (1ull << shift) - 1;
+  {  // the values are read in the second half, after two barriers: have them in L2 by then (one prefetch per line)
+    const u64 i = t0 + (u64)tid * (128 / sizeof(V));
+    if (i < n && i < t0 + BK_PTILE) bk_prefetch_l2(v + i);
+  }
   u32 key[BK_PITEMS], br[BK_PITEMS];
   bool bad = false;
 #pragma unroll
@@ -174,6 +180,14 @@ __global__ void __launch_bounds__(BK_PT, 2) k_bk_part_csr(u64 m, u64 nnz, u64 tc
   for (u32 d = tid; d < (u32)(BK_PTILE + BK_PTILE / 32); d += BK_PT) s_mark[d] = 0;
   const u64 t0 = (u64)blockIdx.x * BK_PTILE;
   const u64 t1 = (t0 + BK_PTILE < nnz ? t0 + BK_PTILE : nnz) - 1;  // last entry of the tile
+  if (tid < BK_PT / 2) {  // the tile's indices and values are read after the row marks: have them in L2 by then
+    const u64 i = t0 + (u64)tid * 32;  // one prefetch per 128 bytes of idx, two per 256 bytes of val
+    if (i <= t1) {
+      bk_prefetch_l2(idx + i);
+      bk_prefetch_l2(val + i);
+      if (sizeof(W) == 8) bk_prefetch_l2(val + i + 16);
+    }
+  }
   if (tid < 2) {  // last row whose start is <= the entry (rows are [ptr[r], ptr[r+1]); empty rows share a start)
     const u64 e = tid == 0 ? t0 : t1;
     u64 lo = 0, hi = m - 1;

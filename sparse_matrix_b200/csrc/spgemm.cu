@@ -21,6 +21,7 @@
 #include "merge.cuh"
 #include "rowhash.cuh"
 #include "esc.cuh"
+#include "msort.cuh"
 
 namespace {
 
@@ -799,7 +800,9 @@ int spgemm_symbolic_dev(spam_handle* h, const spam_dcsr* a, const spam_dcsr* b, 
   const int merge_ok = (b->rows_sorted == 1 && b->nnz < 0xFFFFFFFFull) ? 1 : 0;
   SpgemmPending* p = new SpgemmPending();
   p->a = a; p->b = b; p->b_orig = b_orig; p->d_flop = nullptr; p->d_row_nnz = nullptr; p->d_cptr = nullptr; p->nnz = 0; p->max_nnz = 0;
-  const int mode = (merge_ok ? MODE_MERGE : 0) | (h->use_esc ? MODE_ESC : 0) | (h->use_esc == 2 ? MODE_ESC_HEAVY : 0);
+  // use_esc = 3: the merge-tree bins (msort.cuh) need B's rows sorted, like the merge bin
+  const bool esc_on = h->use_esc == 3 ? merge_ok != 0 : h->use_esc != 0;
+  const int mode = (merge_ok ? MODE_MERGE : 0) | (esc_on ? MODE_ESC : 0) | (h->use_esc == 2 ? MODE_ESC_HEAVY : 0);
   p->max_alen = 0; p->merge_ok = merge_ok; p->mode = mode;
   *out = p;
 #define FAIL_FREE(expr) do { int _s = (expr); if (_s != SPAM_OK) { spgemm_pending_free(h, p); *out = nullptr; return _s; } } while (0)
@@ -1063,10 +1066,26 @@ int numeric_typed(spam_handle* h, SpgemmPending* p, spam_dcsr* c) {
                                                                        cp, cc, cv, h->d_cnt, fb_list);   \
     count_launch(h);                                                                                     \
   }
-  LAUNCH_ESC(ESC_BIN0 + 3, 32)
-  LAUNCH_ESC(ESC_BIN0 + 2, 16)
-  LAUNCH_ESC(ESC_BIN0 + 1, 8)
-  LAUNCH_ESC(ESC_BIN0, 4)
+#define LAUNCH_MSORT(BIN, NW)                                                                            \
+  if (nb.count[BIN]) {                                                                                   \
+    constexpr size_t smem = num_msort_smem<V, NW>();                                                     \
+    CKS(set_smem(h, k_num_msort<V, NW>, smem));                                                          \
+    k_num_msort<V, NW><<<nb.count[BIN], 32 * NW, smem, lane_of(h, BIN)>>>(nb.count[BIN], seg(BIN), ap, ac, av, bp, bc, \
+                                                                         bv, cp, cc, cv);                \
+    count_launch(h);                                                                                     \
+  }
+  if (h->use_esc == 3) {
+    LAUNCH_MSORT(ESC_BIN0 + 3, 32)
+    LAUNCH_MSORT(ESC_BIN0 + 2, 16)
+    LAUNCH_MSORT(ESC_BIN0 + 1, 8)
+    LAUNCH_MSORT(ESC_BIN0, 4)
+  } else {
+    LAUNCH_ESC(ESC_BIN0 + 3, 32)
+    LAUNCH_ESC(ESC_BIN0 + 2, 16)
+    LAUNCH_ESC(ESC_BIN0 + 1, 8)
+    LAUNCH_ESC(ESC_BIN0, 4)
+  }
+#undef LAUNCH_MSORT
 #undef LAUNCH_ESC
   // numeric hash bin b: z <= 32 << b, table 64 << b (key, value) slots.  Team sizes: these kernels are
   // latency-bound (dependent shared-memory and shuffle chains), so the big-table bins get many warps per row

@@ -58,6 +58,19 @@ def handle_nobucket():
 
 
 @pytest.fixture(scope="session")
+def handle_msort():
+    """SPAM_ESC=3: rows that do not compress take the merge-tree bins (msort.cuh) instead of the hash bins."""
+    import sparse_matrix_b200 as S
+    os.environ["SPAM_ESC"] = "3"
+    try:
+        h = S.Handle(0)
+    finally:
+        del os.environ["SPAM_ESC"]
+    yield h
+    h.close()
+
+
+@pytest.fixture(scope="session")
 def handle_esc():
     """SPAM_ESC=2 (and SPAM_SORT_B=0): rows that do not compress take the bucket-sort bins 11..15 (esc.cuh), which are
     off by default because the hash bins measured faster on B200."""

@@ -424,6 +424,63 @@ def test_config3_stencil27_reduced(oracle, handle):
     assert len(idx) == (5 * 40 - 6) ** 3
 
 
+@pytest.mark.parametrize("dtype", ALL_DTYPES)
+def test_merge_tree_bins(oracle, handle_msort, dtype):
+    """SPAM_ESC=3: rows with nnz > 256 and 2 nnz >= products are merged, not hashed (msort.cuh, numeric bins 11..14):
+    len(A row) sorted runs, log2 passes of pairwise merge-path merges in shared memory, equal columns folded in the
+    reference's product order — structure bit-exact and VALUES bit-exact for every dtype, floats included."""
+    h = handle_msort
+    rng = np.random.default_rng(1234)
+    inner, n = 3000, 60000
+    # (1) every product a new column (mostly), A rows of 7 .. 200 entries, B rows of 0 .. 80 entries (empty runs)
+    # (rows past 8192 products would take the hash bins, whose float sums are not bit-identical: none here)
+    deg = np.array([7, 13, 20, 26, 33, 40, 51, 64, 65, 90, 100, 128, 129, 150, 160, 170] + [3] * 10)
+    a = random_csr(rng, len(deg), inner, deg, dtype=dtype, sorted_rows=False)
+    b = random_csr(rng, inner, n, rng.integers(0, 81, size=inner), dtype=dtype, sorted_rows=False)
+    assert G.spgemm_counts(a, b)[1].max() <= 8192
+    c = gpu_mul(a, b, h)
+    st = h.stats()
+    assert all(x > 0 for x in st["num_bin_rows"][11:15]) and sum(st["num_bin_rows"][4:10]) == 0, st["num_bin_rows"]
+    check_against_oracle(oracle, a, b, c, exact_values=True)
+    # (2) a third of the columns produced twice: A references row k of B and, for the first third of its entries,
+    #     also row k + inner of a B that repeats itself — those entries of C are sums of two products
+    deg2 = np.array([12, 21, 42, 60, 90, 120] + [2] * 5)
+    a1 = random_csr(rng, len(deg2), inner, deg2, dtype=dtype, sorted_rows=False)
+    parts = []
+    for lo, hi in zip(a1[2][:-1], a1[2][1:]):
+        rowi = a1[3][int(lo):int(hi)]
+        parts.append(np.concatenate([rowi, rowi[:len(rowi) // 3] + np.uint64(inner)]))
+    idx2 = np.concatenate(parts)
+    off2 = np.concatenate([[0], np.cumsum([len(x) for x in parts])]).astype(np.uint64)
+    if np.dtype(dtype).kind == "f":
+        v2 = rng.uniform(-1, 1, size=len(idx2)).astype(dtype)
+    else:
+        v2 = rng.integers(-50, 51, size=len(idx2)).astype(dtype)
+    a2 = (len(deg2), 2 * inner, off2, idx2, v2)
+    b1 = random_csr(rng, inner, n, 45, dtype=dtype, sorted_rows=True)
+    b2 = (2 * inner, n, np.concatenate([b1[2], b1[2][1:] + b1[2][-1]]), np.concatenate([b1[3], b1[3]]),
+          np.concatenate([b1[4], b1[4][::-1].copy()]))
+    c = gpu_mul(a2, b2, h)
+    st = h.stats()
+    assert sum(st["num_bin_rows"][11:15]) >= 4, st["num_bin_rows"]
+    off, idx, val = check_against_oracle(oracle, a2, b2, c, exact_values=True)
+    assert len(idx) < G.spgemm_counts(a2, b2)[0] * 0.8
+    # (3) B rows of a single entry: as many runs as products (13 passes for 8192 products)
+    a3 = random_csr(rng, 6, 40000, np.array([300, 1000, 2000, 4000, 8000, 5]), dtype=dtype, sorted_rows=False)
+    b3 = random_csr(rng, 40000, 1 << 22, 1, dtype=dtype)
+    c = gpu_mul(a3, b3, h)
+    st = h.stats()
+    assert all(x > 0 for x in st["num_bin_rows"][11:15]), st["num_bin_rows"]
+    check_against_oracle(oracle, a3, b3, c, exact_values=True)
+    # (4) power-law columns
+    if np.dtype(dtype) == np.float64:
+        r = G.rmat(15, 16)
+        c = gpu_mul(r, r, h)
+        st = h.stats()
+        assert all(x > 0 for x in st["num_bin_rows"][11:15]), st["num_bin_rows"]
+        check_against_oracle(oracle, r, r, c)     # hash bins also run here: tolerance
+
+
 def test_config4_rmat_reduced(oracle, handle, handle_esc):
     r = G.rmat(16, 16)
     handle.set_timing(True)
