@@ -144,7 +144,8 @@ def main():
             ts.append(dA.transpose())
             if len(ts) > 1:
                 ts.pop(0).free()
-        ms_t = timed(run_t, stream, reps=10)
+        ms_t = timed(run_t, stream, reps=20)
+        path_t = h.stats()["fallbacks"][4]
         dAT = ts[-1]
         gt = dAT.download()
         t0 = time.perf_counter()
@@ -157,7 +158,8 @@ def main():
         by_t = nnz_a * 12 * 2 + (a[0] + 1) * 8 + (a[1] + 1) * 8      # read A once, write A^T once
         print(json.dumps({"op": "transpose", "workload": "C5 1Mx4M, 8/row, i64", "nnz": nnz_a, "ms": ms_t,
                           "algorithmic_bytes": by_t, "gbs": by_t / ms_t / 1e6, "frac_of_measured_peak": by_t / ms_t / 1e6 / peak,
-                          "parity_ok": ok_t, "cpu_oracle_ms_1thread": cpu_t}), flush=True)
+                          "parity_ok": ok_t, "path": {1: "counting", 2: "radix", 3: "bucket"}.get(path_t, path_t),
+                          "cpu_oracle_ms_1thread": cpu_t}), flush=True)
         cs = []
 
         def run2():

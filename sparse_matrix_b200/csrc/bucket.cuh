@@ -180,14 +180,6 @@ __global__ void __launch_bounds__(BK_PT, 2) k_bk_part_csr(u64 m, u64 nnz, u64 tc
   for (u32 d = tid; d < (u32)(BK_PTILE + BK_PTILE / 32); d += BK_PT) s_mark[d] = 0;
   const u64 t0 = (u64)blockIdx.x * BK_PTILE;
   const u64 t1 = (t0 + BK_PTILE < nnz ? t0 + BK_PTILE : nnz) - 1;  // last entry of the tile
-  if (tid < BK_PT / 2) {  // the tile's indices and values are read after the row marks: have them in L2 by then
-    const u64 i = t0 + (u64)tid * 32;  // one prefetch per 128 bytes of idx, two per 256 bytes of val
-    if (i <= t1) {
-      bk_prefetch_l2(idx + i);
-      bk_prefetch_l2(val + i);
-      if (sizeof(W) == 8) bk_prefetch_l2(val + i + 16);
-    }
-  }
   if (tid < 2) {  // last row whose start is <= the entry (rows are [ptr[r], ptr[r+1]); empty rows share a start)
     const u64 e = tid == 0 ? t0 : t1;
     u64 lo = 0, hi = m - 1;

@@ -482,6 +482,17 @@ int bk_set_smem(spam_handle* h, K kernel, size_t bytes) {
   return SPAM_OK;
 }
 
+// look-back states, ticket and bucket cursors of one call: carved from the handle's grow-only scan workspace, zeroed by
+// its one memset (state[nb], ticket, then nb cursors one 32-byte sector apart)
+static int bk_control(spam_handle* h, u32 nb, u64** state, u32** ticket, u32** cursor) {
+  const u64 words = (u64)nb + 2 + ((u64)nb * BK_CUR_STRIDE * sizeof(u32) + 7) / 8;
+  u32* unused = nullptr;
+  CKS(lookback_workspace(h, words, state, &unused));  // zeroes words + 1 u64
+  *ticket = reinterpret_cast<u32*>(*state + nb);
+  *cursor = reinterpret_cast<u32*>(*state + nb + 2);
+  return SPAM_OK;
+}
+
 // *done = false with SPAM_OK: the path does not apply (shape) or raised a flag (a bucket overflowed, a row is too
 // long) — the caller takes the counting / radix path.  The result arrays are sized for n entries (nnz <= n).
 template <class V>
@@ -494,15 +505,13 @@ int dok_bucket(spam_handle* h, u64 rows, u64 cols, u64 n, const u64* d_r, const 
   u32 *cursor = nullptr, *idx = nullptr;
   uint4* part = nullptr;
   V* val = nullptr;
-  CKS(g.alloc(&cursor, (u64)pl.nb * BK_CUR_STRIDE));
   CKS(g.alloc(&part, (u64)pl.nb * BK_CAP));
   CKS(g.alloc(&idx, n));
   CKS(g.alloc(&val, n));
   u64* state = nullptr;
   u32* ticket = nullptr;
-  CKS(lookback_workspace(h, pl.nb, &state, &ticket));
+  CKS(bk_control(h, pl.nb, &state, &ticket, &cursor));
   CK(cudaMemsetAsync(h->d_cnt, 0, sizeof(Counters), h->stream));
-  CK(cudaMemsetAsync(cursor, 0, (u64)pl.nb * BK_CUR_STRIDE * sizeof(u32), h->stream));
   const size_t psmem = (size_t)pl.nb * 2 * sizeof(u32);
   CKS(bk_set_smem(h, k_bk_part_dok<V>, psmem));
   CKS(bk_set_smem(h, k_bk_build<V, true>, bk_build_smem<V>()));
@@ -705,16 +714,14 @@ static int transpose_bucket(spam_handle* h, const spam_dcsr* a, spam_dcsr** out,
   uint4* part = nullptr;
   u64* t_ptr = nullptr;
   void* t_val = nullptr;
-  CKS(g.alloc(&cursor, (u64)pl.nb * BK_CUR_STRIDE));
   CKS(g.alloc(&part, (u64)pl.nb * BK_CAP));
   CKS(g.alloc(&t_ptr, tc + 1));
   CKS(g.alloc(&t_idx, n));
   CKS(g.alloc_bytes(&t_val, n * es));
   u64* state = nullptr;
   u32* ticket = nullptr;
-  CKS(lookback_workspace(h, pl.nb, &state, &ticket));
+  CKS(bk_control(h, pl.nb, &state, &ticket, &cursor));
   CK(cudaMemsetAsync(h->d_cnt, 0, sizeof(Counters), h->stream));
-  CK(cudaMemsetAsync(cursor, 0, (u64)pl.nb * BK_CUR_STRIDE * sizeof(u32), h->stream));
   const size_t psmem = ((size_t)pl.nb * 2 + BK_PTILE + BK_PTILE / 32) * sizeof(u32);
   const unsigned pgrid = (unsigned)((n + BK_PTILE - 1) / BK_PTILE);
   if (es == 4) {
@@ -754,6 +761,7 @@ int transpose_dev(spam_handle* h, const spam_dcsr* a, spam_dcsr** out) {
   const u64 m = a->rows, n = a->nnz, tc = a->cols;
   if (n >= 0xFFFFFFFFull) return spam_fail(h, SPAM_EOVERFLOW, "more than 2^32-1 entries");
   if (m >= 0xFFFFFFFFull || tc >= 0xFFFFFFFFull) return spam_fail(h, SPAM_ECOLS, "dimension >= 2^32-1");
+  CKS(ensure_matrix_stats(h, a));  // cached per matrix: the CSR invariants every path below relies on (row_ptr monotone, idx < cols)
   h->stats = spam_stats{};
   if (m == 0 || tc == 0) return transpose_radix(h, a, out);
   {

@@ -990,6 +990,9 @@ def test_transpose(oracle, handle, dtype):
     bad.indices[1] = 7
     with pytest.raises(IndexError):
         bad.transpose(handle=handle)
+    bad2 = S.CsrMatrix(3, 2, np.array([1, 1], dtype=dtype), [0, 1], [0, 2, 1, 2])   # row_ptr not monotone
+    with pytest.raises(Exception):
+        bad2.transpose(handle=handle)
 
 
 @pytest.mark.parametrize("tma", ["1", "0"])
