@@ -27,7 +27,7 @@
 
 namespace {
 
-constexpr u32 BK_CAP = 5120;      // records per bucket (shared memory of k_bk_build: 108 KB for 8-byte values, 2 blocks per SM)
+constexpr u32 BK_CAP = 5120;      // records per bucket (shared memory of k_bk_build: 10 bytes per record, 3 blocks per SM)
 constexpr u32 BK_NB_MAX = 8192;   // buckets: the partition kernel keeps two u32 per bucket in shared memory
 constexpr int BK_SHIFT_MAX = 10;  // at most 1024 majors per bucket
 constexpr int BK_PT = 512, BK_PITEMS = 16, BK_PTILE = BK_PT * BK_PITEMS;  // partition tile: 8192 entries
@@ -272,24 +272,28 @@ __device__ __forceinline__ u32 bk_block_scan(const u32* s_in, u32* s_out, u32 r,
 }
 
 template <class V>
-constexpr size_t bk_build_smem() {
-  return (size_t)BK_CAP * (8 + sizeof(V) + 2 + 2) + (size_t)(2 * ((1u << BK_SHIFT_MAX) + 2)) * 4 + 64 * 4;
+constexpr size_t bk_build_smem() {  // 58 KB whatever the value type: three blocks per SM
+  return (size_t)BK_CAP * (4 + 2 + 2 + 2) + (size_t)(2 * ((1u << BK_SHIFT_MAX) + 2)) * 4 + 64 * 4;
 }
 
 // One block per bucket.  out_ptr has majors + 1 entries; out_idx / out_val hold the result (sized for every entry).
 //
-// DEDUPE (DOK): one walk over its segment tells an entry whether a later write of its key exists and how many keys of
-// the segment are smaller.  That count is its final rank unless the segment lost an entry (a rewritten key, a zero):
-// only those segments — about one in ten for C5's 1 % rewrites — are walked a second time.
+// Shared memory holds, per entry in major order, only the minor index, the record's place in the bucket (+ a flag: its
+// value is zero), its major and its rank; stream positions and values stay in the bucket's records (L2): positions are
+// looked at only when two entries of a segment share their minor, values once, when the result is written.
+// One walk over its segment tells an entry how many minors are smaller (its rank) and how many are equal.
+// DEDUPE (DOK): an equal minor means a rewritten key — the later stream position wins; that rank is final unless the
+// segment lost an entry (a rewritten key, a zero): only those segments — about one in ten for C5's 1 % rewrites — are
+// walked a second time.
 template <class V, bool DEDUPE>
-__global__ void __launch_bounds__(BK_BT, 2) k_bk_build(u64 majors, int shift, int mbits, u32 nb, const u32* __restrict__ cursor,
+__global__ void __launch_bounds__(BK_BT, 3) k_bk_build(u64 majors, int shift, int mbits, u32 nb, const u32* __restrict__ cursor,
                                                        const uint4* __restrict__ part, volatile u64* state, u32* ticket,
                                                        u64* __restrict__ out_ptr, u32* __restrict__ out_idx,
                                                        V* __restrict__ out_val, Counters* cnt) {
   extern __shared__ __align__(16) unsigned char s_raw[];
-  u64* s_kp = reinterpret_cast<u64*>(s_raw);                                   // [BK_CAP] minor << 32 | stream position
-  V* s_val = reinterpret_cast<V*>(s_kp + BK_CAP);                              // [BK_CAP]
-  unsigned short* s_seg = reinterpret_cast<unsigned short*>(s_val + BK_CAP);   // [BK_CAP] major_local of a sorted entry
+  u32* s_minor = reinterpret_cast<u32*>(s_raw);                                // [BK_CAP] minor index, ~0 once dropped
+  unsigned short* s_j = reinterpret_cast<unsigned short*>(s_minor + BK_CAP);   // [BK_CAP] record of the entry | 0x8000: zero value
+  unsigned short* s_seg = s_j + BK_CAP;                                        // [BK_CAP] major_local of a sorted entry
   unsigned short* s_rk = s_seg + BK_CAP;                                       // [BK_CAP] rank among the survivors / BK_DROPPED
   u32* s_cnt = reinterpret_cast<u32*>(s_rk + BK_CAP);                          // [R + 2]
   u32* s_off = s_cnt + (1u << BK_SHIFT_MAX) + 2;                               // [R + 2]
@@ -297,6 +301,7 @@ __global__ void __launch_bounds__(BK_BT, 2) k_bk_build(u64 majors, int shift, in
   __shared__ u32 s_b, s_ndrop;
   __shared__ u64 s_basepos;
   constexpr u64 F_AGG = 1ull << 62, F_PFX = 2ull << 62, VMASK = (1ull << 62) - 1;
+  constexpr u32 JMASK = 0x7FFFu;
   constexpr int U = 4;  // global loads in flight per thread in the two passes over the records
   const u32 tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   if (tid == 0) { s_b = atomicAdd(ticket, 1u); s_ndrop = 0; }
@@ -333,56 +338,72 @@ __global__ void __launch_bounds__(BK_BT, 2) k_bk_build(u64 majors, int shift, in
     for (int k = 0; k < U; ++k) { const u32 j = j0 + k * BK_BT; e[k] = j < n ? rec[j] : make_uint4(0u, 0u, 0u, 0u); }
 #pragma unroll
     for (int k = 0; k < U; ++k) {
-      if (j0 + k * BK_BT < n) {
+      const u32 j = j0 + k * BK_BT;
+      if (j < n) {
         const u32 seg = mbits >= 32 ? 0u : (e[k].x >> mbits);
         const u32 p = atomicAdd(&s_cnt[seg], 1u);
-        s_kp[p] = ((u64)(e[k].x & mmask) << 32) | e[k].y;
-        s_val[p] = bk_val<V>(e[k]);
+        // num_traits::Zero::is_zero: -0.0 is zero, NaN is not (spam_dok lib.rs:167-176)
+        const bool zero = DEDUPE && bk_val<V>(e[k]) == (V)0;
+        s_minor[p] = e[k].x & mmask;
+        s_j[p] = (unsigned short)(j | (zero ? 0x8000u : 0u));
         s_seg[p] = (unsigned short)seg;
       }
     }
   }
   __syncthreads();
-  u32 total = n;
   if (DEDUPE) {
     for (u32 t = tid; t < R; t += BK_BT) s_cnt[t] = 0;  // now: entries a segment loses
     __syncthreads();
-    // 3. last write wins, zero deletes (DokMatrix::set_element, spam_dok lib.rs:167-176; is_zero: -0.0 is zero, NaN is
-    //    not); and the rank by column among ALL entries of the segment
-    u32 ndrop = 0;
-    for (u32 p = tid; p < n; p += BK_BT) {
-      const u32 seg = s_seg[p];
-      const u32 lo = s_off[seg], hi = s_off[seg + 1];
-      const u64 me = s_kp[p];
-      const u32 mh = (u32)(me >> 32), ml = (u32)me;
-      bool later = false;
-      u32 rk = 0;
-      if (!too_long)
-        for (u32 q = lo; q < hi; ++q) {
-          const u64 o = s_kp[q];
-          const u32 oh = (u32)(o >> 32), ol = (u32)o;
-          rk += oh < mh ? 1u : 0u;
-          later = later || (oh == mh && ol > ml);
+  }
+  // 3. one walk over the segment: rank by minor; equal minors are settled by the stream position (from the records)
+  u32 ndrop = 0;
+  for (u32 p = tid; p < n; p += BK_BT) {
+    const u32 seg = s_seg[p];
+    const u32 lo = s_off[seg], hi = s_off[seg + 1];
+    const u32 mh = s_minor[p];
+    u32 lt = 0, eq = 0;
+    if (!too_long)
+      for (u32 q = lo; q < hi; ++q) {
+        const u32 o = s_minor[q];
+        lt += o < mh ? 1u : 0u;
+        eq += o == mh ? 1u : 0u;
+      }
+    bool later = false;
+    if (eq > 1) {  // a rewritten key (DOK) / a repeated column in a row of an invalid matrix (transpose)
+      const u32 mypos = rec[s_j[p] & JMASK].y;
+      for (u32 q = lo; q < hi; ++q) {
+        if (q != p && s_minor[q] == mh) {
+          const u32 opos = rec[s_j[q] & JMASK].y;
+          if (DEDUPE) later = later || opos > mypos;  // last write wins
+          else lt += opos < mypos ? 1u : 0u;          // stable
         }
-      const bool drop = later || too_long || s_val[p] == (V)0;
-      s_rk[p] = drop ? (unsigned short)BK_DROPPED : (unsigned short)rk;
-      if (drop) { atomicAdd(&s_cnt[seg], 1u); ++ndrop; }
+      }
     }
+    if (DEDUPE) {
+      const bool drop = later || too_long || (s_j[p] & 0x8000u);
+      s_rk[p] = drop ? (unsigned short)BK_DROPPED : (unsigned short)lt;
+      if (drop) { atomicAdd(&s_cnt[seg], 1u); ++ndrop; }
+    } else {
+      s_rk[p] = (unsigned short)lt;
+    }
+  }
+  u32 total = n;
+  if (DEDUPE) {
     if (ndrop) atomicAdd(&s_ndrop, ndrop);
     __syncthreads();
     total = n - s_ndrop;
     if (tid == 0) state[b] = (b == 0 ? F_PFX : F_AGG) | (u64)total;  // published early: the look-back below rarely waits
     for (u32 p = tid; p < n; p += BK_BT)
-      if (s_rk[p] == BK_DROPPED) s_kp[p] = ~0ull;  // never smaller than a survivor
+      if (s_rk[p] == BK_DROPPED) s_minor[p] = 0xFFFFFFFFu;  // never smaller than a survivor
     __syncthreads();
-    // 4. segments that lost an entry: rank again among the survivors
+    // 4. segments that lost an entry: rank again among the survivors (their minors are distinct)
     for (u32 p = tid; p < n; p += BK_BT) {
       const u32 seg = s_seg[p];
       if (s_rk[p] == BK_DROPPED || s_cnt[seg] == 0) continue;
       const u32 lo = s_off[seg], hi = s_off[seg + 1];
-      const u32 mh = (u32)(s_kp[p] >> 32);
+      const u32 mh = s_minor[p];
       u32 rk = 0;
-      for (u32 q = lo; q < hi; ++q) rk += (u32)(s_kp[q] >> 32) < mh ? 1u : 0u;
+      for (u32 q = lo; q < hi; ++q) rk += s_minor[q] < mh ? 1u : 0u;
       s_rk[p] = (unsigned short)rk;
     }
     __syncthreads();
@@ -390,16 +411,6 @@ __global__ void __launch_bounds__(BK_BT, 2) k_bk_build(u64 majors, int shift, in
     __syncthreads();
     bk_block_scan(s_cnt, s_off, R, s_warp);  // s_off: survivors before each major of the bucket
   } else {
-    // 3'. rank by (minor, position) inside the segment (positions only matter for a repeated column in a row of A)
-    for (u32 p = tid; p < n; p += BK_BT) {
-      const u32 seg = s_seg[p];
-      const u32 lo = s_off[seg], hi = s_off[seg + 1];
-      const u64 me = s_kp[p];
-      u32 rk = 0;
-      if (!too_long)
-        for (u32 q = lo; q < hi; ++q) rk += s_kp[q] < me ? 1u : 0u;
-      s_rk[p] = (unsigned short)rk;
-    }
     __syncthreads();
   }
   // 5. position of the bucket in the result: decoupled look-back over the buckets (ticket order)
@@ -443,8 +454,12 @@ __global__ void __launch_bounds__(BK_BT, 2) k_bk_build(u64 majors, int shift, in
     const u32 rk = s_rk[p];
     if (DEDUPE && rk == BK_DROPPED) continue;
     const u64 o = base + s_off[s_seg[p]] + rk;
-    out_idx[o] = (u32)(s_kp[p] >> 32);
-    out_val[o] = s_val[p];
+    const uint2 vb = reinterpret_cast<const uint2*>(rec + (s_j[p] & JMASK))[1];  // the record's value (L2)
+    unsigned long long bits = (unsigned long long)vb.x | ((unsigned long long)vb.y << 32);
+    V v;
+    memcpy(&v, &bits, sizeof(V));
+    out_idx[o] = s_minor[p];
+    out_val[o] = v;
   }
 }
 
