@@ -8,10 +8,11 @@
 // a 128 MB array are bound by DRAM page activations (242 us of the 531 us of a C5 build).  Here the majors are cut
 // into buckets of 2^shift consecutive majors, sized so that a bucket's entries fit in shared memory:
 //   k_bk_part_*   one pass over the input: a block ranks its tile's entries per bucket in shared memory, takes a slice
-//                 of every bucket with ONE global atomic per (block, bucket), and stores 16-byte records
-//                 (major_local << mbits | minor, stream position, value).  A bucket's region is filled front to back
-//                 by all blocks, so the partially written lines — one per bucket — live in L2 and DRAM sees whole
-//                 lines.  Buckets have a fixed capacity (BK_CAP records): no counting pass, no scan.
+//                 of every bucket with ONE global atomic per (block, bucket), puts the tile in bucket order in shared
+//                 memory and stores 16-byte records (major_local << mbits | minor, stream position, value), consecutive
+//                 threads storing consecutive records of a bucket (whole sectors).  A bucket's region is filled front
+//                 to back by all blocks, so the partially written lines — one per bucket — live in L2 and DRAM sees
+//                 whole lines.  Buckets have a fixed capacity (BK_CAP records): no counting pass, no scan.
 //   k_bk_build    one block per bucket (in major order, handed out by a ticket): counting sort by major inside shared
 //                 memory, then every ENTRY decides for itself — it walks its own segment (neighbouring threads read
 //                 the same words: broadcasts, no bank conflicts, no idle lanes) to find out whether a later write of
@@ -68,43 +69,91 @@ __device__ __forceinline__ V bk_val(const uint4& e) {
 
 __device__ __forceinline__ void bk_prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
+// shared memory of the partition kernels: counts / starts and slice offsets per bucket, the staged tile (8 bytes per entry;
+// the transpose's row marks — BK_PTILE + BK_PTILE / 32 words — use the same space before)
+static size_t bk_part_smem(u32 nb) { return ((size_t)2 * (nb + (nb & 1)) + 2 * BK_PTILE) * sizeof(u32); }
+
 constexpr int BK_CUR_STRIDE = 8;  // one bucket cursor per 32-byte sector: a warp's 32 atomics spread over 8 lines
 
 // Second half of both partition kernels.  br[it] = bucket << 16 | rank inside (block, bucket), or ~0 for an entry that
-// is not placed; entry `it` of thread `tid` is element t0 + it * BK_PT + tid of the input.  One global atomic per
-// (block, bucket) reserves the block's slice of the bucket; four are in flight per thread.
+// is not placed; entry `it` of thread `tid` is element t0 + it * BK_PT + tid of the input.
+// The tile's (key, place, bucket) triples are first put in BUCKET ORDER in shared memory (s_stage, 8 bytes each), so that
+// consecutive threads store consecutive records of a bucket: the stores of a run leave the SM as whole 32-byte sectors.
+// (Scattered 16-byte stores straight from the registers — the first version — are half-sector writes the L2 has to
+// merge or fill: 168 us against 85 us for the same bytes stored contiguously and 73 us with no stores at all,
+// profiles/r02_bucket_dok_transpose.txt.)  One global atomic per (block, bucket) reserves the block's slice of the
+// bucket; four are in flight per thread.  s_hist: counts -> starts inside the tile; s_base: slice start - tile start.
 template <class V>
 __device__ __forceinline__ void bk_part_tail(u32 tid, u32 nb, u64 t0, const u32 (&key)[BK_PITEMS], const u32 (&br)[BK_PITEMS],
-                                             const V* __restrict__ vals, u32* s_hist, u32* s_base, u32* __restrict__ cursor,
-                                             uint4* __restrict__ part, Counters* cnt) {
+                                             const V* __restrict__ vals, u32* s_hist, u32* s_base, uint2* s_stage,
+                                             u32* __restrict__ cursor, uint4* __restrict__ part, Counters* cnt) {
+  __shared__ u32 s_tw[BK_PT / 32 + 1];
+  const u32 lane = tid & 31, wid = tid >> 5;
   __syncthreads();
-  for (u32 d0 = tid; d0 < nb; d0 += 4 * BK_PT) {
+  // exclusive scan of the counts: thread tid owns buckets [tid * C, tid * C + C)
+  const u32 C = (nb + BK_PT - 1) / BK_PT;
+  u32 sum = 0;
+  for (u32 k = 0; k < C; ++k) { const u32 d = tid * C + k; if (d < nb) sum += s_hist[d]; }
+  u32 incl = sum;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const u32 y = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= (u32)d) incl += y;
+  }
+  if (lane == 31) s_tw[wid] = incl;
+  __syncthreads();
+  if (wid == 0) {
+    const u32 w = lane < BK_PT / 32 ? s_tw[lane] : 0u;
+    u32 wi = w;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const u32 y = __shfl_up_sync(0xffffffffu, wi, d);
+      if (lane >= (u32)d) wi += y;
+    }
+    if (lane < BK_PT / 32) s_tw[lane] = wi - w;
+    if (lane == BK_PT / 32 - 1) s_tw[BK_PT / 32] = wi;
+  }
+  __syncthreads();
+  u32 run = s_tw[wid] + incl - sum;
+  const u32 placed = s_tw[BK_PT / 32];
+  for (u32 k0 = 0; k0 < C; k0 += 4) {
     u32 hc[4], bs[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) { const u32 d = d0 + k * BK_PT; hc[k] = d < nb ? s_hist[d] : 0u; }
+    for (int k = 0; k < 4; ++k) { const u32 d = tid * C + k0 + k; hc[k] = (k0 + k < C && d < nb) ? s_hist[d] : 0u; }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) bs[k] = hc[k] ? atomicAdd(&cursor[(u64)(d0 + k * BK_PT) * BK_CUR_STRIDE], hc[k]) : 0u;
+    for (int k = 0; k < 4; ++k) bs[k] = hc[k] ? atomicAdd(&cursor[(u64)(tid * C + k0 + k) * BK_CUR_STRIDE], hc[k]) : 0u;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) if (hc[k]) s_base[d0 + k * BK_PT] = bs[k];
+    for (int k = 0; k < 4; ++k) {
+      const u32 d = tid * C + k0 + k;
+      if (k0 + k < C && d < nb) { s_hist[d] = run; s_base[d] = bs[k] - run; run += hc[k]; }
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int it = 0; it < BK_PITEMS; ++it) {
+    if (br[it] != 0xFFFFFFFFu) {
+      const u32 b = br[it] >> 16;
+      s_stage[s_hist[b] + (br[it] & 0xFFFFu)] = make_uint2(key[it], (b << 16) | (u32)(it * BK_PT + tid));
+    }
   }
   __syncthreads();
   bool over = false;
+  for (u32 q0 = tid; q0 < placed; q0 += 4 * BK_PT) {
+    uint2 e[4];
+    V val[4];
 #pragma unroll
-  for (int half = 0; half < 2; ++half) {
-    constexpr int H = BK_PITEMS / 2;
-    V val[H];
-#pragma unroll
-    for (int k = 0; k < H; ++k) {
-      const int it = half * H + k;
-      if (br[it] != 0xFFFFFFFFu) val[k] = vals[t0 + (u64)it * BK_PT + tid];
+    for (int k = 0; k < 4; ++k) {
+      const u32 q = q0 + k * BK_PT;
+      e[k] = q < placed ? s_stage[q] : make_uint2(0u, 0u);
+      if (q < placed) val[k] = vals[t0 + (e[k].y & 0xFFFFu)];
     }
 #pragma unroll
-    for (int k = 0; k < H; ++k) {
-      const int it = half * H + k;
-      if (br[it] != 0xFFFFFFFFu) {
-        const u32 b = br[it] >> 16;
-        const u32 p = s_base[b] + (br[it] & 0xFFFFu);
-        if (p < BK_CAP) part[(u64)b * BK_CAP + p] = bk_pack(key[it], (u32)(t0 + (u64)it * BK_PT + tid), val[k]);
+    for (int k = 0; k < 4; ++k) {
+      const u32 q = q0 + k * BK_PT;
+      if (q < placed) {
+        const u32 b = e[k].y >> 16;
+        const u32 p = s_base[b] + q;
+        if (p < BK_CAP) part[(u64)b * BK_CAP + p] = bk_pack(e[k].x, (u32)(t0 + (e[k].y & 0xFFFFu)), val[k]);
         else over = true;
       }
     }
@@ -121,6 +170,7 @@ __global__ void __launch_bounds__(BK_PT, 2) k_bk_part_dok(u64 n, u64 rows, u64 c
   extern __shared__ u32 s_bk[];
   u32* s_hist = s_bk;
   u32* s_base = s_bk + nb;
+  uint2* s_stage = reinterpret_cast<uint2*>(s_bk + 2 * (nb + (nb & 1)));  // [BK_PTILE], 8-byte aligned
   const u32 tid = threadIdx.x;
   for (u32 d = tid; d < nb; d += BK_PT) s_hist[d] = 0;
   __syncthreads();
@@ -148,7 +198,7 @@ __global__ void __launch_bounds__(BK_PT, 2) k_bk_part_dok(u64 n, u64 rows, u64 c
     }
   }
   if (bad) atomicOr(&cnt->error, 2u);
-  bk_part_tail<V>(tid, nb, t0, key, br, v, s_hist, s_base, cursor, part, cnt);
+  bk_part_tail<V>(tid, nb, t0, key, br, v, s_hist, s_base, s_stage, cursor, part, cnt);
 }
 
 // CSR entries -> bucket records for the transpose.  key = (col & (2^shift - 1)) << mbits | row.  The row of every entry
@@ -171,7 +221,8 @@ __global__ void __launch_bounds__(BK_PT, 2) k_bk_part_csr(u64 m, u64 nnz, u64 tc
   extern __shared__ u32 s_bk[];
   u32* s_hist = s_bk;
   u32* s_base = s_bk + nb;
-  u32* s_mark = s_bk + 2 * nb;  // [BK_PTILE + BK_PTILE / 32], slot x at x + x / 32: both access patterns below are conflict-free
+  uint2* s_stage = reinterpret_cast<uint2*>(s_bk + 2 * (nb + (nb & 1)));  // [BK_PTILE], 8-byte aligned
+  u32* s_mark = reinterpret_cast<u32*>(s_stage);  // [BK_PTILE + BK_PTILE / 32] while the rows are looked up (the stage is filled later); slot x at x + x / 32: both access patterns below are conflict-free
   auto MK = [](u32 x) { return x + (x >> 5); };
   __shared__ u64 s_rows[2];
   __shared__ u32 s_wmax[BK_PT / 32];
@@ -180,14 +231,21 @@ __global__ void __launch_bounds__(BK_PT, 2) k_bk_part_csr(u64 m, u64 nnz, u64 tc
   for (u32 d = tid; d < (u32)(BK_PTILE + BK_PTILE / 32); d += BK_PT) s_mark[d] = 0;
   const u64 t0 = (u64)blockIdx.x * BK_PTILE;
   const u64 t1 = (t0 + BK_PTILE < nnz ? t0 + BK_PTILE : nnz) - 1;  // last entry of the tile
-  if (tid < 2) {  // last row whose start is <= the entry (rows are [ptr[r], ptr[r+1]); empty rows share a start)
-    const u64 e = tid == 0 ? t0 : t1;
-    u64 lo = 0, hi = m - 1;
-    while (lo < hi) {
-      const u64 mid = (lo + hi + 1) >> 1;
-      if (ptr[mid] <= e) lo = mid; else hi = mid - 1;
+  if (wid < 2) {  // last row whose start is <= the entry (rows are [ptr[r], ptr[r+1]); empty rows share a start):
+    // a 32-ary search by one warp — 4 round trips to row_ptr for a million rows where a binary search by one thread
+    // took 20, with the whole block waiting behind it
+    const u64 e = wid == 0 ? t0 : t1;
+    u64 lo = 0, len = m;  // candidates [lo, lo + len); ptr[lo] <= e throughout (ptr[0] = 0)
+    while (len > 1) {
+      const u64 step = (len + 31) / 32;
+      const u64 probe = lo + (u64)lane * step;
+      const bool ok = probe < lo + len && ptr[probe] <= e;  // true for a prefix of the lanes, lane 0 included
+      const unsigned mk = __ballot_sync(0xffffffffu, ok);
+      const u64 adv = (u64)(31 - __clz(mk)) * step;
+      len = (len - adv) < step ? (len - adv) : step;
+      lo += adv;
     }
-    s_rows[tid] = lo;
+    if (lane == 0) s_rows[wid] = lo;
   }
   __syncthreads();
   const u64 r0 = s_rows[0], r1 = s_rows[1];
@@ -233,7 +291,7 @@ __global__ void __launch_bounds__(BK_PT, 2) k_bk_part_csr(u64 m, u64 nnz, u64 tc
     }
   }
   if (bad) atomicOr(&cnt->error, 2u);
-  bk_part_tail<W>(tid, nb, t0, key, br, val, s_hist, s_base, cursor, part, cnt);
+  bk_part_tail<W>(tid, nb, t0, key, br, val, s_hist, s_base, s_stage, cursor, part, cnt);
 }
 
 // exclusive scan of s_in[0 .. r) (r <= 2 * BK_BT) into s_out[0 .. r], s_out[r] = total; returns the total to every

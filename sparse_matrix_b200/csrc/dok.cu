@@ -512,7 +512,7 @@ int dok_bucket(spam_handle* h, u64 rows, u64 cols, u64 n, const u64* d_r, const 
   u32* ticket = nullptr;
   CKS(bk_control(h, pl.nb, &state, &ticket, &cursor));
   CK(cudaMemsetAsync(h->d_cnt, 0, sizeof(Counters), h->stream));
-  const size_t psmem = (size_t)pl.nb * 2 * sizeof(u32);
+  const size_t psmem = bk_part_smem(pl.nb);
   CKS(bk_set_smem(h, k_bk_part_dok<V>, psmem));
   CKS(bk_set_smem(h, k_bk_build<V, true>, bk_build_smem<V>()));
   k_bk_part_dok<V><<<(unsigned)((n + BK_PTILE - 1) / BK_PTILE), BK_PT, psmem, h->stream>>>(
@@ -722,7 +722,7 @@ static int transpose_bucket(spam_handle* h, const spam_dcsr* a, spam_dcsr** out,
   u32* ticket = nullptr;
   CKS(bk_control(h, pl.nb, &state, &ticket, &cursor));
   CK(cudaMemsetAsync(h->d_cnt, 0, sizeof(Counters), h->stream));
-  const size_t psmem = ((size_t)pl.nb * 2 + BK_PTILE + BK_PTILE / 32) * sizeof(u32);
+  const size_t psmem = bk_part_smem(pl.nb);
   const unsigned pgrid = (unsigned)((n + BK_PTILE - 1) / BK_PTILE);
   if (es == 4) {
     CKS(bk_set_smem(h, k_bk_part_csr<uint32_t>, psmem));
