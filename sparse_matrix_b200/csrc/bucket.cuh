@@ -30,7 +30,7 @@ namespace {
 
 constexpr u32 BK_CAP = 5120;      // records per bucket (shared memory of k_bk_build: 10 bytes per record, 3 blocks per SM)
 constexpr u32 BK_NB_MAX = 8192;   // buckets: the partition kernel keeps two u32 per bucket in shared memory
-constexpr int BK_SHIFT_MAX = 10;  // at most 1024 majors per bucket
+constexpr int BK_SHIFT_MAX = 11;  // at most 2048 majors per bucket (bk_block_scan: 4 per thread)
 constexpr int BK_PT = 512, BK_PITEMS = 16, BK_PTILE = BK_PT * BK_PITEMS;  // partition tile: 8192 entries
 constexpr int BK_BT = 512;        // threads of the build kernel
 constexpr u32 BK_SEG_MAX = 512;   // longest segment the all-pairs loops are allowed to take (quadratic per segment)
@@ -294,12 +294,15 @@ __global__ void __launch_bounds__(BK_PT, 2) k_bk_part_csr(u64 m, u64 nnz, u64 tc
   bk_part_tail<W>(tid, nb, t0, key, br, val, s_hist, s_base, s_stage, cursor, part, cnt);
 }
 
-// exclusive scan of s_in[0 .. r) (r <= 2 * BK_BT) into s_out[0 .. r], s_out[r] = total; returns the total to every
+// exclusive scan of s_in[0 .. r) (r <= 4 * BK_BT) into s_out[0 .. r], s_out[r] = total; returns the total to every
 // thread.  s_in and s_out may be the same array.  Ends with a barrier.
 __device__ __forceinline__ u32 bk_block_scan(const u32* s_in, u32* s_out, u32 r, u32* s_warp) {
   const u32 tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const u32 a = 2 * tid < r ? s_in[2 * tid] : 0u, b = 2 * tid + 1 < r ? s_in[2 * tid + 1] : 0u;
-  u32 incl = a + b;
+  u32 a[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) a[k] = 4 * tid + k < r ? s_in[4 * tid + k] : 0u;
+  const u32 mine = a[0] + a[1] + a[2] + a[3];
+  u32 incl = mine;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
     const u32 y = __shfl_up_sync(0xffffffffu, incl, d);
@@ -320,18 +323,22 @@ __device__ __forceinline__ u32 bk_block_scan(const u32* s_in, u32* s_out, u32 r,
     if (lane == BK_BT / 32 - 1) s_warp[BK_BT / 32] = wi;
   }
   __syncthreads();
-  const u32 excl = s_warp[wid] + incl - (a + b);
-  if (2 * tid < r) s_out[2 * tid] = excl;
-  if (2 * tid + 1 < r) s_out[2 * tid + 1] = excl + a;
+  u32 excl = s_warp[wid] + incl - mine;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (4 * tid + k < r) s_out[4 * tid + k] = excl;
+    excl += a[k];
+  }
   const u32 total = s_warp[BK_BT / 32];
   if (tid == 0) s_out[r] = total;
   __syncthreads();
   return total;
 }
 
-template <class V>
-constexpr size_t bk_build_smem() {  // 58 KB whatever the value type: three blocks per SM
-  return (size_t)BK_CAP * (4 + 2 + 2 + 2) + (size_t)(2 * ((1u << BK_SHIFT_MAX) + 2)) * 4 + 64 * 4;
+// shared memory of k_bk_build: 10 bytes per record + two counters per major of the bucket (56 KB for 512 majors, 66 KB for
+// 2048: three blocks per SM either way, and what is not claimed stays L1 for the second pass over the records)
+static size_t bk_build_smem(int shift) {
+  return (size_t)BK_CAP * (4 + 2 + 2 + 2) + (size_t)(2 * ((1u << shift) + 2)) * 4 + 64 * 4;
 }
 
 // One block per bucket.  out_ptr has majors + 1 entries; out_idx / out_val hold the result (sized for every entry).
@@ -353,9 +360,10 @@ __global__ void __launch_bounds__(BK_BT, 3) k_bk_build(u64 majors, int shift, in
   unsigned short* s_j = reinterpret_cast<unsigned short*>(s_minor + BK_CAP);   // [BK_CAP] record of the entry | 0x8000: zero value
   unsigned short* s_seg = s_j + BK_CAP;                                        // [BK_CAP] major_local of a sorted entry
   unsigned short* s_rk = s_seg + BK_CAP;                                       // [BK_CAP] rank among the survivors / BK_DROPPED
+  const u32 R = 1u << shift;
   u32* s_cnt = reinterpret_cast<u32*>(s_rk + BK_CAP);                          // [R + 2]
-  u32* s_off = s_cnt + (1u << BK_SHIFT_MAX) + 2;                               // [R + 2]
-  u32* s_warp = s_off + (1u << BK_SHIFT_MAX) + 2;                              // [64]
+  u32* s_off = s_cnt + R + 2;                                                  // [R + 2]
+  u32* s_warp = s_off + R + 2;                                                 // [64]
   __shared__ u32 s_b, s_ndrop;
   __shared__ u64 s_basepos;
   constexpr u64 F_AGG = 1ull << 62, F_PFX = 2ull << 62, VMASK = (1ull << 62) - 1;
@@ -363,7 +371,6 @@ __global__ void __launch_bounds__(BK_BT, 3) k_bk_build(u64 majors, int shift, in
   constexpr int U = 4;  // global loads in flight per thread in the two passes over the records
   const u32 tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   if (tid == 0) { s_b = atomicAdd(ticket, 1u); s_ndrop = 0; }
-  const u32 R = 1u << shift;
   for (u32 t = tid; t <= R; t += BK_BT) s_cnt[t] = 0;
   __syncthreads();
   const u32 b = s_b;

@@ -514,10 +514,10 @@ int dok_bucket(spam_handle* h, u64 rows, u64 cols, u64 n, const u64* d_r, const 
   CK(cudaMemsetAsync(h->d_cnt, 0, sizeof(Counters), h->stream));
   const size_t psmem = bk_part_smem(pl.nb);
   CKS(bk_set_smem(h, k_bk_part_dok<V>, psmem));
-  CKS(bk_set_smem(h, k_bk_build<V, true>, bk_build_smem<V>()));
+  CKS(bk_set_smem(h, k_bk_build<V, true>, bk_build_smem(BK_SHIFT_MAX)));
   k_bk_part_dok<V><<<(unsigned)((n + BK_PTILE - 1) / BK_PTILE), BK_PT, psmem, h->stream>>>(
       n, rows, cols, pl.shift, pl.mbits, pl.nb, d_r, d_c, d_v, cursor, part, h->d_cnt);
-  k_bk_build<V, true><<<pl.nb, BK_BT, bk_build_smem<V>(), h->stream>>>(rows, pl.shift, pl.mbits, pl.nb, cursor, part, state,
+  k_bk_build<V, true><<<pl.nb, BK_BT, bk_build_smem(pl.shift), h->stream>>>(rows, pl.shift, pl.mbits, pl.nb, cursor, part, state,
                                                                        ticket, out->ptr, idx, val, h->d_cnt);
   count_launch(h, 2);
   CK(cudaGetLastError());
@@ -726,17 +726,17 @@ static int transpose_bucket(spam_handle* h, const spam_dcsr* a, spam_dcsr** out,
   const unsigned pgrid = (unsigned)((n + BK_PTILE - 1) / BK_PTILE);
   if (es == 4) {
     CKS(bk_set_smem(h, k_bk_part_csr<uint32_t>, psmem));
-    CKS(bk_set_smem(h, k_bk_build<uint32_t, false>, bk_build_smem<uint32_t>()));
+    CKS(bk_set_smem(h, k_bk_build<uint32_t, false>, bk_build_smem(BK_SHIFT_MAX)));
     k_bk_part_csr<uint32_t><<<pgrid, BK_PT, psmem, h->stream>>>(m, n, tc, pl.shift, pl.mbits, pl.nb, a->ptr, a->idx,
                                                                (const uint32_t*)a->val, cursor, part, h->d_cnt);
-    k_bk_build<uint32_t, false><<<pl.nb, BK_BT, bk_build_smem<uint32_t>(), h->stream>>>(
+    k_bk_build<uint32_t, false><<<pl.nb, BK_BT, bk_build_smem(pl.shift), h->stream>>>(
         tc, pl.shift, pl.mbits, pl.nb, cursor, part, state, ticket, t_ptr, t_idx, (uint32_t*)t_val, h->d_cnt);
   } else {
     CKS(bk_set_smem(h, k_bk_part_csr<uint64_t>, psmem));
-    CKS(bk_set_smem(h, k_bk_build<uint64_t, false>, bk_build_smem<uint64_t>()));
+    CKS(bk_set_smem(h, k_bk_build<uint64_t, false>, bk_build_smem(BK_SHIFT_MAX)));
     k_bk_part_csr<uint64_t><<<pgrid, BK_PT, psmem, h->stream>>>(m, n, tc, pl.shift, pl.mbits, pl.nb, a->ptr, a->idx,
                                                                (const uint64_t*)a->val, cursor, part, h->d_cnt);
-    k_bk_build<uint64_t, false><<<pl.nb, BK_BT, bk_build_smem<uint64_t>(), h->stream>>>(
+    k_bk_build<uint64_t, false><<<pl.nb, BK_BT, bk_build_smem(pl.shift), h->stream>>>(
         tc, pl.shift, pl.mbits, pl.nb, cursor, part, state, ticket, t_ptr, t_idx, (uint64_t*)t_val, h->d_cnt);
   }
   count_launch(h, 2);
