@@ -28,7 +28,7 @@
 
 namespace {
 
-constexpr u32 BK_CAP = 5120;      // records per bucket (shared memory of k_bk_build: 10 bytes per record, 3 blocks per SM)
+constexpr u32 BK_CAP = 5040;      // records per bucket: 10 bytes each in k_bk_build; 3 blocks of 512-major buckets fit the 164 KB carve-out, 92 KB stay L1
 constexpr u32 BK_NB_MAX = 8192;   // buckets: the partition kernel keeps two u32 per bucket in shared memory
 constexpr int BK_SHIFT_MAX = 11;  // at most 2048 majors per bucket (bk_block_scan: 4 per thread)
 constexpr int BK_PT = 512, BK_PITEMS = 16, BK_PTILE = BK_PT * BK_PITEMS;  // partition tile: 8192 entries
