@@ -158,3 +158,20 @@ def test_transpose_and_triplet_stream(oracle):
     nzero = int(len(a[3]) * 0.02)
     assert len(idx) == len(a[3]) - nzero           # the zero writes deleted exactly that many entries
     assert np.all(np.diff(off.astype(np.int64)) <= np.diff(a[2].astype(np.int64)))
+
+
+def test_bucket_path_plan_on_the_host(tmp_path):
+    """The plan of the DOK -> CSR / transpose bucket path (bucket.cuh: bk_plan — bucket width, bucket count, key packing,
+    shared-memory budgets) is host code: compiled with nvcc and run on the CPU (no kernel is launched) over the C5 shapes,
+    the shapes the path must refuse, and 200 000 random shapes checked against its invariants."""
+    import shutil
+    import subprocess
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not found")
+    src = os.path.join(os.path.dirname(__file__), "cpp", "test_bk_plan.cu")
+    exe = str(tmp_path / "test_bk_plan")
+    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O1", "-o", exe, src],
+                          stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and "bk_plan ok" in out.stdout, out.stdout + out.stderr
