@@ -415,6 +415,22 @@ def test_config2_poisson_full_size(oracle, handle):
     assert np.array_equal(y1, y2)        # small integers: exact in f64
     dC.free()
     dA.free()
+    # the same matrix as CsrMatrix<T, false>: every row's entries shuffled.  B's sorted copy is made on the device by two
+    # transposes (bucket path with 8192 column buckets, 21 M entries) and the product must be the same, bit for bit.
+    rng = np.random.default_rng(7)
+    lens = np.diff(p[2].astype(np.int64))
+    perm = np.argsort(np.repeat(np.arange(p[0]), lens) + rng.random(len(p[3])), kind="stable")
+    dU = S.DeviceCsr.upload(S.CsrMatrix(p[0], p[1], p[4][perm], p[3][perm], p[2], is_sorted=False), handle)
+    dT = dU.transpose()
+    assert handle.stats()["fallbacks"][4] == 3                        # bucket path
+    dT.free()
+    dCu = dU.matmul(dU)
+    assert handle.stats()["num_bin_rows"][MERGE] == 4_194_304          # multiplied by the sorted copy: merge bin
+    cu = dCu.download()
+    assert np.array_equal(cu.offsets, c.offsets) and np.array_equal(cu.indices, c.indices)
+    assert np.array_equal(cu.vals.view(np.uint8), c.vals.view(np.uint8))
+    dCu.free()
+    dU.free()
 
 
 def test_config3_stencil27_reduced(oracle, handle):
