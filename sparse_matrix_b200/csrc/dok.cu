@@ -6,7 +6,10 @@
 // LAST write of the stream unless that write is zero.  BTreeMap iteration order is (row, col)
 // lexicographic (spam_dok/src/lib.rs:234-242); empty rows get repeated offsets (lib.rs:321,325).
 //
-// Two paths, chosen after a histogram of the stream by row (one small host sync):
+// The default is the BUCKET PATH of bucket.cuh (one partition pass into buckets of consecutive rows, one build pass per
+// bucket in shared memory, one host sync; dok_bucket / transpose_bucket below).  It hands shapes it does not take, crowded
+// buckets and very long rows to the two paths of this file, chosen after a histogram of the stream by row (one small host
+// sync):
 //
 //  COUNTING PATH (no row holds more than SEG_MAX = 32 triplets — C5: 8 per row): CSR is a counting sort by row,
 //    1. k_dok_hist     raw count per row (L2 atomics), index validation
